@@ -1,0 +1,179 @@
+/* b200fem.h -- C ABI of the B200-native matrix-free operator-apply path.
+ *
+ * Drop-in boundary for sfem's matrix-free hot path. Every entry point is
+ * extern "C", takes plain pointers and sizes, returns int (0 = B200FEM_SUCCESS, 1 = B200FEM_FAILURE,
+ * same convention as SFEM_SUCCESS / SFEM_FAILURE, base/sfem_base.hpp:12-13 of the reference) and
+ * never throws. There is NO CPU fallback: a call without a usable CUDA device fails.
+ *
+ * Conventions shared with the reference's operator-level C functions
+ * (operators/laplacian.hpp, operators/linear_elasticity.hpp, operators/.../cuda/cu_*.cu):
+ *   - connectivity is SoA `elements[nxe][nelements]`, int32 (idx_t), HOST memory at plan creation;
+ *   - geometry factors are fp32 (jacobian_t / geom_t) even for fp64 vectors, HOST memory at plan
+ *     creation: FFF `[nelements*6]` AoS, adjugate `[nelements*9]` AoS, determinant `[nelements]`;
+ *   - vectors are DEVICE pointers of `real_type` (B200FEM_F64 / B200FEM_F32);
+ *   - vector fields (linear elasticity) are AoS `[nnodes*3]` = the reference's block_size-3 layout
+ *     (frontend/ops/sfem_LinearElasticity.cpp:540-550 hands &u[0],&u[1],&u[2] with stride 3);
+ *   - apply ACCUMULATES: y += A x (callers zero first: algebra/sfem_cg.hpp:226-230);
+ *   - `stream` is a cudaStream_t passed by value as void* (NULL = default stream); all launches are
+ *     asynchronous with respect to the host unless stated otherwise.
+ */
+#ifndef B200FEM_H
+#define B200FEM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FEM_SUCCESS 0
+#define B200FEM_FAILURE 1
+
+/* real_t of the vectors; value == sizeof */
+#define B200FEM_F32 4
+#define B200FEM_F64 8
+
+/* element families (numeric values follow smesh::ElemType as far as the reference shows them) */
+#define B200FEM_TET4 4
+#define B200FEM_HEX8 8
+#define B200FEM_SSHEX8 800 /* semi-structured hex8; the refinement level is a separate argument */
+
+/* scatter strategies of b200fem_op_set_option("scatter", ...) */
+#define B200FEM_SCATTER_AUTO 0
+#define B200FEM_SCATTER_ATOMIC 1  /* red.global.add on every element dof                        */
+#define B200FEM_SCATTER_COLORED 2 /* element colouring, plain read-modify-write, one launch/colour */
+
+typedef struct b200fem_op_s *b200fem_op_t; /* opaque operator plan (device connectivity + geometry) */
+
+/* ------------------------------------------------------------------------------------------
+ * Runtime helpers (what smesh::Buffer / sfem::BLAS<T>::allocate give the reference's device path,
+ * algebra/cuda/sfem_cuda_blas.cu:497-514)
+ * ---------------------------------------------------------------------------------------- */
+const char *b200fem_last_error(void);          /* message of the last failure on this thread        */
+int b200fem_device_count(int *count);
+int b200fem_set_device(int device);
+int b200fem_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *global_mem_bytes);
+int b200fem_malloc(void **ptr, size_t bytes);  /* zero-filled, like BLAS<T>::allocate (calloc)      */
+int b200fem_free(void *ptr);
+int b200fem_host_malloc(void **ptr, size_t bytes); /* pinned host memory                            */
+int b200fem_host_free(void *ptr);
+int b200fem_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int b200fem_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int b200fem_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int b200fem_stream_create(void **stream);
+int b200fem_stream_destroy(void *stream);
+int b200fem_stream_synchronize(void *stream);
+int b200fem_device_synchronize(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Geometry caches (setup path). Replace tet4_fff_fill (operators/tet4/tet4_fff.cpp:4-27),
+ * hex8_fff_fill (operators/hex8/hex8_fff.cpp:5-37) and hex8_adjugate_and_det_fill
+ * (operators/hex8/hex8_jacobian.cpp:5-38). Host in, host out; the work runs on the device.
+ * For B200FEM_SSHEX8 pass the 8 macro corners as `elements` (rows of the level-L lattice corners).
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_fff_fill(int element_type, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
+                     const float *const *points, float *fff /* [nelements*6] */);
+int b200fem_adjugate_and_det_fill(int element_type, ptrdiff_t nelements, ptrdiff_t nnodes,
+                                  const int32_t *const *elements, const float *const *points,
+                                  float *adjugate /* [nelements*9] */, float *determinant /* [nelements] */);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator plans.
+ *   b200fem_laplacian_create   <- laplacian_apply_opt(type, ne, elements, fff, u, out)
+ *                                 (operators/laplacian.cpp:197-236): TET4 -> tet4_laplacian_apply_opt
+ *                                 (operators/tet4/tet4_laplacian.cpp:237), HEX8 -> hex8_laplacian_apply_opt
+ *                                 (operators/hex8/hex8_laplacian.cpp:309), SSHEX8 ->
+ *                                 affine_sshex8_laplacian_stencil_apply_fff
+ *                                 (operators/sshex8/sshex8_laplacian.cpp:698); GPU twin being superseded:
+ *                                 cu_laplacian_apply (frontend/cuda/sfem_Function_incore_cuda.cpp:683-697).
+ *   b200fem_linear_elasticity_create <- HEX8: affine_hex8_linear_elasticity_apply_adjugate_soa
+ *                                 (operators/hex8/hex8_linear_elasticity.cpp:625), SSHEX8:
+ *                                 affine_sshex8_linear_elasticity_apply_macro_adjugate
+ *                                 (operators/sshex8/sshex8_linear_elasticity.cpp:275).
+ * `level` is ignored unless element_type == B200FEM_SSHEX8 (then nxe = (level+1)^3 rows of
+ * `elements`, local lattice index z*(L+1)^2 + y*(L+1) + x, operators/sshex8/sshex8.hpp:18).
+ * The plan copies and re-lays-out connectivity and geometry on the current device; the host
+ * arrays may be released after the call. No allocation happens in apply.
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_laplacian_create(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements, ptrdiff_t nnodes,
+                             const int32_t *const *elements, const float *fff, int real_type);
+int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements,
+                                     ptrdiff_t nnodes, const int32_t *const *elements, const float *adjugate,
+                                     const float *determinant, double mu, double lambda, int real_type);
+int b200fem_op_destroy(b200fem_op_t op);
+
+/* y += A x  (sfem::Op::apply(x, h, out), frontend/ops/sfem_Op.hpp:214; Operator<T>::apply,
+ * algebra/sfem_Operator.hpp:16) */
+int b200fem_op_apply(b200fem_op_t op, const void *x, void *y, void *stream);
+/* y = A x : same result as zeros(y) followed by apply, without reading y where no other element
+ * contributes. This is the fused form the device CG / Chebyshev below use. */
+int b200fem_op_apply_overwrite(b200fem_op_t op, const void *x, void *y, void *stream);
+/* diag += diag(A)  (Op::hessian_diag, frontend/ops/sfem_Op.hpp:194; laplacian_diag,
+ * operators/laplacian.cpp:156-195; affine_hex8_linear_elasticity_diag,
+ * operators/hex8/hex8_linear_elasticity.cpp:1043) */
+int b200fem_op_diag(b200fem_op_t op, void *diag, void *stream);
+/* 6 entries per node of the symmetric 3x3 block diagonal, AoS [nnodes*6] order
+ * (00,01,02,11,12,22)  (Op::hessian_block_diag_sym, frontend/ops/sfem_Op.hpp:138) */
+int b200fem_op_block_diag_sym(b200fem_op_t op, void *bdiag, void *stream);
+
+ptrdiff_t b200fem_op_rows(b200fem_op_t op); /* nnodes * block_size */
+int b200fem_op_block_size(b200fem_op_t op);
+int b200fem_op_real_type(b200fem_op_t op);
+/* Canonical algorithmic bytes per apply: ne*(nxe*4 + geometry bytes) + rows*2*sizeof(real)
+ * (the reference's own accounting, notebook/SEMISTRUCTURED.md:20). */
+double b200fem_op_algorithmic_bytes(b200fem_op_t op);
+/* Bytes the plan actually streams per apply (compressed connectivity, y read when accumulating). */
+double b200fem_op_streamed_bytes(b200fem_op_t op, int overwrite);
+int b200fem_op_gpu_launches_per_apply(b200fem_op_t op, int overwrite);
+int b200fem_op_set_option(b200fem_op_t op, const char *key, int value);
+int b200fem_op_get_option(b200fem_op_t op, const char *key, int *value);
+
+/* ------------------------------------------------------------------------------------------
+ * Dirichlet constraints on device vectors (operators/boundary_conditions/dirichlet.cpp:95-105,
+ * 247-258; CUDA twins cuda/cu_boundary_condition.cu:31,79). `idx` is a DEVICE int32 list of node
+ * ids; the dof touched is idx[i]*block_size + component.
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_constraint_nodes_copy_vec(int real_type, ptrdiff_t n, const int32_t *idx, int block_size, int component,
+                                      const void *source, void *dest, void *stream);
+int b200fem_constraint_nodes_to_value_vec(int real_type, ptrdiff_t n, const int32_t *idx, int block_size,
+                                          int component, double value, void *values, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Vector kernels = the 13 virtuals of sfem::BLAS<T> (algebra/sfem_tpl_blas.hpp:15-33), semantics
+ * of OpenMP_BLAS (algebra/openmp/sfem_openmp_blas.hpp:22-123). Scalars cross the ABI as double.
+ * dot / norm2 accumulate in fp64 regardless of real_type.
+ * `*_async` variants leave the result in DEVICE memory (one double) and do not synchronise.
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_blas_zeros(int real_type, ptrdiff_t n, void *x, void *stream);
+int b200fem_blas_values(int real_type, ptrdiff_t n, double value, void *x, void *stream);
+int b200fem_blas_copy(int real_type, ptrdiff_t n, const void *src, void *dest, void *stream);
+int b200fem_blas_scal(int real_type, ptrdiff_t n, double alpha, void *x, void *stream);
+int b200fem_blas_axpy(int real_type, ptrdiff_t n, double alpha, const void *x, void *y, void *stream);
+int b200fem_blas_axpby(int real_type, ptrdiff_t n, double alpha, const void *x, double beta, void *y, void *stream);
+int b200fem_blas_zaxpby(int real_type, ptrdiff_t n, double alpha, const void *x, double beta, const void *y, void *z,
+                        void *stream);
+int b200fem_blas_xypaz(int real_type, ptrdiff_t n, const void *x, const void *y, double alpha, void *z,
+                       void *stream);
+int b200fem_blas_reciprocal(int real_type, ptrdiff_t n, double alpha, void *x, void *stream);
+int b200fem_blas_dot(int real_type, ptrdiff_t n, const void *x, const void *y, double *result_host, void *stream);
+int b200fem_blas_norm2(int real_type, ptrdiff_t n, const void *x, double *result_host, void *stream);
+int b200fem_blas_dot_async(int real_type, ptrdiff_t n, const void *x, const void *y, double *result_dev,
+                           void *stream);
+
+/* Fused solver updates with the reference's recurrences:
+ *   cg_update_x_r_rtr : x += alpha p; r -= alpha Ap; *rtr = (r,r)   (algebra/sfem_cg.hpp:23-44)
+ *   cg_update_p       : p = z + beta p                               (algebra/sfem_cg.hpp:64-74)
+ *   cheb3_update      : p = beta p - rhs + Ax ... see algebra/sfem_Chebyshev3.hpp:35-52
+ * rtr is returned on the host (synchronises the stream). */
+int b200fem_cg_update_x_r_rtr(int real_type, ptrdiff_t n, double alpha, const void *p, const void *Ap, void *x,
+                              void *r, double *rtr_host, void *stream);
+int b200fem_cg_update_p(int real_type, ptrdiff_t n, double beta, const void *z, void *p, void *stream);
+/* p = beta p - rhs + Ax ; x -= alpha p   (chebyshev3_host_::iteration_update) */
+int b200fem_cheb3_update(int real_type, ptrdiff_t n, double alpha, double beta, const void *rhs, const void *Ax,
+                         void *p, void *x, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FEM_H */

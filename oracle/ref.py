@@ -1,0 +1,180 @@
+"""ctypes access to the oracle libraries. TEST INFRASTRUCTURE ONLY.
+
+Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import this module; nothing under `sfem_b200/` does.
+
+Two interchangeable back-ends expose the same extern "C" entry points (the reference's own
+operator-level C functions, e.g. `tet4_laplacian_apply_opt`,
+operators/tet4/tet4_laplacian.cpp:237 of the reference):
+
+* kind="reference": `oracle/_ref/libsfem_ref_{f64,f32}[_fast].so` -- the reference's own sources
+  compiled out of tree by `oracle/Makefile` (target `ref`);
+* kind="port": `oracle/liboracle_port_{f64,f32}.so` -- our plain-C restatement
+  (`oracle/oracle_port.c`), pinned against the reference build by `tests/test_oracle.py` and
+  against the committed fixtures in `tests/golden/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_idx_pp = C.POINTER(C.POINTER(C.c_int32))
+c_f32_pp = C.POINTER(C.POINTER(C.c_float))
+
+
+def _soa_ptrs(arr: np.ndarray, ctype):
+    """pointer-to-pointers view of a C-contiguous [k][n] array (keeps `arr` alive via closure)."""
+    assert arr.flags["C_CONTIGUOUS"]
+    k = arr.shape[0]
+    ptrs = (C.POINTER(ctype) * k)()
+    for i in range(k):
+        ptrs[i] = arr[i].ctypes.data_as(C.POINTER(ctype))
+    return ptrs
+
+
+def lib_path(kind: str, real: str, fast: bool = False) -> str:
+    if kind == "reference":
+        return os.path.join(HERE, "_ref", f"libsfem_ref_{real}{'_fast' if fast else ''}.so")
+    if kind == "port":
+        return os.path.join(HERE, f"liboracle_port_{real}.so")
+    raise ValueError(kind)
+
+
+def available(kind: str, real: str = "f64", fast: bool = False) -> bool:
+    return os.path.exists(lib_path(kind, real, fast))
+
+
+class Oracle:
+    """Thin numpy front for one oracle library (one real type)."""
+
+    def __init__(self, kind: str = "reference", real: str = "f64", fast: bool = False):
+        self.kind, self.real = kind, real
+        self.rt = np.float64 if real == "f64" else np.float32
+        self.crt = C.c_double if real == "f64" else C.c_float
+        path = lib_path(kind, real, fast)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle {'ref' if kind == 'reference' else 'port'}`")
+        self.lib = C.CDLL(path)
+
+    # ---- helpers
+    def _r(self, a):
+        a = np.ascontiguousarray(a, dtype=self.rt)
+        return a, a.ctypes.data_as(C.POINTER(self.crt))
+
+    @staticmethod
+    def _f32(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def _call(self, name, *args):
+        fn = getattr(self.lib, name)
+        fn.restype = C.c_int
+        rc = fn(*args)
+        if rc != 0:
+            raise RuntimeError(f"{name} returned {rc}")
+
+    # ---- geometry
+    def tet4_fff_fill(self, elements, points):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        ne = el.shape[1]
+        fff = np.zeros(ne * 6, dtype=np.float32)
+        self._call("tet4_fff_fill", C.c_ssize_t(ne), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+                   fff.ctypes.data_as(C.POINTER(C.c_float)))
+        return fff
+
+    def hex8_fff_fill(self, elements, points):
+        """FFF at the element centre from the 8 corners (works for the macro corners of sshex8)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        ne = el.shape[1]
+        fff = np.zeros(ne * 6, dtype=np.float32)
+        self._call("hex8_fff_fill", C.c_ssize_t(ne), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+                   fff.ctypes.data_as(C.POINTER(C.c_float)))
+        return fff
+
+    def hex8_adjugate_and_det_fill(self, elements, points):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        ne = el.shape[1]
+        adj = np.zeros(ne * 9, dtype=np.float32)
+        det = np.zeros(ne, dtype=np.float32)
+        self._call("hex8_adjugate_and_det_fill", C.c_ssize_t(ne), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+                   adj.ctypes.data_as(C.POINTER(C.c_float)), det.ctypes.data_as(C.POINTER(C.c_float)))
+        return adj, det
+
+    # ---- Laplacian
+    def tet4_laplacian_apply_opt(self, elements, fff, u, out=None):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        u, pu = self._r(u)
+        out = np.zeros_like(u) if out is None else np.ascontiguousarray(out, dtype=self.rt)
+        self._call("tet4_laplacian_apply_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf, pu,
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def tet4_laplacian_diag_opt(self, elements, fff, nnodes):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        out = np.zeros(nnodes, dtype=self.rt)
+        self._call("tet4_laplacian_diag_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf,
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def hex8_laplacian_apply_opt(self, elements, fff, u, out=None):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        u, pu = self._r(u)
+        out = np.zeros_like(u) if out is None else np.ascontiguousarray(out, dtype=self.rt)
+        self._call("hex8_laplacian_apply_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf, pu,
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def sshex8_laplacian_apply(self, level, elements, fff, u, out=None):
+        """affine_sshex8_laplacian_stencil_apply_fff (operators/sshex8/sshex8_laplacian.cpp:698)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        u, pu = self._r(u)
+        out = np.zeros_like(u) if out is None else np.ascontiguousarray(out, dtype=self.rt)
+        self._call("affine_sshex8_laplacian_stencil_apply_fff", C.c_int(level), C.c_ssize_t(el.shape[1]),
+                   _soa_ptrs(el, C.c_int32), pf, pu, out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    # ---- linear elasticity (u/out AoS [nn*3])
+    def hex8_linear_elasticity_apply(self, elements, adjugate_aos, det, mu, lam, u, nnodes, out=None):
+        """affine_hex8_linear_elasticity_apply_adjugate_soa (operators/hex8/hex8_linear_elasticity.cpp:625);
+        the Op hands it SoA adjugate streams (frontend/ops/sfem_LinearElasticity.cpp:275-277)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        ne = el.shape[1]
+        adj_soa = np.ascontiguousarray(np.asarray(adjugate_aos, dtype=np.float32).reshape(ne, 9).T)
+        det, pd = self._f32(det)
+        u, _ = self._r(u)
+        out = np.zeros_like(u) if out is None else np.ascontiguousarray(out, dtype=self.rt)
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("affine_hex8_linear_elasticity_apply_adjugate_soa", C.c_ssize_t(ne), C.c_ssize_t(nnodes),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(adj_soa, C.c_float), pd, self.crt(mu), self.crt(lam),
+                   C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
+    def sshex8_linear_elasticity_apply(self, level, elements, adjugate_aos, det, mu, lam, u, nnodes, out=None):
+        """affine_sshex8_linear_elasticity_apply_macro_adjugate
+        (operators/sshex8/sshex8_linear_elasticity.cpp:275)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        ne = el.shape[1]
+        adj, pa = self._f32(adjugate_aos)
+        det, pd = self._f32(det)
+        u, _ = self._r(u)
+        out = np.zeros_like(u) if out is None else np.ascontiguousarray(out, dtype=self.rt)
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("affine_sshex8_linear_elasticity_apply_macro_adjugate", C.c_int(level), C.c_ssize_t(ne),
+                   C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), None, pa, pd, self.crt(mu), self.crt(lam),
+                   C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out

@@ -1,0 +1,1 @@
+/* empty stand-in for the missing external/smesh submodule */

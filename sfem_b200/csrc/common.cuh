@@ -1,0 +1,124 @@
+// Shared device/host helpers for the b200fem kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "b200fem.h"
+
+namespace b200fem {
+
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+
+#define B2_CUDA(call)                                                          \
+    do {                                                                       \
+        if (!::b200fem::cuda_ok((call), #call, __FILE__, __LINE__)) return B200FEM_FAILURE; \
+    } while (0)
+
+#define B2_FAIL(msg)                       \
+    do {                                   \
+        ::b200fem::set_error(msg);         \
+        return B200FEM_FAILURE;            \
+    } while (0)
+
+#define B2_CHECK_LAUNCH() B2_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached SM count of the current device
+
+// fire-and-forget global add: compiles to RED.E.ADD.F64/F32 (no return value requested)
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T ldg_stream(const T *p) {
+    return __ldcs(p);  // evict-first: connectivity / geometry are read exactly once per apply
+}
+
+// Owning device buffer (plan storage)
+template <typename T>
+struct DeviceArray {
+    T *ptr = nullptr;
+    size_t n = 0;
+    DeviceArray() = default;
+    DeviceArray(const DeviceArray &) = delete;
+    DeviceArray &operator=(const DeviceArray &) = delete;
+    ~DeviceArray() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return B200FEM_SUCCESS;
+        B2_CUDA(cudaMalloc((void **)&ptr, count * sizeof(T)));
+        return B200FEM_SUCCESS;
+    }
+    int upload(const T *host, size_t count) {
+        if (alloc(count) != B200FEM_SUCCESS) return B200FEM_FAILURE;
+        if (count) B2_CUDA(cudaMemcpy(ptr, host, count * sizeof(T), cudaMemcpyHostToDevice));
+        return B200FEM_SUCCESS;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// Operator plan base: everything behind b200fem_op_t
+struct OpBase {
+    int elem_type = 0;
+    int level = 0;
+    int real_type = B200FEM_F64;
+    int block_size = 1;
+    ptrdiff_t ne = 0, nn = 0;
+    int nxe = 0;
+    double geom_bytes_per_elem = 0;
+    int scatter = B200FEM_SCATTER_AUTO;
+    virtual ~OpBase() {}
+    virtual int apply(const void *x, void *y, bool overwrite, cudaStream_t s) = 0;
+    virtual int diag(void *d, cudaStream_t s) {
+        (void)d; (void)s;
+        set_error("diag not implemented for this operator");
+        return B200FEM_FAILURE;
+    }
+    virtual int block_diag_sym(void *d, cudaStream_t s) {
+        (void)d; (void)s;
+        set_error("block_diag_sym not implemented for this operator");
+        return B200FEM_FAILURE;
+    }
+    virtual double streamed_bytes(bool overwrite) const { (void)overwrite; return algorithmic_bytes(); }
+    virtual int launches(bool overwrite) const { (void)overwrite; return 1; }
+    virtual int set_option(const char *key, int value);
+    virtual int get_option(const char *key, int *value);
+    double algorithmic_bytes() const {
+        return double(ne) * (double(nxe) * 4.0 + geom_bytes_per_elem) + double(nn) * block_size * 2.0 * real_type;
+    }
+};
+
+// factories implemented in the per-element translation units
+OpBase *make_tet4_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type);
+OpBase *make_hex8_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type);
+OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff,
+                              int real_type);
+OpBase *make_hex8_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
+                                    const float *determinant, double mu, double lambda, int real_type);
+OpBase *make_sshex8_linear_elasticity(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                                      const float *adjugate, const float *determinant, double mu, double lambda,
+                                      int real_type);
+
+// Greedy element colouring on the host (nodes shared => different colour). Returns the element
+// permutation grouped by colour and the colour offsets.
+void color_elements(ptrdiff_t ne, ptrdiff_t nn, int nxe, const int32_t *const *elements, std::string *err,
+                    int32_t **perm_out, int32_t **offsets_out, int *ncolors_out);
+
+}  // namespace b200fem

@@ -1,0 +1,297 @@
+// Runtime helpers and the operator-plan half of the C ABI (include/b200fem.h).
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200fem {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line) {
+    if (e == cudaSuccess) return true;
+    char buf[1024];
+    snprintf(buf, sizeof(buf), "CUDA error '%s' (%d) in %s at %s:%d", cudaGetErrorString(e), (int)e, what, file, line);
+    g_last_error = buf;
+    return false;
+}
+
+int sm_count() {
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+int OpBase::set_option(const char *key, int value) {
+    if (!strcmp(key, "scatter")) {
+        scatter = value;
+        return B200FEM_SUCCESS;
+    }
+    set_error(std::string("unknown option: ") + key);
+    return B200FEM_FAILURE;
+}
+
+int OpBase::get_option(const char *key, int *value) {
+    if (!strcmp(key, "scatter")) {
+        *value = scatter;
+        return B200FEM_SUCCESS;
+    }
+    set_error(std::string("unknown option: ") + key);
+    return B200FEM_FAILURE;
+}
+
+// Greedy colouring, elements visited in their given order; colour = smallest one not used by any
+// element sharing a node. 64-bit masks per node (<= 64 colours; hex/tet meshes need 8..~40).
+void color_elements(ptrdiff_t ne, ptrdiff_t nn, int nxe, const int32_t *const *elements, std::string *err,
+                    int32_t **perm_out, int32_t **offsets_out, int *ncolors_out) {
+    std::vector<uint64_t> node_mask((size_t)nn, 0);
+    std::vector<int8_t> color((size_t)ne, 0);
+    int ncolors = 0;
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        uint64_t used = 0;
+        for (int v = 0; v < nxe; ++v) used |= node_mask[elements[v][e]];
+        int c = 0;
+        while (c < 64 && ((used >> c) & 1ull)) ++c;
+        if (c >= 64) {
+            *err = "element colouring needs more than 64 colours";
+            *perm_out = nullptr;
+            *offsets_out = nullptr;
+            *ncolors_out = 0;
+            return;
+        }
+        color[e] = (int8_t)c;
+        ncolors = std::max(ncolors, c + 1);
+        for (int v = 0; v < nxe; ++v) node_mask[elements[v][e]] |= (1ull << c);
+    }
+    int32_t *offsets = (int32_t *)malloc(sizeof(int32_t) * (ncolors + 1));
+    int32_t *perm = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<ptrdiff_t>(ne, 1));
+    std::vector<int32_t> count(ncolors + 1, 0);
+    for (ptrdiff_t e = 0; e < ne; ++e) count[color[e] + 1]++;
+    for (int c = 0; c < ncolors; ++c) count[c + 1] += count[c];
+    for (int c = 0; c <= ncolors; ++c) offsets[c] = count[c];
+    for (ptrdiff_t e = 0; e < ne; ++e) perm[count[color[e]]++] = (int32_t)e;
+    *perm_out = perm;
+    *offsets_out = offsets;
+    *ncolors_out = ncolors;
+}
+
+}  // namespace b200fem
+
+using namespace b200fem;
+
+struct b200fem_op_s {
+    OpBase *impl;
+};
+
+extern "C" {
+
+const char *b200fem_last_error(void) { return g_last_error.c_str(); }
+
+int b200fem_device_count(int *count) {
+    B2_CUDA(cudaGetDeviceCount(count));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_set_device(int device) {
+    B2_CUDA(cudaSetDevice(device));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_device_info(int *sms, int *cc_major, int *cc_minor, size_t *global_mem_bytes) {
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    B2_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (global_mem_bytes) *global_mem_bytes = p.totalGlobalMem;
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_malloc(void **ptr, size_t bytes) {
+    *ptr = nullptr;
+    if (bytes == 0) return B200FEM_SUCCESS;
+    B2_CUDA(cudaMalloc(ptr, bytes));
+    B2_CUDA(cudaMemset(*ptr, 0, bytes));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_free(void *ptr) {
+    if (ptr) B2_CUDA(cudaFree(ptr));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_host_malloc(void **ptr, size_t bytes) {
+    *ptr = nullptr;
+    if (bytes == 0) return B200FEM_SUCCESS;
+    B2_CUDA(cudaMallocHost(ptr, bytes));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_host_free(void *ptr) {
+    if (ptr) B2_CUDA(cudaFreeHost(ptr));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    B2_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_stream_create(void **stream) {
+    cudaStream_t s;
+    B2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_stream_destroy(void *stream) {
+    B2_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_stream_synchronize(void *stream) {
+    B2_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_device_synchronize(void) {
+    B2_CUDA(cudaDeviceSynchronize());
+    return B200FEM_SUCCESS;
+}
+
+static int check_common(b200fem_op_t *op, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, int real_type) {
+    if (!op) B2_FAIL("op output pointer is NULL");
+    *op = nullptr;
+    if (ne < 0 || nn < 0) B2_FAIL("negative sizes");
+    if (ne > 0 && !elements) B2_FAIL("elements is NULL");
+    if (real_type != B200FEM_F32 && real_type != B200FEM_F64) B2_FAIL("real_type must be B200FEM_F32 or B200FEM_F64");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B2_FAIL("no CUDA device: b200fem has no CPU fallback");
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_laplacian_create(b200fem_op_t *op, int element_type, int level, ptrdiff_t ne, ptrdiff_t nn,
+                             const int32_t *const *elements, const float *fff, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (ne > 0 && !fff) B2_FAIL("fff is NULL");
+    OpBase *impl = nullptr;
+    switch (element_type) {
+        case B200FEM_TET4: impl = make_tet4_laplacian(ne, nn, elements, fff, real_type); break;
+        case B200FEM_HEX8: impl = make_hex8_laplacian(ne, nn, elements, fff, real_type); break;
+        case B200FEM_SSHEX8:
+            if (level < 2) B2_FAIL("sshex8 level must be >= 2");
+            impl = make_sshex8_laplacian(level, ne, nn, elements, fff, real_type);
+            break;
+        default: B2_FAIL("laplacian: unsupported element type");
+    }
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int level, ptrdiff_t ne, ptrdiff_t nn,
+                                     const int32_t *const *elements, const float *adjugate, const float *determinant,
+                                     double mu, double lambda, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (ne > 0 && (!adjugate || !determinant)) B2_FAIL("adjugate/determinant is NULL");
+    OpBase *impl = nullptr;
+    switch (element_type) {
+        case B200FEM_HEX8: impl = make_hex8_linear_elasticity(ne, nn, elements, adjugate, determinant, mu, lambda, real_type); break;
+        case B200FEM_SSHEX8:
+            if (level < 2) B2_FAIL("sshex8 level must be >= 2");
+            impl = make_sshex8_linear_elasticity(level, ne, nn, elements, adjugate, determinant, mu, lambda, real_type);
+            break;
+        default: B2_FAIL("linear elasticity: unsupported element type");
+    }
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_op_destroy(b200fem_op_t op) {
+    if (op) {
+        delete op->impl;
+        delete op;
+    }
+    return B200FEM_SUCCESS;
+}
+
+#define B2_OP_CHECK(op)                      \
+    if (!(op) || !(op)->impl) B2_FAIL("invalid operator handle")
+
+int b200fem_op_apply(b200fem_op_t op, const void *x, void *y, void *stream) {
+    B2_OP_CHECK(op);
+    if (op->impl->ne == 0) return B200FEM_SUCCESS;
+    if (!x || !y) B2_FAIL("apply: NULL vector");
+    return op->impl->apply(x, y, false, as_stream(stream));
+}
+
+int b200fem_op_apply_overwrite(b200fem_op_t op, const void *x, void *y, void *stream) {
+    B2_OP_CHECK(op);
+    if (!y) B2_FAIL("apply: NULL vector");
+    if (op->impl->ne == 0) {
+        B2_CUDA(cudaMemsetAsync(y, 0, (size_t)op->impl->nn * op->impl->block_size * op->impl->real_type, as_stream(stream)));
+        return B200FEM_SUCCESS;
+    }
+    if (!x) B2_FAIL("apply: NULL vector");
+    return op->impl->apply(x, y, true, as_stream(stream));
+}
+
+int b200fem_op_diag(b200fem_op_t op, void *diag, void *stream) {
+    B2_OP_CHECK(op);
+    if (op->impl->ne == 0) return B200FEM_SUCCESS;
+    if (!diag) B2_FAIL("diag: NULL vector");
+    return op->impl->diag(diag, as_stream(stream));
+}
+
+int b200fem_op_block_diag_sym(b200fem_op_t op, void *bdiag, void *stream) {
+    B2_OP_CHECK(op);
+    if (op->impl->ne == 0) return B200FEM_SUCCESS;
+    if (!bdiag) B2_FAIL("block_diag_sym: NULL vector");
+    return op->impl->block_diag_sym(bdiag, as_stream(stream));
+}
+
+ptrdiff_t b200fem_op_rows(b200fem_op_t op) { return (op && op->impl) ? op->impl->nn * op->impl->block_size : -1; }
+int b200fem_op_block_size(b200fem_op_t op) { return (op && op->impl) ? op->impl->block_size : -1; }
+int b200fem_op_real_type(b200fem_op_t op) { return (op && op->impl) ? op->impl->real_type : -1; }
+double b200fem_op_algorithmic_bytes(b200fem_op_t op) { return (op && op->impl) ? op->impl->algorithmic_bytes() : -1.0; }
+double b200fem_op_streamed_bytes(b200fem_op_t op, int overwrite) {
+    return (op && op->impl) ? op->impl->streamed_bytes(overwrite != 0) : -1.0;
+}
+int b200fem_op_gpu_launches_per_apply(b200fem_op_t op, int overwrite) {
+    return (op && op->impl) ? op->impl->launches(overwrite != 0) : -1;
+}
+int b200fem_op_set_option(b200fem_op_t op, const char *key, int value) {
+    B2_OP_CHECK(op);
+    return op->impl->set_option(key, value);
+}
+int b200fem_op_get_option(b200fem_op_t op, const char *key, int *value) {
+    B2_OP_CHECK(op);
+    return op->impl->get_option(key, value);
+}
+
+}  // extern "C"

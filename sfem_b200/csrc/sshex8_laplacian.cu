@@ -1,0 +1,393 @@
+// sshex8 (semi-structured hex8) Laplacian, matrix-free -- the north-star kernel.
+//
+// Replaces affine_sshex8_laplacian_stencil_apply_fff (operators/sshex8/sshex8_laplacian.cpp:698-769 of
+// the reference) and affine_sshex8_laplacian_diag (:333-435); supersedes the CUDA twin
+// cu_affine_sshex8_laplacian_apply_kernel_warp (operators/sshex8/cuda/cu_sshex8_laplacian_warp.hpp:4-99).
+//
+// Kernel shape (per CTA iteration = one batch of EPB macro elements, persistent grid):
+//   1. gather   : all threads copy the (L+1)^3 lattice values of each element into a shared-memory tile,
+//                 layout tile[z][slot][y][x]  (row stride N = L+1 doubles, odd => conflict-free LDS.64);
+//   2. compute  : thread (slot, y) owns one x-row and marches over z (sshex8_laplacian_core.cuh): per
+//                 input plane 3 rows are read from shared memory and 3 output planes are advanced
+//                 (225 FMA per 27 shared loads); the finished output plane overwrites the input plane
+//                 one step behind (in place, one barrier per step);
+//   3. scatter  : interior nodes (owned by exactly one element) are written with plain stores /
+//                 read-modify-write, skeleton nodes with RED.ADD.
+//
+// Connectivity in HBM comes in two layouts, chosen at plan creation:
+//   MODE_EXPLICIT : int32 AoS [ne][(L+1)^3]   (one coalesced 4 B/node stream, any numbering)
+//   MODE_BOXES    : 27 affine "entity boxes" per element (8 corners, 12 edges, 6 faces, 1 interior),
+//                   each (base, sx, sy, sz) so that id(x,y,z) = base + sx x + sy y + sz z inside the
+//                   box: 432 B per element instead of 2916 B at L = 8. Every numbering that orders the
+//                   nodes of an edge / face / interior affinely in the local lattice (the reference's
+//                   generator, mesh/sfem_hex8_mesh_graph.cpp:447-735, does) is detected; anything else
+//                   (e.g. the hierarchical renumbering) falls back to MODE_EXPLICIT.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "sshex8_laplacian_core.cuh"
+
+namespace b200fem {
+
+static constexpr int kModeExplicit = 0;
+static constexpr int kModeBoxes = 1;
+
+struct BoxDesc {
+    int32_t base, sx, sy, sz;  // id = base + sx*x + sy*y + sz*z (absolute lattice coordinates)
+};
+
+template <int L>
+__device__ __forceinline__ int box_of(int x, int y, int z) {
+    const int cx = (x == 0) ? 0 : (x == L ? 2 : 1);
+    const int cy = (y == 0) ? 0 : (y == L ? 2 : 1);
+    const int cz = (z == 0) ? 0 : (z == L ? 2 : 1);
+    return cx + 3 * cy + 9 * cz;
+}
+
+template <typename T, int L, int BT, int MODE, bool OVERWRITE, bool INTERIOR_EXCLUSIVE>
+__global__ void __launch_bounds__(BT)
+    sshex8_laplacian_kernel(const ptrdiff_t ne, const int32_t *__restrict__ idx_aos,
+                            const BoxDesc *__restrict__ boxes, const float *__restrict__ fff,
+                            const T *__restrict__ u, T *__restrict__ y) {
+    constexpr int N = L + 1;
+    constexpr int NXE = N * N * N;
+    constexpr int EPB = BT / N;           // elements per batch
+    constexpr int ZS = EPB * N * N;       // tile plane stride
+    constexpr int NCOMPUTE = EPB * N;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // [EPB][27] box descriptors first (16 B aligned for LDS.128), then the tile
+    BoxDesc *sbox = reinterpret_cast<BoxDesc *>(smem_raw);
+    T *tile = reinterpret_cast<T *>(smem_raw + (MODE == kModeBoxes ? EPB * 27 * sizeof(BoxDesc) : 0));
+
+    const int tid = threadIdx.x;
+    const ptrdiff_t nbatches = (ne + EPB - 1) / EPB;
+
+    for (ptrdiff_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+        const ptrdiff_t e0 = batch * EPB;
+        const int nslots = (int)((ne - e0) < (ptrdiff_t)EPB ? (ne - e0) : (ptrdiff_t)EPB);
+
+        if (MODE == kModeBoxes) {
+            const int32_t *src = reinterpret_cast<const int32_t *>(boxes + e0 * 27);
+            int32_t *dst = reinterpret_cast<int32_t *>(sbox);
+            for (int i = tid; i < nslots * 27 * 4; i += BT) dst[i] = ldg_stream(&src[i]);
+            __syncthreads();
+        }
+
+        // ---- 1. gather
+        for (int slot = 0; slot < nslots; ++slot) {
+            const ptrdiff_t e = e0 + slot;
+#pragma unroll 4
+            for (int n = tid; n < NXE; n += BT) {
+                const int z = n / (N * N), rem = n - z * (N * N);
+                const int yy = rem / N, x = rem - yy * N;
+                int32_t id;
+                if (MODE == kModeExplicit) {
+                    id = ldg_stream(&idx_aos[e * NXE + n]);
+                } else {
+                    const BoxDesc d = sbox[slot * 27 + box_of<L>(x, yy, z)];
+                    id = d.base + d.sx * x + d.sy * yy + d.sz * z;
+                }
+                tile[z * ZS + (slot * N + yy) * N + x] = u[id];
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. compute (in place)
+        {
+            const bool active = tid < NCOMPUTE && (tid / N) < nslots;
+            Sshex8LaplacianRow<T, L> row;
+            const int slot = tid / N, yrow = tid - slot * N;
+            if (active) {
+                T f[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) f[k] = (T)__ldg(&fff[(e0 + slot) * 6 + k]);
+                row.init(f, yrow);
+            }
+            T *base = tile + slot * N * N;
+            for (int zp = 0; zp <= L; ++zp) {
+                if (active) row.step(zp, base + zp * ZS, N);
+                __syncthreads();
+                if (active) row.write_and_rotate(zp, base + (zp > 0 ? zp - 1 : 0) * ZS, N);
+            }
+            if (active) row.write_last(base + L * ZS, N);
+        }
+        __syncthreads();
+
+        // ---- 3. scatter
+        for (int slot = 0; slot < nslots; ++slot) {
+            const ptrdiff_t e = e0 + slot;
+#pragma unroll 4
+            for (int n = tid; n < NXE; n += BT) {
+                const int z = n / (N * N), rem = n - z * (N * N);
+                const int yy = rem / N, x = rem - yy * N;
+                const T val = tile[z * ZS + (slot * N + yy) * N + x];
+                if (MODE == kModeExplicit) {
+                    const int32_t id = __ldg(&idx_aos[e * NXE + n]);
+                    red_add(&y[id], val);
+                } else {
+                    const int b = box_of<L>(x, yy, z);
+                    const BoxDesc d = sbox[slot * 27 + b];
+                    const int32_t id = d.base + d.sx * x + d.sy * yy + d.sz * z;
+                    if (INTERIOR_EXCLUSIVE && b == 13) {
+                        if (OVERWRITE)
+                            y[id] = val;
+                        else
+                            y[id] += val;
+                    } else {
+                        red_add(&y[id], val);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// diag += diag(A): one thread per (element, lattice node)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sshex8_laplacian_diag_kernel(const int L, const ptrdiff_t ne, const int32_t *__restrict__ idx_aos,
+                                 const BoxDesc *__restrict__ boxes, const float *__restrict__ fff, T *__restrict__ diag) {
+    const int N = L + 1, NXE = N * N * N;
+    const ptrdiff_t total = ne * NXE;
+    for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ptrdiff_t)gridDim.x * blockDim.x) {
+        const ptrdiff_t e = i / NXE;
+        const int n = (int)(i - e * NXE);
+        const int z = n / (N * N), rem = n - z * (N * N);
+        const int yy = rem / N, x = rem - yy * N;
+        int32_t id;
+        if (idx_aos) {
+            id = idx_aos[i];
+        } else {
+            const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1),
+                      cz = (z == 0) ? 0 : (z == L ? 2 : 1);
+            const BoxDesc d = boxes[e * 27 + cx + 3 * cy + 9 * cz];
+            id = d.base + d.sx * x + d.sy * yy + d.sz * z;
+        }
+        const T h = T(1) / T(L);
+        const T Sxx = (T)fff[e * 6 + 0] * h, Sxy = (T)fff[e * 6 + 1] * h, Sxz = (T)fff[e * 6 + 2] * h,
+                Syy = (T)fff[e * 6 + 3] * h, Syz = (T)fff[e * 6 + 4] * h, Szz = (T)fff[e * 6 + 5] * h;
+        const T m0 = T(2.0 / 3.0);
+        const T sx = (x == 0) ? T(-1) : (x == L ? T(1) : T(0));
+        const T sy = (yy == 0) ? T(-1) : (yy == L ? T(1) : T(0));
+        const T sz = (z == 0) ? T(-1) : (z == L ? T(1) : T(0));
+        const T hx = (sx != T(0)) ? T(0.5) : T(1), hy = (sy != T(0)) ? T(0.5) : T(1), hz = (sz != T(0)) ? T(0.5) : T(1);
+        T d = (Sxx + Syy + Szz) * T(2) * m0 * m0 * hx * hy * hz;
+        d += T(0.5) * m0 * (Sxy * sx * sy * hz + Sxz * sx * sz * hy + Syz * sy * sz * hx);
+        red_add(&diag[id], d);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+struct Sshex8Laplacian final : OpBase {
+    int mode = kModeExplicit;
+    bool interior_exclusive = false;
+    int32_t shared_prefix = 0;          // nodes [0, shared_prefix) receive RED.ADD contributions
+    DeviceArray<int32_t> idx_aos;       // MODE_EXPLICIT: [ne][nxe]
+    DeviceArray<BoxDesc> boxes;         // MODE_BOXES: [ne][27]
+    DeviceArray<float> fff;             // [ne][6]
+    int ctas_per_sm = 4;
+
+    template <typename T, int L, int MODE, bool OVERWRITE, bool IE>
+    int launch(const T *x, T *y, cudaStream_t s) {
+        constexpr int BT = 64;
+        constexpr int N = L + 1;
+        constexpr int EPB = BT / N;
+        const size_t smem = (size_t)EPB * N * N * N * sizeof(T) + (MODE == kModeBoxes ? (size_t)EPB * 27 * sizeof(BoxDesc) : 0);
+        auto kern = sshex8_laplacian_kernel<T, L, BT, MODE, OVERWRITE, IE>;
+        static bool configured = false;
+        if (!configured) {
+            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        const ptrdiff_t nbatches = (ne + EPB - 1) / EPB;
+        const int grid = (int)std::min<ptrdiff_t>(nbatches, (ptrdiff_t)sm_count() * ctas_per_sm);
+        kern<<<grid, BT, smem, s>>>(ne, idx_aos.ptr, boxes.ptr, fff.ptr, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+
+    template <typename T, int L>
+    int apply_L(const T *x, T *y, bool overwrite, cudaStream_t s) {
+        if (mode == kModeBoxes && interior_exclusive) {
+            if (overwrite) {
+                if (shared_prefix > 0) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)shared_prefix * sizeof(T), s));
+                return launch<T, L, kModeBoxes, true, true>(x, y, s);
+            }
+            return launch<T, L, kModeBoxes, false, true>(x, y, s);
+        }
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * sizeof(T), s));
+        if (mode == kModeBoxes) return launch<T, L, kModeBoxes, false, false>(x, y, s);
+        return launch<T, L, kModeExplicit, false, false>(x, y, s);
+    }
+
+    template <typename T>
+    int apply_t(const T *x, T *y, bool overwrite, cudaStream_t s) {
+        switch (level) {
+            case 2: return apply_L<T, 2>(x, y, overwrite, s);
+            case 4: return apply_L<T, 4>(x, y, overwrite, s);
+            case 8: return apply_L<T, 8>(x, y, overwrite, s);
+            default: B2_FAIL("sshex8 laplacian: level must be 2, 4 or 8 (other levels: not built yet)");
+        }
+    }
+
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, overwrite, s)
+                                        : apply_t<float>((const float *)x, (float *)y, overwrite, s);
+    }
+
+    int diag(void *d, cudaStream_t s) override {
+        const ptrdiff_t total = ne * nxe;
+        const int grid = (int)std::min<ptrdiff_t>((total + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        if (real_type == B200FEM_F64)
+            sshex8_laplacian_diag_kernel<double><<<grid, 256, 0, s>>>(level, ne, idx_aos.ptr, boxes.ptr, fff.ptr, (double *)d);
+        else
+            sshex8_laplacian_diag_kernel<float><<<grid, 256, 0, s>>>(level, ne, idx_aos.ptr, boxes.ptr, fff.ptr, (float *)d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+
+    double streamed_bytes(bool overwrite) const override {
+        const double idx = (mode == kModeBoxes) ? 27.0 * sizeof(BoxDesc) : 4.0 * nxe;
+        double vec = double(nn) * real_type * 2.0;                 // x read, y written
+        if (!overwrite) vec += double(nn) * real_type;             // y read as well
+        return double(ne) * (idx + 24.0) + vec;
+    }
+    int launches(bool overwrite) const override { return overwrite ? 2 : 1; }
+
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "ctas_per_sm")) {
+            if (value < 1 || value > 32) B2_FAIL("ctas_per_sm out of range");
+            ctas_per_sm = value;
+            return B200FEM_SUCCESS;
+        }
+        if (!strcmp(key, "explicit_index")) {
+            if (value && mode == kModeBoxes) {
+                if (idx_aos.n == 0) B2_FAIL("explicit index was not kept");
+                mode = kModeExplicit;
+            } else if (!value && boxes.n != 0) {
+                mode = kModeBoxes;
+            }
+            return B200FEM_SUCCESS;
+        }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "mode")) { *value = mode; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "interior_exclusive")) { *value = interior_exclusive ? 1 : 0; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "shared_prefix")) { *value = shared_prefix; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "ctas_per_sm")) { *value = ctas_per_sm; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
+};
+
+// Fit the 27 entity boxes of every element; returns false if some box is not affine in the lattice.
+static bool fit_boxes(int L, ptrdiff_t ne, const int32_t *const *elements, std::vector<BoxDesc> &out, bool *exclusive,
+                      int32_t *shared_prefix) {
+    const int N = L + 1;
+    out.resize((size_t)ne * 27);
+    auto lidx = [N](int x, int y, int z) { return z * N * N + y * N + x; };
+    const int lo[3] = {0, 1, L}, hi[3] = {0, L - 1, L};
+    int64_t min_interior = INT64_MAX, max_skeleton = -1;
+    bool compact = true;
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        for (int cz = 0; cz < 3; ++cz)
+            for (int cy = 0; cy < 3; ++cy)
+                for (int cx = 0; cx < 3; ++cx) {
+                    const int x0 = lo[cx], y0 = lo[cy], z0 = lo[cz];
+                    const int x1 = hi[cx], y1 = hi[cy], z1 = hi[cz];
+                    const int64_t b0 = elements[lidx(x0, y0, z0)][e];
+                    const int64_t sx = (x1 > x0) ? (int64_t)elements[lidx(x0 + 1, y0, z0)][e] - b0 : 0;
+                    const int64_t sy = (y1 > y0) ? (int64_t)elements[lidx(x0, y0 + 1, z0)][e] - b0 : 0;
+                    const int64_t sz = (z1 > z0) ? (int64_t)elements[lidx(x0, y0, z0 + 1)][e] - b0 : 0;
+                    for (int z = z0; z <= z1; ++z)
+                        for (int y = y0; y <= y1; ++y)
+                            for (int x = x0; x <= x1; ++x) {
+                                const int64_t id = elements[lidx(x, y, z)][e];
+                                if (id != b0 + sx * (x - x0) + sy * (y - y0) + sz * (z - z0)) return false;
+                                if (cx == 1 && cy == 1 && cz == 1) {
+                                    if (id < min_interior) min_interior = id;
+                                } else if (id > max_skeleton) {
+                                    max_skeleton = id;
+                                }
+                            }
+                    const int64_t base = b0 - sx * x0 - sy * y0 - sz * z0;
+                    if (base < INT32_MIN || base > INT32_MAX) return false;
+                    out[(size_t)e * 27 + cx + 3 * cy + 9 * cz] = BoxDesc{(int32_t)base, (int32_t)sx, (int32_t)sy, (int32_t)sz};
+                    if (cx == 1 && cy == 1 && cz == 1 && L > 2) {
+                        if (sx != 1 || sy != (L - 1) || sz != (int64_t)(L - 1) * (L - 1)) compact = false;
+                    }
+                }
+    }
+    // interior nodes are exclusive when every interior box is a compact block, the blocks are
+    // disjoint, and no skeleton id falls into the interior range
+    bool excl = compact && (ne == 0 || max_skeleton < min_interior);
+    if (excl && ne > 1) {
+        std::vector<int64_t> bases((size_t)ne);
+        for (ptrdiff_t e = 0; e < ne; ++e) bases[e] = elements[lidx(1, 1, 1)][e];
+        std::sort(bases.begin(), bases.end());
+        const int64_t vol = (int64_t)(L - 1) * (L - 1) * (L - 1);
+        for (ptrdiff_t e = 1; e < ne; ++e)
+            if (bases[e] - bases[e - 1] < vol) {
+                excl = false;
+                break;
+            }
+    }
+    *exclusive = excl;
+    *shared_prefix = excl ? (int32_t)(ne ? min_interior : 0) : 0;
+    return true;
+}
+
+OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff,
+                              int real_type) {
+    const int N = level + 1, nxe = N * N * N;
+    for (int v = 0; v < nxe; ++v)
+        for (ptrdiff_t e = 0; e < ne; ++e)
+            if (elements[v][e] < 0 || elements[v][e] >= nn) {
+                set_error("sshex8 laplacian: node index out of range");
+                return nullptr;
+            }
+    auto *op = new Sshex8Laplacian();
+    op->elem_type = B200FEM_SSHEX8;
+    op->level = level;
+    op->real_type = real_type;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = nxe;
+    op->geom_bytes_per_elem = 24;
+
+    std::vector<BoxDesc> boxes;
+    bool excl = false;
+    int32_t prefix = 0;
+    const bool affine = fit_boxes(level, ne, elements, boxes, &excl, &prefix);
+    int rc = 0;
+    if (affine) {
+        op->mode = kModeBoxes;
+        op->interior_exclusive = excl;
+        op->shared_prefix = prefix;
+        rc |= op->boxes.upload(boxes.data(), boxes.size());
+    }
+    // The explicit index is always kept: it is the fallback, serves the diag kernel when boxes are
+    // absent, and lets tests run both connectivity modes on the same plan.
+    {
+        std::vector<int32_t> aos((size_t)ne * nxe);
+        for (int v = 0; v < nxe; ++v) {
+            const int32_t *row = elements[v];
+            for (ptrdiff_t e = 0; e < ne; ++e) aos[(size_t)e * nxe + v] = row[e];
+        }
+        rc |= op->idx_aos.upload(aos.data(), aos.size());
+    }
+    rc |= op->fff.upload(fff, (size_t)ne * 6);
+    if (rc) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+}  // namespace b200fem

@@ -1,0 +1,340 @@
+"""ctypes binding of the C ABI in include/b200fem.h (libb200fem.so, built in-tree by
+`sfem_b200/csrc/Makefile`). This is plumbing for the tests and bench.py: the product is the shared
+library and the C++ host layer in `sfem_b200/host/`. There is no CPU fallback -- importing this module
+without the built library raises, and every call needs a CUDA device.
+
+Vectors are torch CUDA tensors (torch = device memory + streams only); connectivity / geometry are
+numpy host arrays exactly as the reference's operator-level C functions take them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200fem.so")
+
+F32, F64 = 4, 8
+TET4, HEX8, SSHEX8 = 4, 8, 800
+SCATTER_AUTO, SCATTER_ATOMIC, SCATTER_COLORED = 0, 1, 2
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C sfem_b200/csrc`). b200fem has no CPU fallback."
+    )
+_lib = C.CDLL(LIB_PATH)
+
+c_idx_pp = C.POINTER(C.POINTER(C.c_int32))
+c_f32_pp = C.POINTER(C.POINTER(C.c_float))
+vp, i32, f64, ssz = C.c_void_p, C.c_int, C.c_double, C.c_ssize_t
+
+_SIG = {
+    "b200fem_device_count": [C.POINTER(i32)],
+    "b200fem_set_device": [i32],
+    "b200fem_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)],
+    "b200fem_malloc": [C.POINTER(vp), C.c_size_t],
+    "b200fem_free": [vp],
+    "b200fem_host_malloc": [C.POINTER(vp), C.c_size_t],
+    "b200fem_host_free": [vp],
+    "b200fem_memcpy_h2d": [vp, vp, C.c_size_t, vp],
+    "b200fem_memcpy_d2h": [vp, vp, C.c_size_t, vp],
+    "b200fem_memcpy_d2d": [vp, vp, C.c_size_t, vp],
+    "b200fem_stream_create": [C.POINTER(vp)],
+    "b200fem_stream_destroy": [vp],
+    "b200fem_stream_synchronize": [vp],
+    "b200fem_device_synchronize": [],
+    "b200fem_fff_fill": [i32, ssz, ssz, c_idx_pp, c_f32_pp, C.POINTER(C.c_float)],
+    "b200fem_adjugate_and_det_fill": [i32, ssz, ssz, c_idx_pp, c_f32_pp, C.POINTER(C.c_float), C.POINTER(C.c_float)],
+    "b200fem_laplacian_create": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32],
+    "b200fem_linear_elasticity_create": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float), f64, f64, i32],
+    "b200fem_op_destroy": [vp],
+    "b200fem_op_apply": [vp, vp, vp, vp],
+    "b200fem_op_apply_overwrite": [vp, vp, vp, vp],
+    "b200fem_op_diag": [vp, vp, vp],
+    "b200fem_op_block_diag_sym": [vp, vp, vp],
+    "b200fem_op_block_size": [vp],
+    "b200fem_op_real_type": [vp],
+    "b200fem_op_gpu_launches_per_apply": [vp, i32],
+    "b200fem_op_set_option": [vp, C.c_char_p, i32],
+    "b200fem_op_get_option": [vp, C.c_char_p, C.POINTER(i32)],
+    "b200fem_constraint_nodes_copy_vec": [i32, ssz, vp, i32, i32, vp, vp, vp],
+    "b200fem_constraint_nodes_to_value_vec": [i32, ssz, vp, i32, i32, f64, vp, vp],
+    "b200fem_blas_zeros": [i32, ssz, vp, vp],
+    "b200fem_blas_values": [i32, ssz, f64, vp, vp],
+    "b200fem_blas_copy": [i32, ssz, vp, vp, vp],
+    "b200fem_blas_scal": [i32, ssz, f64, vp, vp],
+    "b200fem_blas_axpy": [i32, ssz, f64, vp, vp, vp],
+    "b200fem_blas_axpby": [i32, ssz, f64, vp, f64, vp, vp],
+    "b200fem_blas_zaxpby": [i32, ssz, f64, vp, f64, vp, vp, vp],
+    "b200fem_blas_xypaz": [i32, ssz, vp, vp, f64, vp, vp],
+    "b200fem_blas_reciprocal": [i32, ssz, f64, vp, vp],
+    "b200fem_blas_dot": [i32, ssz, vp, vp, C.POINTER(f64), vp],
+    "b200fem_blas_norm2": [i32, ssz, vp, C.POINTER(f64), vp],
+    "b200fem_blas_dot_async": [i32, ssz, vp, vp, vp, vp],
+    "b200fem_cg_update_x_r_rtr": [i32, ssz, f64, vp, vp, vp, vp, C.POINTER(f64), vp],
+    "b200fem_cg_update_p": [i32, ssz, f64, vp, vp, vp],
+    "b200fem_cheb3_update": [i32, ssz, f64, f64, vp, vp, vp, vp, vp],
+}
+for _name, _args in _SIG.items():
+    _fn = getattr(_lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = i32
+_lib.b200fem_last_error.restype = C.c_char_p
+_lib.b200fem_op_rows.argtypes = [vp]
+_lib.b200fem_op_rows.restype = ssz
+_lib.b200fem_op_algorithmic_bytes.argtypes = [vp]
+_lib.b200fem_op_algorithmic_bytes.restype = f64
+_lib.b200fem_op_streamed_bytes.argtypes = [vp, i32]
+_lib.b200fem_op_streamed_bytes.restype = f64
+
+
+class B200FemError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise B200FemError(f"{what}: {_lib.b200fem_last_error().decode()}")
+
+
+def raw():
+    """The ctypes CDLL (for symbol checks)."""
+    return _lib
+
+
+def declared_symbols():
+    """Every entry point include/b200fem.h declares (parsed from the header)."""
+    import re
+
+    hdr = open(os.path.join(HERE, "..", "include", "b200fem.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200fem_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def _soa_ptrs(arr: np.ndarray, ctype):
+    k = arr.shape[0]
+    ptrs = (C.POINTER(ctype) * k)()
+    for i in range(k):
+        ptrs[i] = arr[i].ctypes.data_as(C.POINTER(ctype))
+    return ptrs
+
+
+def _rt(dtype) -> int:
+    import torch
+
+    if dtype in (torch.float64, np.float64, "f64", F64):
+        return F64
+    if dtype in (torch.float32, np.float32, "f32", F32):
+        return F32
+    raise ValueError(f"unsupported real type {dtype}")
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _vec(t, n=None):
+    assert t.is_cuda and t.is_contiguous(), "vectors must be contiguous CUDA tensors"
+    if n is not None:
+        assert t.numel() >= n
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# geometry
+# --------------------------------------------------------------------------------------------
+def fff_fill(element_type: int, elements: np.ndarray, points: np.ndarray) -> np.ndarray:
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    out = np.zeros(el.shape[1] * 6, dtype=np.float32)
+    check(_lib.b200fem_fff_fill(element_type, el.shape[1], pts.shape[1], _soa_ptrs(el, C.c_int32),
+                                _soa_ptrs(pts, C.c_float), out.ctypes.data_as(C.POINTER(C.c_float))), "fff_fill")
+    return out
+
+
+def adjugate_and_det_fill(element_type: int, elements: np.ndarray, points: np.ndarray):
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    adj = np.zeros(el.shape[1] * 9, dtype=np.float32)
+    det = np.zeros(el.shape[1], dtype=np.float32)
+    check(_lib.b200fem_adjugate_and_det_fill(element_type, el.shape[1], pts.shape[1], _soa_ptrs(el, C.c_int32),
+                                             _soa_ptrs(pts, C.c_float), adj.ctypes.data_as(C.POINTER(C.c_float)),
+                                             det.ctypes.data_as(C.POINTER(C.c_float))), "adjugate_and_det_fill")
+    return adj, det
+
+
+# --------------------------------------------------------------------------------------------
+# operator plans
+# --------------------------------------------------------------------------------------------
+class Op:
+    """Owner of a b200fem_op_t. `apply(x, y)` accumulates (y += A x) like sfem::Op::apply."""
+
+    def __init__(self, handle, nnodes):
+        self._h = handle
+        self.nnodes = nnodes
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.b200fem_op_destroy(h)
+
+    @property
+    def rows(self):
+        return int(_lib.b200fem_op_rows(self._h))
+
+    @property
+    def block_size(self):
+        return int(_lib.b200fem_op_block_size(self._h))
+
+    @property
+    def algorithmic_bytes(self):
+        return float(_lib.b200fem_op_algorithmic_bytes(self._h))
+
+    def streamed_bytes(self, overwrite=False):
+        return float(_lib.b200fem_op_streamed_bytes(self._h, int(overwrite)))
+
+    def launches(self, overwrite=False):
+        return int(_lib.b200fem_op_gpu_launches_per_apply(self._h, int(overwrite)))
+
+    def set_option(self, key: str, value: int):
+        check(_lib.b200fem_op_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
+
+    def get_option(self, key: str) -> int:
+        v = i32(0)
+        check(_lib.b200fem_op_get_option(self._h, key.encode(), C.byref(v)), f"get_option({key})")
+        return v.value
+
+    def apply(self, x, y):
+        _vec(x, self.rows), _vec(y, self.rows)
+        check(_lib.b200fem_op_apply(self._h, _p(x), _p(y), _stream()), "op_apply")
+        return y
+
+    def apply_overwrite(self, x, y):
+        _vec(x, self.rows), _vec(y, self.rows)
+        check(_lib.b200fem_op_apply_overwrite(self._h, _p(x), _p(y), _stream()), "op_apply_overwrite")
+        return y
+
+    def diag(self, d):
+        _vec(d, self.rows)
+        check(_lib.b200fem_op_diag(self._h, _p(d), _stream()), "op_diag")
+        return d
+
+    def block_diag_sym(self, d):
+        _vec(d, self.nnodes * 6)
+        check(_lib.b200fem_op_block_diag_sym(self._h, _p(d), _stream()), "op_block_diag_sym")
+        return d
+
+
+def laplacian(element_type: int, elements: np.ndarray, fff: np.ndarray, nnodes: int, dtype, level: int = 0) -> Op:
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    f = np.ascontiguousarray(fff, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_laplacian_create(C.byref(h), element_type, level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
+                                        f.ctypes.data_as(C.POINTER(C.c_float)), _rt(dtype)), "laplacian_create")
+    return Op(h, nnodes)
+
+
+def linear_elasticity(element_type: int, elements: np.ndarray, adjugate: np.ndarray, determinant: np.ndarray, mu: float,
+                      lam: float, nnodes: int, dtype, level: int = 0) -> Op:
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    a = np.ascontiguousarray(adjugate, dtype=np.float32)
+    d = np.ascontiguousarray(determinant, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_linear_elasticity_create(C.byref(h), element_type, level, el.shape[1], nnodes,
+                                                _soa_ptrs(el, C.c_int32), a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                d.ctypes.data_as(C.POINTER(C.c_float)), mu, lam, _rt(dtype)),
+          "linear_elasticity_create")
+    return Op(h, nnodes)
+
+
+# --------------------------------------------------------------------------------------------
+# vector kernels (torch tensors in, same semantics as sfem::BLAS<T>)
+# --------------------------------------------------------------------------------------------
+class blas:
+    @staticmethod
+    def zeros(x):
+        check(_lib.b200fem_blas_zeros(_rt(x.dtype), x.numel(), _p(x), _stream()), "zeros")
+
+    @staticmethod
+    def values(v, x):
+        check(_lib.b200fem_blas_values(_rt(x.dtype), x.numel(), v, _p(x), _stream()), "values")
+
+    @staticmethod
+    def copy(src, dst):
+        check(_lib.b200fem_blas_copy(_rt(src.dtype), src.numel(), _p(src), _p(dst), _stream()), "copy")
+
+    @staticmethod
+    def scal(a, x):
+        check(_lib.b200fem_blas_scal(_rt(x.dtype), x.numel(), a, _p(x), _stream()), "scal")
+
+    @staticmethod
+    def axpy(a, x, y):
+        check(_lib.b200fem_blas_axpy(_rt(x.dtype), x.numel(), a, _p(x), _p(y), _stream()), "axpy")
+
+    @staticmethod
+    def axpby(a, x, b, y):
+        check(_lib.b200fem_blas_axpby(_rt(x.dtype), x.numel(), a, _p(x), b, _p(y), _stream()), "axpby")
+
+    @staticmethod
+    def zaxpby(a, x, b, y, z):
+        check(_lib.b200fem_blas_zaxpby(_rt(x.dtype), x.numel(), a, _p(x), b, _p(y), _p(z), _stream()), "zaxpby")
+
+    @staticmethod
+    def xypaz(x, y, a, z):
+        check(_lib.b200fem_blas_xypaz(_rt(x.dtype), x.numel(), _p(x), _p(y), a, _p(z), _stream()), "xypaz")
+
+    @staticmethod
+    def reciprocal(a, x):
+        check(_lib.b200fem_blas_reciprocal(_rt(x.dtype), x.numel(), a, _p(x), _stream()), "reciprocal")
+
+    @staticmethod
+    def dot(x, y) -> float:
+        r = f64(0)
+        check(_lib.b200fem_blas_dot(_rt(x.dtype), x.numel(), _p(x), _p(y), C.byref(r), _stream()), "dot")
+        return r.value
+
+    @staticmethod
+    def norm2(x) -> float:
+        r = f64(0)
+        check(_lib.b200fem_blas_norm2(_rt(x.dtype), x.numel(), _p(x), C.byref(r), _stream()), "norm2")
+        return r.value
+
+    @staticmethod
+    def dot_async(x, y, result_dev):
+        check(_lib.b200fem_blas_dot_async(_rt(x.dtype), x.numel(), _p(x), _p(y), _p(result_dev), _stream()), "dot_async")
+
+    @staticmethod
+    def cg_update_x_r_rtr(alpha, p, Ap, x, r) -> float:
+        out = f64(0)
+        check(_lib.b200fem_cg_update_x_r_rtr(_rt(x.dtype), x.numel(), alpha, _p(p), _p(Ap), _p(x), _p(r), C.byref(out),
+                                              _stream()), "cg_update_x_r_rtr")
+        return out.value
+
+    @staticmethod
+    def cg_update_p(beta, z, p):
+        check(_lib.b200fem_cg_update_p(_rt(p.dtype), p.numel(), beta, _p(z), _p(p), _stream()), "cg_update_p")
+
+    @staticmethod
+    def cheb3_update(alpha, beta, rhs, Ax, p, x):
+        check(_lib.b200fem_cheb3_update(_rt(x.dtype), x.numel(), alpha, beta, _p(rhs), _p(Ax), _p(p), _p(x), _stream()),
+              "cheb3_update")
+
+
+def constraint_nodes_copy_vec(idx, block_size, component, source, dest):
+    check(_lib.b200fem_constraint_nodes_copy_vec(_rt(source.dtype), idx.numel(), _p(idx), block_size, component,
+                                                 _p(source), _p(dest), _stream()), "constraint_nodes_copy_vec")
+
+
+def constraint_nodes_to_value_vec(idx, block_size, component, value, values):
+    check(_lib.b200fem_constraint_nodes_to_value_vec(_rt(values.dtype), idx.numel(), _p(idx), block_size, component,
+                                                     value, _p(values), _stream()), "constraint_nodes_to_value_vec")

@@ -1,0 +1,299 @@
+"""GPU parity tests proper: every operator of the path, through the C ABI, against the oracle on the
+same seeded inputs. Bars (BASELINE.json north_star): relative L2 <= 1e-12 in fp64, <= 1e-5 in fp32."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-12, "f32": 1e-5}
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _dt(real):
+    torch = _torch()
+    return torch.float64 if real == "f64" else torch.float32
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _fields(points, seed):
+    from sfem_b200 import mesh
+
+    nn = points.shape[1]
+    return {
+        "ones": np.ones(nn),
+        "quadratic": mesh.quadratic_field(points),
+        "random": np.random.default_rng(seed).uniform(-1, 1, nn),
+    }
+
+
+def _orc(oracles, real):
+    return oracles.get(("reference", real)) or oracles[("port", real)]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+def test_tet4_laplacian(oracles, real, scatter):
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    el, pts = mesh.box_tet4(9, 7, 8)
+    pts = mesh.warp_points(pts)
+    fff = orc.tet4_fff_fill(el, pts)
+    nn = pts.shape[1]
+    op = lib.laplacian(lib.TET4, el, fff, nn, _dt(real))
+    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    for name, u in _fields(pts, 3).items():
+        ref = orc.tet4_laplacian_apply_opt(el, fff, u)
+        x = torch.from_numpy(u).to(_dt(real)).cuda()
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        if name == "ones":
+            assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+        else:
+            assert _rel(y.cpu().numpy(), ref) < TOL[real], name
+    # accumulate semantics: a second apply doubles the result
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    # overwrite form
+    y.fill_(7.0)
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    # diagonal
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    assert _rel(d.cpu().numpy(), orc.tet4_laplacian_diag_opt(el, fff, nn)) < TOL[real]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+def test_hex8_laplacian(oracles, real, scatter):
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    el, pts = mesh.box_hex8(7, 6, 5)
+    pts = mesh.shear_points(pts)
+    fff = orc.hex8_fff_fill(el, pts)
+    nn = pts.shape[1]
+    op = lib.laplacian(lib.HEX8, el, fff, nn, _dt(real))
+    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    for name, u in _fields(pts, 4).items():
+        ref = orc.hex8_laplacian_apply_opt(el, fff, u)
+        x = torch.from_numpy(u).to(_dt(real)).cuda()
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        if name == "ones":
+            assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+        else:
+            assert _rel(y.cpu().numpy(), ref) < TOL[real], name
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+def test_hex8_linear_elasticity(oracles, real, scatter):
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    el, pts = mesh.box_hex8(6, 5, 7)
+    pts = mesh.shear_points(pts)
+    adj, det = orc.hex8_adjugate_and_det_fill(el, pts)
+    nn = pts.shape[1]
+    mu, lam = 1.3, 0.7
+    op = lib.linear_elasticity(lib.HEX8, el, adj, det, mu, lam, nn, _dt(real))
+    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    assert op.block_size == 3 and op.rows == nn * 3
+    u = np.random.default_rng(5).uniform(-1, 1, nn * 3)
+    ref = orc.hex8_linear_elasticity_apply(el, adj, det, mu, lam, u, nn)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    # rigid translation is in the kernel
+    t = np.tile(np.array([0.3, -1.2, 0.5]), nn)
+    y.zero_()
+    op.apply(torch.from_numpy(t).to(_dt(real)).cuda(), y)
+    assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level", [2, 4, 8])
+@pytest.mark.parametrize("explicit", [0, 1])
+def test_sshex8_laplacian(oracles, real, level, explicit):
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    # 23 macro elements: not a multiple of any batch size -> ragged last batch
+    m = mesh.sshex8_box(level, 23, 1, 1) if level == 2 else mesh.sshex8_box(level, 3, 2, 3)
+    mpts = mesh.shear_points(m["m_points"])
+    fff = orc.hex8_fff_fill(m["m_elements"], mpts)
+    nn = m["n_nodes"]
+    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=level)
+    assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
+    op.set_option("explicit_index", explicit)
+    u = np.random.default_rng(level).uniform(-1, 1, nn)
+    ref = orc.sshex8_laplacian_apply(level, m["elements"], fff, u)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    y.fill_(3.0)
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    ones = torch.ones_like(x)
+    y.zero_()
+    op.apply(ones, y)
+    assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+
+
+def test_sshex8_laplacian_hierarchical_numbering(oracles):
+    """Non-affine numbering (coarse lattices first) must take the explicit-index path and still match."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, "f64")
+    L = 4
+    m = mesh.sshex8_box(L, 2, 3, 2)
+    el, mapping, _ = mesh.sshex8_hierarchical_renumbering(L, m["elements"], m["n_nodes"])
+    fff = orc.hex8_fff_fill(m["m_elements"], mesh.shear_points(m["m_points"]))
+    nn = m["n_nodes"]
+    op = lib.laplacian(lib.SSHEX8, el, fff, nn, torch.float64, level=L)
+    assert op.get_option("mode") == 0
+    u = np.random.default_rng(9).uniform(-1, 1, nn)
+    ref = orc.sshex8_laplacian_apply(L, el, fff, u)
+    x = torch.from_numpy(u).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < 1e-12
+
+
+def test_sshex8_laplacian_diag_matches_unit_applies(oracles):
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, "f64")
+    L = 4
+    m = mesh.sshex8_box(L, 2, 1, 1)
+    fff = orc.hex8_fff_fill(m["m_elements"], mesh.shear_points(m["m_points"]))
+    nn = m["n_nodes"]
+    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, torch.float64, level=L)
+    d = torch.zeros(nn, dtype=torch.float64, device="cuda")
+    op.diag(d)
+    ref = np.zeros(nn)
+    for i in range(nn):
+        e = np.zeros(nn)
+        e[i] = 1
+        ref[i] = orc.sshex8_laplacian_apply(L, m["elements"], fff, e)[i]
+    assert _rel(d.cpu().numpy(), ref) < 1e-12
+
+
+def test_geometry_fill(oracles):
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, "f64")
+    el, pts = mesh.box_tet4(6, 5, 4)
+    pts = mesh.warp_points(pts)
+    assert _rel(lib.fff_fill(lib.TET4, el, pts), orc.tet4_fff_fill(el, pts)) < 1e-5
+    el, pts = mesh.box_hex8(6, 5, 4)
+    pts = mesh.warp_points(pts)
+    assert _rel(lib.fff_fill(lib.HEX8, el, pts), orc.hex8_fff_fill(el, pts)) < 1e-6
+    adj, det = lib.adjugate_and_det_fill(lib.HEX8, el, pts)
+    radj, rdet = orc.hex8_adjugate_and_det_fill(el, pts)
+    assert _rel(adj, radj) < 1e-6 and _rel(det, rdet) < 1e-6
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("n", [0, 1, 7, 1000, 1 << 20 | 5])
+def test_blas(real, n):
+    torch = _torch()
+    from sfem_b200.lib import blas
+
+    dt = _dt(real)
+    tol = 1e-14 if real == "f64" else 1e-6
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.rand(n, dtype=dt, device="cuda", generator=g) - 0.5
+    y = torch.rand(n, dtype=dt, device="cuda", generator=g) - 0.5
+    z = torch.rand(n, dtype=dt, device="cuda", generator=g) - 0.5
+    xn, yn, zn = (t.cpu().numpy().astype(np.float64) for t in (x, y, z))
+
+    assert abs(blas.dot(x, y) - float(xn @ yn)) <= tol * max(1.0, float(np.abs(xn) @ np.abs(yn)))
+    assert abs(blas.norm2(x) - float(np.sqrt(xn @ xn))) <= tol * max(1.0, float(np.sqrt(xn @ xn)))
+
+    def close(t, ref):
+        return n == 0 or _rel(t.cpu().numpy(), ref) < tol
+
+    t = y.clone(); blas.axpy(0.7, x, t); assert close(t, yn + 0.7 * xn)
+    t = y.clone(); blas.axpby(0.7, x, -1.1, t); assert close(t, 0.7 * xn - 1.1 * yn)
+    t = z.clone(); blas.zaxpby(0.7, x, -1.1, y, t); assert close(t, 0.7 * xn - 1.1 * yn)
+    t = z.clone(); blas.xypaz(x, y, 0.3, t); assert close(t, xn * yn + 0.3 * zn)
+    t = x.clone(); blas.scal(-2.5, t); assert close(t, -2.5 * xn)
+    t = x.clone(); blas.values(1.25, t); assert close(t, np.full(n, 1.25))
+    t = x.clone(); blas.zeros(t); assert n == 0 or float(t.abs().max()) == 0.0
+    t = torch.empty_like(x); blas.copy(x, t); assert n == 0 or torch.equal(t, x)
+    t = x.clone()
+    if n > 2:
+        t[1] = 0.0
+    blas.reciprocal(2.0, t)
+    ref = np.where(xn != 0, 2.0 / np.where(xn != 0, xn, 1), 0.0)
+    if n > 2:
+        ref[1] = 0.0
+    assert close(t, ref)
+    # unaligned views take the scalar path
+    if n > 8:
+        xv, yv = x[1:], y[1:]
+        assert abs(blas.dot(xv, yv) - float(xn[1:] @ yn[1:])) <= tol * max(1.0, float(np.abs(xn) @ np.abs(yn)))
+        t = yv.clone(); blas.axpy(0.5, xv, t); assert close(t, yn[1:] + 0.5 * xn[1:])
+
+    # fused CG / Chebyshev updates
+    p, Ap, xx, r = x.clone(), y.clone(), z.clone(), (x * y).clone()
+    pn, An, xxn, rn = xn, yn, zn, (x * y).cpu().numpy().astype(np.float64)
+    rtr = blas.cg_update_x_r_rtr(0.37, p, Ap, xx, r)
+    rr = rn - 0.37 * An
+    assert close(xx, xxn + 0.37 * pn) and close(r, rr)
+    assert abs(rtr - float(rr @ rr)) <= tol * max(1.0, float(rr @ rr))
+    t = x.clone(); blas.cg_update_p(0.9, y, t); assert close(t, yn + 0.9 * xn)
+    pp, xs = x.clone(), z.clone()
+    blas.cheb3_update(0.2, 0.6, y, (x * y), pp, xs)
+    pr = 0.6 * xn - yn + rn
+    assert close(pp, pr) and close(xs, zn - 0.2 * pr)
+
+
+def test_dot_is_reproducible():
+    torch = _torch()
+    from sfem_b200.lib import blas
+
+    x = torch.rand(3_000_001, dtype=torch.float64, device="cuda")
+    y = torch.rand(3_000_001, dtype=torch.float64, device="cuda")
+    vals = {blas.dot(x, y) for _ in range(5)}
+    assert len(vals) == 1
+
+
+def test_dirichlet_kernels():
+    torch = _torch()
+    from sfem_b200 import lib
+
+    n, bs = 1000, 3
+    src = torch.rand(n * bs, dtype=torch.float64, device="cuda")
+    dst = torch.zeros_like(src)
+    idx = torch.tensor([0, 5, 17, 999], dtype=torch.int32, device="cuda")
+    lib.constraint_nodes_copy_vec(idx, bs, 1, src, dst)
+    ref = np.zeros(n * bs)
+    ii = idx.cpu().numpy() * bs + 1
+    ref[ii] = src.cpu().numpy()[ii]
+    assert np.array_equal(dst.cpu().numpy(), ref)
+    lib.constraint_nodes_to_value_vec(idx, bs, 2, -4.5, dst)
+    ref[idx.cpu().numpy() * bs + 2] = -4.5
+    assert np.array_equal(dst.cpu().numpy(), ref)
