@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "sshex8_laplacian_core.cuh"
+#include "sshex8_laplacian_stream.cuh"
 
 namespace b200fem {
 
@@ -191,7 +192,58 @@ struct Sshex8Laplacian final : OpBase {
     DeviceArray<int32_t> idx_aos;       // MODE_EXPLICIT: [ne][nxe]
     DeviceArray<BoxDesc> boxes;         // MODE_BOXES: [ne][27]
     DeviceArray<float> fff;             // [ne][6]
+    DeviceArray<Sshex8Header> headers;  // MODE_BOXES: [ne] boxes + fff, what the streaming kernel reads
     int ctas_per_sm = 4;
+    int stream_cfg = 0;                 // which team shape / ring depth (see launch_stream)
+    int use_stream = 1;                 // 0 = the batch kernel below (kept for explicit connectivity)
+
+    template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN>
+    int launch_stream_cfg(const T *x, T *y, cudaStream_t s) {
+        using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
+        auto kern = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN>;
+        static bool configured = false;
+        if (!configured) {
+            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+            configured = true;
+        }
+        const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;
+        const int grid = (int)std::min<ptrdiff_t>((ngroups + NTEAM - 1) / NTEAM, (ptrdiff_t)sm_count());
+        kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers.ptr, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+
+    // team shapes per level: cfg 0 is the default, the others are tuning alternatives (bench sweeps them)
+    template <typename T, int L, bool PLAIN>
+    int launch_stream(const T *x, T *y, cudaStream_t s) {
+        constexpr bool F64 = sizeof(T) == 8;
+        if constexpr (L == 8) {
+            switch (stream_cfg) {
+                default:
+                case 0: return launch_stream_cfg<T, L, 1, 8, 8, PLAIN>(x, y, s);
+                case 1: return launch_stream_cfg<T, L, 2, 4, 7, PLAIN>(x, y, s);
+                case 2: return launch_stream_cfg<T, L, 1, 8, 6, PLAIN>(x, y, s);
+                case 3: return launch_stream_cfg<T, L, 2, 4, 5, PLAIN>(x, y, s);
+                case 4: return launch_stream_cfg<T, L, 4, 2, F64 ? 7 : 9, PLAIN>(x, y, s);
+                case 5: return launch_stream_cfg<T, L, 1, 6, 9, PLAIN>(x, y, s);
+            }
+        }
+        else if constexpr (L == 4) {
+            switch (stream_cfg) {
+                default:
+                case 0: return launch_stream_cfg<T, L, 1, 8, 5, PLAIN>(x, y, s);
+                case 1: return launch_stream_cfg<T, L, 1, 16, 5, PLAIN>(x, y, s);
+                case 2: return launch_stream_cfg<T, L, 2, 8, 5, PLAIN>(x, y, s);
+            }
+        }
+        else {
+            switch (stream_cfg) {
+                default:
+                case 0: return launch_stream_cfg<T, L, 1, 8, 3, PLAIN>(x, y, s);
+                case 1: return launch_stream_cfg<T, L, 1, 16, 3, PLAIN>(x, y, s);
+            }
+        }
+    }
 
     template <typename T, int L, int MODE, bool OVERWRITE, bool IE>
     int launch(const T *x, T *y, cudaStream_t s) {
@@ -214,6 +266,14 @@ struct Sshex8Laplacian final : OpBase {
 
     template <typename T, int L>
     int apply_L(const T *x, T *y, bool overwrite, cudaStream_t s) {
+        if (mode == kModeBoxes && use_stream) {
+            if (overwrite && interior_exclusive) {
+                if (shared_prefix > 0) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)shared_prefix * sizeof(T), s));
+                return launch_stream<T, L, true>(x, y, s);
+            }
+            if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * sizeof(T), s));
+            return launch_stream<T, L, false>(x, y, s);
+        }
         if (mode == kModeBoxes && interior_exclusive) {
             if (overwrite) {
                 if (shared_prefix > 0) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)shared_prefix * sizeof(T), s));
@@ -266,6 +326,8 @@ struct Sshex8Laplacian final : OpBase {
             ctas_per_sm = value;
             return B200FEM_SUCCESS;
         }
+        if (!strcmp(key, "stream_cfg")) { stream_cfg = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_stream")) { use_stream = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "explicit_index")) {
             if (value && mode == kModeBoxes) {
                 if (idx_aos.n == 0) B2_FAIL("explicit index was not kept");
@@ -282,6 +344,8 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "interior_exclusive")) { *value = interior_exclusive ? 1 : 0; return B200FEM_SUCCESS; }
         if (!strcmp(key, "shared_prefix")) { *value = shared_prefix; return B200FEM_SUCCESS; }
         if (!strcmp(key, "ctas_per_sm")) { *value = ctas_per_sm; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "stream_cfg")) { *value = stream_cfg; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_stream")) { *value = use_stream; return B200FEM_SUCCESS; }
         return OpBase::get_option(key, value);
     }
 };
@@ -371,6 +435,17 @@ OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32
         op->interior_exclusive = excl;
         op->shared_prefix = prefix;
         rc |= op->boxes.upload(boxes.data(), boxes.size());
+        std::vector<Sshex8Header> hdrs((size_t)ne);
+        for (ptrdiff_t e = 0; e < ne; ++e) {
+            Sshex8Header &h = hdrs[(size_t)e];
+            for (int b = 0; b < 27; ++b) {
+                const BoxDesc &d = boxes[(size_t)e * 27 + b];
+                h.box[b][0] = d.base; h.box[b][1] = d.sx; h.box[b][2] = d.sy; h.box[b][3] = d.sz;
+            }
+            for (int k = 0; k < 6; ++k) h.fff[k] = fff[e * 6 + k];
+            h.pad[0] = h.pad[1] = 0.f;
+        }
+        rc |= op->headers.upload(hdrs.data(), hdrs.size());
     }
     // The explicit index is always kept: it is the fallback, serves the diag kernel when boxes are
     // absent, and lets tests run both connectivity modes on the same plan.

@@ -1,0 +1,270 @@
+// sshex8 Laplacian, "plane-streaming" kernel (boxes connectivity): the production path of the north-star
+// operator. See sshex8_laplacian.cu for what is computed and sshex8_laplacian_core.cuh for the per-thread
+// arithmetic; this file is only about how the data moves.
+//
+// Shape. A persistent grid of one CTA per SM. A CTA is NTEAM independent *teams* of TW warps; a team owns
+// EPT = floor(32 TW / N) macro elements at a time (N = L+1 lattice rows per element, one lane per row) and
+// walks an endless stream of z-planes:  step t  ->  group t / N (EPT consecutive elements), plane t % N.
+// Per step a team
+//   1. computes plane t out of its shared-memory ring slot t % D (Sshex8LaplacianRow::step: 27 LDS.64 and
+//      ~250 DFMA per lane), and writes the output plane that became final to a staging buffer;
+//   2. waits for its own cp.async copies of plane t+1, then passes the ONE team barrier of the step
+//      (__syncwarp for TW = 1, a named barrier otherwise);
+//   3. issues the gather of plane t+D straight into the ring slot it just finished with
+//      (cp.async 8/4 B per node, addresses from the element's 27 box descriptors: no registers held,
+//      (D-1) planes = (D-1) EPT N^2 sizeof(T) bytes in flight per team);
+//   4. scatters the staged output plane: interior nodes (owned by exactly one element) with plain
+//      coalesced stores when overwriting, skeleton nodes with RED.ADD.
+// There is no CTA-wide barrier and no phase in which the memory system or the FP64 pipe waits for the
+// other: loads, DFMAs and stores of different planes overlap inside every team, and the 8 warps of an SM
+// drift apart freely.
+//
+// Element headers. The plan stores, per element, 27 box descriptors (16 B each) + the 6 fp32 FFF + pad =
+// 29 x 16 B, fetched with cp.async one whole group ahead of their first use (three header buffers per team).
+#pragma once
+#include "common.cuh"
+#include "sshex8_laplacian_core.cuh"
+
+namespace b200fem {
+
+struct Sshex8Header {   // 464 B, 16-byte aligned
+    int32_t box[27][4];  // base, sx, sy, sz  (id = base + sx x + sy y + sz z)
+    float fff[6];
+    float pad[2];
+};
+static_assert(sizeof(Sshex8Header) == 29 * 16, "header must be 29 x 16 B");
+
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_value(T *smem, const T *gmem) {
+    if (sizeof(T) == 8)
+        cp_async_8(smem, gmem);
+    else
+        cp_async_4(smem, gmem);
+}
+
+template <int TW>
+__device__ __forceinline__ void team_barrier(int team) {
+    if (TW == 1) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;\n" ::"r"(team + 1), "n"(TW * 32) : "memory");
+    }
+}
+
+template <typename T, int L, int TW, int NTEAM, int D>
+struct Sshex8StreamCfg {
+    static constexpr int N = L + 1;
+    static constexpr int NN = N * N;
+    static constexpr int TL = TW * 32;               // lanes per team
+    static constexpr int EPT = TL / N;               // elements per team-group
+    static constexpr int PLANE = EPT * NN;           // values per plane of a group
+    static constexpr int KMAX = (PLANE + TL - 1) / TL;  // copy/scatter items per lane per plane
+    static constexpr int HDR16 = EPT * 29;           // 16-byte chunks of a group's headers
+    static constexpr size_t ring_bytes = (size_t)D * PLANE * sizeof(T);
+    static constexpr size_t stage_bytes = (size_t)3 * PLANE * sizeof(T);
+    static constexpr size_t hdr_bytes = (size_t)3 * EPT * sizeof(Sshex8Header);
+    static constexpr size_t team_bytes = ((ring_bytes + stage_bytes + 15) / 16) * 16 + hdr_bytes;
+    static constexpr size_t smem_bytes = team_bytes * NTEAM;
+    static constexpr int threads = NTEAM * TL;
+    static_assert(D >= 2 && D <= N, "ring depth must be in [2, N]");
+    static_assert(EPT >= 1, "team too small for this level");
+};
+
+// PLAIN_INTERIOR: interior nodes are exclusive to their element and y is being overwritten -> plain stores.
+template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN_INTERIOR>
+__global__ void __launch_bounds__(NTEAM *TW * 32, 1)
+    sshex8_laplacian_stream_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers,
+                                   const T *__restrict__ u, T *__restrict__ y) {
+    using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
+    constexpr int N = Cfg::N, NN = Cfg::NN, TL = Cfg::TL, EPT = Cfg::EPT, PLANE = Cfg::PLANE, KMAX = Cfg::KMAX;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int team = threadIdx.x / TL;
+    const int tl = threadIdx.x - team * TL;  // lane within the team
+    unsigned char *tbase = smem_raw + (size_t)team * Cfg::team_bytes;
+    T *ring = reinterpret_cast<T *>(tbase);                       // [D][PLANE]
+    T *stage = ring + (size_t)D * PLANE;                          // [3][PLANE]
+    Sshex8Header *hdr = reinterpret_cast<Sshex8Header *>(tbase + ((Cfg::ring_bytes + Cfg::stage_bytes + 15) / 16) * 16);  // [3][EPT]
+
+    // ---- work of this team: groups gteam, gteam + nteams, ...
+    const ptrdiff_t ngroups = (ne + EPT - 1) / EPT;
+    const ptrdiff_t nteams = (ptrdiff_t)gridDim.x * NTEAM;
+    const ptrdiff_t gteam = (ptrdiff_t)blockIdx.x * NTEAM + team;
+    if (gteam >= ngroups) return;
+    const int my_groups = (int)((ngroups - gteam + nteams - 1) / nteams);
+    const int T_steps = my_groups * N;
+
+    // ---- per-lane copy/scatter items: plane position p = tl + k TL -> (slot, x, y), interior first
+    //      packed: bits 0-7 slot*NN + y*N + x (smem offset in the plane), 8-11 x, 12-15 y, 16-19 cx+3cy, 20-27 slot
+    unsigned pk[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int p = tl + k * TL;
+        unsigned v = 0xffffffffu;
+        if (p < PLANE) {
+            const int slot = p / NN, q = p - slot * NN;
+            int x, yy;
+            constexpr int NI = (L - 1) * (L - 1);
+            if (q < NI) {
+                yy = 1 + q / (L - 1);
+                x = 1 + q - (yy - 1) * (L - 1);
+            } else if (q < NI + N) {
+                yy = 0;
+                x = q - NI;
+            } else if (q < NI + 2 * N) {
+                yy = L;
+                x = q - NI - N;
+            } else if (q < NI + 2 * N + (L - 1)) {
+                x = 0;
+                yy = 1 + q - (NI + 2 * N);
+            } else {
+                x = L;
+                yy = 1 + q - (NI + 2 * N + (L - 1));
+            }
+            const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
+            v = (unsigned)(slot * NN + yy * N + x) | ((unsigned)x << 12) | ((unsigned)yy << 17) | ((unsigned)(cx + 3 * cy) << 22) |
+                ((unsigned)slot << 26);
+        }
+        pk[k] = v;
+    }
+    // field extractors (offset: 12 bits, x: 5 bits, y: 5 bits, cxy: 4 bits, slot: 6 bits)
+#define PK_OFF(v) ((int)((v)&0xfffu))
+#define PK_X(v) ((int)(((v) >> 12) & 31u))
+#define PK_Y(v) ((int)(((v) >> 17) & 31u))
+#define PK_CXY(v) ((int)(((v) >> 22) & 15u))
+#define PK_SLOT(v) ((int)((v) >> 26))
+
+    auto group_of = [&](int g_local) -> ptrdiff_t { return gteam + (ptrdiff_t)g_local * nteams; };
+
+    auto issue_headers = [&](int g_local) {
+        if (g_local >= my_groups) return;
+        const ptrdiff_t e0 = group_of(g_local) * EPT;
+        const ptrdiff_t nvalid = (ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT;
+        const int4 *src = reinterpret_cast<const int4 *>(headers + e0);
+        int4 *dst = reinterpret_cast<int4 *>(hdr + (size_t)(g_local % 3) * EPT);
+        for (int i = tl; i < (int)nvalid * 29; i += TL) cp_async_16(dst + i, src + i);
+    };
+
+    auto issue_plane = [&](int s) {  // gather plane of step s into ring slot s % D
+        if (s >= T_steps) return;
+        const int g_local = s / N, zp = s - g_local * N;
+        const ptrdiff_t e0 = group_of(g_local) * EPT;
+        const int nvalid = (int)((ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT);
+        const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT;
+        T *dst = ring + (size_t)(s % D) * PLANE;
+        const int cz9 = (zp == 0) ? 0 : (zp == L ? 18 : 9);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const unsigned v = pk[k];
+            if (v == 0xffffffffu) continue;
+            const int slot = PK_SLOT(v);
+            if (slot >= nvalid) continue;
+            const int4 d = *reinterpret_cast<const int4 *>(h[slot].box[PK_CXY(v) + cz9]);
+            const int id = d.x + d.y * PK_X(v) + d.z * PK_Y(v) + d.w * zp;
+            cp_async_value(dst + PK_OFF(v), u + id);
+        }
+    };
+
+    auto scatter_plane = [&](const T *src, int g_local, int z) {
+        const ptrdiff_t e0 = group_of(g_local) * EPT;
+        const int nvalid = (int)((ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT);
+        const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT;
+        const int cz9 = (z == 0) ? 0 : (z == L ? 18 : 9);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const unsigned v = pk[k];
+            if (v == 0xffffffffu) continue;
+            const int slot = PK_SLOT(v);
+            if (slot >= nvalid) continue;
+            const int b = PK_CXY(v) + cz9;
+            const int4 d = *reinterpret_cast<const int4 *>(h[slot].box[b]);
+            const int id = d.x + d.y * PK_X(v) + d.z * PK_Y(v) + d.w * z;
+            const T val = src[PK_OFF(v)];
+            if (PLAIN_INTERIOR && b == 13)
+                __stcs(&y[id], val);
+            else
+                red_add(&y[id], val);
+        }
+    };
+
+    // ---- prologue: headers of groups 0 and 1, then planes 0 .. D-1
+    issue_headers(0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    team_barrier<TW>(team);
+    issue_headers(1);
+#pragma unroll 1
+    for (int s = 0; s < D; ++s) {
+        issue_plane(s);
+        cp_async_commit();
+    }
+    cp_async_wait<D - 1>();
+    team_barrier<TW>(team);
+
+    // ---- stream
+    const bool compute_lane = tl < EPT * N;
+    const int slot = compute_lane ? tl / N : 0;
+    const int yrow = compute_lane ? tl - slot * N : 0;
+    Sshex8LaplacianRow<T, L> row;
+
+    int g_local = 0, zp = 0;
+#pragma unroll 1
+    for (int t = 0; t < T_steps; ++t) {
+        const T *plane = ring + (size_t)(t % D) * PLANE + slot * NN;
+        T *st0 = stage + (size_t)(t % 3) * PLANE + slot * NN;
+        T *st1 = stage + (size_t)((t + 1) % 3) * PLANE + slot * NN;
+        if (compute_lane) {
+            if (zp == 0) {
+                const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT + slot;
+                T f[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                row.init(f, yrow);
+            }
+            row.step(zp, plane, N);
+            row.write_and_rotate(zp, st0, N);  // output plane zp-1 (nothing at zp == 0)
+            if (zp == L) row.write_last(st1, N);
+        }
+        cp_async_wait<D - 2>();
+        team_barrier<TW>(team);
+
+        // headers of group g+2 travel with the first plane of group g+1
+        const int s_next = t + D;
+        if (s_next < T_steps && (s_next % N) == 0) issue_headers(s_next / N + 1);
+        issue_plane(s_next);
+        cp_async_commit();
+
+        if (zp > 0) scatter_plane(stage + (size_t)(t % 3) * PLANE, g_local, zp - 1);
+        if (zp == L) scatter_plane(stage + (size_t)((t + 1) % 3) * PLANE, g_local, L);
+
+        if (++zp == N) {
+            zp = 0;
+            ++g_local;
+        }
+    }
+    cp_async_wait<0>();
+#undef PK_OFF
+#undef PK_X
+#undef PK_Y
+#undef PK_CXY
+#undef PK_SLOT
+}
+
+}  // namespace b200fem
