@@ -34,6 +34,23 @@
 
 namespace b200fem {
 
+// a*b + c as ONE fused instruction on the device (the compiler may not contract `acc += a*b + c*d`
+// into a chain of FMAs on its own: the inner sum has to be rounded first)
+B2_HD double b2_fma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+B2_HD float b2_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+
 template <typename T, int L>
 struct Sshex8LaplacianRow {
     static constexpr int N = L + 1;
@@ -51,38 +68,40 @@ struct Sshex8LaplacianRow {
         const T h = T(1) / T(L);
         const T Sxx = fff[0] * h, Sxy = fff[1] * h, Sxz = fff[2] * h, Syy = fff[3] * h, Syz = fff[4] * h,
                 Szz = fff[5] * h;
-        const T Mt[3] = {T(1.0 / 6.0), T(2.0 / 3.0), T(1.0 / 6.0)};
-        const T Kt[3] = {T(-1), T(2), T(-1)};
+        const T m0 = T(1.0 / 6.0), m1 = T(2.0 / 3.0);
         // y-class factors: taps that leave the lattice vanish, in-plane taps of boundary rows are halved
-        T fy[3] = {T(1), T(1), T(1)};
-        T sy = T(0);
-        if (y == 0) {
-            fy[0] = T(0);
-            fy[1] = T(0.5);
-            sy = T(-1);
-        } else if (y == L) {
-            fy[2] = T(0);
-            fy[1] = T(0.5);
-            sy = T(1);
-        }
+        const T f0 = (y == 0) ? T(0) : T(1);
+        const T f1 = (y == 0 || y == L) ? T(0.5) : T(1);
+        const T f2 = (y == L) ? T(0) : T(1);
+        const T sy = (y == 0) ? T(-1) : ((y == L) ? T(1) : T(0));
+        // separable pieces (Kx = (-1,2,-1), Mx = (m0,m1,m0), Dx = (-1,0,1))
+        //   even-in-x part:  A(dz,dy)[|dx|]   odd-in-x part: B(dz,dy) * dx
+        const T fy[3] = {f0, f1, f2};
+        const T Mt[3] = {m0, m1, m0};
+        const T Kt[3] = {T(-1), T(2), T(-1)};
 #pragma unroll
         for (int iz = 0; iz < 3; ++iz) {
 #pragma unroll
             for (int iy = 0; iy < 3; ++iy) {
-#pragma unroll
-                for (int ix = 0; ix < 3; ++ix) {
-                    const T dx = T(ix - 1), dy = T(iy - 1), dz = T(iz - 1);
-                    const T v = Sxx * Kt[ix] * Mt[iy] * Mt[iz] + Syy * Mt[ix] * Kt[iy] * Mt[iz] +
-                                Szz * Mt[ix] * Mt[iy] * Kt[iz] -
-                                T(0.5) * (Sxy * dx * dy * Mt[iz] + Sxz * dx * dz * Mt[iy] + Syz * dy * dz * Mt[ix]);
-                    c[iz][iy][ix] = v * fy[iy];
-                }
+                const T mm = Mt[iy] * Mt[iz];
+                const T km = Syy * (Kt[iy] * Mt[iz]) + Szz * (Mt[iy] * Kt[iz]);
+                // dy dz term (zero unless both are +-1): -1/2 Syz dy dz M(dx)
+                const T dydz = (iy == 1 || iz == 1) ? T(0) : ((iy == iz) ? T(-0.5) : T(0.5)) * Syz;
+                // dx-odd term: -1/2 (Sxy dy M(dz) + Sxz dz M(dy)) * dx
+                const T oy = (iy == 1) ? T(0) : ((iy == 2) ? T(-0.5) : T(0.5)) * Sxy * Mt[iz];
+                const T oz = (iz == 1) ? T(0) : ((iz == 2) ? T(-0.5) : T(0.5)) * Sxz * Mt[iy];
+                const T even_side = -Sxx * mm + m0 * km + m0 * dydz;    // dx = +-1
+                const T even_mid = T(2) * Sxx * mm + m1 * km + m1 * dydz;  // dx = 0
+                const T odd = oy + oz;                                   // coefficient of dx
+                c[iz][iy][0] = (even_side - odd) * fy[iy];
+                c[iz][iy][1] = even_mid * fy[iy];
+                c[iz][iy][2] = (even_side + odd) * fy[iy];
             }
         }
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            gz[d] = T(0.5) * Sxy * sy * Mt[d];   // times sigma_x at use
-            gy[d] = T(0.5) * Sxz * Mt[d] * fy[d]; // times sigma_x sigma_z at use
+            gz[d] = T(0.5) * Sxy * sy * Mt[d];    // times sigma_x at use
+            gy[d] = T(0.5) * Sxz * Mt[d] * fy[d];  // times sigma_x sigma_z at use
         }
         gx = T(0.5) * Syz * sy;  // times sigma_z at use
 #pragma unroll
@@ -91,16 +110,18 @@ struct Sshex8LaplacianRow {
 
     // acc[x] += sum_dx cc[dx+1] * r[x+dx] with the x-boundary rule (h0 = r[0]/2, hL = r[L]/2)
     B2_HD static void row_taps(const T cc[3], const T r[N], const T h0, const T hL, T acc[N]) {
-        acc[0] += cc[1] * h0 + cc[2] * r[1];
+        acc[0] = b2_fma(cc[1], h0, b2_fma(cc[2], r[1], acc[0]));
 #pragma unroll
-        for (int x = 1; x < L; ++x) acc[x] += cc[0] * r[x - 1] + cc[1] * r[x] + cc[2] * r[x + 1];
-        acc[L] += cc[0] * r[L - 1] + cc[1] * hL;
+        for (int x = 1; x < L; ++x) acc[x] = b2_fma(cc[0], r[x - 1], b2_fma(cc[1], r[x], b2_fma(cc[2], r[x + 1], acc[x])));
+        acc[L] = b2_fma(cc[0], r[L - 1], b2_fma(cc[1], hL, acc[L]));
     }
 
-    // Consume input plane zp. `plane` points at this element's plane zp; row yy starts at
-    // plane[yy * ystride]. Reads only; the caller synchronises before write_plane().
-    B2_HD void step(const int zp, const T *plane, const int ystride) {
-        const bool zlo = (zp == 0), zhi = (zp == L);
+    // Consume input plane zp. ZC = 0: zp == 0, 1: 0 < zp < L, 2: zp == L (compile-time plane class, so
+    // the interior planes carry no boundary code). `plane` points at this element's plane zp; row yy
+    // starts at plane[yy * ystride]. Reads only.
+    template <int ZC>
+    B2_HD void step_class(const T *plane, const int ystride) {
+        constexpr bool zlo = (ZC == 0), zhi = (ZC == 2);
         if (zhi) {
 #pragma unroll
             for (int x = 0; x < N; ++x) accC[x] *= T(2);  // exact; undone below => dz = 0 taps get 1/2
@@ -120,42 +141,42 @@ struct Sshex8LaplacianRow {
             if (iy == 1) {
                 // edges parallel to z: raw end values of the row itself
                 if (!zlo) {
-                    accP[0] -= gz[2] * r[0];
-                    accP[L] += gz[2] * r[L];
+                    accP[0] = b2_fma(-gz[2], r[0], accP[0]);
+                    accP[L] = b2_fma(gz[2], r[L], accP[L]);
                 }
-                accC[0] -= gz[1] * r[0];
-                accC[L] += gz[1] * r[L];
+                accC[0] = b2_fma(-gz[1], r[0], accC[0]);
+                accC[L] = b2_fma(gz[1], r[L], accC[L]);
                 if (!zhi) {
-                    accN[0] -= gz[0] * r[0];
-                    accN[L] += gz[0] * r[L];
+                    accN[0] = b2_fma(-gz[0], r[0], accN[0]);
+                    accN[L] = b2_fma(gz[0], r[L], accN[L]);
+                }
+            }
+            if (zlo || zhi) {
+                // edges parallel to y (x and z extreme); applied after the halving below, so pre-double
+                const T sz2 = zlo ? T(-2) : T(2);
+                accC[0] = b2_fma(-sz2 * gy[iy], r[0], accC[0]);
+                accC[L] = b2_fma(sz2 * gy[iy], r[L], accC[L]);
+                if (iy == 1 && (y == 0 || y == L)) {
+                    // edges parallel to x (y and z extreme): 1-D mass row along x (pre-doubled as well)
+                    const T g = gx * sz2;
+                    const T m[3] = {g * T(1.0 / 6.0), g * T(2.0 / 3.0), g * T(1.0 / 6.0)};
+                    row_taps(m, r, h0, hL, accC);
                 }
             }
         }
         if (zlo || zhi) {
 #pragma unroll
             for (int x = 0; x < N; ++x) accC[x] *= T(0.5);
-            // terms that live on the z = 0 / z = L planes only and are not halved
-            const T sz = zlo ? T(-1) : T(1);
-#pragma unroll
-            for (int iy = 0; iy < 3; ++iy) {
-                int yy = y + iy - 1;
-                yy = yy < 0 ? 0 : (yy > L ? L : yy);
-                const T *row = plane + yy * ystride;
-                // edges parallel to y (x and z extreme)
-                accC[0] -= sz * gy[iy] * row[0];
-                accC[L] += sz * gy[iy] * row[L];
-            }
-            if (y == 0 || y == L) {
-                // edges parallel to x (y and z extreme): 1-D mass row along x
-                const T *row = plane + y * ystride;
-                T r[N];
-#pragma unroll
-                for (int x = 0; x < N; ++x) r[x] = row[x];
-                const T g = gx * sz;
-                const T m[3] = {g * T(1.0 / 6.0), g * T(2.0 / 3.0), g * T(1.0 / 6.0)};
-                row_taps(m, r, T(0.5) * r[0], T(0.5) * r[L], accC);
-            }
         }
+    }
+
+    B2_HD void step(const int zp, const T *plane, const int ystride) {
+        if (zp == 0)
+            step_class<0>(plane, ystride);
+        else if (zp == L)
+            step_class<2>(plane, ystride);
+        else
+            step_class<1>(plane, ystride);
     }
 
     // After step(zp) and a barrier: emit finished output plane zp-1 (zp >= 1), then rotate.

@@ -87,13 +87,69 @@ struct Sshex8StreamCfg {
     static_assert(EPT >= 1, "team too small for this level");
 };
 
+// interior-first order of the N x N positions of a lattice plane: the (L-1)^2 interior positions
+// (contiguous in global memory for the compact numbering), then the y = 0 row, the y = L row, the x = 0
+// column and the x = L column
+template <int L>
+__device__ __forceinline__ void plane_pos_to_xy(const int q, int &x, int &yy) {
+    constexpr int N = L + 1, NI = (L - 1) * (L - 1);
+    if (q < NI) {
+        yy = 1 + q / (L - 1);
+        x = 1 + q - (yy - 1) * (L - 1);
+    } else if (q < NI + N) {
+        yy = 0;
+        x = q - NI;
+    } else if (q < NI + 2 * N) {
+        yy = L;
+        x = q - NI - N;
+    } else if (q < NI + 2 * N + (L - 1)) {
+        x = 0;
+        yy = 1 + q - (NI + 2 * N);
+    } else {
+        x = L;
+        yy = 1 + q - (NI + 2 * N + (L - 1));
+    }
+}
+
+// one value: plain streaming store (exclusive interior node, y overwritten) or RED.ADD, branch-free
+__device__ __forceinline__ void store_or_red(double *p, const double v, const int plain) {
+    asm volatile(
+        "{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.global.cs.f64 [%0], %1;\n @!q red.global.add.f64 [%0], %1;\n}\n" ::"l"(p),
+        "d"(v), "r"(plain)
+        : "memory");
+}
+__device__ __forceinline__ void store_or_red(float *p, const float v, const int plain) {
+    asm volatile(
+        "{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.global.cs.f32 [%0], %1;\n @!q red.global.add.f32 [%0], %1;\n}\n" ::"l"(p),
+        "f"(v), "r"(plain)
+        : "memory");
+}
+
+// Per-lane description of one copy/scatter item whose (slot, position) does not change over time.
+struct PlaneItem {
+    int x, yy;   // lattice coordinates in the plane
+    int hoff;    // byte offset of its box descriptor inside a header buffer, cz = 0 (slot*464 + cxy*16)
+    int soff;    // element offset inside a plane buffer (slot*NN + yy*N + x)
+    int center;  // 1 if the position is interior in x and y
+    int slot;    // element slot of the group, -1 = no item
+};
+
 // PLAIN_INTERIOR: interior nodes are exclusive to their element and y is being overwritten -> plain stores.
 template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN_INTERIOR>
 __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     sshex8_laplacian_stream_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers,
                                    const T *__restrict__ u, T *__restrict__ y) {
     using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
-    constexpr int N = Cfg::N, NN = Cfg::NN, TL = Cfg::TL, EPT = Cfg::EPT, PLANE = Cfg::PLANE, KMAX = Cfg::KMAX;
+    constexpr int N = Cfg::N, NN = Cfg::NN, TL = Cfg::TL, EPT = Cfg::EPT, PLANE = Cfg::PLANE;
+    // Item mapping. If a team has no more lanes than a plane has positions (TL <= NN), lane `tl` serves
+    // position r*TL + tl of EVERY slot for the R full rounds r (so x, y, box class and smem offset are
+    // per-lane constants and the slot enters as an immediate), and the LO = NN - R*TL left-over
+    // positions of all slots are dealt round-robin over XR extra rounds. Otherwise (small levels) all
+    // PLANE positions are dealt round-robin.
+    constexpr bool STRUCT = (TL <= NN);
+    constexpr int R = STRUCT ? NN / TL : 0;
+    constexpr int LO = STRUCT ? NN - R * TL : NN;
+    constexpr int XR = (LO * EPT + TL - 1) / TL;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int team = threadIdx.x / TL;
@@ -101,7 +157,8 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     unsigned char *tbase = smem_raw + (size_t)team * Cfg::team_bytes;
     T *ring = reinterpret_cast<T *>(tbase);                       // [D][PLANE]
     T *stage = ring + (size_t)D * PLANE;                          // [3][PLANE]
-    Sshex8Header *hdr = reinterpret_cast<Sshex8Header *>(tbase + ((Cfg::ring_bytes + Cfg::stage_bytes + 15) / 16) * 16);  // [3][EPT]
+    unsigned char *hdr_bytes = tbase + ((Cfg::ring_bytes + Cfg::stage_bytes + 15) / 16) * 16;  // [3][EPT] headers
+    constexpr int HBUF = EPT * (int)sizeof(Sshex8Header);
 
     // ---- work of this team: groups gteam, gteam + nteams, ...
     const ptrdiff_t ngroups = (ne + EPT - 1) / EPT;
@@ -111,96 +168,97 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     const int my_groups = (int)((ngroups - gteam + nteams - 1) / nteams);
     const int T_steps = my_groups * N;
 
-    // ---- per-lane copy/scatter items: plane position p = tl + k TL -> (slot, x, y), interior first
-    //      packed: bits 0-7 slot*NN + y*N + x (smem offset in the plane), 8-11 x, 12-15 y, 16-19 cx+3cy, 20-27 slot
-    unsigned pk[KMAX];
+    // ---- per-lane items
+    PlaneItem full[R > 0 ? R : 1];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-        const int p = tl + k * TL;
-        unsigned v = 0xffffffffu;
-        if (p < PLANE) {
-            const int slot = p / NN, q = p - slot * NN;
-            int x, yy;
-            constexpr int NI = (L - 1) * (L - 1);
-            if (q < NI) {
-                yy = 1 + q / (L - 1);
-                x = 1 + q - (yy - 1) * (L - 1);
-            } else if (q < NI + N) {
-                yy = 0;
-                x = q - NI;
-            } else if (q < NI + 2 * N) {
-                yy = L;
-                x = q - NI - N;
-            } else if (q < NI + 2 * N + (L - 1)) {
-                x = 0;
-                yy = 1 + q - (NI + 2 * N);
-            } else {
-                x = L;
-                yy = 1 + q - (NI + 2 * N + (L - 1));
-            }
-            const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
-            v = (unsigned)(slot * NN + yy * N + x) | ((unsigned)x << 12) | ((unsigned)yy << 17) | ((unsigned)(cx + 3 * cy) << 22) |
-                ((unsigned)slot << 26);
-        }
-        pk[k] = v;
+    for (int r = 0; r < R; ++r) {
+        int x, yy;
+        plane_pos_to_xy<L>(r * TL + tl, x, yy);
+        const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
+        full[r] = PlaneItem{x, yy, (cx + 3 * cy) * 16, yy * N + x, (cx == 1 && cy == 1) ? 1 : 0, 0};
     }
-    // field extractors (offset: 12 bits, x: 5 bits, y: 5 bits, cxy: 4 bits, slot: 6 bits)
-#define PK_OFF(v) ((int)((v)&0xfffu))
-#define PK_X(v) ((int)(((v) >> 12) & 31u))
-#define PK_Y(v) ((int)(((v) >> 17) & 31u))
-#define PK_CXY(v) ((int)(((v) >> 22) & 15u))
-#define PK_SLOT(v) ((int)((v) >> 26))
+    PlaneItem extra[XR > 0 ? XR : 1];
+#pragma unroll
+    for (int k = 0; k < XR; ++k) {
+        const int j = k * TL + tl;
+        PlaneItem it{0, 0, 0, 0, 0, -1};
+        if (j < LO * EPT) {
+            const int slot = j / LO;
+            int x, yy;
+            plane_pos_to_xy<L>(R * TL + (j - slot * LO), x, yy);
+            const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
+            it = PlaneItem{x, yy, slot * (int)sizeof(Sshex8Header) + (cx + 3 * cy) * 16, slot * NN + yy * N + x,
+                           (cx == 1 && cy == 1) ? 1 : 0, slot};
+        }
+        extra[k] = it;
+    }
 
     auto group_of = [&](int g_local) -> ptrdiff_t { return gteam + (ptrdiff_t)g_local * nteams; };
+    auto valid_slots = [&](int g_local) -> int {
+        const ptrdiff_t left = ne - group_of(g_local) * EPT;
+        return (int)(left < (ptrdiff_t)EPT ? left : (ptrdiff_t)EPT);
+    };
 
     auto issue_headers = [&](int g_local) {
         if (g_local >= my_groups) return;
-        const ptrdiff_t e0 = group_of(g_local) * EPT;
-        const ptrdiff_t nvalid = (ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT;
-        const int4 *src = reinterpret_cast<const int4 *>(headers + e0);
-        int4 *dst = reinterpret_cast<int4 *>(hdr + (size_t)(g_local % 3) * EPT);
-        for (int i = tl; i < (int)nvalid * 29; i += TL) cp_async_16(dst + i, src + i);
+        const int nvalid = valid_slots(g_local);
+        const int4 *src = reinterpret_cast<const int4 *>(headers + group_of(g_local) * EPT);
+        int4 *dst = reinterpret_cast<int4 *>(hdr_bytes + (g_local % 3) * HBUF);
+        for (int i = tl; i < nvalid * 29; i += TL) cp_async_16(dst + i, src + i);
+    };
+
+    // id of item `it` of slot-relative header base hb (already offset by the z class)
+    auto item_id = [&](const unsigned char *hb, const PlaneItem &it, const int z) -> int {
+        const int4 d = *reinterpret_cast<const int4 *>(hb + it.hoff);
+        return d.x + d.y * it.x + d.z * it.yy + d.w * z;
     };
 
     auto issue_plane = [&](int s) {  // gather plane of step s into ring slot s % D
         if (s >= T_steps) return;
         const int g_local = s / N, zp = s - g_local * N;
-        const ptrdiff_t e0 = group_of(g_local) * EPT;
-        const int nvalid = (int)((ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT);
-        const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT;
+        const int nvalid = valid_slots(g_local);
+        const unsigned char *hb = hdr_bytes + (g_local % 3) * HBUF + ((zp == 0) ? 0 : (zp == L ? 18 : 9)) * 16;
         T *dst = ring + (size_t)(s % D) * PLANE;
-        const int cz9 = (zp == 0) ? 0 : (zp == L ? 18 : 9);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            const unsigned v = pk[k];
-            if (v == 0xffffffffu) continue;
-            const int slot = PK_SLOT(v);
-            if (slot >= nvalid) continue;
-            const int4 d = *reinterpret_cast<const int4 *>(h[slot].box[PK_CXY(v) + cz9]);
-            const int id = d.x + d.y * PK_X(v) + d.z * PK_Y(v) + d.w * zp;
-            cp_async_value(dst + PK_OFF(v), u + id);
+        for (int sl = 0; sl < EPT; ++sl) {
+            if (R > 0 && sl < nvalid) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int id = item_id(hb + sl * (int)sizeof(Sshex8Header), full[r], zp);
+                    cp_async_value(dst + sl * NN + full[r].soff, u + id);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < XR; ++k) {
+            if (extra[k].slot >= 0 && extra[k].slot < nvalid) {
+                const int id = item_id(hb, extra[k], zp);
+                cp_async_value(dst + extra[k].soff, u + id);
+            }
         }
     };
 
     auto scatter_plane = [&](const T *src, int g_local, int z) {
-        const ptrdiff_t e0 = group_of(g_local) * EPT;
-        const int nvalid = (int)((ne - e0) < (ptrdiff_t)EPT ? (ne - e0) : (ptrdiff_t)EPT);
-        const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT;
-        const int cz9 = (z == 0) ? 0 : (z == L ? 18 : 9);
+        const int nvalid = valid_slots(g_local);
+        const int zc = (z == 0) ? 0 : (z == L ? 2 : 1);
+        const unsigned char *hb = hdr_bytes + (g_local % 3) * HBUF + zc * 9 * 16;
+        const int zplain = (PLAIN_INTERIOR && zc == 1) ? 1 : 0;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            const unsigned v = pk[k];
-            if (v == 0xffffffffu) continue;
-            const int slot = PK_SLOT(v);
-            if (slot >= nvalid) continue;
-            const int b = PK_CXY(v) + cz9;
-            const int4 d = *reinterpret_cast<const int4 *>(h[slot].box[b]);
-            const int id = d.x + d.y * PK_X(v) + d.z * PK_Y(v) + d.w * z;
-            const T val = src[PK_OFF(v)];
-            if (PLAIN_INTERIOR && b == 13)
-                __stcs(&y[id], val);
-            else
-                red_add(&y[id], val);
+        for (int sl = 0; sl < EPT; ++sl) {
+            if (R > 0 && sl < nvalid) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int id = item_id(hb + sl * (int)sizeof(Sshex8Header), full[r], z);
+                    store_or_red(y + id, src[sl * NN + full[r].soff], zplain & full[r].center);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < XR; ++k) {
+            if (extra[k].slot >= 0 && extra[k].slot < nvalid) {
+                const int id = item_id(hb, extra[k], z);
+                store_or_red(y + id, src[extra[k].soff], zplain & extra[k].center);
+            }
         }
     };
 
@@ -232,7 +290,7 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
         T *st1 = stage + (size_t)((t + 1) % 3) * PLANE + slot * NN;
         if (compute_lane) {
             if (zp == 0) {
-                const Sshex8Header *h = hdr + (size_t)(g_local % 3) * EPT + slot;
+                const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
                 T f[6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
@@ -260,11 +318,6 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
         }
     }
     cp_async_wait<0>();
-#undef PK_OFF
-#undef PK_X
-#undef PK_Y
-#undef PK_CXY
-#undef PK_SLOT
 }
 
 }  // namespace b200fem
