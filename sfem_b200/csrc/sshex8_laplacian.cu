@@ -200,15 +200,22 @@ struct Sshex8Laplacian final : OpBase {
     template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN>
     int launch_stream_cfg(const T *x, T *y, cudaStream_t s) {
         using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
-        auto kern = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN>;
+        auto kern = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, false>;
+        auto tail = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, true>;
         static bool configured = false;
         if (!configured) {
             B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+            B2_CUDA(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
             configured = true;
         }
-        const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;
-        const int grid = (int)std::min<ptrdiff_t>((ngroups + NTEAM - 1) / NTEAM, (ptrdiff_t)sm_count());
-        kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers.ptr, x, y);
+        // full groups in the main launch, the ne % EPT left-over elements in a one-CTA clean-up launch
+        const ptrdiff_t ngroups = ne / Cfg::EPT;
+        const ptrdiff_t ne_main = ngroups * Cfg::EPT;
+        if (ngroups > 0) {
+            const int grid = (int)std::min<ptrdiff_t>((ngroups + NTEAM - 1) / NTEAM, (ptrdiff_t)sm_count());
+            kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne_main, headers.ptr, x, y);
+        }
+        if (ne_main < ne) tail<<<1, Cfg::threads, Cfg::smem_bytes, s>>>(ne - ne_main, headers.ptr + ne_main, x, y);
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
     }

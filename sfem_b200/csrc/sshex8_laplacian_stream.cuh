@@ -34,13 +34,15 @@ struct Sshex8Header {   // 464 B, 16-byte aligned
 };
 static_assert(sizeof(Sshex8Header) == 29 * 16, "header must be 29 x 16 B");
 
+// The 4/8-byte copies and the scatter stores below carry NO "memory" clobber on purpose: their ordering
+// against ordinary shared-memory traffic is established by the team barrier and cp.async.wait_group (which
+// do clobber), and without it the compiler is free to hoist the descriptor loads of all items of a plane
+// above the first copy instead of serialising LDS -> IMAD chain -> LDGSTS item by item.
 __device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -115,14 +117,12 @@ __device__ __forceinline__ void plane_pos_to_xy(const int q, int &x, int &yy) {
 __device__ __forceinline__ void store_or_red(double *p, const double v, const int plain) {
     asm volatile(
         "{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.global.cs.f64 [%0], %1;\n @!q red.global.add.f64 [%0], %1;\n}\n" ::"l"(p),
-        "d"(v), "r"(plain)
-        : "memory");
+        "d"(v), "r"(plain));
 }
 __device__ __forceinline__ void store_or_red(float *p, const float v, const int plain) {
     asm volatile(
         "{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.global.cs.f32 [%0], %1;\n @!q red.global.add.f32 [%0], %1;\n}\n" ::"l"(p),
-        "f"(v), "r"(plain)
-        : "memory");
+        "f"(v), "r"(plain));
 }
 
 // Per-lane description of one copy/scatter item whose (slot, position) does not change over time.
@@ -135,7 +135,9 @@ struct PlaneItem {
 };
 
 // PLAIN_INTERIOR: interior nodes are exclusive to their element and y is being overwritten -> plain stores.
-template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN_INTERIOR>
+// CHECK_TAIL: the last group may hold fewer than EPT elements (only the small clean-up launch pays for the
+// checks; the main launch covers floor(ne / EPT) full groups).
+template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN_INTERIOR, bool CHECK_TAIL>
 __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     sshex8_laplacian_stream_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers,
                                    const T *__restrict__ u, T *__restrict__ y) {
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     constexpr int R = STRUCT ? NN / TL : 0;
     constexpr int LO = STRUCT ? NN - R * TL : NN;
     constexpr int XR = (LO * EPT + TL - 1) / TL;
+    constexpr int NIT = EPT * R + XR;  // items per lane per plane
+    constexpr int HSZ = (int)sizeof(Sshex8Header);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int team = threadIdx.x / TL;
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     T *ring = reinterpret_cast<T *>(tbase);                       // [D][PLANE]
     T *stage = ring + (size_t)D * PLANE;                          // [3][PLANE]
     unsigned char *hdr_bytes = tbase + ((Cfg::ring_bytes + Cfg::stage_bytes + 15) / 16) * 16;  // [3][EPT] headers
-    constexpr int HBUF = EPT * (int)sizeof(Sshex8Header);
+    constexpr int HBUF = EPT * HSZ;
 
     // ---- work of this team: groups gteam, gteam + nteams, ...
     const ptrdiff_t ngroups = (ne + EPT - 1) / EPT;
@@ -168,35 +172,52 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     const int my_groups = (int)((ngroups - gteam + nteams - 1) / nteams);
     const int T_steps = my_groups * N;
 
-    // ---- per-lane items
-    PlaneItem full[R > 0 ? R : 1];
+    // ---- per-lane items: (x, y) in the plane, header byte offset of the box class at cz = 0, plane offset
+    int it_x[NIT], it_y[NIT], it_h[NIT], it_s[NIT];
+    unsigned center_mask = 0, valid_mask = 0;
+    int it_slot[XR > 0 ? XR : 1];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int x, yy;
-        plane_pos_to_xy<L>(r * TL + tl, x, yy);
-        const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
-        full[r] = PlaneItem{x, yy, (cx + 3 * cy) * 16, yy * N + x, (cx == 1 && cy == 1) ? 1 : 0, 0};
-    }
-    PlaneItem extra[XR > 0 ? XR : 1];
-#pragma unroll
-    for (int k = 0; k < XR; ++k) {
-        const int j = k * TL + tl;
-        PlaneItem it{0, 0, 0, 0, 0, -1};
-        if (j < LO * EPT) {
-            const int slot = j / LO;
-            int x, yy;
-            plane_pos_to_xy<L>(R * TL + (j - slot * LO), x, yy);
-            const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
-            it = PlaneItem{x, yy, slot * (int)sizeof(Sshex8Header) + (cx + 3 * cy) * 16, slot * NN + yy * N + x,
-                           (cx == 1 && cy == 1) ? 1 : 0, slot};
+    for (int i = 0; i < NIT; ++i) {
+        int slot, pos;
+        bool valid = true;
+        if (i < EPT * R) {
+            slot = i / (R > 0 ? R : 1);
+            pos = (i - slot * R) * TL + tl;
+        } else {
+            const int j = (i - EPT * R) * TL + tl;
+            valid = j < LO * EPT;
+            slot = valid ? j / LO : 0;
+            pos = valid ? R * TL + (j - slot * LO) : 0;
+            it_slot[i - EPT * R] = valid ? slot : EPT;  // EPT = never valid
         }
-        extra[k] = it;
+        int x, yy;
+        plane_pos_to_xy<L>(pos, x, yy);
+        const int cx = (x == 0) ? 0 : (x == L ? 2 : 1), cy = (yy == 0) ? 0 : (yy == L ? 2 : 1);
+        it_x[i] = x;
+        it_y[i] = yy;
+        it_h[i] = slot * HSZ + (cx + 3 * cy) * 16;
+        it_s[i] = slot * NN + yy * N + x;
+        if (cx == 1 && cy == 1) center_mask |= 1u << i;
+        if (valid) valid_mask |= 1u << i;
     }
 
     auto group_of = [&](int g_local) -> ptrdiff_t { return gteam + (ptrdiff_t)g_local * nteams; };
     auto valid_slots = [&](int g_local) -> int {
+        if (!CHECK_TAIL) return EPT;
         const ptrdiff_t left = ne - group_of(g_local) * EPT;
         return (int)(left < (ptrdiff_t)EPT ? left : (ptrdiff_t)EPT);
+    };
+    // which items exist for this group (bit i)
+    auto item_mask = [&](int g_local) -> unsigned {
+        if (!CHECK_TAIL) return valid_mask;
+        const int nvalid = valid_slots(g_local);
+        unsigned m = 0;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int slot = (i < EPT * R) ? i / (R > 0 ? R : 1) : it_slot[i - EPT * R];
+            if (slot < nvalid) m |= 1u << i;
+        }
+        return m & valid_mask;
     };
 
     auto issue_headers = [&](int g_local) {
@@ -207,58 +228,63 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
         for (int i = tl; i < nvalid * 29; i += TL) cp_async_16(dst + i, src + i);
     };
 
-    // id of item `it` of slot-relative header base hb (already offset by the z class)
-    auto item_id = [&](const unsigned char *hb, const PlaneItem &it, const int z) -> int {
-        const int4 d = *reinterpret_cast<const int4 *>(hb + it.hoff);
-        return d.x + d.y * it.x + d.z * it.yy + d.w * z;
+    // Node ids of a plane: id(z) = I + S z with (I, S) fixed over the z-interior planes of a group, so the
+    // 7 interior planes of a level-8 element cost one IMAD per node; planes 0 and L read their own boxes.
+    auto plane_set = [&](int g_local, int zc, int (&I)[NIT], int (&S)[NIT]) {
+        const unsigned char *hb = hdr_bytes + (g_local % 3) * HBUF + zc * 9 * 16;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int4 d = *reinterpret_cast<const int4 *>(hb + it_h[i]);
+            I[i] = d.x + d.y * it_x[i] + d.z * it_y[i];
+            S[i] = d.w;
+        }
     };
+
+    int ldI[NIT], ldS[NIT];  // z-interior set of the group whose planes are being gathered
+    int scI[NIT], scS[NIT];  // z-interior set of the group whose planes are being scattered
 
     auto issue_plane = [&](int s) {  // gather plane of step s into ring slot s % D
         if (s >= T_steps) return;
         const int g_local = s / N, zp = s - g_local * N;
-        const int nvalid = valid_slots(g_local);
-        const unsigned char *hb = hdr_bytes + (g_local % 3) * HBUF + ((zp == 0) ? 0 : (zp == L ? 18 : 9)) * 16;
+        const unsigned m = item_mask(g_local);
         T *dst = ring + (size_t)(s % D) * PLANE;
+        if (zp == 0) plane_set(g_local, 1, ldI, ldS);  // the set of the group the gather is entering
+        int id[NIT];
+        if (zp == 0 || zp == L) {
+            int I[NIT], S[NIT];
+            plane_set(g_local, zp == 0 ? 0 : 2, I, S);
 #pragma unroll
-        for (int sl = 0; sl < EPT; ++sl) {
-            if (R > 0 && sl < nvalid) {
+            for (int i = 0; i < NIT; ++i) id[i] = I[i] + S[i] * zp;
+        } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int id = item_id(hb + sl * (int)sizeof(Sshex8Header), full[r], zp);
-                    cp_async_value(dst + sl * NN + full[r].soff, u + id);
-                }
-            }
+            for (int i = 0; i < NIT; ++i) id[i] = ldI[i] + ldS[i] * zp;
         }
 #pragma unroll
-        for (int k = 0; k < XR; ++k) {
-            if (extra[k].slot >= 0 && extra[k].slot < nvalid) {
-                const int id = item_id(hb, extra[k], zp);
-                cp_async_value(dst + extra[k].soff, u + id);
-            }
+        for (int i = 0; i < NIT; ++i) {
+            if ((m >> i) & 1u) cp_async_value(dst + it_s[i], u + id[i]);
         }
     };
 
     auto scatter_plane = [&](const T *src, int g_local, int z) {
-        const int nvalid = valid_slots(g_local);
-        const int zc = (z == 0) ? 0 : (z == L ? 2 : 1);
-        const unsigned char *hb = hdr_bytes + (g_local % 3) * HBUF + zc * 9 * 16;
-        const int zplain = (PLAIN_INTERIOR && zc == 1) ? 1 : 0;
+        const unsigned m = item_mask(g_local);
+        int id[NIT];
+        unsigned plain = 0;
+        if (z == 0 || z == L) {
+            int I[NIT], S[NIT];
+            plane_set(g_local, z == 0 ? 0 : 2, I, S);
 #pragma unroll
-        for (int sl = 0; sl < EPT; ++sl) {
-            if (R > 0 && sl < nvalid) {
+            for (int i = 0; i < NIT; ++i) id[i] = I[i] + S[i] * z;
+        } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int id = item_id(hb + sl * (int)sizeof(Sshex8Header), full[r], z);
-                    store_or_red(y + id, src[sl * NN + full[r].soff], zplain & full[r].center);
-                }
-            }
+            for (int i = 0; i < NIT; ++i) id[i] = scI[i] + scS[i] * z;
+            if (PLAIN_INTERIOR) plain = center_mask;
         }
+        T val[NIT];
 #pragma unroll
-        for (int k = 0; k < XR; ++k) {
-            if (extra[k].slot >= 0 && extra[k].slot < nvalid) {
-                const int id = item_id(hb, extra[k], z);
-                store_or_red(y + id, src[extra[k].soff], zplain & extra[k].center);
-            }
+        for (int i = 0; i < NIT; ++i) val[i] = src[it_s[i]];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            if ((m >> i) & 1u) store_or_red(y + id[i], val[i], (int)((plain >> i) & 1u));
         }
     };
 
@@ -288,6 +314,7 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
         const T *plane = ring + (size_t)(t % D) * PLANE + slot * NN;
         T *st0 = stage + (size_t)(t % 3) * PLANE + slot * NN;
         T *st1 = stage + (size_t)((t + 1) % 3) * PLANE + slot * NN;
+        if (zp == 0) plane_set(g_local, 1, scI, scS);
         if (compute_lane) {
             if (zp == 0) {
                 const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
