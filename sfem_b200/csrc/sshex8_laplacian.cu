@@ -227,9 +227,9 @@ struct Sshex8Laplacian final : OpBase {
         if constexpr (L == 8) {
             switch (stream_cfg) {
                 default:
-                case 0: return launch_stream_cfg<T, L, 1, 8, 8, PLAIN>(x, y, s);
+                case 0: return launch_stream_cfg<T, L, 1, 8, 6, PLAIN>(x, y, s);
                 case 1: return launch_stream_cfg<T, L, 2, 4, 7, PLAIN>(x, y, s);
-                case 2: return launch_stream_cfg<T, L, 1, 8, 6, PLAIN>(x, y, s);
+                case 2: return launch_stream_cfg<T, L, 1, 8, 8, PLAIN>(x, y, s);
                 case 3: return launch_stream_cfg<T, L, 2, 4, 5, PLAIN>(x, y, s);
                 case 4: return launch_stream_cfg<T, L, 4, 2, F64 ? 7 : 9, PLAIN>(x, y, s);
                 case 5: return launch_stream_cfg<T, L, 1, 6, 9, PLAIN>(x, y, s);
