@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the matrix-free apply hot path (BASELINE.json metric).
 
-A "step" is one matrix-free Laplacian apply  y += A x  (the reference's Op::apply contract,
-frontend/ops/sfem_Op.hpp:214) over the whole sshex8 mesh of config C3:
-level-8 semi-structured hex8 on a 64^3 macro mesh, 135 005 697 dofs, fp64, synthetic unit cube.
-Per rank the mesh is one such block (weak scaling); with N > 1 ranks the global mesh is an N-long
-stack of blocks along z and every apply ends with the interface exchange (NCCL).
+A "step" is one matrix-free Laplacian apply over the sshex8 mesh of config C3:
+level-8 semi-structured hex8 on a 64^3 macro mesh per GPU, 135 005 697 dofs, fp64, synthetic unit cube.
+What is timed is  y = A x  -- the pair `zeros(y); Op::apply(x, y)` every solver of the reference issues
+(algebra/sfem_cg.hpp:226-230, sfem_Multigrid.hpp:271), fused into one C-ABI call
+(b200fem_op_apply_overwrite). The strict accumulate form  y += A x  is timed beside it.
 
-Prints ONE JSON line (see DESIGN.md "Measurement" for every field). `--impl reference` times the
+With N > 1 ranks (torchrun, one process per GPU) the global mesh is an N-long stack of such blocks along z
+(weak scaling). Every rank holds its block plus the aura layer of the block above
+(sfem_b200/parallel.py, the reference's owned/ghost/aura scheme) and every step starts with the NCCL halo
+gather of x. `value` counts the dofs all ranks own.
+
+Prints ONE JSON line (DESIGN.md "Measurement" explains every field). `--impl reference` times the
 reference's own OpenMP kernel (oracle/_ref, else the oracle port) on the host cores instead.
 """
 from __future__ import annotations
@@ -42,28 +47,12 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, overwrite)")
+    ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, vector kernels)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return f"sshex8 Laplacian apply, level {a.level}, {a.macro}^3 macro elements per GPU, {a.real}"
-
-
-def build_mesh(a):
-    from sfem_b200 import mesh
-
-    t0 = time.time()
-    m = mesh.sshex8_box(a.level, a.macro, a.macro, a.macro, with_points=False)
-    m["t_mesh"] = time.time() - t0
-    return m
-
-
-def macro_fff(m):
-    """FFF of the macro elements (unit cube box: computed with the product's own geometry kernel)."""
-    from sfem_b200 import lib
-
-    return lib.fff_fill(lib.HEX8, m["m_elements"], m["m_points"])
+    return f"C3: sshex8 Laplacian apply, level {a.level}, {a.macro}^3 macro elements per GPU, {a.real}"
 
 
 class ClockSampler:
@@ -74,17 +63,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device=0):
-        self.device = device
-        self.rows = []
-        self.proc = None
+        self.device, self.rows, self.proc = device, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)  # let the first samples land before the timed region starts
         except Exception:
             self.proc = None
 
@@ -95,13 +83,13 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -110,62 +98,72 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(a, m, fff, steps, warmup):
-    """The reference's own OpenMP kernel (oracle/_ref `_fast` build = its Release flags) on the host."""
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own OpenMP kernel on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(a, elements, fff, nn, steps, warmup):
+    """affine_sshex8_laplacian_stencil_apply_fff from oracle/_ref (the reference's sources, its Release
+    flags) -- or the oracle port when the reference build is absent -- with all host threads."""
     from oracle.ref import Oracle, available
 
-    kind = "reference" if available("reference", a.real, fast=True) else "port"
-    orc = Oracle(kind, a.real, fast=(kind == "reference"))
-    nn = m["n_nodes"]
-    u = np.random.default_rng(42).uniform(-1, 1, nn).astype(orc.rt)
-    y = np.zeros(nn, dtype=orc.rt)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     os.environ.setdefault("OMP_PROC_BIND", "true")
+    kind = "reference" if available("reference", a.real, fast=True) else "port"
+    orc = Oracle(kind, a.real, fast=(kind == "reference"))
+    u = np.random.default_rng(42).uniform(-1, 1, nn).astype(orc.rt)
+    y = np.zeros(nn, dtype=orc.rt)
     for _ in range(warmup):
-        orc.sshex8_laplacian_apply(a.level, m["elements"], fff, u, out=y)
+        orc.sshex8_laplacian_apply(a.level, elements, fff, u, out=y)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.sshex8_laplacian_apply(a.level, m["elements"], fff, u, out=y)
+        y[:] = 0  # the reference's callers zero the output before every apply
+        orc.sshex8_laplacian_apply(a.level, elements, fff, u, out=y)
     dt = (time.perf_counter() - t0) / steps
     return {"value": nn / dt / 1e9, "unit": UNIT, "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
-            "sample": f"full workload ({nn} dofs), {steps} applies after {warmup} warm-up, wall clock",
+            "sample": f"the full workload ({nn} dofs), {steps} x (zero y + apply) after {warmup} warm-up, wall clock, "
+                      f"OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}",
             "ms_per_step": dt * 1e3}
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    m = build_mesh(a)
     from oracle.ref import Oracle, available
+    from sfem_b200 import mesh
 
+    m = mesh.sshex8_box(a.level, a.macro, a.macro, a.macro, with_points=False)
     kind = "reference" if available("reference", "f64") else "port"
     fff = Oracle(kind, "f64").hex8_fff_fill(m["m_elements"], m["m_points"])
-    steps = max(1, min(a.steps, 10))
-    warm = max(1, min(a.warmup, 2))
-    cb = cpu_reference_run(a, m, fff, steps, warm)
+    steps = max(1, min(a.steps, 20))
+    warm = max(1, min(a.warmup, 3))
+    cb = cpu_reference_run(a, m["elements"], fff, m["n_nodes"], steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.real, "data": "synthetic",
-        "config": {"workload": workload_name(a) + " (reference OpenMP kernel on host cores, one rank's block)"},
+        "config": {"workload": workload_name(a) + " -- reference OpenMP kernel on the host cores (one rank's block)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------
+# b200 arm
+# ------------------------------------------------------------------------------------------------------
 def time_steps(fn, steps, warmup, torch, barrier=None):
+    """CUDA events on the current stream (the one every C-ABI call is launched on), sync on both sides."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -186,61 +184,77 @@ def time_steps(fn, steps, warmup, torch, barrier=None):
 def run_b200(a):
     import torch
 
-    from sfem_b200 import lib
+    from sfem_b200 import lib, mesh, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
     dt = torch.float64 if a.real == "f64" else torch.float32
-    m = build_mesh(a)
-    fff = macro_fff(m)
-    nn = m["n_nodes"]
+    ndt = np.float64 if a.real == "f64" else np.float32
     t0 = time.time()
-    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, dt, level=a.level)
+    if world == 1:
+        m = mesh.sshex8_box(a.level, a.macro, a.macro, a.macro, with_points=False)
+        elements, n_local, n_owned = m["elements"], m["n_nodes"], m["n_nodes"]
+        m_el, m_pts = m["m_elements"], m["m_points"]
+        lm = None
+    else:
+        lm = parallel.sshex8_slab(a.level, a.macro, a.macro, a.macro, rank, world)
+        elements, n_local, n_owned = lm.elements, lm.n_local, lm.n_owned
+        m_el, m_pts = lm.extra["m_elements"], lm.extra["m_points"]
+    t_mesh = time.time() - t0
+    fff = lib.fff_fill(lib.HEX8, m_el, m_pts)  # macro-element FFF from the product's own geometry kernel
+    t0 = time.time()
+    op = lib.laplacian(lib.SSHEX8, elements, fff, n_local, dt, level=a.level)
     t_plan = time.time() - t0
+    assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
 
-    u_host = np.random.default_rng(42 + rank).uniform(-1, 1, nn).astype(np.float64 if a.real == "f64" else np.float32)
-    x = torch.from_numpy(u_host).cuda()
+    u_host = np.random.default_rng(42 + rank).uniform(-1, 1, n_local).astype(ndt)
+    x = torch.from_numpy(u_host).to(dev)
     y = torch.zeros_like(x)
-
-    halo = None
-    if world > 1:
-        from sfem_b200.parallel import SlabHalo
-
-        halo = SlabHalo(m, a.level, a.macro, rank, world, dt)
+    halo = parallel.HaloExchange(lm, 1, device=dev) if lm is not None else None
 
     def step():
-        op.apply(x, y)
         if halo is not None:
-            halo.exchange_add(y)
+            halo.gather(x)
+        op.apply_overwrite(x, y)
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = time_steps(step, a.steps, a.warmup, torch, barrier)
+    ms = max_over_ranks(time_steps(step, a.steps, a.warmup, torch, barrier))
     clocks = sampler.stop() if rank == 0 else None
+
+    total_owned = n_owned
     if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.tensor([n_owned], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        total_owned = int(t.item())
 
-    # kernel-only time of the dominant kernel (no halo), for the roofline object
-    ms_kernel = time_steps(lambda: op.apply(x, y), a.steps, 1, torch) if halo is not None else ms
-    ms_overwrite = time_steps(lambda: op.apply_overwrite(x, y), max(3, a.steps // 2), 1, torch)
+    # the dominant kernel alone (no halo): overwrite form = [memset of the skeleton ranges + stream kernel]
+    ms_kernel = time_steps(lambda: op.apply_overwrite(x, y), a.steps, 2, torch)
+    ms_accumulate = time_steps(lambda: op.apply(x, y), max(3, a.steps // 2), 2, torch)
 
-    # e2e: host buffers, H2D of x and D2H of y inside the timed region, through the C ABI
+    # e2e: HOST buffers through the C ABI, H2D of x and D2H of y inside the timed region
     e2e = None
     if not a.no_e2e:
         xh = torch.from_numpy(u_host).pin_memory()
@@ -248,20 +262,17 @@ def run_b200(a):
 
         def e2e_step():
             x.copy_(xh, non_blocking=True)
-            y.zero_()
-            op.apply(x, y)
             if halo is not None:
-                halo.exchange_add(y)
+                halo.gather(x)
+            op.apply_overwrite(x, y)
             yh.copy_(y, non_blocking=True)
 
-        k = max(2, min(a.steps, 5))
-        ms_e2e = time_steps(e2e_step, k, 1, torch, barrier)
-        if dist is not None:
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": nn * world / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nn * x.element_size()),
-               "d2h_bytes_per_step": int(nn * x.element_size()), "ms_per_step": ms_e2e, "steps": k}
+        k = max(3, min(a.steps, 5))
+        ms_e2e = max_over_ranks(time_steps(e2e_step, k, 1, torch, barrier))
+        e2e = {"value": total_owned / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_local * x.element_size()), "d2h_bytes_per_step": int(n_local * x.element_size()),
+               "ms_per_step": ms_e2e, "steps": k,
+               "note": "pinned host x -> device, y = A x through the C ABI, device y -> pinned host, every step"}
 
     if rank != 0:
         if dist is not None:
@@ -276,38 +287,42 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg = op.algorithmic_bytes
     achieved = alg / (ms_kernel * 1e-3) / 1e9
+    launches_per_step = op.launches(True) + (len(halo.send_idx) if halo is not None else 0)
     line = {
-        "metric": METRIC, "value": nn * world / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "metric": METRIC, "value": total_owned / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.real, "data": "synthetic",
         "config": {
-            "workload": workload_name(a), "dofs_per_gpu": nn, "macro_elements_per_gpu": int(m["elements"].shape[1]),
-            "semantics": "y += A x (accumulate)", "l2_policy": "inputs (2.9 GB/apply) larger than L2, no flush",
-            "connectivity": "boxes" if op.get_option("mode") == 1 else "explicit",
-            "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+            "workload": workload_name(a), "dofs_owned_total": total_owned, "dofs_local_rank0": n_local,
+            "macro_elements_rank0": int(elements.shape[1]),
+            "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair as one call (b200fem_op_apply_overwrite)",
+            "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
+            "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
+            "parallelism": f"z-slab x{world}, owned/ghost/aura, NCCL halo gather of x per step" if world > 1 else "single GPU",
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "algorithmic_bytes": alg, "streamed_bytes": op.streamed_bytes(False),
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-            "kernel_ms": ms_kernel,
+            "traffic": None, "algorithmic_bytes": alg, "streamed_bytes": op.streamed_bytes(True),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
+            "kernel": "sshex8_laplacian_stream_kernel (+ the memsets of the skeleton ranges that belong to the call)",
+            "kernel_ms": ms_kernel, "frac_of_8TBs_nominal": achieved / 8000.0,
         },
-        "apply_overwrite": {"value": nn / (ms_overwrite * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_overwrite,
-                            "note": "y = A x (fused zero + apply, what the device CG uses)"},
-        "gpu_launches": op.launches(False) * a.steps,
+        "apply_accumulate": {"value": n_local / (ms_accumulate * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_accumulate,
+                             "note": "strict y += A x on rank 0's local mesh (b200fem_op_apply)"},
+        "gpu_launches": launches_per_step * a.steps,
         "clocks": clocks,
-        "setup_s": {"mesh": m["t_mesh"], "plan": t_plan},
+        "setup_s": {"mesh": t_mesh, "plan": t_plan},
     }
     if e2e:
         line["e2e"] = e2e
     if not a.no_cpu_baseline and world == 1:
         try:
-            cb = cpu_reference_run(a, m, fff, 5, 1)
+            cb = cpu_reference_run(a, elements, fff, n_local, 20, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
     if a.extras:
-        from sfem_b200.extras_bench import run_extras
+        from tools.extras_bench import run_extras
 
         line["extras"] = run_extras(torch)
     print(json.dumps(line), flush=True)

@@ -173,6 +173,20 @@ int b200fem_cg_update_p(int real_type, ptrdiff_t n, double beta, const void *z, 
 int b200fem_cheb3_update(int real_type, ptrdiff_t n, double alpha, double beta, const void *rhs, const void *Ax,
                          void *p, void *x, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Halo exchange helpers. The reference's distributed apply (frontend/sfem_ParallelMatrixFreeOperator.cpp:
+ * 78-105) keeps every rank's nodes as [owned | ghosts + aura] and pulls the ghost values from their owners
+ * before the local apply (smesh::Exchange::gather, source unavailable). On the GPU the owner side packs the
+ * requested owned values into one contiguous send buffer per apply (b200fem_halo_pack), NCCL moves the
+ * buffers, and the receiver's ghost block is contiguous so no unpack is needed. unpack_add is the reverse
+ * path (smesh::Exchange::scatter_add): dst[idx[i]] += src[i]; the indices of one call must be distinct.
+ * `idx` is a DEVICE int32 list of local node ids, values are block_size components per node.
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_halo_pack(int real_type, ptrdiff_t n, const int32_t *idx, int block_size, const void *src, void *dst,
+                      void *stream);
+int b200fem_halo_unpack_add(int real_type, ptrdiff_t n, const int32_t *idx, int block_size, const void *src,
+                            void *dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

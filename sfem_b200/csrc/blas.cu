@@ -10,6 +10,7 @@
 //     pinned slot.
 #include <math.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -432,6 +433,33 @@ __global__ void constraint_value_kernel(ptrdiff_t n, const int32_t *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// halo pack / unpack (what smesh::Exchange::gather / scatter_add do around their MPI calls)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool ADD>
+__global__ void __launch_bounds__(256)
+    halo_index_kernel(ptrdiff_t n, const int32_t *__restrict__ idx, int bs, const T *__restrict__ src, T *__restrict__ dst) {
+    const ptrdiff_t total = n * bs;
+    for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ptrdiff_t)gridDim.x * blockDim.x) {
+        const ptrdiff_t node = i / bs;
+        const int c = (int)(i - node * bs);
+        if (ADD)
+            dst[(ptrdiff_t)idx[node] * bs + c] += src[i];  // unpack-add: indices of one message are distinct
+        else
+            dst[i] = src[(ptrdiff_t)idx[node] * bs + c];    // pack
+    }
+}
+
+template <typename T, bool ADD>
+static int halo_index_t(ptrdiff_t n, const int32_t *idx, int bs, const T *src, T *dst, cudaStream_t s) {
+    if (n <= 0) return B200FEM_SUCCESS;
+    const ptrdiff_t total = n * bs;
+    const int grid = (int)std::min<ptrdiff_t>((total + 255) / 256, (ptrdiff_t)sm_count() * 8);
+    halo_index_kernel<T, ADD><<<grid, 256, 0, s>>>(n, idx, bs, src, dst);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
 }  // namespace b200fem
 
 using namespace b200fem;
@@ -559,6 +587,18 @@ int b200fem_constraint_nodes_to_value_vec(int rt, ptrdiff_t n, const int32_t *id
         B2_FAIL("bad real_type");
     B2_CHECK_LAUNCH();
     return B200FEM_SUCCESS;
+}
+
+int b200fem_halo_pack(int rt, ptrdiff_t n, const int32_t *idx, int bs, const void *src, void *dst, void *stream) {
+    if (bs < 1) B2_FAIL("halo_pack: block_size must be >= 1");
+    B2_REAL_DISPATCH(rt, (halo_index_t<double, false>(n, idx, bs, (const double *)src, (double *)dst, as_stream(stream))),
+                     (halo_index_t<float, false>(n, idx, bs, (const float *)src, (float *)dst, as_stream(stream))));
+}
+
+int b200fem_halo_unpack_add(int rt, ptrdiff_t n, const int32_t *idx, int bs, const void *src, void *dst, void *stream) {
+    if (bs < 1) B2_FAIL("halo_unpack_add: block_size must be >= 1");
+    B2_REAL_DISPATCH(rt, (halo_index_t<double, true>(n, idx, bs, (const double *)src, (double *)dst, as_stream(stream))),
+                     (halo_index_t<float, true>(n, idx, bs, (const float *)src, (float *)dst, as_stream(stream))));
 }
 
 }  // extern "C"

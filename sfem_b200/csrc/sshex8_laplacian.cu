@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(256)
 struct Sshex8Laplacian final : OpBase {
     int mode = kModeExplicit;
     bool interior_exclusive = false;
-    int32_t shared_prefix = 0;          // nodes [0, shared_prefix) receive RED.ADD contributions
+    int32_t shared_prefix = 0;          // first skeleton range is [0, shared_prefix) (informational)
+    std::vector<std::pair<int64_t, int64_t>> zero_ranges;  // skeleton id ranges = what an overwriting apply zeroes
     DeviceArray<int32_t> idx_aos;       // MODE_EXPLICIT: [ne][nxe]
     DeviceArray<BoxDesc> boxes;         // MODE_BOXES: [ne][27]
     DeviceArray<float> fff;             // [ne][6]
@@ -271,11 +273,18 @@ struct Sshex8Laplacian final : OpBase {
         return B200FEM_SUCCESS;
     }
 
+    template <typename T>
+    int zero_skeleton(T *y, cudaStream_t s) {
+        for (const auto &r : zero_ranges)
+            B2_CUDA(cudaMemsetAsync(y + r.first, 0, (size_t)(r.second - r.first) * sizeof(T), s));
+        return B200FEM_SUCCESS;
+    }
+
     template <typename T, int L>
     int apply_L(const T *x, T *y, bool overwrite, cudaStream_t s) {
         if (mode == kModeBoxes && use_stream) {
             if (overwrite && interior_exclusive) {
-                if (shared_prefix > 0) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)shared_prefix * sizeof(T), s));
+                if (zero_skeleton(y, s)) return B200FEM_FAILURE;
                 return launch_stream<T, L, true>(x, y, s);
             }
             if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * sizeof(T), s));
@@ -283,7 +292,7 @@ struct Sshex8Laplacian final : OpBase {
         }
         if (mode == kModeBoxes && interior_exclusive) {
             if (overwrite) {
-                if (shared_prefix > 0) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)shared_prefix * sizeof(T), s));
+                if (zero_skeleton(y, s)) return B200FEM_FAILURE;
                 return launch<T, L, kModeBoxes, true, true>(x, y, s);
             }
             return launch<T, L, kModeBoxes, false, true>(x, y, s);
@@ -325,7 +334,10 @@ struct Sshex8Laplacian final : OpBase {
         if (!overwrite) vec += double(nn) * real_type;             // y read as well
         return double(ne) * (idx + 24.0) + vec;
     }
-    int launches(bool overwrite) const override { return overwrite ? 2 : 1; }
+    int launches(bool overwrite) const override {
+        // kernels + memset nodes; the clean-up launch of the streaming kernel exists when ne % EPT != 0 (EPT = 3 at L = 8)
+        return 1 + (overwrite ? (int)std::max<size_t>(zero_ranges.size(), 1) : 0);
+    }
 
     int set_option(const char *key, int value) override {
         if (!strcmp(key, "ctas_per_sm")) {
@@ -358,13 +370,16 @@ struct Sshex8Laplacian final : OpBase {
 };
 
 // Fit the 27 entity boxes of every element; returns false if some box is not affine in the lattice.
-static bool fit_boxes(int L, ptrdiff_t ne, const int32_t *const *elements, std::vector<BoxDesc> &out, bool *exclusive,
-                      int32_t *shared_prefix) {
+// Also decides whether the interior nodes are exclusive to their element (compact (L-1)^3 blocks that
+// no other element references). If so, `zero_ranges` receives the complementary id ranges -- the
+// skeleton, everything that receives RED.ADD contributions -- which is what an overwriting apply has to
+// zero first (one range for the reference's numbering, two for an [owned | ghost] local numbering).
+static bool fit_boxes(int L, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, std::vector<BoxDesc> &out,
+                      bool *exclusive, std::vector<std::pair<int64_t, int64_t>> &zero_ranges) {
     const int N = L + 1;
     out.resize((size_t)ne * 27);
     auto lidx = [N](int x, int y, int z) { return z * N * N + y * N + x; };
     const int lo[3] = {0, 1, L}, hi[3] = {0, L - 1, L};
-    int64_t min_interior = INT64_MAX, max_skeleton = -1;
     bool compact = true;
     for (ptrdiff_t e = 0; e < ne; ++e) {
         for (int cz = 0; cz < 3; ++cz)
@@ -381,11 +396,6 @@ static bool fit_boxes(int L, ptrdiff_t ne, const int32_t *const *elements, std::
                             for (int x = x0; x <= x1; ++x) {
                                 const int64_t id = elements[lidx(x, y, z)][e];
                                 if (id != b0 + sx * (x - x0) + sy * (y - y0) + sz * (z - z0)) return false;
-                                if (cx == 1 && cy == 1 && cz == 1) {
-                                    if (id < min_interior) min_interior = id;
-                                } else if (id > max_skeleton) {
-                                    max_skeleton = id;
-                                }
                             }
                     const int64_t base = b0 - sx * x0 - sy * y0 - sz * z0;
                     if (base < INT32_MIN || base > INT32_MAX) return false;
@@ -395,22 +405,47 @@ static bool fit_boxes(int L, ptrdiff_t ne, const int32_t *const *elements, std::
                     }
                 }
     }
-    // interior nodes are exclusive when every interior box is a compact block, the blocks are
-    // disjoint, and no skeleton id falls into the interior range
-    bool excl = compact && (ne == 0 || max_skeleton < min_interior);
-    if (excl && ne > 1) {
-        std::vector<int64_t> bases((size_t)ne);
-        for (ptrdiff_t e = 0; e < ne; ++e) bases[e] = elements[lidx(1, 1, 1)][e];
-        std::sort(bases.begin(), bases.end());
+    zero_ranges.clear();
+    bool excl = compact;
+    if (excl) {
+        // reference counts: interior ids must be hit exactly once overall, by an interior position
+        std::vector<uint8_t> interior((size_t)nn, 0);
         const int64_t vol = (int64_t)(L - 1) * (L - 1) * (L - 1);
-        for (ptrdiff_t e = 1; e < ne; ++e)
-            if (bases[e] - bases[e - 1] < vol) {
-                excl = false;
-                break;
+        for (ptrdiff_t e = 0; e < ne && excl; ++e) {
+            const int64_t b = elements[lidx(1, 1, 1)][e];
+            if (b + vol > nn) excl = false;
+            for (int64_t k = 0; k < vol && excl; ++k) {
+                if (interior[(size_t)(b + k)]) excl = false;
+                interior[(size_t)(b + k)] = 1;
             }
+        }
+        for (ptrdiff_t e = 0; e < ne && excl; ++e)
+            for (int z = 0; z <= L && excl; ++z)
+                for (int y = 0; y <= L && excl; ++y)
+                    for (int x = 0; x <= L; ++x) {
+                        const bool in = x > 0 && x < L && y > 0 && y < L && z > 0 && z < L;
+                        if (!in && interior[(size_t)elements[lidx(x, y, z)][e]]) {
+                            excl = false;
+                            break;
+                        }
+                    }
+        if (excl) {
+            int64_t start = -1;
+            for (int64_t i = 0; i <= (int64_t)nn; ++i) {
+                const bool skel = (i < (int64_t)nn) && !interior[(size_t)i];
+                if (skel && start < 0) start = i;
+                if (!skel && start >= 0) {
+                    zero_ranges.emplace_back(start, i);
+                    start = -1;
+                }
+            }
+            if (zero_ranges.size() > 8) {  // scattered skeleton: not worth a memset per run
+                zero_ranges.clear();
+                excl = false;
+            }
+        }
     }
     *exclusive = excl;
-    *shared_prefix = excl ? (int32_t)(ne ? min_interior : 0) : 0;
     return true;
 }
 
@@ -434,13 +469,12 @@ OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32
 
     std::vector<BoxDesc> boxes;
     bool excl = false;
-    int32_t prefix = 0;
-    const bool affine = fit_boxes(level, ne, elements, boxes, &excl, &prefix);
+    const bool affine = fit_boxes(level, ne, nn, elements, boxes, &excl, op->zero_ranges);
     int rc = 0;
     if (affine) {
         op->mode = kModeBoxes;
         op->interior_exclusive = excl;
-        op->shared_prefix = prefix;
+        op->shared_prefix = (excl && !op->zero_ranges.empty() && op->zero_ranges[0].first == 0) ? (int32_t)op->zero_ranges[0].second : 0;
         rc |= op->boxes.upload(boxes.data(), boxes.size());
         std::vector<Sshex8Header> hdrs((size_t)ne);
         for (ptrdiff_t e = 0; e < ne; ++e) {

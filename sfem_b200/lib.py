@@ -63,6 +63,8 @@ _SIG = {
     "b200fem_op_get_option": [vp, C.c_char_p, C.POINTER(i32)],
     "b200fem_constraint_nodes_copy_vec": [i32, ssz, vp, i32, i32, vp, vp, vp],
     "b200fem_constraint_nodes_to_value_vec": [i32, ssz, vp, i32, i32, f64, vp, vp],
+    "b200fem_halo_pack": [i32, ssz, vp, i32, vp, vp, vp],
+    "b200fem_halo_unpack_add": [i32, ssz, vp, i32, vp, vp, vp],
     "b200fem_blas_zeros": [i32, ssz, vp, vp],
     "b200fem_blas_values": [i32, ssz, f64, vp, vp],
     "b200fem_blas_copy": [i32, ssz, vp, vp, vp],
@@ -338,3 +340,14 @@ def constraint_nodes_copy_vec(idx, block_size, component, source, dest):
 def constraint_nodes_to_value_vec(idx, block_size, component, value, values):
     check(_lib.b200fem_constraint_nodes_to_value_vec(_rt(values.dtype), idx.numel(), _p(idx), block_size, component,
                                                      value, _p(values), _stream()), "constraint_nodes_to_value_vec")
+
+
+def halo_pack(idx, block_size, src, dst):
+    """dst[i*bs + c] = src[idx[i]*bs + c] (owner side of smesh::Exchange::gather)."""
+    check(_lib.b200fem_halo_pack(_rt(src.dtype), idx.numel(), _p(idx), block_size, _p(src), _p(dst), _stream()), "halo_pack")
+
+
+def halo_unpack_add(idx, block_size, src, dst):
+    """dst[idx[i]*bs + c] += src[i*bs + c] (owner side of smesh::Exchange::scatter_add)."""
+    check(_lib.b200fem_halo_unpack_add(_rt(src.dtype), idx.numel(), _p(idx), block_size, _p(src), _p(dst), _stream()),
+          "halo_unpack_add")

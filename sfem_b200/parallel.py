@@ -1,0 +1,232 @@
+"""Distributed apply: mesh partition, halo plan and the NCCL exchange (one process per GPU).
+
+Mirrors the reference's distributed matrix-free apply (frontend/sfem_ParallelMatrixFreeOperator.cpp:78-105,
+tested by frontend/tests/mpi/sfem_ParallelLaplacianApplyTest.cpp:62-141):
+
+* every rank keeps its nodes in the order [owned | ghosts + aura] and every element that touches one of
+  its owned nodes (its own elements plus a one-element-deep *aura* of its neighbours' elements);
+* apply = copy the owned part of x, pull the ghost/aura values from their owners (`Exchange::gather`),
+  run the local operator over all local elements, keep the owned rows. There is no reverse scatter:
+  interface rows are completed by redundant computation on the aura layer;
+* dot products / norms run over the owned entries only and are summed over the ranks
+  (algebra/parallel/sfem_parallel_cg.hpp:169-172).
+
+`external/smesh` (Exchange, distributed Mesh, Communicator) is absent from the reference checkout, so the
+partition and the exchange plan are built here from that observable contract. The transport is
+`torch.distributed` (NCCL over NVLink on the GPUs, gloo in the CPU tests): per apply one grouped
+send/recv per neighbour of packed owned values (packed by `b200fem_halo_pack`), received straight into
+the contiguous ghost block of the local vector -- ghosts are ordered by owner, so no unpack kernel.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+idx_t = np.int32
+
+
+@dataclass
+class LocalMesh:
+    """One rank's share of a mesh, nodes ordered [owned | ghosts sorted by (owner, global id)]."""
+
+    elements: np.ndarray          # [nxe][n_local_elements] int32, local node ids; owned elements first
+    n_owned_elements: int
+    n_owned: int                  # owned nodes
+    n_local: int                  # owned + ghost/aura nodes
+    global_ids: np.ndarray        # [n_local] int64
+    owner: np.ndarray             # [n_local] int32 rank owning each local node
+    rank: int = 0
+    world: int = 1
+    extra: dict = field(default_factory=dict)
+
+
+def renumber_owned_first(elements: np.ndarray, global_ids: np.ndarray, owner: np.ndarray, rank: int):
+    """Stable renumbering to [owned | ghosts by owner]; keeps the relative order inside every class, so
+    entity-wise affine numberings (sshex8 boxes) stay affine."""
+    key = np.where(owner == rank, -1, owner).astype(np.int64)
+    order = np.argsort(key, kind="stable")          # new position -> old id
+    new_of_old = np.empty_like(order)
+    new_of_old[order] = np.arange(order.size)
+    return new_of_old[elements].astype(idx_t), global_ids[order], owner[order].astype(np.int32), int((owner == rank).sum())
+
+
+def partition_elements_by_coordinate(elements: np.ndarray, points: np.ndarray, world: int, axis: int = 2) -> np.ndarray:
+    """Element -> part by sorting centroids along one axis into `world` equal chunks (a stand-in for the
+    reference's SFC / METIS partitions, whose sources are not in the checkout)."""
+    c = points[axis][elements].astype(np.float64).mean(axis=0)
+    order = np.argsort(c, kind="stable")
+    part = np.empty(elements.shape[1], dtype=np.int32)
+    bounds = np.linspace(0, order.size, world + 1).astype(np.int64)
+    for p in range(world):
+        part[order[bounds[p]:bounds[p + 1]]] = p
+    return part
+
+
+def distribute(elements: np.ndarray, n_nodes: int, elem_part: np.ndarray, rank: int, world: int) -> LocalMesh:
+    """Cut one rank's LocalMesh out of a global mesh held in memory (tests, moderate sizes).
+
+    node owner = lowest part among the elements touching it; local elements = own elements + aura
+    (foreign elements touching an owned node)."""
+    el = np.asarray(elements, dtype=np.int64)
+    owner = np.full(n_nodes, world, dtype=np.int32)
+    for v in range(el.shape[0]):
+        np.minimum.at(owner, el[v], elem_part)
+    own_e = np.flatnonzero(elem_part == rank)
+    touches_owned = (owner[el] == rank).any(axis=0)
+    aura_e = np.flatnonzero(touches_owned & (elem_part != rank))
+    loc_e = np.concatenate([own_e, aura_e])
+    loc_nodes = np.unique(el[:, loc_e])
+    local_of_global = np.full(n_nodes, -1, dtype=np.int64)
+    local_of_global[loc_nodes] = np.arange(loc_nodes.size)
+    lel = local_of_global[el[:, loc_e]]
+    lel, gids, own, n_owned = renumber_owned_first(lel, loc_nodes.astype(np.int64), owner[loc_nodes], rank)
+    return LocalMesh(elements=np.ascontiguousarray(lel), n_owned_elements=int(own_e.size), n_owned=n_owned,
+                     n_local=int(loc_nodes.size), global_ids=gids, owner=own, rank=rank, world=world)
+
+
+def sshex8_box_lattice_keys(L: int, mx: int, my: int, elements: np.ndarray, n_nodes: int, z0_macro: int = 0):
+    """Global lattice key (iz*nyg + iy)*nxg + ix and global iz of every node of an sshex8 box mesh whose
+    macro cells are ordered z-major with x fastest (mesh.sshex8_box); z0_macro = first global macro layer."""
+    from . import mesh
+
+    ne = elements.shape[1]
+    e = np.arange(ne, dtype=np.int64)
+    ex, ey, ez = e % mx, (e // mx) % my, e // (mx * my)
+    nxg, nyg = mx * L + 1, my * L + 1
+    gid = np.empty(n_nodes, dtype=np.int64)
+    izl = np.empty(n_nodes, dtype=np.int64)
+    for z in range(L + 1):
+        for y in range(L + 1):
+            for x in range(L + 1):
+                ids = elements[mesh.sshex8_lidx(L, x, y, z)]
+                iz = (ez + z0_macro) * L + z
+                gid[ids] = (iz * nyg + (ey * L + y)) * nxg + (ex * L + x)
+                izl[ids] = iz
+    return gid, izl
+
+
+def sshex8_slab(level: int, mx: int, my: int, mz: int, rank: int, world: int) -> LocalMesh:
+    """Weak-scaling fixture: the global mesh is a stack of `world` blocks of mx*my*mz macro elements along
+    z, refined to `level`; this builds rank `rank`'s LocalMesh directly (its block plus the aura layer of
+    the block above), without ever materialising the global mesh. Interface planes belong to the lower rank.
+    """
+    from . import mesh
+
+    L = level
+    has_aura = rank < world - 1
+    mz_loc = mz + (1 if has_aura else 0)
+    z0 = rank * mz  # first macro layer of this rank in the global stack
+    m_el, m_pts = mesh.box_hex8(mx + 1, my + 1, mz_loc + 1, 1.0, 1.0, float(mz_loc) / mz)
+    m_pts[2] += np.float32(float(z0) / mz)
+    el, nn, istart, _ = mesh.sshex8_from_hex8(L, m_el, None)
+    gid, izl = sshex8_box_lattice_keys(L, mx, my, el, nn, z0)
+    owner = np.clip((izl + mz * L - 1) // (mz * L) - 1, 0, world - 1).astype(np.int32)
+    lel, gids, own, n_owned = renumber_owned_first(el, gid, owner, rank)
+    return LocalMesh(elements=np.ascontiguousarray(lel), n_owned_elements=mx * my * mz, n_owned=n_owned, n_local=nn,
+                     global_ids=gids, owner=own, rank=rank, world=world,
+                     extra=dict(level=L, m_elements=m_el, m_points=m_pts))
+
+
+class HaloExchange:
+    """`gather(x_local)`: fill the ghost block of a local vector from the owners (Exchange::gather)."""
+
+    def __init__(self, lm: LocalMesh, block_size: int = 1, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world, self.bs = lm.rank, lm.world, block_size
+        self.n_owned, self.n_local = lm.n_owned, lm.n_local
+        self.device = device
+        self.peers, self.recv_ranges, self.send_idx = [], {}, {}
+        if self.world == 1:
+            return
+        # what I need: ghosts are sorted by owner, so each peer's block is contiguous
+        ghost_owner = lm.owner[lm.n_owned:]
+        ghost_gid = lm.global_ids[lm.n_owned:]
+        need = {}
+        for p in np.unique(ghost_owner):
+            sel = np.flatnonzero(ghost_owner == p)
+            assert sel.size == sel[-1] - sel[0] + 1
+            self.recv_ranges[int(p)] = (lm.n_owned + int(sel[0]), lm.n_owned + int(sel[-1]) + 1)
+            need[int(p)] = ghost_gid[sel]
+        # tell every owner which of its nodes I need (setup only: pickled through all_gather_object)
+        all_need = [None] * self.world
+        dist.all_gather_object(all_need, need, group=group)
+        owned_gid = lm.global_ids[:lm.n_owned]
+        sorter = np.argsort(owned_gid, kind="stable")
+        for q, nd in enumerate(all_need):
+            if q == self.rank or self.rank not in nd:
+                continue
+            want = nd[self.rank]
+            pos = np.searchsorted(owned_gid, want, sorter=sorter)
+            loc = sorter[np.clip(pos, 0, sorter.size - 1)]
+            assert np.array_equal(owned_gid[loc], want), "a peer asked for a node this rank does not own"
+            self.send_idx[q] = torch.from_numpy(loc.astype(np.int32)).to(device) if device is not None else torch.from_numpy(loc.astype(np.int32))
+        self.peers = sorted(set(self.recv_ranges) | set(self.send_idx))
+        self.send_buf = {}
+        self.bytes_sent_per_gather = sum(int(v.numel()) for v in self.send_idx.values())
+
+    def _send_buffer(self, q, like):
+        n = self.send_idx[q].numel() * self.bs
+        b = self.send_buf.get((q, like.dtype))
+        if b is None or b.numel() != n:
+            b = self.torch.empty(n, dtype=like.dtype, device=like.device)
+            self.send_buf[(q, like.dtype)] = b
+        return b
+
+    def gather(self, x_local):
+        """x_local: [n_local * block_size]; on return its ghost block holds the owners' values."""
+        if self.world == 1 or not self.peers:
+            return x_local
+        torch, dist = self.torch, self.dist
+        ops = []
+        for q in self.peers:
+            if q in self.send_idx:
+                buf = self._send_buffer(q, x_local)
+                if x_local.is_cuda:
+                    from . import lib
+
+                    lib.halo_pack(self.send_idx[q], self.bs, x_local, buf)
+                else:  # gloo host-logic tests only: no CUDA extension on this path
+                    idx = self.send_idx[q].long()
+                    buf.copy_(x_local.view(-1, self.bs)[idx].reshape(-1))
+                ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
+            if q in self.recv_ranges:
+                a, b = self.recv_ranges[q]
+                ops.append(dist.P2POp(dist.irecv, x_local[a * self.bs:b * self.bs], q, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return x_local
+
+
+class ParallelMatrixFreeOperator:
+    """Operator<T> over the owned dofs: y = A x with halo gather (rows() = owned dofs,
+    row_allocation_size() = local dofs), same contract as sfem::ParallelMatrixFreeOperator."""
+
+    def __init__(self, local_op, exchange: HaloExchange, x_local, y_local):
+        self.op, self.ex = local_op, exchange
+        self.x_local, self.y_local = x_local, y_local
+        self.owned_dofs = exchange.n_owned * exchange.bs
+        self.local_dofs = exchange.n_local * exchange.bs
+
+    def rows(self):
+        return self.owned_dofs
+
+    def row_allocation_size(self):
+        return self.local_dofs
+
+    def apply(self, x_owned, y_owned):
+        """y_owned = A x_owned (the reference zeroes its scratch output first, so this IS its result)."""
+        xl, yl = self.x_local, self.y_local
+        xl[: self.owned_dofs].copy_(x_owned)
+        self.ex.gather(xl)
+        self.op.apply_overwrite(xl, yl)
+        y_owned.copy_(yl[: self.owned_dofs])
+        return y_owned
+
+    def apply_local(self):
+        """Same, for callers that keep their vectors at local size (x in self.x_local, y in self.y_local)."""
+        self.ex.gather(self.x_local)
+        self.op.apply_overwrite(self.x_local, self.y_local)

@@ -1,0 +1,128 @@
+"""Secondary measurements for bench.py --extras: the other BASELINE.json configs that fit one GPU and the
+vector kernels, each as apply throughput + fraction of the measured HBM copy bandwidth. Not bench lines."""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def _time(fn, torch, steps=20, warmup=3, flush=None):
+    """ms per call; with `flush` (a big tensor) L2 is overwritten between calls and each call timed alone."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    tot = 0.0
+    for _ in range(steps):
+        flush.add_(1.0)  # 512 MB read + write: evicts the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def _entry(name, rows, alg_bytes, ms, extra=None):
+    d = {"name": name, "rows": int(rows), "ms": ms, "gdof_s": rows / ms / 1e6, "alg_GB_s": alg_bytes / ms / 1e6,
+         "frac_of_measured_hbm": alg_bytes / ms / 1e6 / _peak()}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "blas")):
+    from sfem_b200 import lib, mesh
+
+    out = []
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")
+    if "c1" in which:  # tet4 Laplacian fp64, 56^3 nodes (BASELINE config 1) and a 100x larger cube
+        for n in (56, 260):
+            el, pts = mesh.box_tet4(n, n, n)
+            fff = lib.fff_fill(lib.TET4, el, pts)
+            nn = pts.shape[1]
+            for scatter in ("atomic",):
+                op = lib.laplacian(lib.TET4, el, fff, nn, torch.float64)
+                x = torch.rand(nn, dtype=torch.float64, device="cuda")
+                y = torch.zeros_like(x)
+                ms = _time(lambda: op.apply_overwrite(x, y), torch, flush=flush if n == 56 else None)
+                out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, y = A x" + (", L2 flushed" if n == 56 else "") + ")",
+                                  nn, op.algorithmic_bytes, ms))
+                if n == 56:
+                    ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                    out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, y = A x, L2-resident)", nn,
+                                      op.algorithmic_bytes, ms))
+                del op
+    if "c2" in which or "hex8lap" in which:
+        el, pts = mesh.box_hex8(129, 129, 129)
+        nn = pts.shape[1]
+        if "c2" in which:  # hex8 linear elasticity fp64, 128^3 elements (BASELINE config 2)
+            adj, det = lib.adjugate_and_det_fill(lib.HEX8, el, pts)
+            for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
+                op = lib.linear_elasticity(lib.HEX8, el, adj, det, 1.0, 1.0, nn, dt)
+                x = torch.rand(nn * 3, dtype=dt, device="cuda")
+                y = torch.zeros_like(x)
+                ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                out.append(_entry(f"C2 hex8 linear elasticity {rt} 128^3 (y = A x)", nn * 3, op.algorithmic_bytes, ms))
+                del op
+        if "hex8lap" in which:
+            fff = lib.fff_fill(lib.HEX8, el, pts)
+            op = lib.laplacian(lib.HEX8, el, fff, nn, torch.float64)
+            x = torch.rand(nn, dtype=torch.float64, device="cuda")
+            y = torch.zeros_like(x)
+            ms = _time(lambda: op.apply_overwrite(x, y), torch)
+            out.append(_entry("hex8 Laplacian f64 128^3 (y = A x)", nn, op.algorithmic_bytes, ms))
+            del op
+    if "c3f32" in which:
+        m = mesh.sshex8_box(8, 64, 64, 64, with_points=False)
+        fff = lib.fff_fill(lib.HEX8, m["m_elements"], m["m_points"])
+        nn = m["n_nodes"]
+        op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, torch.float32, level=8)
+        x = torch.rand(nn, dtype=torch.float32, device="cuda")
+        y = torch.zeros_like(x)
+        ms = _time(lambda: op.apply_overwrite(x, y), torch)
+        out.append(_entry("C3 sshex8 Laplacian L8 f32 64^3 macro (y = A x)", nn, op.algorithmic_bytes, ms))
+        del op, m
+    if "blas" in which:
+        from sfem_b200.lib import blas
+
+        n = 135_005_697
+        a, b, c, d = (torch.rand(n, dtype=torch.float64, device="cuda") for _ in range(4))
+        for name, words, fn in (
+            ("dot", 2, lambda: blas.dot(a, b)),
+            ("axpby", 3, lambda: blas.axpby(0.5, a, 0.25, b)),
+            ("zaxpby", 3, lambda: blas.zaxpby(0.5, a, 0.25, b, c)),
+            ("cg_update_x_r_rtr", 6, lambda: blas.cg_update_x_r_rtr(1e-3, a, b, c, d)),
+            ("cg_update_p", 3, lambda: blas.cg_update_p(0.5, a, b)),
+            ("cheb3_update", 6, lambda: blas.cheb3_update(1e-3, 0.5, a, b, c, d)),
+        ):
+            ms = _time(fn, torch, steps=10)
+            out.append(_entry(f"blas {name} f64 n=135M", n, words * 8.0 * n, ms))
+    return out
+
+
+if __name__ == "__main__":
+    import sys
+
+    import torch
+
+    sys.path.insert(0, ROOT)
+    for e in run_extras(torch):
+        print(json.dumps(e), flush=True)
