@@ -297,3 +297,36 @@ def test_dirichlet_kernels():
     lib.constraint_nodes_to_value_vec(idx, bs, 2, -4.5, dst)
     ref[idx.cpu().numpy() * bs + 2] = -4.5
     assert np.array_equal(dst.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_golden_vectors_on_gpu(real):
+    """The CUDA path against the committed reference outputs (tests/golden, generated from oracle/_ref): needs no
+    oracle library on the box."""
+    import os
+
+    torch = _torch()
+    from sfem_b200 import lib
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    dt = _dt(real)
+
+    def run(op, u):
+        x = torch.from_numpy(np.asarray(u)).to(dt).cuda()
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        return y.cpu().numpy()
+
+    g = np.load(os.path.join(gold, "tet4_laplacian.npz"))
+    nn = g["points"].shape[1]
+    assert _rel(run(lib.laplacian(lib.TET4, g["elements"], g["fff"], nn, dt), g["u"]), g[f"y_{real}"]) < TOL[real]
+    g = np.load(os.path.join(gold, "hex8.npz"))
+    nn = g["points"].shape[1]
+    assert _rel(run(lib.laplacian(lib.HEX8, g["elements"], g["fff"], nn, dt), g["u"]), g[f"y_lap_{real}"]) < TOL[real]
+    op = lib.linear_elasticity(lib.HEX8, g["elements"], g["adjugate"], g["determinant"], float(g["mu"]), float(g["lam"]), nn, dt)
+    assert _rel(run(op, g["u3"]), g[f"y_le_{real}"]) < TOL[real]
+    for L in (2, 4, 8):
+        g = np.load(os.path.join(gold, f"sshex8_L{L}.npz"))
+        nn = g["u"].size
+        op = lib.laplacian(lib.SSHEX8, g["elements"], g["fff"], nn, dt, level=L)
+        assert _rel(run(op, g["u"]), g[f"y_lap_{real}"]) < TOL[real], L

@@ -1,0 +1,141 @@
+"""The oracle itself, on CPU: (1) the reference-compiled library (oracle/_ref, when present) and our plain-C
+restatement (oracle/oracle_port.c) against the known answers the reference's own tests hold for this path, (2) the
+restatement against the reference build on seeded inputs, (3) both against the committed vectors in tests/golden/
+(generated from oracle/_ref by tests/golden/make_golden.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+TOL = {"f64": 1e-12, "f32": 2e-5}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _kinds(oracles, real):
+    return [k for k in ("reference", "port") if (k, real) in oracles]
+
+
+def test_unit_tet_matrix_known_answer(oracles):
+    """tests/ref/oracle.py of the reference: A_ij = grad_i . grad_j / 6 on the unit tet."""
+    g = np.array([[-1, -1, -1], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
+    A = g @ g.T / 6
+    el = np.array([[0], [1], [2], [3]], dtype=np.int32)
+    pts = np.array([[0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+    for kind in _kinds(oracles, "f64"):
+        orc = oracles[(kind, "f64")]
+        fff = orc.tet4_fff_fill(el, pts)
+        for j in range(4):
+            e = np.zeros(4)
+            e[j] = 1
+            assert np.allclose(orc.tet4_laplacian_apply_opt(el, fff, e), A[:, j], atol=1e-7), kind
+        assert np.allclose(orc.tet4_laplacian_diag_opt(el, fff, 4), np.diag(A), atol=1e-7)
+
+
+def test_stencil_known_answer(oracles):
+    """Known answer in the spirit of operators/stencil/tests/sfem_StencilTest.cpp:143-218 (a quadratic field
+    gives a constant at every interior stencil row): for u = x^2 + y^2 + z^2 on a unit-cube macro element the
+    interior rows of the assembled level-L operator are  int grad u . grad phi_i = -int (Laplace u) phi_i = -6 h^3
+    (h = 1/L) -- exact for trilinear elements on a uniform lattice."""
+    from sfem_b200 import mesh
+
+    for L in (4, 8):
+        m = mesh.sshex8_box(L, 1, 1, 1)
+        x, y, z = (m["points"][d].astype(np.float64) for d in range(3))
+        u = x * x + y * y + z * z
+        h = 1.0 / L
+        for kind in _kinds(oracles, "f64"):
+            orc = oracles[(kind, "f64")]
+            fff = orc.hex8_fff_fill(m["m_elements"], m["m_points"])
+            out = orc.sshex8_laplacian_apply(L, m["elements"], fff, u)
+            interior = m["elements"][[mesh.sshex8_lidx(L, a, b, c) for a in range(1, L) for b in range(1, L) for c in range(1, L)], 0]
+            assert np.allclose(out[interior], -6 * h * h * h, atol=1e-12), (kind, L)
+
+
+def test_constants_and_symmetry(oracles):
+    from sfem_b200 import mesh
+
+    m = mesh.sshex8_box(4, 2, 2, 1)
+    mp = mesh.shear_points(m["m_points"])
+    nn = m["n_nodes"]
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(-1, 1, nn), rng.uniform(-1, 1, nn)
+    for kind in _kinds(oracles, "f64"):
+        orc = oracles[(kind, "f64")]
+        fff = orc.hex8_fff_fill(m["m_elements"], mp)
+        assert np.abs(orc.sshex8_laplacian_apply(4, m["elements"], fff, np.ones(nn))).max() < 1e-12
+        Aa, Ab = orc.sshex8_laplacian_apply(4, m["elements"], fff, a), orc.sshex8_laplacian_apply(4, m["elements"], fff, b)
+        assert abs(b @ Aa - a @ Ab) < 1e-11 * abs(b @ Aa)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_port_matches_reference_build(oracles, real):
+    """Pins the restatement: every function of oracle_port.c against the reference's own code."""
+    if ("reference", real) not in oracles or ("port", real) not in oracles:
+        pytest.skip("needs both oracle libraries")
+    from sfem_b200 import mesh
+
+    ref, port = oracles[("reference", real)], oracles[("port", real)]
+    tol = TOL[real]
+    rng = np.random.default_rng(11)
+    el, pts = mesh.box_tet4(6, 5, 4)
+    pts = mesh.warp_points(pts)
+    fr, fp = ref.tet4_fff_fill(el, pts), port.tet4_fff_fill(el, pts)
+    assert _rel(fp, fr) < 2e-6
+    u = rng.uniform(-1, 1, pts.shape[1])
+    assert _rel(port.tet4_laplacian_apply_opt(el, fr, u), ref.tet4_laplacian_apply_opt(el, fr, u)) < tol
+    assert _rel(port.tet4_laplacian_diag_opt(el, fr, pts.shape[1]), ref.tet4_laplacian_diag_opt(el, fr, pts.shape[1])) < tol
+
+    el, pts = mesh.box_hex8(5, 6, 4)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    assert _rel(port.hex8_fff_fill(el, pts), ref.hex8_fff_fill(el, pts)) < 1e-6
+    ar, dr = ref.hex8_adjugate_and_det_fill(el, pts)
+    ap, dp = port.hex8_adjugate_and_det_fill(el, pts)
+    assert _rel(ap, ar) < 1e-6 and _rel(dp, dr) < 1e-6
+    fr = ref.hex8_fff_fill(el, pts)
+    u = rng.uniform(-1, 1, nn)
+    assert _rel(port.hex8_laplacian_apply_opt(el, fr, u), ref.hex8_laplacian_apply_opt(el, fr, u)) < tol
+    u3 = rng.uniform(-1, 1, nn * 3)
+    assert _rel(port.hex8_linear_elasticity_apply(el, ar, dr, 1.3, 0.7, u3, nn),
+                ref.hex8_linear_elasticity_apply(el, ar, dr, 1.3, 0.7, u3, nn)) < tol
+
+    for L in (2, 4):
+        m = mesh.sshex8_box(L, 2, 1, 2)
+        mp = mesh.shear_points(m["m_points"])
+        fr = ref.hex8_fff_fill(m["m_elements"], mp)
+        ar, dr = ref.hex8_adjugate_and_det_fill(m["m_elements"], mp)
+        nn = m["n_nodes"]
+        u = rng.uniform(-1, 1, nn)
+        assert _rel(port.sshex8_laplacian_apply(L, m["elements"], fr, u), ref.sshex8_laplacian_apply(L, m["elements"], fr, u)) < tol
+        u3 = rng.uniform(-1, 1, nn * 3)
+        assert _rel(port.sshex8_linear_elasticity_apply(L, m["elements"], ar, dr, 1.3, 0.7, u3, nn),
+                    ref.sshex8_linear_elasticity_apply(L, m["elements"], ar, dr, 1.3, 0.7, u3, nn)) < tol
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_golden_vectors(oracles, real):
+    """Both oracle libraries reproduce the committed reference outputs."""
+    for kind in _kinds(oracles, real):
+        orc = oracles[(kind, real)]
+        tol = TOL[real]
+        g = np.load(os.path.join(GOLD, "tet4_laplacian.npz"))
+        assert _rel(orc.tet4_laplacian_apply_opt(g["elements"], g["fff"], g["u"]), g[f"y_{real}"]) < tol, kind
+        g = np.load(os.path.join(GOLD, "hex8.npz"))
+        nn = g["points"].shape[1]
+        assert _rel(orc.hex8_laplacian_apply_opt(g["elements"], g["fff"], g["u"]), g[f"y_lap_{real}"]) < tol, kind
+        assert _rel(orc.hex8_linear_elasticity_apply(g["elements"], g["adjugate"], g["determinant"], float(g["mu"]), float(g["lam"]),
+                                                     g["u3"], nn), g[f"y_le_{real}"]) < tol, kind
+        for L in (2, 4, 8):
+            g = np.load(os.path.join(GOLD, f"sshex8_L{L}.npz"))
+            assert _rel(orc.sshex8_laplacian_apply(L, g["elements"], g["fff"], g["u"]), g[f"y_lap_{real}"]) < tol, (kind, L)
+            if "y_le_f64" in g and real == "f64":
+                nn = g["u"].size
+                assert _rel(orc.sshex8_linear_elasticity_apply(L, g["elements"], g["adjugate"], g["determinant"], float(g["mu"]),
+                                                               float(g["lam"]), g["u3"], nn), g["y_le_f64"]) < tol, (kind, L)
