@@ -187,6 +187,47 @@ int b200fem_halo_pack(int real_type, ptrdiff_t n, const int32_t *idx, int block_
 int b200fem_halo_unpack_add(int real_type, ptrdiff_t n, const int32_t *idx, int block_size, const void *src,
                             void *dst, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multigrid transfer between two lattices of one semi-structured macro mesh.
+ * Replaces sshex8_restrict / sshex8_prolongate (operators/sshex8/sshex8_interpolate.cpp:633-775, 259-615)
+ * and, with coarse_level = 1, sshex8_hierarchical_restriction / _prolongation (:12-127, 129-237), as wired by
+ * create_hierarchical_prolongation / _restriction (frontend/sfem_API.hpp:503-584). Arguments follow the
+ * reference: `*_elements` is HOST SoA connectivity with ((level*stride)+1)^3 rows; lattice node (x,y,z) of
+ * the level-`level` lattice is row sshex8_lidx(level*stride, x*stride, y*stride, z*stride)
+ * (operators/sshex8/sshex8.hpp:18). The plan also holds the element-to-node incidence count of the fine
+ * lattice (sshex8_element_node_incidence_count, sshex8_interpolate.cpp:239-257), uint16 per fine node.
+ *   restrict  : to[coarse] += W (from[fine] / count[fine])      (caller zeroes `to`, as in the reference)
+ *   prolongate: to[fine]    = W^T from[coarse]                   (every fine lattice node is written)
+ * Vectors are DEVICE arrays, AoS with `vec_size` components per node.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct b200fem_transfer_s *b200fem_transfer_t;
+int b200fem_sshex8_transfer_create(b200fem_transfer_t *t, ptrdiff_t nelements, int fine_level, int fine_stride,
+                                   const int32_t *const *fine_elements, ptrdiff_t n_fine_nodes, int coarse_level,
+                                   int coarse_stride, const int32_t *const *coarse_elements, ptrdiff_t n_coarse_nodes);
+int b200fem_transfer_destroy(b200fem_transfer_t t);
+ptrdiff_t b200fem_transfer_fine_nodes(b200fem_transfer_t t);
+ptrdiff_t b200fem_transfer_coarse_nodes(b200fem_transfer_t t);
+int b200fem_transfer_incidence_count(b200fem_transfer_t t, uint16_t *count_host /* [n_fine_nodes] */);
+int b200fem_transfer_restrict(b200fem_transfer_t t, int real_type, int vec_size, const void *from, void *to,
+                              void *stream);
+int b200fem_transfer_prolongate(b200fem_transfer_t t, int real_type, int vec_size, const void *from, void *to,
+                                void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Smoother kernels. ShiftableJacobi (algebra/sfem_ShiftableJacobi.hpp:17-57) needs nothing beyond
+ * b200fem_blas_copy / _axpy / _reciprocal / _xypaz. ShiftableBlockSymJacobi (:67-144; kernels
+ * algebra/openmp/sfem_openmp_ShiftableJacobi.hpp:30-226):
+ *   setup: inv_diag[b] = relaxation * inverse( sym3x3(sym_diag6[b] (+ shift6[b])) with the rows of constrained
+ *          dofs replaced by identity rows )        -- sym_diag_to_diag, add_sym_diag_to_diag, apply_mask,
+ *          inplace_invert, scal in one pass. `shift6` may be NULL. `constraints_mask` is a DEVICE bit mask in
+ *          the reference's mask_t layout (bit i%8 of byte i/8 for dof i, algebra/sfem_mask.hpp:13-26) or NULL.
+ *   apply: y[b*3+i] += sum_j inv_diag[b*9+i*3+j] x[b*3+j]
+ * ---------------------------------------------------------------------------------------- */
+int b200fem_block_sym_jacobi_setup(int real_type, ptrdiff_t n_blocks, const void *sym_diag6, const void *shift6,
+                                   const void *constraints_mask, double relaxation, void *inv_diag9, void *stream);
+int b200fem_block_jacobi_apply(int real_type, ptrdiff_t n_blocks, const void *inv_diag9, const void *x, void *y,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -178,3 +178,75 @@ class Oracle:
                    C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), None, pa, pd, self.crt(mu), self.crt(lam),
                    C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
         return out
+
+    def sshex8_linear_elasticity_diag(self, level, elements, points, mu, lam, nnodes):
+        """affine_sshex8_linear_elasticity_diag (operators/sshex8/sshex8_linear_elasticity.cpp:971);
+        `points` is SoA fp32 [3][nnodes] indexed by sshex8 node id (only the macro corners are read)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 3, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("affine_sshex8_linear_elasticity_diag", C.c_int(level), C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3),
+                   op[0], op[1], op[2])
+        return out
+
+    def sshex8_linear_elasticity_block_diag_sym(self, level, elements, points, mu, lam, nnodes):
+        """affine_sshex8_linear_elasticity_block_diag_sym (:1102); AoS [nnodes*6] (00 01 02 11 12 22)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 6, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(6)]
+        self._call("affine_sshex8_linear_elasticity_block_diag_sym", C.c_int(level), C.c_ssize_t(el.shape[1]),
+                   C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam),
+                   C.c_ssize_t(6), *op)
+        return out
+
+    # ---- multigrid transfer (operators/sshex8/sshex8_interpolate.cpp)
+    def sshex8_element_node_incidence_count(self, level, stride, elements, nnodes):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        count = np.zeros(nnodes, dtype=np.uint16)
+        self._call("sshex8_element_node_incidence_count", C.c_int(level), C.c_int(stride), C.c_ssize_t(el.shape[1]),
+                   _soa_ptrs(el, C.c_int32), count.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return count
+
+    def sshex8_hierarchical_restriction(self, level, elements, count, vec_size, frm, n_to):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        frm, pf = self._r(frm)
+        to = np.zeros(n_to * vec_size, dtype=self.rt)
+        self._call("sshex8_hierarchical_restriction", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32),
+                   count.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_int(vec_size), pf, to.ctypes.data_as(C.POINTER(self.crt)))
+        return to
+
+    def sshex8_hierarchical_prolongation(self, level, elements, vec_size, frm, n_to):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        frm, pf = self._r(frm)
+        to = np.zeros(n_to * vec_size, dtype=self.rt)
+        self._call("sshex8_hierarchical_prolongation", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32),
+                   C.c_int(vec_size), pf, to.ctypes.data_as(C.POINTER(self.crt)))
+        return to
+
+    def sshex8_restrict(self, from_level, from_stride, from_elements, count, to_level, to_stride, to_elements, vec_size,
+                        frm, n_to):
+        fe = np.ascontiguousarray(from_elements, dtype=np.int32)
+        te = np.ascontiguousarray(to_elements, dtype=np.int32)
+        frm, pf = self._r(frm)
+        to = np.zeros(n_to * vec_size, dtype=self.rt)
+        self._call("sshex8_restrict", C.c_ssize_t(fe.shape[1]), C.c_int(from_level), C.c_int(from_stride),
+                   _soa_ptrs(fe, C.c_int32), count.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_int(to_level),
+                   C.c_int(to_stride), _soa_ptrs(te, C.c_int32), C.c_int(vec_size), pf,
+                   to.ctypes.data_as(C.POINTER(self.crt)))
+        return to
+
+    def sshex8_prolongate(self, from_level, from_stride, from_elements, to_level, to_stride, to_elements, vec_size, frm,
+                          n_to):
+        fe = np.ascontiguousarray(from_elements, dtype=np.int32)
+        te = np.ascontiguousarray(to_elements, dtype=np.int32)
+        frm, pf = self._r(frm)
+        to = np.zeros(n_to * vec_size, dtype=self.rt)
+        self._call("sshex8_prolongate", C.c_ssize_t(fe.shape[1]), C.c_int(from_level), C.c_int(from_stride),
+                   _soa_ptrs(fe, C.c_int32), C.c_int(to_level), C.c_int(to_stride), _soa_ptrs(te, C.c_int32),
+                   C.c_int(vec_size), pf, to.ctypes.data_as(C.POINTER(self.crt)))
+        return to

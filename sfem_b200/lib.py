@@ -80,6 +80,13 @@ _SIG = {
     "b200fem_cg_update_x_r_rtr": [i32, ssz, f64, vp, vp, vp, vp, C.POINTER(f64), vp],
     "b200fem_cg_update_p": [i32, ssz, f64, vp, vp, vp],
     "b200fem_cheb3_update": [i32, ssz, f64, f64, vp, vp, vp, vp, vp],
+    "b200fem_sshex8_transfer_create": [C.POINTER(vp), ssz, i32, i32, c_idx_pp, ssz, i32, i32, c_idx_pp, ssz],
+    "b200fem_transfer_destroy": [vp],
+    "b200fem_transfer_incidence_count": [vp, C.POINTER(C.c_uint16)],
+    "b200fem_transfer_restrict": [vp, i32, i32, vp, vp, vp],
+    "b200fem_transfer_prolongate": [vp, i32, i32, vp, vp, vp],
+    "b200fem_block_sym_jacobi_setup": [i32, ssz, vp, vp, vp, f64, vp, vp],
+    "b200fem_block_jacobi_apply": [i32, ssz, vp, vp, vp, vp],
 }
 for _name, _args in _SIG.items():
     _fn = getattr(_lib, _name)
@@ -90,6 +97,9 @@ _lib.b200fem_op_rows.argtypes = [vp]
 _lib.b200fem_op_rows.restype = ssz
 _lib.b200fem_op_algorithmic_bytes.argtypes = [vp]
 _lib.b200fem_op_algorithmic_bytes.restype = f64
+for _name in ("b200fem_transfer_fine_nodes", "b200fem_transfer_coarse_nodes"):
+    getattr(_lib, _name).argtypes = [vp]
+    getattr(_lib, _name).restype = ssz
 _lib.b200fem_op_streamed_bytes.argtypes = [vp, i32]
 _lib.b200fem_op_streamed_bytes.restype = f64
 
@@ -351,3 +361,59 @@ def halo_unpack_add(idx, block_size, src, dst):
     """dst[idx[i]*bs + c] += src[i*bs + c] (owner side of smesh::Exchange::scatter_add)."""
     check(_lib.b200fem_halo_unpack_add(_rt(src.dtype), idx.numel(), _p(idx), block_size, _p(src), _p(dst), _stream()),
           "halo_unpack_add")
+
+
+# --------------------------------------------------------------------------------------------
+# multigrid transfer + smoothers
+# --------------------------------------------------------------------------------------------
+class Transfer:
+    """Owner of a b200fem_transfer_t: restriction / prolongation between two lattices of one sshex8 macro
+    mesh (sshex8_restrict / sshex8_prolongate / the hierarchical pair of the reference)."""
+
+    def __init__(self, fine_level, fine_stride, fine_elements, n_fine_nodes, coarse_level, coarse_stride,
+                 coarse_elements, n_coarse_nodes):
+        fe = np.ascontiguousarray(fine_elements, dtype=np.int32)
+        ce = np.ascontiguousarray(coarse_elements, dtype=np.int32)
+        h = vp()
+        check(_lib.b200fem_sshex8_transfer_create(C.byref(h), fe.shape[1], fine_level, fine_stride, _soa_ptrs(fe, C.c_int32),
+                                                  n_fine_nodes, coarse_level, coarse_stride, _soa_ptrs(ce, C.c_int32),
+                                                  n_coarse_nodes), "sshex8_transfer_create")
+        self._h = h
+        self.n_fine, self.n_coarse = n_fine_nodes, n_coarse_nodes
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.b200fem_transfer_destroy(h)
+
+    def incidence_count(self) -> np.ndarray:
+        out = np.zeros(self.n_fine, dtype=np.uint16)
+        check(_lib.b200fem_transfer_incidence_count(self._h, out.ctypes.data_as(C.POINTER(C.c_uint16))), "incidence_count")
+        return out
+
+    def restrict(self, frm, to, vec_size=1):
+        """to[coarse] += R from[fine] (the caller zeroes `to`, like the reference)."""
+        _vec(frm, self.n_fine * vec_size), _vec(to, self.n_coarse * vec_size)
+        check(_lib.b200fem_transfer_restrict(self._h, _rt(frm.dtype), vec_size, _p(frm), _p(to), _stream()), "restrict")
+        return to
+
+    def prolongate(self, frm, to, vec_size=1):
+        """to[fine] = P from[coarse]."""
+        _vec(frm, self.n_coarse * vec_size), _vec(to, self.n_fine * vec_size)
+        check(_lib.b200fem_transfer_prolongate(self._h, _rt(frm.dtype), vec_size, _p(frm), _p(to), _stream()), "prolongate")
+        return to
+
+
+def block_sym_jacobi_setup(sym_diag6, relaxation, inv_diag9, shift6=None, mask=None):
+    n_blocks = sym_diag6.numel() // 6
+    check(_lib.b200fem_block_sym_jacobi_setup(_rt(sym_diag6.dtype), n_blocks, _p(sym_diag6),
+                                              _p(shift6) if shift6 is not None else None,
+                                              _p(mask) if mask is not None else None, relaxation, _p(inv_diag9), _stream()),
+          "block_sym_jacobi_setup")
+    return inv_diag9
+
+
+def block_jacobi_apply(inv_diag9, x, y):
+    check(_lib.b200fem_block_jacobi_apply(_rt(x.dtype), x.numel() // 3, _p(inv_diag9), _p(x), _p(y), _stream()),
+          "block_jacobi_apply")
+    return y

@@ -48,7 +48,7 @@ def _entry(name, rows, alg_bytes, ms, extra=None):
     return d
 
 
-def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "blas")):
+def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "transfer", "blas")):
     from sfem_b200 import lib, mesh
 
     out = []
@@ -100,6 +100,36 @@ def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "blas")):
         ms = _time(lambda: op.apply_overwrite(x, y), torch)
         out.append(_entry("C3 sshex8 Laplacian L8 f32 64^3 macro (y = A x)", nn, op.algorithmic_bytes, ms))
         del op, m
+    if "c5le" in which or "transfer" in which:
+        # one GPU's share of BASELINE config 5: sshex8 L8 linear elasticity, 44^3 macro elements (~131 M dofs)
+        mm = 44
+        m = mesh.sshex8_box(8, mm, mm, mm, with_points=False)
+        nn = m["n_nodes"]
+        if "c5le" in which:
+            adj, det = lib.adjugate_and_det_fill(lib.HEX8, m["m_elements"], m["m_points"])
+            for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
+                op = lib.linear_elasticity(lib.SSHEX8, m["elements"], adj, det, 1.0, 1.0, nn, dt, level=8)
+                x = torch.rand(nn * 3, dtype=dt, device="cuda")
+                y = torch.zeros_like(x)
+                ms = _time(lambda: op.apply_overwrite(x, y), torch, steps=10)
+                flops = 2.0 * 444 * 512 * m["elements"].shape[1]
+                out.append(_entry(f"C5 shard sshex8 linear elasticity L8 {rt} {mm}^3 macro (y = A x)", nn * 3,
+                                  op.algorithmic_bytes, ms, {"fp_ops_TFLOPs": flops / ms / 1e9}))
+                del op, x, y
+        if "transfer" in which:
+            tr = lib.Transfer(8, 1, m["elements"], nn, 1, 8, m["elements"], nn)
+            for vs in (1, 3):
+                f = torch.rand(nn * vs, dtype=torch.float64, device="cuda")
+                c = torch.zeros(nn * vs, dtype=torch.float64, device="cuda")
+                ms = _time(lambda: tr.restrict(f, c, vs), torch, steps=10)
+                out.append(_entry(f"sshex8 hierarchical restriction L8 -> 1, vec_size {vs}, f64", nn * vs,
+                                  nn * vs * 8.0 + nn * 2.0 + m["elements"].size * 4.0, ms))
+                ms = _time(lambda: tr.prolongate(c, f, vs), torch, steps=10)
+                out.append(_entry(f"sshex8 hierarchical prolongation 1 -> L8, vec_size {vs}, f64", nn * vs,
+                                  nn * vs * 8.0 + m["elements"].size * 4.0, ms))
+                del f, c
+            del tr
+        del m
     if "blas" in which:
         from sfem_b200.lib import blas
 
@@ -124,5 +154,6 @@ if __name__ == "__main__":
     import torch
 
     sys.path.insert(0, ROOT)
-    for e in run_extras(torch):
+    which = tuple(sys.argv[1].split(",")) if len(sys.argv) > 1 else None
+    for e in (run_extras(torch, which) if which else run_extras(torch)):
         print(json.dumps(e), flush=True)
