@@ -1,0 +1,242 @@
+"""ctypes front of the C++ host layer (sfem_b200/host/b200fem_host.hpp through host_capi.cpp ->
+libb200fem_host.so): Function, ConjugateGradient, Chebyshev3, StationaryIteration, ShiftableJacobi,
+ShiftableBlockSymJacobi and Multigrid with the reference's interfaces (algebra/sfem_cg.hpp, sfem_Chebyshev3.hpp,
+sfem_Stationary.hpp, sfem_ShiftableJacobi.hpp, sfem_Multigrid.hpp, frontend/sfem_Function.cpp), running entirely on
+the CUDA kernels behind include/b200fem.h. Plumbing for tests and bench.py; no CPU fallback.
+
+The object-graph calls mirror oracle/ref_solvers.py (the reference's own solver headers) one to one, so a parity
+test builds the same solver twice and compares iteration counts and solutions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import lib as _l
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200fem_host.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build it with `make -C sfem_b200/host` (after sfem_b200/csrc).")
+_h = C.CDLL(LIB_PATH)
+
+vp, i32, f64, ssz = C.c_void_p, C.c_int, C.c_double, C.c_ssize_t
+APPLY_CB = C.CFUNCTYPE(i32, vp, vp, vp)
+REDUCE_CB = C.CFUNCTYPE(f64, vp, f64)
+
+_SIG = {
+    "b200host_blas": (vp, [i32, REDUCE_CB, vp]),
+    "b200host_blas_launches": (C.c_long, [vp]),
+    "b200host_function": (vp, [i32, ssz, i32]),
+    "b200host_function_add_operator": (i32, [vp, vp]),
+    "b200host_function_add_dirichlet": (i32, [vp, vp, ssz, i32, f64]),
+    "b200host_function_apply_constraints": (i32, [vp, vp]),
+    "b200host_function_apply_zero_constraints": (i32, [vp, vp]),
+    "b200host_function_set_value_to_constrained_dofs": (i32, [vp, f64, vp]),
+    "b200host_function_hessian_diag": (i32, [vp, vp]),
+    "b200host_function_hessian_block_diag_sym": (i32, [vp, vp]),
+    "b200host_function_launches_per_apply": (i32, [vp, i32]),
+    "b200host_callback_op": (vp, [i32, ssz, ssz, APPLY_CB, APPLY_CB, vp]),
+    "b200host_restriction": (vp, [i32, vp, i32, vp]),
+    "b200host_prolongation": (vp, [i32, vp, i32, vp]),
+    "b200host_cg": (vp, [vp, vp, vp, f64, f64, i32]),
+    "b200host_jacobi": (vp, [vp, vp, ssz, f64]),
+    "b200host_block_sym_jacobi": (vp, [vp, vp, ssz, vp, f64]),
+    "b200host_stationary": (vp, [vp, vp, vp, i32]),
+    "b200host_cheb3": (vp, [vp, vp, f64, i32, f64, f64, i32, i32]),
+    "b200host_cheb3_init_with_ones": (i32, [vp]),
+    "b200host_cheb3_eig_max": (f64, [vp]),
+    "b200host_cheb3_power_method_iterations": (i32, [vp]),
+    "b200host_cheb3_set_initial_guess_zero": (i32, [vp, i32]),
+    "b200host_mg": (vp, [vp, i32, f64, i32, i32]),
+    "b200host_mg_add_level": (i32, [vp, vp, vp, vp, vp]),
+    "b200host_apply": (i32, [vp, vp, vp]),
+    "b200host_apply_overwrite": (i32, [vp, vp, vp]),
+    "b200host_rows": (ssz, [vp]),
+    "b200host_iterations": (i32, [vp]),
+    "b200host_residual_history": (i32, [vp, C.POINTER(f64), i32]),
+    "b200host_destroy": (None, [vp]),
+}
+for _n, (_r, _a) in _SIG.items():
+    getattr(_h, _n).restype = _r
+    getattr(_h, _n).argtypes = _a
+
+
+def raw():
+    return _h
+
+
+def exported_symbols():
+    return sorted(_SIG)
+
+
+class Handle:
+    def __init__(self, ptr, keep=()):
+        if not ptr:
+            raise _l.B200FemError("host layer returned NULL: " + _l.raw().b200fem_last_error().decode())
+        self.ptr, self.keep = ptr, list(keep)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _h.b200host_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Blas(Handle):
+    """DeviceBLAS<T>; `allreduce(value) -> global sum` makes every dot / norm a distributed one."""
+
+    def __init__(self, dtype, allreduce=None):
+        self.rt = _l._rt(dtype)
+        cb = REDUCE_CB(lambda _ctx, v: float(allreduce(v))) if allreduce else C.cast(None, REDUCE_CB)
+        super().__init__(_h.b200host_blas(self.rt, cb, None), keep=[cb, allreduce])
+
+    def launches(self) -> int:
+        return _h.b200host_blas_launches(self.ptr)
+
+
+class Function(Handle):
+    """Operators (lib.Op plans) + Dirichlet conditions on one space; is itself the Operator of make_linear_op(f)."""
+
+    def __init__(self, dtype, n_nodes: int, block_size: int = 1):
+        import torch
+
+        self.rt, self.n_nodes, self.block_size, self.dtype = _l._rt(dtype), n_nodes, block_size, dtype
+        self._torch = torch
+        super().__init__(_h.b200host_function(self.rt, n_nodes, block_size))
+
+    @property
+    def n_dofs(self):
+        return self.n_nodes * self.block_size
+
+    def add_operator(self, op: _l.Op):
+        self.keep.append(op)
+        _h.b200host_function_add_operator(self.ptr, op.handle)
+
+    def add_dirichlet(self, nodes, component: int, value: float):
+        idx = self._torch.as_tensor(np.ascontiguousarray(nodes, dtype=np.int32)).cuda()
+        self.keep.append(idx)
+        _h.b200host_function_add_dirichlet(self.ptr, _p(idx), idx.numel(), component, value)
+
+    def apply_constraints(self, x):
+        _l.check(_h.b200host_function_apply_constraints(self.ptr, _p(x)), "apply_constraints")
+
+    def apply_zero_constraints(self, x):
+        _l.check(_h.b200host_function_apply_zero_constraints(self.ptr, _p(x)), "apply_zero_constraints")
+
+    def set_value_to_constrained_dofs(self, v, x):
+        _l.check(_h.b200host_function_set_value_to_constrained_dofs(self.ptr, v, _p(x)), "set_value_to_constrained_dofs")
+
+    def hessian_diag(self, d):
+        _l.check(_h.b200host_function_hessian_diag(self.ptr, _p(d)), "hessian_diag")
+
+    def hessian_block_diag_sym(self, d):
+        _l.check(_h.b200host_function_hessian_block_diag_sym(self.ptr, _p(d)), "hessian_block_diag_sym")
+
+    def launches_per_apply(self, overwrite=True) -> int:
+        return _h.b200host_function_launches_per_apply(self.ptr, int(overwrite))
+
+
+def callback_op(dtype, rows, cols, apply, overwrite=None) -> Handle:
+    """Operator from Python callables taking raw device addresses: apply(x_addr, y_addr) accumulates."""
+    a = APPLY_CB(lambda _c, x, y: int(apply(x, y) or 0))
+    o = APPLY_CB(lambda _c, x, y: int(overwrite(x, y) or 0)) if overwrite else C.cast(None, APPLY_CB)
+    return Handle(_h.b200host_callback_op(_l._rt(dtype), rows, cols, a, o, None), keep=[a, o, apply, overwrite])
+
+
+def restriction(dtype, transfer: _l.Transfer, vec_size=1, coarse_function: Function | None = None) -> Handle:
+    return Handle(_h.b200host_restriction(_l._rt(dtype), transfer.handle, vec_size,
+                                          coarse_function.ptr if coarse_function else None), keep=[transfer, coarse_function])
+
+
+def prolongation(dtype, transfer: _l.Transfer, vec_size=1, fine_function: Function | None = None) -> Handle:
+    return Handle(_h.b200host_prolongation(_l._rt(dtype), transfer.handle, vec_size,
+                                           fine_function.ptr if fine_function else None), keep=[transfer, fine_function])
+
+
+def cg(blas: Blas, op: Handle, precond: Handle | None = None, rtol=1e-10, atol=1e-16, max_it=10000) -> Handle:
+    return Handle(_h.b200host_cg(blas.ptr, op.ptr, precond.ptr if precond else None, rtol, atol, max_it),
+                  keep=[blas, op, precond])
+
+
+def jacobi(blas: Blas, diag, relaxation: float) -> Handle:
+    return Handle(_h.b200host_jacobi(blas.ptr, _p(diag), diag.numel(), relaxation), keep=[blas, diag])
+
+
+def block_sym_jacobi(blas: Blas, diag6, mask, relaxation: float) -> Handle:
+    return Handle(_h.b200host_block_sym_jacobi(blas.ptr, _p(diag6), diag6.numel() // 6, _p(mask), relaxation),
+                  keep=[blas, diag6, mask])
+
+
+def stationary(blas: Blas, op: Handle, precond: Handle, max_it: int) -> Handle:
+    return Handle(_h.b200host_stationary(blas.ptr, op.ptr, precond.ptr, max_it), keep=[blas, op, precond])
+
+
+def cheb3(blas: Blas, op: Handle, eig_tol=1e-6, eig_max_it=1000, scale_eig_max=1.0, scale_eig_min=0.06, max_it=3,
+          initial_guess_zero=False, init="ones") -> Handle:
+    h = Handle(_h.b200host_cheb3(blas.ptr, op.ptr, eig_tol, eig_max_it, scale_eig_max, scale_eig_min, max_it,
+                                 int(initial_guess_zero)), keep=[blas, op])
+    if init == "ones":
+        _h.b200host_cheb3_init_with_ones(h.ptr)
+    return h
+
+
+def cheb3_eig_max(h: Handle) -> float:
+    return _h.b200host_cheb3_eig_max(h.ptr)
+
+
+def cheb3_power_method_iterations(h: Handle) -> int:
+    return _h.b200host_cheb3_power_method_iterations(h.ptr)
+
+
+def cheb3_set_initial_guess_zero(h: Handle, val: bool):
+    _h.b200host_cheb3_set_initial_guess_zero(h.ptr, int(val))
+
+
+def mg(blas: Blas, max_it=10, atol=1e-10, cycle_type=1, verbose=False) -> Handle:
+    return Handle(_h.b200host_mg(blas.ptr, max_it, atol, cycle_type, int(verbose)), keep=[blas])
+
+
+def mg_add_level(m: Handle, op, smoother: Handle, prolong, restrict):
+    p = lambda h: h.ptr if h is not None else None
+    _h.b200host_mg_add_level(m.ptr, p(op), smoother.ptr, p(prolong), p(restrict))
+    m.keep += [op, smoother, prolong, restrict]
+
+
+def apply(obj: Handle, b, x) -> int:
+    """Solvers: solve A x = b in place in x. Operators: x += A b. Returns the reference's int code (0 = success)."""
+    return _h.b200host_apply(obj.ptr, _p(b), _p(x))
+
+
+def apply_overwrite(obj: Handle, x, y) -> int:
+    return _h.b200host_apply_overwrite(obj.ptr, _p(x), _p(y))
+
+
+def iterations(obj: Handle) -> int:
+    return _h.b200host_iterations(obj.ptr)
+
+
+def residual_history(obj: Handle) -> np.ndarray:
+    n = _h.b200host_residual_history(obj.ptr, None, 0)
+    out = np.zeros(max(n, 0))
+    if n > 0:
+        _h.b200host_residual_history(obj.ptr, out.ctypes.data_as(C.POINTER(f64)), n)
+    return out
+
+
+def constraints_mask(n_dofs: int, block_size: int, conditions) -> np.ndarray:
+    """Bit mask of constrained dofs in the reference's mask_t layout (algebra/sfem_mask.hpp:13-44; built by
+    Function::constraints_mask): bit (i % 8) of byte (i / 8) for dof i = node * block_size + component."""
+    m = np.zeros((n_dofs + 7) // 8, dtype=np.uint8)
+    for nodes, comp, _v in conditions:
+        dof = np.asarray(nodes, dtype=np.int64) * block_size + comp
+        np.bitwise_or.at(m, dof // 8, (1 << (dof % 8)).astype(np.uint8))
+    return m

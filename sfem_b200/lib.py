@@ -201,6 +201,10 @@ class Op:
             _lib.b200fem_op_destroy(h)
 
     @property
+    def handle(self):
+        return self._h
+
+    @property
     def rows(self):
         return int(_lib.b200fem_op_rows(self._h))
 
@@ -385,6 +389,10 @@ class Transfer:
         h, self._h = getattr(self, "_h", None), None
         if h:
             _lib.b200fem_transfer_destroy(h)
+
+    @property
+    def handle(self):
+        return self._h
 
     def incidence_count(self) -> np.ndarray:
         out = np.zeros(self.n_fine, dtype=np.uint16)

@@ -1,0 +1,147 @@
+"""Two interchangeable back-ends for the solver parity tests.
+
+RefBackend : the reference's own solver headers (oracle/_ref/libsfem_ref_solvers_*.so) on the CPU with OpenMP_BLAS,
+             operators = numpy closures over the oracle's element kernels.
+GpuBackend : sfem_b200.host (C++ host layer) over the CUDA kernels.
+A solver case (tests/helpers/solver_cases.py) is written once against this small interface and run on both."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import problems as P
+
+
+class RefBackend:
+    name = "reference"
+
+    def __init__(self, orc, rs):
+        self.orc, self.rs, self.rt = orc, rs, rs.rt
+
+    def zeros(self, n):
+        return np.zeros(n, dtype=self.rt)
+
+    def from_numpy(self, a):
+        return np.ascontiguousarray(a, dtype=self.rt)
+
+    def to_numpy(self, v):
+        return np.array(v, dtype=np.float64)
+
+    def linear_op(self, p, coarse=False):
+        if coarse:
+            return self.rs.make_op(p.ref_linear_op(p.ref_coarse_apply, p.coarse_conditions), p.n_coarse_nodes * p.block_size)
+        return self.rs.make_op(p.ref_linear_op(p.ref_apply), p.n_dofs)
+
+    def apply_constraints(self, p, x):
+        p.apply_constraints_host(x)
+
+    def diag(self, p):
+        """Function::hessian_diag + value 1 on the constrained dofs (frontend/sfem_Function.cpp:430-447)."""
+        d = self.from_numpy(p.ref_diag())
+        d[p.constrained_dofs()] = 1
+        return d
+
+    def transfer(self, p):
+        return P.ref_transfer_ops(self.rs, self.orc, p)
+
+    def cg(self, op, precond=None, **kw):
+        return self.rs.cg(op, precond, **kw)
+
+    def jacobi(self, diag, relaxation):
+        return self.rs.jacobi(diag, relaxation)
+
+    def stationary(self, op, precond, max_it):
+        return self.rs.stationary(op, precond, max_it)
+
+    def cheb3(self, op, **kw):
+        return self.rs.cheb3(op, **kw)
+
+    def cheb3_eig_max(self, h):
+        return self.rs.cheb3_eig_max(h)
+
+    def mg(self, **kw):
+        return self.rs.mg(**kw)
+
+    def mg_add_level(self, *a):
+        self.rs.mg_add_level(*a)
+
+    def apply(self, obj, b, x):
+        return self.rs.apply(obj, b, x)
+
+    def iterations(self, obj):
+        return self.rs.iterations(obj)
+
+
+class GpuBackend:
+    name = "b200"
+
+    def __init__(self, real):
+        import torch
+
+        from sfem_b200 import host
+
+        self.torch, self.host = torch, host
+        self.dtype = torch.float64 if real == "f64" else torch.float32
+        self.blas = host.Blas(self.dtype)
+        self._functions = {}
+
+    def zeros(self, n):
+        return self.torch.zeros(n, dtype=self.dtype, device="cuda")
+
+    def from_numpy(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dtype).cuda()
+
+    def to_numpy(self, v):
+        return v.detach().cpu().numpy().astype(np.float64)
+
+    def function(self, p, coarse=False):
+        key = (id(p), coarse)
+        if key not in self._functions:
+            self._functions[key] = P.gpu_function(p, self.dtype, coarse)
+        return self._functions[key]
+
+    def linear_op(self, p, coarse=False):
+        return self.function(p, coarse)
+
+    def apply_constraints(self, p, x):
+        self.function(p).apply_constraints(x)
+
+    def diag(self, p):
+        f = self.function(p)
+        d = self.zeros(p.n_dofs)
+        f.hessian_diag(d)
+        f.set_value_to_constrained_dofs(1.0, d)
+        return d
+
+    def transfer(self, p):
+        t = P.gpu_transfer(p)
+        return (self.host.restriction(self.dtype, t, p.block_size, self.function(p, True)),
+                self.host.prolongation(self.dtype, t, p.block_size, self.function(p, False)))
+
+    def cg(self, op, precond=None, **kw):
+        return self.host.cg(self.blas, op, precond, **kw)
+
+    def jacobi(self, diag, relaxation):
+        return self.host.jacobi(self.blas, diag, relaxation)
+
+    def stationary(self, op, precond, max_it):
+        return self.host.stationary(self.blas, op, precond, max_it)
+
+    def cheb3(self, op, **kw):
+        return self.host.cheb3(self.blas, op, **kw)
+
+    def cheb3_eig_max(self, h):
+        return self.host.cheb3_eig_max(h)
+
+    def mg(self, **kw):
+        return self.host.mg(self.blas, **kw)
+
+    def mg_add_level(self, *a):
+        self.host.mg_add_level(*a)
+
+    def apply(self, obj, b, x):
+        rc = self.host.apply(obj, b, x)
+        self.torch.cuda.synchronize()
+        return rc
+
+    def iterations(self, obj):
+        return self.host.iterations(obj)

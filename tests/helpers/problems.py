@@ -1,0 +1,175 @@
+"""Boundary-value problems shared by the solver parity tests: each one is described once (mesh arrays, geometry
+factors from the oracle, Dirichlet node sets) and instantiated twice --
+  * `ref_*`  : numpy closures over the oracle's element kernels, to be driven by the REFERENCE's own solver headers
+               (oracle/ref_solvers.py), i.e. Function::apply = sum of ops + copy of the constrained dofs
+               (frontend/sfem_Function.cpp:481-496);
+  * `gpu_*`  : the same objects on the device through sfem_b200.host (C++ host layer over the C ABI).
+Patterns follow the reference's drivers: Poisson with u = -1 / +1 on two opposite faces and zero rhs
+(drivers/poisson.exe.cpp:122-129), elasticity with (-1,0,0) / (1,0,0) on the x-faces
+(ssmg/tests/sfem_SSGMGTest.cpp:158-169), 2-level mgsolve (drivers/mgsolve.cpp:170-290)."""
+from __future__ import annotations
+
+import numpy as np
+
+from sfem_b200 import mesh
+
+
+class Problem:
+    """block_size, n_nodes, conditions = [(nodes int32[], component, value)], fine/coarse operator descriptions."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def n_dofs(self):
+        return self.n_nodes * self.block_size
+
+    # ---- host (oracle) side -------------------------------------------------------------------------------
+    def constrained_dofs(self, conditions=None, block_size=None):
+        bs = self.block_size if block_size is None else block_size
+        conds = self.conditions if conditions is None else conditions
+        if not conds:
+            return np.zeros(0, dtype=np.int64)
+        return np.concatenate([np.asarray(n, dtype=np.int64) * bs + c for n, c, _ in conds])
+
+    def apply_constraints_host(self, x, conditions=None):
+        for n, c, v in self.conditions if conditions is None else conditions:
+            x[np.asarray(n, dtype=np.int64) * self.block_size + c] = v
+        return x
+
+    def ref_linear_op(self, apply_fn, conditions=None):
+        """Function::apply as a `fn(x, y)` closure: y += A x, then y[c] = x[c]."""
+        cd = self.constrained_dofs(conditions)
+
+        def fn(x, y):
+            y += apply_fn(np.array(x, copy=True))
+            y[cd] = x[cd]
+
+        return fn
+
+
+def _face_nodes(points, axis, value, eps=1e-6):
+    return np.where(np.abs(points[axis] - value) < eps)[0].astype(np.int32)
+
+
+def poisson_tet4(orc, n=12):
+    el, pts = mesh.box_tet4(n, n, n)
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    fff = orc.tet4_fff_fill(el, pts)
+    nn = pts.shape[1]
+    conds = [(_face_nodes(pts, 2, 0.0), 0, -1.0), (_face_nodes(pts, 2, 1.0), 0, 1.0)]
+    p = Problem(kind="tet4_laplacian", block_size=1, n_nodes=nn, elements=el, points=pts, fff=fff, conditions=conds)
+    p.ref_apply = lambda x: orc.tet4_laplacian_apply_opt(el, fff, x)
+    p.ref_diag = lambda: orc.tet4_laplacian_diag_opt(el, fff, nn)
+    p.exact = 2.0 * pts[2].astype(np.float64) - 1.0
+    return p
+
+
+def poisson_sshex8(orc, L=4, mx=3, my=2, mz=2):
+    m = mesh.sshex8_box(L, mx, my, mz)
+    mpts = np.ascontiguousarray(m["m_points"], dtype=np.float32)
+    fff = orc.hex8_fff_fill(m["m_elements"], mpts)
+    nn = m["n_nodes"]
+    pts = m["points"]
+    conds = [(_face_nodes(pts, 0, 0.0), 0, -1.0), (_face_nodes(pts, 0, 1.0), 0, 1.0)]
+    p = Problem(kind="sshex8_laplacian", block_size=1, n_nodes=nn, level=L, elements=m["elements"], fff=fff, m=m,
+                points=pts, conditions=conds)
+    p.ref_apply = lambda x: orc.sshex8_laplacian_apply(L, m["elements"], fff, x)
+    # coarse level = the hex8 macro mesh on the macro node ids (a prefix of the sshex8 numbering)
+    mel = m["m_elements"]
+    n_macro = int(mel.max()) + 1
+    p.n_coarse_nodes = n_macro
+    p.coarse_elements = mel
+    p.coarse_conditions = [(n[n < n_macro], c, v) for n, c, v in conds]
+    p.ref_coarse_apply = lambda x: orc.hex8_laplacian_apply_opt(mel, fff, x)
+    p.exact = 2.0 * pts[0].astype(np.float64) - 1.0
+    return p
+
+
+def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0):
+    m = mesh.sshex8_box(L, mx, my, mz)
+    mpts = np.ascontiguousarray(m["m_points"], dtype=np.float32)
+    adj, det = orc.hex8_adjugate_and_det_fill(m["m_elements"], mpts)
+    nn = m["n_nodes"]
+    pts = m["points"]
+    left, right = _face_nodes(pts, 0, 0.0), _face_nodes(pts, 0, 1.0)
+    conds = [(left, 0, -1.0), (left, 1, 0.0), (left, 2, 0.0), (right, 0, 1.0), (right, 1, 0.0), (right, 2, 0.0)]
+    p = Problem(kind="sshex8_linear_elasticity", block_size=3, n_nodes=nn, level=L, elements=m["elements"], adj=adj, det=det,
+                mu=mu, lam=lam, m=m, points=pts, conditions=conds)
+    p.ref_apply = lambda x: orc.sshex8_linear_elasticity_apply(L, m["elements"], adj, det, mu, lam, x, nn)
+    mel = m["m_elements"]
+    n_macro = int(mel.max()) + 1
+    p.n_coarse_nodes = n_macro
+    p.coarse_elements = mel
+    p.coarse_conditions = [(n[n < n_macro], c, v) for n, c, v in conds]
+    p.ref_coarse_apply = lambda x: orc.hex8_linear_elasticity_apply(mel, adj, det, mu, lam, x, n_macro)
+    return p
+
+
+def level1_lattice(mel):
+    """hex8 (VTK corner order) -> rows of a level-1 sshex8 lattice."""
+    lat = np.zeros((8, mel.shape[1]), dtype=np.int32)
+    for k, (cx, cy, cz) in enumerate(mesh.HEX8_CORNERS):
+        lat[mesh.sshex8_lidx(1, cx, cy, cz)] = mel[k]
+    return lat
+
+
+# ---- reference-side object graphs (oracle/ref_solvers.RefSolvers) ---------------------------------------------
+def ref_transfer_ops(rs, orc, p):
+    """(restriction, prolongation) as create_gmg_data wires them (algebra/mg/sfem_GeometricMultigrid.cpp:38-64):
+    hierarchical restriction followed by apply_zero_constraints on the coarse space, hierarchical prolongation
+    followed by apply_zero_constraints on the fine space."""
+    L, el, nn, nc, bs = p.level, p.elements, p.n_nodes, p.n_coarse_nodes, p.block_size
+    count = orc.sshex8_element_node_incidence_count(L, 1, el, nn)
+    fine_cd = p.constrained_dofs()
+    coarse_cd = p.constrained_dofs(p.coarse_conditions)
+
+    p.ref_restrict_calls = 0
+
+    def restrict(frm, to):
+        p.ref_restrict_calls += 1
+        r = orc.sshex8_hierarchical_restriction(L, el, count, bs, np.array(frm, copy=True), nn)
+        to += r[: nc * bs]
+        to[coarse_cd] = 0
+
+    def prolong(frm, to):
+        full = np.zeros(nn * bs, dtype=frm.dtype)
+        full[: nc * bs] = frm
+        to[:] = orc.sshex8_hierarchical_prolongation(L, el, bs, full, nn)
+        to[fine_cd] = 0
+
+    return rs.make_op(restrict, nc * bs, nn * bs), rs.make_op(prolong, nn * bs, nc * bs)
+
+
+# ---- device-side object graphs (sfem_b200.host) ---------------------------------------------------------------
+def gpu_function(p, dtype, coarse=False):
+    from sfem_b200 import host, lib
+
+    if not coarse:
+        f = host.Function(dtype, p.n_nodes, p.block_size)
+        if p.kind == "tet4_laplacian":
+            op = lib.laplacian(lib.TET4, p.elements, p.fff, p.n_nodes, dtype)
+        elif p.kind == "sshex8_laplacian":
+            op = lib.laplacian(lib.SSHEX8, p.elements, p.fff, p.n_nodes, dtype, level=p.level)
+        elif p.kind == "sshex8_linear_elasticity":
+            op = lib.linear_elasticity(lib.SSHEX8, p.elements, p.adj, p.det, p.mu, p.lam, p.n_nodes, dtype, level=p.level)
+        else:
+            raise ValueError(p.kind)
+        conds = p.conditions
+    else:
+        f = host.Function(dtype, p.n_coarse_nodes, p.block_size)
+        if p.kind == "sshex8_laplacian":
+            op = lib.laplacian(lib.HEX8, p.coarse_elements, p.fff, p.n_coarse_nodes, dtype)
+        else:
+            op = lib.linear_elasticity(lib.HEX8, p.coarse_elements, p.adj, p.det, p.mu, p.lam, p.n_coarse_nodes, dtype)
+        conds = p.coarse_conditions
+    f.add_operator(op)
+    for nodes, comp, val in conds:
+        f.add_dirichlet(nodes, comp, val)
+    return f
+
+
+def gpu_transfer(p):
+    from sfem_b200 import lib
+
+    return lib.Transfer(p.level, 1, p.elements, p.n_nodes, 1, 1, level1_lattice(p.coarse_elements), p.n_coarse_nodes)

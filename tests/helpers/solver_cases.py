@@ -1,0 +1,95 @@
+"""Solver cases, written once and run on the reference (CPU) and on the B200 host layer (tests/helpers/backends.py).
+Each returns {"iterations": int | list, "x": float64 ndarray, ...}. Parameters follow the reference's drivers:
+poisson.exe.cpp:20 (rtol 1e-6), frontend/tests/sfem_PoissonTest.cpp:149 (1e-9), drivers/mgsolve.cpp:64-71
+(SFEM_TOL 1e-9, SFEM_CHEB_EIG_MAX_SCALE 1.02, SFEM_CHEB_EIG_TOL 1e-5, SFEM_SMOOTHER_SWEEPS 3, coarse CG rtol 1e-8 /
+atol 1e-10 / max_it 40000)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _bvp_vectors(B, p):
+    x, b = B.zeros(p.n_dofs), B.zeros(p.n_dofs)
+    B.apply_constraints(p, x)
+    B.apply_constraints(p, b)
+    return x, b
+
+
+def cg(B, p, rtol=1e-6):
+    A = B.linear_op(p)
+    s = B.cg(A, None, rtol=rtol, atol=1e-16, max_it=10000)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(s, b, x)
+    return dict(rc=rc, iterations=B.iterations(s), x=B.to_numpy(x))
+
+
+def pcg_jacobi(B, p, rtol=1e-9):
+    A = B.linear_op(p)
+    d = B.diag(p)
+    s = B.cg(A, B.jacobi(d, 1.0), rtol=rtol, atol=1e-16, max_it=10000)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(s, b, x)
+    return dict(rc=rc, iterations=B.iterations(s), x=B.to_numpy(x))
+
+
+def stationary_jacobi(B, p, sweeps=25):
+    A = B.linear_op(p)
+    d = B.diag(p)
+    s = B.stationary(A, B.jacobi(d, 0.6), sweeps)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(s, b, x)
+    return dict(rc=rc, iterations=B.iterations(s), x=B.to_numpy(x))
+
+
+def chebyshev(B, p, sweeps=5):
+    """power method from the ones vector + one smoothing call on the boundary-value problem"""
+    A = B.linear_op(p)
+    c = B.cheb3(A, eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
+                initial_guess_zero=False)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(c, b, x)
+    return dict(rc=rc, iterations=B.iterations(c), eig_max=B.cheb3_eig_max(c), x=B.to_numpy(x))
+
+
+def mg_two_level(B, p, sweeps=3, tol=1e-9, max_cycles=40):
+    """drivers/mgsolve.cpp: Chebyshev3 smoother on the fine sshex8 operator, CG on the derefined (hex8) operator."""
+    A, Ac = B.linear_op(p), B.linear_op(p, coarse=True)
+    R, Pr = B.transfer(p)
+    smoother = B.cheb3(A, eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
+                       initial_guess_zero=False)
+    coarse = B.cg(Ac, None, rtol=1e-8, atol=1e-10, max_it=40000)
+    mg = B.mg(max_it=max_cycles, atol=tol)
+    B.mg_add_level(mg, A, smoother, None, R)
+    B.mg_add_level(mg, None, coarse, Pr, None)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(mg, b, x)
+    out = dict(rc=rc, eig_max=B.cheb3_eig_max(smoother), x=B.to_numpy(x), last_coarse_iterations=B.iterations(coarse))
+    it = B.iterations(mg)  # the reference's Multigrid has no iterations() accessor: -1 there
+    # cycles executed = fine-level restrictions performed (sfem_Multigrid.hpp:62-67, 299-303)
+    out["iterations"] = it if it >= 0 else p.ref_restrict_calls
+    return out
+
+
+def pcg_mg(B, p, sweeps=3, rtol=1e-9):
+    """SFEM_USE_MG_PRECONDITIONER (drivers/mgsolve.cpp:262-272): CG preconditioned by one multigrid cycle."""
+    A, Ac = B.linear_op(p), B.linear_op(p, coarse=True)
+    R, Pr = B.transfer(p)
+    smoother = B.cheb3(A, eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
+                       initial_guess_zero=False)
+    coarse = B.cg(Ac, None, rtol=1e-8, atol=1e-10, max_it=40000)
+    mg = B.mg(max_it=1, atol=0.0)
+    B.mg_add_level(mg, A, smoother, None, R)
+    B.mg_add_level(mg, None, coarse, Pr, None)
+    ksp = B.cg(A, mg, rtol=rtol, atol=1e-16, max_it=200)
+    x, b = _bvp_vectors(B, p)
+    rc = B.apply(ksp, b, x)
+    return dict(rc=rc, iterations=B.iterations(ksp), x=B.to_numpy(x))
+
+
+def residual_norm(p, x, apply_fn):
+    """|| b - A x || of the constrained operator, evaluated with the oracle on the host."""
+    b = np.zeros(p.n_dofs)
+    p.apply_constraints_host(b)
+    r = np.zeros(p.n_dofs)
+    p.ref_linear_op(apply_fn)(np.asarray(x, dtype=np.float64), r)
+    return float(np.linalg.norm(b - r))

@@ -37,3 +37,16 @@ def test_bad_arguments_are_reported():
     rc = lib.raw().b200fem_laplacian_create(C.byref(h), lib.TET4, 0, 1, 1, None, None, 3)
     assert rc == 1 and lib.raw().b200fem_last_error()
     assert lib.raw().b200fem_op_apply(None, None, None, None) == 1
+
+
+def test_host_layer_library_exports():
+    """libb200fem_host.so (C++ host layer behind C entry points) loads and exports what sfem_b200/host.py binds."""
+    from sfem_b200 import host
+
+    missing = [n for n in host.exported_symbols() if not hasattr(host.raw(), n)]
+    assert not missing, missing
+    # object construction needs no device; solving does (no CPU fallback: allocation fails without a GPU)
+    import torch
+
+    b = host.Blas(torch.float64)
+    assert b.launches() == 0
