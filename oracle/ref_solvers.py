@@ -143,8 +143,10 @@ class RefSolvers:
               initial_guess_zero=False, es=HOST, init="ones") -> Handle:
         h = Handle(self, self.lib.refsolv_cheb3(op.ptr, eig_tol, eig_max_it, scale_eig_max, scale_eig_min, max_it,
                                                 int(initial_guess_zero), es), keep=[op])
-        if init == "ones":
+        if isinstance(init, str) and init == "ones":
             self.lib.refsolv_cheb3_init_with_ones(h.ptr)
+        elif init is not None:  # numpy start vector (HOST) or device address (DEVICE)
+            self.lib.refsolv_cheb3_init(h.ptr, init.ctypes.data if isinstance(init, np.ndarray) else init)
         return h
 
     def cheb3_eig_max(self, h: Handle) -> float:

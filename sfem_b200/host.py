@@ -47,6 +47,7 @@ _SIG = {
     "b200host_stationary": (vp, [vp, vp, vp, i32]),
     "b200host_cheb3": (vp, [vp, vp, f64, i32, f64, f64, i32, i32]),
     "b200host_cheb3_init_with_ones": (i32, [vp]),
+    "b200host_cheb3_init": (i32, [vp, vp]),
     "b200host_cheb3_eig_max": (f64, [vp]),
     "b200host_cheb3_power_method_iterations": (i32, [vp]),
     "b200host_cheb3_set_initial_guess_zero": (i32, [vp, i32]),
@@ -184,8 +185,10 @@ def cheb3(blas: Blas, op: Handle, eig_tol=1e-6, eig_max_it=1000, scale_eig_max=1
           initial_guess_zero=False, init="ones") -> Handle:
     h = Handle(_h.b200host_cheb3(blas.ptr, op.ptr, eig_tol, eig_max_it, scale_eig_max, scale_eig_min, max_it,
                                  int(initial_guess_zero)), keep=[blas, op])
-    if init == "ones":
+    if isinstance(init, str) and init == "ones":
         _h.b200host_cheb3_init_with_ones(h.ptr)
+    elif init is not None:
+        _h.b200host_cheb3_init(h.ptr, _p(init))  # device tensor: the power method's start vector
     return h
 
 

@@ -257,6 +257,16 @@ int b200host_cheb3_init_with_ones(void *c) {
         std::static_pointer_cast<Chebyshev3<float>>(b->obj)->init_with_ones();
     return 0;
 }
+/* power method from a caller-provided DEVICE guess vector (Chebyshev3::init, sfem_Chebyshev3.hpp:163-174) */
+int b200host_cheb3_init(void *c, const void *guess_dev) {
+    Box *b = (Box *)c;
+    if (b->kind != K_CHEB) return 1;
+    if (b->real_type == B200FEM_F64)
+        std::static_pointer_cast<Chebyshev3<double>>(b->obj)->init((const double *)guess_dev);
+    else
+        std::static_pointer_cast<Chebyshev3<float>>(b->obj)->init((const float *)guess_dev);
+    return 0;
+}
 double b200host_cheb3_eig_max(void *c) {
     Box *b = (Box *)c;
     return DISPATCH(b->real_type, (double)std::static_pointer_cast<Chebyshev3<double>>(b->obj)->eig_max,

@@ -19,17 +19,18 @@ from oracle.ref_solvers import RefSolvers  # noqa: E402
 
 def cases(orc):
     return {
-        "cg_tet4_rtol1e-6": (solver_cases.cg, lambda: problems.poisson_tet4(orc, 12), dict(rtol=1e-6)),
-        "cg_tet4_rtol1e-9": (solver_cases.cg, lambda: problems.poisson_tet4(orc, 12), dict(rtol=1e-9)),
-        "pcg_jacobi_tet4": (solver_cases.pcg_jacobi, lambda: problems.poisson_tet4(orc, 12), {}),
-        "stationary_jacobi_tet4": (solver_cases.stationary_jacobi, lambda: problems.poisson_tet4(orc, 8), {}),
-        "cg_sshex8_L4": (solver_cases.cg, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2), dict(rtol=1e-9)),
-        "cheb_sshex8_L4": (solver_cases.chebyshev, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2), {}),
-        "cheb_elasticity_L2": (solver_cases.chebyshev, lambda: problems.elasticity_sshex8(orc, 2, 3, 2, 2), {}),
-        "mg2_poisson_L4": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2), {}),
-        "mg2_poisson_L8": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 8, 3, 2, 2), dict(sweeps=10)),
-        "mg2_elasticity_L4": (solver_cases.mg_two_level, lambda: problems.elasticity_sshex8(orc, 4, 3, 2, 2), {}),
-        "pcg_mg_poisson_L4": (solver_cases.pcg_mg, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2), {}),
+        "cg_tet4_rtol1e-6": (solver_cases.cg, lambda: problems.poisson_tet4(orc, 12, generic=True), dict(rtol=1e-6)),
+        "cg_tet4_rtol1e-9": (solver_cases.cg, lambda: problems.poisson_tet4(orc, 12, generic=True), dict(rtol=1e-9)),
+        "pcg_jacobi_tet4": (solver_cases.pcg_jacobi, lambda: problems.poisson_tet4(orc, 12, generic=True), {}),
+        "stationary_jacobi_tet4": (solver_cases.stationary_jacobi, lambda: problems.poisson_tet4(orc, 8, generic=True), {}),
+        "cg_sshex8_L4": (solver_cases.cg, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), dict(rtol=1e-9)),
+        "cheb_sshex8_L4": (solver_cases.chebyshev, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), {}),
+        "cheb_elasticity_L2": (solver_cases.chebyshev, lambda: problems.elasticity_sshex8(orc, 2, 3, 2, 2, generic=True),
+                               dict(random_start=True)),
+        "mg2_poisson_L4": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), {}),
+        "mg2_poisson_L8": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 8, 3, 2, 2, generic=True), dict(sweeps=10)),
+        "mg2_elasticity_L4": (solver_cases.mg_two_level, lambda: problems.elasticity_sshex8(orc, 4, 3, 2, 2, generic=True), dict(sweeps=8, max_cycles=60)),
+        "pcg_mg_poisson_L4": (solver_cases.pcg_mg, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), {}),
     }
 
 

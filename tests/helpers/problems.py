@@ -52,28 +52,42 @@ def _face_nodes(points, axis, value, eps=1e-6):
     return np.where(np.abs(points[axis] - value) < eps)[0].astype(np.int32)
 
 
-def poisson_tet4(orc, n=12):
+def _rhs(n, seed):
+    """Generic right-hand side: makes CG iteration counts a property of the operator's spectrum instead of the
+    symmetry of a plate problem (where they hinge on rounding)."""
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)
+
+
+def poisson_tet4(orc, n=12, generic=False):
+    """generic=False: the reference's plate problem on the unit cube (known linear answer).
+    generic=True: warped coordinates (sfem_ParallelLaplacianApplyTest.cpp:22-35) and a seeded random rhs."""
     el, pts = mesh.box_tet4(n, n, n)
     pts = np.ascontiguousarray(pts, dtype=np.float32)
+    conds = [(_face_nodes(pts, 2, 0.0), 0, -1.0), (_face_nodes(pts, 2, 1.0), 0, 1.0)]
+    if generic:
+        pts = np.ascontiguousarray(mesh.warp_points(pts), dtype=np.float32)
     fff = orc.tet4_fff_fill(el, pts)
     nn = pts.shape[1]
-    conds = [(_face_nodes(pts, 2, 0.0), 0, -1.0), (_face_nodes(pts, 2, 1.0), 0, 1.0)]
-    p = Problem(kind="tet4_laplacian", block_size=1, n_nodes=nn, elements=el, points=pts, fff=fff, conditions=conds)
+    p = Problem(kind="tet4_laplacian", block_size=1, n_nodes=nn, elements=el, points=pts, fff=fff, conditions=conds,
+                rhs=_rhs(nn, 7) if generic else None)
     p.ref_apply = lambda x: orc.tet4_laplacian_apply_opt(el, fff, x)
     p.ref_diag = lambda: orc.tet4_laplacian_diag_opt(el, fff, nn)
     p.exact = 2.0 * pts[2].astype(np.float64) - 1.0
     return p
 
 
-def poisson_sshex8(orc, L=4, mx=3, my=2, mz=2):
+def poisson_sshex8(orc, L=4, mx=3, my=2, mz=2, generic=False):
+    """generic=True: sheared macro mesh (every element stays affine) and a seeded random rhs."""
     m = mesh.sshex8_box(L, mx, my, mz)
     mpts = np.ascontiguousarray(m["m_points"], dtype=np.float32)
+    if generic:
+        mpts = np.ascontiguousarray(mesh.shear_points(mpts), dtype=np.float32)
     fff = orc.hex8_fff_fill(m["m_elements"], mpts)
     nn = m["n_nodes"]
     pts = m["points"]
     conds = [(_face_nodes(pts, 0, 0.0), 0, -1.0), (_face_nodes(pts, 0, 1.0), 0, 1.0)]
     p = Problem(kind="sshex8_laplacian", block_size=1, n_nodes=nn, level=L, elements=m["elements"], fff=fff, m=m,
-                points=pts, conditions=conds)
+                points=pts, conditions=conds, rhs=_rhs(nn, 11) if generic else None)
     p.ref_apply = lambda x: orc.sshex8_laplacian_apply(L, m["elements"], fff, x)
     # coarse level = the hex8 macro mesh on the macro node ids (a prefix of the sshex8 numbering)
     mel = m["m_elements"]
@@ -86,16 +100,18 @@ def poisson_sshex8(orc, L=4, mx=3, my=2, mz=2):
     return p
 
 
-def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0):
+def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0, generic=False):
     m = mesh.sshex8_box(L, mx, my, mz)
     mpts = np.ascontiguousarray(m["m_points"], dtype=np.float32)
+    if generic:
+        mpts = np.ascontiguousarray(mesh.shear_points(mpts), dtype=np.float32)
     adj, det = orc.hex8_adjugate_and_det_fill(m["m_elements"], mpts)
     nn = m["n_nodes"]
     pts = m["points"]
     left, right = _face_nodes(pts, 0, 0.0), _face_nodes(pts, 0, 1.0)
     conds = [(left, 0, -1.0), (left, 1, 0.0), (left, 2, 0.0), (right, 0, 1.0), (right, 1, 0.0), (right, 2, 0.0)]
     p = Problem(kind="sshex8_linear_elasticity", block_size=3, n_nodes=nn, level=L, elements=m["elements"], adj=adj, det=det,
-                mu=mu, lam=lam, m=m, points=pts, conditions=conds)
+                mu=mu, lam=lam, m=m, points=pts, conditions=conds, rhs=_rhs(nn * 3, 13) if generic else None)
     p.ref_apply = lambda x: orc.sshex8_linear_elasticity_apply(L, m["elements"], adj, det, mu, lam, x, nn)
     mel = m["m_elements"]
     n_macro = int(mel.max()) + 1

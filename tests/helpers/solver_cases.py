@@ -9,7 +9,8 @@ import numpy as np
 
 
 def _bvp_vectors(B, p):
-    x, b = B.zeros(p.n_dofs), B.zeros(p.n_dofs)
+    x = B.zeros(p.n_dofs)
+    b = B.from_numpy(p.rhs) if getattr(p, "rhs", None) is not None else B.zeros(p.n_dofs)
     B.apply_constraints(p, x)
     B.apply_constraints(p, b)
     return x, b
@@ -41,11 +42,16 @@ def stationary_jacobi(B, p, sweeps=25):
     return dict(rc=rc, iterations=B.iterations(s), x=B.to_numpy(x))
 
 
-def chebyshev(B, p, sweeps=5):
-    """power method from the ones vector + one smoothing call on the boundary-value problem"""
+def chebyshev(B, p, sweeps=5, random_start=False):
+    """power method + one smoothing call on the boundary-value problem. Start vector: ones (mgsolve.cpp:183), or a
+    seeded random vector (Chebyshev3::init_with_random) -- from ones the interior rows of A 1 vanish up to rounding,
+    so WHEN the dominant eigenvector emerges from the noise depends on the summation order of the kernels."""
     A = B.linear_op(p)
+    init = "ones"
+    if random_start:
+        init = B.from_numpy(np.random.default_rng(5).uniform(-0.5, 0.5, p.n_dofs))
     c = B.cheb3(A, eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
-                initial_guess_zero=False)
+                initial_guess_zero=False, init=init)
     x, b = _bvp_vectors(B, p)
     rc = B.apply(c, b, x)
     return dict(rc=rc, iterations=B.iterations(c), eig_max=B.cheb3_eig_max(c), x=B.to_numpy(x))
@@ -88,7 +94,7 @@ def pcg_mg(B, p, sweeps=3, rtol=1e-9):
 
 def residual_norm(p, x, apply_fn):
     """|| b - A x || of the constrained operator, evaluated with the oracle on the host."""
-    b = np.zeros(p.n_dofs)
+    b = np.array(p.rhs, dtype=np.float64) if getattr(p, "rhs", None) is not None else np.zeros(p.n_dofs)
     p.apply_constraints_host(b)
     r = np.zeros(p.n_dofs)
     p.ref_linear_op(apply_fn)(np.asarray(x, dtype=np.float64), r)
