@@ -32,6 +32,7 @@
 #include "sshex8_boxes.cuh"
 #include "sshex8_laplacian_core.cuh"
 #include "sshex8_laplacian_stream.cuh"
+#include "sshex8_laplacian_tma.cuh"
 
 namespace b200fem {
 
@@ -193,6 +194,13 @@ struct Sshex8Laplacian final : OpBase {
     DeviceArray<BoxDesc> boxes;         // MODE_BOXES: [ne][27]
     DeviceArray<float> fff;             // [ne][6]
     DeviceArray<Sshex8Header> headers;  // MODE_BOXES: [ne] boxes + fff, what the streaming kernel reads
+    DeviceArray<Sshex8TmaHeader> tma_headers;  // MODE_BOXES with contiguous boxes: what the TMA kernel reads
+    bool tma_ok = false;                // every entity box is a contiguous id run (and descriptors fit int16)
+    // 1 = entity-box TMA kernel where it applies. Off by default in round 1: measured at C3 it is on par with the
+    // plane-streaming kernel (fp64 1.05 vs 0.98 ms, profiles/r01d_*): its warps spend half of every group waiting
+    // for their own loads / stores because one buffer per element is all that fits next to 250 registers x 8 warps.
+    int use_tma = 0;
+    int tma_cfg = 0;                    // 0 = edges / corners per node, 1 = all 27 boxes as bulk copies
     int ctas_per_sm = 4;
     int stream_cfg = 0;                 // which team shape / ring depth (see launch_stream)
     int use_stream = 1;                 // 0 = the batch kernel below (kept for explicit connectivity)
@@ -218,6 +226,31 @@ struct Sshex8Laplacian final : OpBase {
         if (ne_main < ne) tail<<<1, Cfg::threads, Cfg::smem_bytes, s>>>(ne - ne_main, headers.ptr + ne_main, x, y);
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
+    }
+
+    template <typename T, int L, bool PLAIN>
+    int launch_tma(const T *x, T *y, cudaStream_t s) {
+        constexpr int NWARP = 8;
+        using Cfg = Sshex8TmaCfg<T, L, NWARP>;
+        auto kern = tma_cfg == 1 ? sshex8_laplacian_tma_kernel<T, L, NWARP, PLAIN, false>
+                                 : sshex8_laplacian_tma_kernel<T, L, NWARP, PLAIN, true>;
+        static bool configured[2] = {false, false};
+        if (!configured[tma_cfg == 1]) {
+            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+            configured[tma_cfg == 1] = true;
+        }
+        const ptrdiff_t ngroups = (ne + Cfg::EPW - 1) / Cfg::EPW;
+        if (ngroups == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ngroups + NWARP - 1) / NWARP, (ptrdiff_t)sm_count());
+        kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, nn, tma_headers.ptr, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+
+    // bulk copies need 16-byte aligned vectors; anything else takes the plane-streaming kernel
+    template <typename T>
+    bool tma_applies(const T *x, const T *y) const {
+        return tma_ok && use_tma && level >= 4 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
     }
 
     // team shapes per level: cfg 0 is the default, the others are tuning alternatives (bench sweeps them)
@@ -281,12 +314,13 @@ struct Sshex8Laplacian final : OpBase {
     template <typename T, int L>
     int apply_L(const T *x, T *y, bool overwrite, cudaStream_t s) {
         if (mode == kModeBoxes && use_stream) {
+            const bool tma = tma_applies(x, y);
             if (overwrite && interior_exclusive) {
                 if (zero_skeleton(y, s)) return B200FEM_FAILURE;
-                return launch_stream<T, L, true>(x, y, s);
+                return tma ? launch_tma<T, L, true>(x, y, s) : launch_stream<T, L, true>(x, y, s);
             }
             if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * sizeof(T), s));
-            return launch_stream<T, L, false>(x, y, s);
+            return tma ? launch_tma<T, L, false>(x, y, s) : launch_stream<T, L, false>(x, y, s);
         }
         if (mode == kModeBoxes && interior_exclusive) {
             if (overwrite) {
@@ -327,7 +361,8 @@ struct Sshex8Laplacian final : OpBase {
     }
 
     double streamed_bytes(bool overwrite) const override {
-        const double idx = (mode == kModeBoxes) ? 27.0 * sizeof(BoxDesc) : 4.0 * nxe;
+        const double idx = (mode == kModeBoxes) ? ((tma_ok && use_tma && level >= 4) ? double(sizeof(Sshex8TmaHeader)) - 24.0 : 27.0 * sizeof(BoxDesc))
+                                                : 4.0 * nxe;
         double vec = double(nn) * real_type * 2.0;                 // x read, y written
         if (!overwrite) vec += double(nn) * real_type;             // y read as well
         return double(ne) * (idx + 24.0) + vec;
@@ -345,6 +380,8 @@ struct Sshex8Laplacian final : OpBase {
         }
         if (!strcmp(key, "stream_cfg")) { stream_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_stream")) { use_stream = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_tma")) { use_tma = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "tma_cfg")) { tma_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "explicit_index")) {
             if (value && mode == kModeBoxes) {
                 if (idx_aos.n == 0) B2_FAIL("explicit index was not kept");
@@ -363,9 +400,59 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "ctas_per_sm")) { *value = ctas_per_sm; return B200FEM_SUCCESS; }
         if (!strcmp(key, "stream_cfg")) { *value = stream_cfg; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_stream")) { *value = use_stream; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_tma")) { *value = use_tma; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "tma_ok")) { *value = tma_ok ? 1 : 0; return B200FEM_SUCCESS; }
         return OpBase::get_option(key, value);
     }
 };
+
+// Per-element headers of the TMA kernel (sshex8_laplacian_tma.cuh). Returns false if some box is not a contiguous
+// id run or a descriptor does not fit 16 bits: the plan then keeps the plane-streaming kernel.
+template <typename T, int L>
+static bool build_tma_headers_L(ptrdiff_t ne, const std::vector<BoxDesc> &boxes, const float *fff,
+                                std::vector<Sshex8TmaHeader> &out) {
+    constexpr int AL = 16 / (int)sizeof(T);
+    const int lo[3] = {0, 1, L}, hi[3] = {0, L - 1, L};
+    out.assign((size_t)ne, Sshex8TmaHeader{});
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        Sshex8TmaHeader &h = out[(size_t)e];
+        for (int b = 0; b < 27; ++b) {
+            const BoxDesc &d = boxes[(size_t)e * 27 + b];
+            const int c[3] = {b % 3, (b / 3) % 3, b / 9};
+            const int64_t st[3] = {d.sx, d.sy, d.sz};
+            int64_t mn = d.base, mx = d.base;
+            for (int a = 0; a < 3; ++a) {
+                const int64_t v0 = st[a] * lo[c[a]], v1 = st[a] * hi[c[a]];
+                mn += std::min(v0, v1);
+                mx += std::max(v0, v1);
+            }
+            const int64_t count = tma_box_count<L>(b);
+            if (mx - mn + 1 != count) return false;
+            const int64_t shift = mn & (AL - 1);
+            const int64_t A = (int64_t)tma_box_region<T, L>(b) + shift + ((int64_t)d.base - mn);
+            if (A < INT16_MIN || A > INT16_MAX) return false;
+            for (int a = 0; a < 3; ++a)
+                if (st[a] < INT16_MIN || st[a] > INT16_MAX) return false;
+            h.gmin[b] = (int32_t)mn;
+            h.desc[b][0] = (int16_t)A;
+            h.desc[b][1] = (int16_t)d.sx;
+            h.desc[b][2] = (int16_t)d.sy;
+            h.desc[b][3] = (int16_t)d.sz;
+        }
+        for (int k = 0; k < 6; ++k) h.fff[k] = fff[e * 6 + k];
+    }
+    return true;
+}
+template <typename T>
+static bool build_tma_headers(int level, ptrdiff_t ne, const std::vector<BoxDesc> &boxes, const float *fff,
+                              std::vector<Sshex8TmaHeader> &out) {
+    switch (level) {
+        case 2: return build_tma_headers_L<T, 2>(ne, boxes, fff, out);
+        case 4: return build_tma_headers_L<T, 4>(ne, boxes, fff, out);
+        case 8: return build_tma_headers_L<T, 8>(ne, boxes, fff, out);
+        default: return false;
+    }
+}
 
 OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff,
                               int real_type) {
@@ -405,6 +492,14 @@ OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32
             h.pad[0] = h.pad[1] = 0.f;
         }
         rc |= op->headers.upload(hdrs.data(), hdrs.size());
+        // TMA headers: every box must be a contiguous id run
+        std::vector<Sshex8TmaHeader> th;
+        const bool ok = (real_type == B200FEM_F64) ? build_tma_headers<double>(level, ne, boxes, fff, th)
+                                                   : build_tma_headers<float>(level, ne, boxes, fff, th);
+        if (ok) {
+            rc |= op->tma_headers.upload(th.data(), th.size());
+            op->tma_ok = true;
+        }
     }
     // The explicit index is always kept: it is the fallback, serves the diag kernel when boxes are
     // absent, and lets tests run both connectivity modes on the same plan.

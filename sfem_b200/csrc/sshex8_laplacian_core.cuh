@@ -59,7 +59,10 @@ struct Sshex8LaplacianRow {
     T gz[3];        // z-edge term on the raw end values of the dy = 0 row: +-gz[dz+1]
     T gy[3];        // y-edge term (only on output planes 0 / L, dz = 0): +-sigma_z * gy[dy+1]
     T gx;           // x-edge term: sigma_y/2 * Syz (times sigma_z, times the 1-D mass row)
-    T accP[N], accC[N], accN[N];  // output planes zp-1, zp, zp+1
+    // accumulators of three consecutive output planes. With phase P the roles are: plane zp-1 -> acc[(P+2)%3],
+    // plane zp -> acc[P], plane zp+1 -> acc[(P+1)%3]. The dense-plane API below keeps P = 1 and rotates the
+    // registers after every step; callers that unroll z use P = zp % 3 and never move a register.
+    T acc[3][N];
     int y;
 
     // fff: the macro element's 6 FFF entries already widened to T (00 01 02 11 12 22)
@@ -105,7 +108,7 @@ struct Sshex8LaplacianRow {
         }
         gx = T(0.5) * Syz * sy;  // times sigma_z at use
 #pragma unroll
-        for (int x = 0; x < N; ++x) accP[x] = accC[x] = accN[x] = T(0);
+        for (int x = 0; x < N; ++x) acc[0][x] = acc[1][x] = acc[2][x] = T(0);
     }
 
     // acc[x] += sum_dx cc[dx+1] * r[x+dx] with the x-boundary rule (h0 = r[0]/2, hL = r[L]/2)
@@ -117,23 +120,22 @@ struct Sshex8LaplacianRow {
     }
 
     // Consume input plane zp. ZC = 0: zp == 0, 1: 0 < zp < L, 2: zp == L (compile-time plane class, so
-    // the interior planes carry no boundary code). `plane` points at this element's plane zp; row yy
-    // starts at plane[yy * ystride]. Reads only.
-    template <int ZC>
-    B2_HD void step_class(const T *plane, const int ystride) {
+    // the interior planes carry no boundary code). `load_row(iy, r)` fills r[0..L] with the lattice values of
+    // row clamp(y + iy - 1, 0, L) of plane zp (clamped rows carry a zero coefficient). Reads only.
+    template <int ZC, int P, class RowLoader>
+    B2_HD void step_class_with(RowLoader &&load_row) {
         constexpr bool zlo = (ZC == 0), zhi = (ZC == 2);
+        T(&accP)[N] = acc[(P + 2) % 3];
+        T(&accC)[N] = acc[P % 3];
+        T(&accN)[N] = acc[(P + 1) % 3];
         if (zhi) {
 #pragma unroll
             for (int x = 0; x < N; ++x) accC[x] *= T(2);  // exact; undone below => dz = 0 taps get 1/2
         }
 #pragma unroll
         for (int iy = 0; iy < 3; ++iy) {
-            int yy = y + iy - 1;
-            yy = yy < 0 ? 0 : (yy > L ? L : yy);  // clamped rows carry a zero coefficient
-            const T *row = plane + yy * ystride;
             T r[N];
-#pragma unroll
-            for (int x = 0; x < N; ++x) r[x] = row[x];
+            load_row(iy, r);
             const T h0 = T(0.5) * r[0], hL = T(0.5) * r[L];
             if (!zlo) row_taps(c[2][iy], r, h0, hL, accP);  // output plane zp-1 sees this plane at dz = +1
             row_taps(c[1][iy], r, h0, hL, accC);
@@ -170,6 +172,19 @@ struct Sshex8LaplacianRow {
         }
     }
 
+    // dense-plane form: `plane` points at this element's plane zp; row yy starts at plane[yy * ystride]
+    template <int ZC>
+    B2_HD void step_class(const T *plane, const int ystride) {
+        const int yrow = y;
+        step_class_with<ZC, 1>([plane, ystride, yrow](const int iy, T(&r)[N]) {
+            int yy = yrow + iy - 1;
+            yy = yy < 0 ? 0 : (yy > L ? L : yy);
+            const T *row = plane + yy * ystride;
+#pragma unroll
+            for (int x = 0; x < N; ++x) r[x] = row[x];
+        });
+    }
+
     B2_HD void step(const int zp, const T *plane, const int ystride) {
         if (zp == 0)
             step_class<0>(plane, ystride);
@@ -179,26 +194,47 @@ struct Sshex8LaplacianRow {
             step_class<1>(plane, ystride);
     }
 
+    // compile-time plane index: phase zp % 3, no register rotation (see `acc`)
+    template <int ZP, class RowLoader>
+    B2_HD void step_static(RowLoader &&load_row) {
+        step_class_with<(ZP == 0 ? 0 : (ZP == L ? 2 : 1)), ZP % 3>(load_row);
+    }
+    // after step_static<ZP>: the finished output plane ZP-1 (ZP >= 1) ...
+    template <int ZP>
+    B2_HD T (&finished_plane())[N] {
+        return acc[(ZP + 2) % 3];
+    }
+    // ... which then becomes the accumulator of plane ZP+2
+    template <int ZP>
+    B2_HD void recycle() {
+#pragma unroll
+        for (int x = 0; x < N; ++x) acc[(ZP + 2) % 3][x] = T(0);
+    }
+
     // After step(zp) and a barrier: emit finished output plane zp-1 (zp >= 1), then rotate.
     B2_HD void write_and_rotate(const int zp, T *out_plane_prev, const int ystride) {
         if (zp > 0) {
             T *row = out_plane_prev + y * ystride;
 #pragma unroll
-            for (int x = 0; x < N; ++x) row[x] = accP[x];
+            for (int x = 0; x < N; ++x) row[x] = acc[0][x];
         }
+        rotate();
+    }
+
+    B2_HD void rotate() {
 #pragma unroll
         for (int x = 0; x < N; ++x) {
-            accP[x] = accC[x];
-            accC[x] = accN[x];
-            accN[x] = T(0);
+            acc[0][x] = acc[1][x];
+            acc[1][x] = acc[2][x];
+            acc[2][x] = T(0);
         }
     }
 
-    // After the last step/rotate: accP holds output plane L.
+    // After the last step/rotate: acc[0] holds output plane L.
     B2_HD void write_last(T *out_plane_L, const int ystride) {
         T *row = out_plane_L + y * ystride;
 #pragma unroll
-        for (int x = 0; x < N; ++x) row[x] = accP[x];
+        for (int x = 0; x < N; ++x) row[x] = acc[0][x];
     }
 };
 

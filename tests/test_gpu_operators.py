@@ -130,8 +130,8 @@ def test_hex8_linear_elasticity(oracles, real, scatter):
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
 @pytest.mark.parametrize("level", [2, 4, 8])
-@pytest.mark.parametrize("explicit", [0, 1])
-def test_sshex8_laplacian(oracles, real, level, explicit):
+@pytest.mark.parametrize("path", ["tma", "stream", "explicit"])
+def test_sshex8_laplacian(oracles, real, level, path):
     torch = _torch()
     from sfem_b200 import lib, mesh
 
@@ -143,16 +143,26 @@ def test_sshex8_laplacian(oracles, real, level, explicit):
     nn = m["n_nodes"]
     op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=level)
     assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
-    op.set_option("explicit_index", explicit)
+    assert op.get_option("tma_ok") == 1  # every entity box of the generator's numbering is a contiguous id run
+    op.set_option("explicit_index", int(path == "explicit"))
+    op.set_option("use_tma", int(path == "tma"))  # the TMA kernel serves level >= 4; level 2 streams either way
     u = np.random.default_rng(level).uniform(-1, 1, nn)
     ref = orc.sshex8_laplacian_apply(level, m["elements"], fff, u)
     x = torch.from_numpy(u).to(_dt(real)).cuda()
     y = torch.zeros_like(x)
     op.apply(x, y)
     assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    op.apply(x, y)  # accumulate
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
     y.fill_(3.0)
     op.apply_overwrite(x, y)
     assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    # vectors that are not 16-byte aligned (views shifted by one entry) must give the same answer
+    xs = torch.zeros(nn + 1, dtype=_dt(real), device="cuda")
+    ys = torch.full((nn + 1,), 7.0, dtype=_dt(real), device="cuda")
+    xs[1:] = x
+    op.apply_overwrite(xs[1:], ys[1:])
+    assert _rel(ys[1:].cpu().numpy(), ref) < TOL[real] and float(ys[0]) == 7.0
     ones = torch.ones_like(x)
     y.zero_()
     op.apply(ones, y)
