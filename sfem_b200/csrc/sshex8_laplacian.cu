@@ -260,12 +260,16 @@ struct Sshex8Laplacian final : OpBase {
         if constexpr (L == 8) {
             switch (stream_cfg) {
                 default:
-                case 0: return launch_stream_cfg<T, L, 1, 8, 6, PLAIN>(x, y, s);
+                case 0:  // fp32 runs the z-unrolled loop, which wants the ring slots static (depth 3 divides N = 9)
+                    if constexpr (F64) return launch_stream_cfg<T, L, 1, 8, 6, PLAIN>(x, y, s);
+                    else return launch_stream_cfg<T, L, 1, 8, 3, PLAIN>(x, y, s);
                 case 1: return launch_stream_cfg<T, L, 2, 4, 7, PLAIN>(x, y, s);
                 case 2: return launch_stream_cfg<T, L, 1, 8, 8, PLAIN>(x, y, s);
                 case 3: return launch_stream_cfg<T, L, 2, 4, 5, PLAIN>(x, y, s);
                 case 4: return launch_stream_cfg<T, L, 4, 2, F64 ? 7 : 9, PLAIN>(x, y, s);
                 case 5: return launch_stream_cfg<T, L, 1, 6, 9, PLAIN>(x, y, s);
+                case 6: return launch_stream_cfg<T, L, 1, 8, 9, PLAIN>(x, y, s);
+                case 7: return launch_stream_cfg<T, L, 1, 8, 3, PLAIN>(x, y, s);
             }
         }
         else if constexpr (L == 4) {

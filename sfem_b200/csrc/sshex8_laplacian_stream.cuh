@@ -22,6 +22,8 @@
 // Element headers. The plan stores, per element, 27 box descriptors (16 B each) + the 6 fp32 FFF + pad =
 // 29 x 16 B, fetched with cp.async one whole group ahead of their first use (three header buffers per team).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "sshex8_laplacian_core.cuh"
 
@@ -59,6 +61,14 @@ __device__ __forceinline__ void cp_async_value(T *smem, const T *gmem) {
         cp_async_8(smem, gmem);
     else
         cp_async_4(smem, gmem);
+}
+
+template <int Z0, int Z1, class F>
+__device__ __forceinline__ void static_for_z(F &&f) {
+    if constexpr (Z0 < Z1) {
+        f(std::integral_constant<int, Z0>{});
+        static_for_z<Z0 + 1, Z1>(f);
+    }
 }
 
 template <int TW>
@@ -308,6 +318,67 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     const int yrow = compute_lane ? tl - slot * N : 0;
     Sshex8LaplacianRow<T, L> row;
 
+    // Two forms of the same loop. fp32: z unrolled (static accumulator phases of the core: no register rotation, no
+    // per-step branching; 0.82 -> 0.71 ms at C3). fp64: the rolled loop -- unrolled, the 27 fp64 accumulators +
+    // 27 coefficients no longer fit 255 registers (spills, 0.98 -> 1.14 ms).
+    if constexpr (sizeof(T) == 4) {
+    // z is unrolled (static accumulator phases of the core: no register rotation, no per-step branching); ring and
+    // staging slots are compile-time whenever the ring depth divides N
+    constexpr bool RING_STATIC = (N % D == 0);
+#pragma unroll 1
+    for (int g_local = 0; g_local < my_groups; ++g_local) {
+        static_for_z<0, N>([&](auto zc) {
+            constexpr int zp = decltype(zc)::value;
+            const int t = g_local * N + zp;
+            const int rslot = RING_STATIC ? (zp % D) : (t % D);
+            const int s0 = (N % 3 == 0) ? (zp % 3) : (t % 3), s1 = (N % 3 == 0) ? ((zp + 1) % 3) : ((t + 1) % 3);
+            const T *plane = ring + (size_t)rslot * PLANE + slot * NN;
+            T *st0 = stage + (size_t)s0 * PLANE + slot * NN;
+            T *st1 = stage + (size_t)s1 * PLANE + slot * NN;
+            if constexpr (zp == 0) plane_set(g_local, 1, scI, scS);
+            if (compute_lane) {
+                if constexpr (zp == 0) {
+                    const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
+                    T f[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                    row.init(f, yrow);
+                }
+                row.template step_static<zp>([plane, yrow](const int iy, T(&r)[N]) {
+                    int yy = yrow + iy - 1;
+                    yy = yy < 0 ? 0 : (yy > L ? L : yy);
+                    const T *rp = plane + yy * N;
+#pragma unroll
+                    for (int x = 0; x < N; ++x) r[x] = rp[x];
+                });
+                if constexpr (zp > 0) {  // output plane zp-1 is final
+                    T *orow = st0 + yrow * N;
+                    const T(&fin)[N] = row.template finished_plane<zp>();
+#pragma unroll
+                    for (int x = 0; x < N; ++x) orow[x] = fin[x];
+                    row.template recycle<zp>();
+                }
+                if constexpr (zp == L) {
+                    T *orow = st1 + yrow * N;
+                    const T(&fin)[N] = row.template finished_plane<L + 1>();
+#pragma unroll
+                    for (int x = 0; x < N; ++x) orow[x] = fin[x];
+                }
+            }
+            cp_async_wait<D - 2>();
+            team_barrier<TW>(team);
+
+            // headers of group g+2 travel with the first plane of group g+1
+            const int s_next = t + D;
+            if (s_next < T_steps && (s_next % N) == 0) issue_headers(s_next / N + 1);
+            issue_plane(s_next);
+            cp_async_commit();
+
+            if constexpr (zp > 0) scatter_plane(stage + (size_t)s0 * PLANE, g_local, zp - 1);
+            if constexpr (zp == L) scatter_plane(stage + (size_t)s1 * PLANE, g_local, L);
+        });
+    }
+    } else {
     int g_local = 0, zp = 0;
 #pragma unroll 1
     for (int t = 0; t < T_steps; ++t) {
@@ -343,6 +414,7 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
             zp = 0;
             ++g_local;
         }
+    }
     }
     cp_async_wait<0>();
 }
