@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-solves", action="store_true", help="skip the CG / multigrid solve times (tools/solver_bench.py)")
     ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, vector kernels)")
     return ap.parse_args()
 
@@ -285,6 +286,13 @@ def run_b200(a):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None  # dram__bytes_read + dram__bytes_write of the dominant kernel, from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if a.real == "f64" and a.macro == 64 and a.level == 8:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     alg = op.algorithmic_bytes
     achieved = alg / (ms_kernel * 1e-3) / 1e9
     launches_per_step = op.launches(True) + (len(halo.send_idx) if halo is not None else 0)
@@ -302,7 +310,7 @@ def run_b200(a):
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "algorithmic_bytes": alg, "streamed_bytes": op.streamed_bytes(True),
+            "traffic": traffic, "algorithmic_bytes": alg, "streamed_bytes": op.streamed_bytes(True),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
             "kernel": "sshex8_laplacian_stream_kernel (+ the memsets of the skeleton ranges that belong to the call)",
             "kernel_ms": ms_kernel, "frac_of_8TBs_nominal": achieved / 8000.0,
@@ -321,6 +329,12 @@ def run_b200(a):
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+    if not a.no_solves and world == 1:
+        from tools.solver_bench import run_solves
+
+        del op, x, y
+        torch.cuda.empty_cache()
+        line["solves"] = run_solves(torch, cg_macro=a.macro, mg_macro=max(4, a.macro // 2), peak_gbs=peak)
     if a.extras:
         from tools.extras_bench import run_extras
 

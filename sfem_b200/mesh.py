@@ -286,3 +286,26 @@ def sshex8_derefine(L: int, elements: np.ndarray, to_level: int) -> np.ndarray:
         for xi in range(to_level + 1)
     ]
     return np.ascontiguousarray(elements[lat])
+
+
+def sshex8_face_nodes(L: int, elements: np.ndarray, m_points: np.ndarray, axis: int, value: float, eps=1e-6) -> np.ndarray:
+    """Node ids of an sshex8 box mesh on the plane {coordinate[axis] == value}, from the connectivity and the MACRO
+    corner coordinates only (no per-node coordinates: 135 M nodes x 3 floats is 1.6 GB at config C3). Only for
+    axis-aligned boxes whose macro elements are axis-aligned (the box generators above)."""
+    N = L + 1
+    rng = np.arange(N)
+    out = []
+    for side in (0, L):
+        fixed = [0, 0, 0]
+        fixed[axis] = side
+        corner = elements[sshex8_lidx(L, *fixed)]  # macro node id of that corner, per element
+        sel = np.abs(m_points[axis][corner].astype(np.float64) - value) < eps
+        if not sel.any():
+            continue
+        a, b = [d for d in range(3) if d != axis]
+        for i in rng:
+            for j in rng:
+                c = [0, 0, 0]
+                c[axis], c[a], c[b] = side, i, j
+                out.append(elements[sshex8_lidx(L, *c)][sel])
+    return np.unique(np.concatenate(out)).astype(np.int32) if out else np.zeros(0, dtype=np.int32)
