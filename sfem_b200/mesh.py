@@ -309,3 +309,23 @@ def sshex8_face_nodes(L: int, elements: np.ndarray, m_points: np.ndarray, axis: 
                 c[axis], c[a], c[b] = side, i, j
                 out.append(elements[sshex8_lidx(L, *c)][sel])
     return np.unique(np.concatenate(out)).astype(np.int32) if out else np.zeros(0, dtype=np.int32)
+
+
+def sshex8_face_nodes_macro(L: int, elements: np.ndarray, m_elements: np.ndarray, m_points: np.ndarray, axis: int,
+                            value: float, eps=1e-6) -> np.ndarray:
+    """Like sshex8_face_nodes, for connectivity whose corner rows are NOT macro node ids (e.g. the owned-first local
+    numbering of sfem_b200.parallel): the macro elements on the plane are found through `m_elements` / `m_points`."""
+    N = L + 1
+    out = []
+    a, b = [d for d in range(3) if d != axis]
+    for side in (0, 1):
+        k = int(np.flatnonzero((HEX8_CORNERS[:, axis] == side) & (HEX8_CORNERS[:, a] == 0) & (HEX8_CORNERS[:, b] == 0))[0])
+        sel = np.abs(m_points[axis][m_elements[k]].astype(np.float64) - value) < eps
+        if not sel.any():
+            continue
+        for i in range(N):
+            for j in range(N):
+                c = [0, 0, 0]
+                c[axis], c[a], c[b] = side * L, i, j
+                out.append(elements[sshex8_lidx(L, *c)][sel])
+    return np.unique(np.concatenate(out)).astype(np.int32) if out else np.zeros(0, dtype=np.int32)
