@@ -43,6 +43,8 @@ extern "C" {
 #define B200FEM_SCATTER_AUTO 0
 #define B200FEM_SCATTER_ATOMIC 1  /* red.global.add on every element dof                        */
 #define B200FEM_SCATTER_COLORED 2 /* element colouring, plain read-modify-write, one launch/colour */
+#define B200FEM_SCATTER_PATCH 3   /* element patches staged in shared memory, fixed-order sums, one red per
+                                     (patch, node): the default of the tet4 / hex8 operators              */
 
 typedef struct b200fem_op_s *b200fem_op_t; /* opaque operator plan (device connectivity + geometry) */
 

@@ -25,6 +25,7 @@
 #include "coloring.cuh"
 #include "common.cuh"
 #include "hex8_local.cuh"
+#include "patch.cuh"
 
 namespace b200fem {
 
@@ -201,14 +202,73 @@ __global__ void __launch_bounds__(128)
 
 // ---------------------------------------------------------------------------------------------
 
+// element operators of the patch kernel (patch.cuh): same arithmetic as the kernels above
+template <typename T>
+struct Hex8LaplacianLocal {
+    const float *fff;  // SoA [6][ne]
+    ptrdiff_t ne;
+    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[8], T (&out)[8]) const {
+        T f[6], ul[8], ol[8];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ul[kVtkToLex[v]] = uin[v];
+        hex8_laplacian_local(f, ul, ol);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) out[v] = ol[kVtkToLex[v]];
+    }
+};
+
+template <typename T>
+struct Hex8LinearElasticityLocal {
+    const float *adjugate;     // SoA [9][ne]
+    const float *determinant;  // [ne]
+    ptrdiff_t ne;
+    T mu, lambda;
+    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[24], T (&out)[24]) const {
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
+        const T det = (T)ldg_stream(&determinant[e]);
+        T c[3][8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) c[a][kVtkToLex[v]] = uin[v * 3 + a];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) haar_forward(c[a]);
+        T AAt_mu[6], lam_idet, mu_idet;
+        le_prepare(A, det, mu, lambda, AAt_mu, lam_idet, mu_idet);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            T O[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) O[k] = T(0);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                T t[3][3];
+                le_coeff(A, AAt_mu, lam_idet, mu_idet, a, b, t);
+                haar_grad_grad(t, c[b], O);
+            }
+            haar_inverse_unscaled(O);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) out[v * 3 + a] = T(0.125) * O[kVtkToLex[v]];
+        }
+    }
+};
+
 struct Hex8Laplacian final : OpBase {
     DeviceArray<int32_t> elements;  // [8][ne]
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
+    PatchPlan patch;
+    static constexpr int kPatchE = 512;
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(1, sizeof(T)) <= 200 * 1024)
+            return launch_patch_apply<T, 8, 1, kPatchE, 256>(patch, Hex8LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
@@ -250,10 +310,15 @@ struct Hex8LinearElasticity final : OpBase {
     DeviceArray<float> determinant; // [ne]
     double mu = 1, lambda = 1;
     ColorPlan colors;
+    PatchPlan patch;
+    static constexpr int kPatchE = 256;
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(3, sizeof(T)) <= 200 * 1024)
+            return launch_patch_apply<T, 8, 3, kPatchE, 128>(
+                patch, Hex8LinearElasticityLocal<T>{adjugate.ptr, determinant.ptr, ne, (T)mu, (T)lambda}, x, y, s);
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
@@ -317,13 +382,16 @@ OpBase *make_hex8_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *el
     op->nn = nn;
     op->nxe = 8;
     op->geom_bytes_per_elem = 24;
+    // measured at 128^3 (profiles/r01f_extras_patch.jsonl): with 8 elements per node the patch kernel does not beat
+    // RED.ADD for hex8 in fp64 (0.354 vs 0.303 ms elasticity, 0.112 vs 0.105 ms Laplacian); it stays selectable
     op->scatter = B200FEM_SCATTER_ATOMIC;
     std::vector<int32_t> el;
     std::vector<float> f;
     soa_copy(8, ne, elements, el);
     aos_to_soa(6, ne, fff, f);
     op->colors.keep(8, ne, elements);
-    if (op->elements.upload(el.data(), el.size()) || op->fff.upload(f.data(), f.size())) {
+    if (op->patch.build(8, Hex8Laplacian::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
+        op->fff.upload(f.data(), f.size())) {
         delete op;
         return nullptr;
     }
@@ -344,6 +412,8 @@ OpBase *make_hex8_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     op->nn = nn;
     op->nxe = 8;
     op->geom_bytes_per_elem = 40;
+    // measured at 128^3 (profiles/r01f_extras_patch.jsonl): with 8 elements per node the patch kernel does not beat
+    // RED.ADD for hex8 in fp64 (0.354 vs 0.303 ms elasticity, 0.112 vs 0.105 ms Laplacian); it stays selectable
     op->scatter = B200FEM_SCATTER_ATOMIC;
     op->mu = mu;
     op->lambda = lambda;
@@ -352,7 +422,8 @@ OpBase *make_hex8_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     soa_copy(8, ne, elements, el);
     aos_to_soa(9, ne, adjugate, a);
     op->colors.keep(8, ne, elements);
-    if (op->elements.upload(el.data(), el.size()) || op->adjugate.upload(a.data(), a.size()) ||
+    if (op->patch.build(8, Hex8LinearElasticity::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
+        op->adjugate.upload(a.data(), a.size()) ||
         op->determinant.upload(determinant, (size_t)ne)) {
         delete op;
         return nullptr;

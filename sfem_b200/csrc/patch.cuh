@@ -1,0 +1,183 @@
+// Atomic-free scatter for the thread-per-element operators (tet4 / hex8): element PATCHES staged in shared memory.
+//
+// The per-element kernels gather NXE values and scatter NXE results with one 8-byte access each: every access moves
+// a 32-byte L2 sector and every result is a RED.ADD, so the L2 / atomic units limit them at 13-26 % of the HBM
+// roofline although the streams are perfectly coalesced. A patch is a run of E consecutive elements. At plan creation
+// we record, per patch: the sorted list of the U unique nodes it touches, the 16-bit LOCAL index of every element
+// corner, and a node -> (corner, element) incidence list in CSR form. The kernel then
+//   1. stages x[unique nodes] in shared memory (U coalesced-ish loads instead of NXE * E gathers),
+//   2. runs the element operator from shared memory and writes the NXE * BS results of every element to its own
+//      shared-memory slots (no conflict: slot = (component, corner, element)),
+//   3. sums, per unique node, the slots of its incidence list in a fixed order and issues ONE RED.ADD per
+//      (node, component) -- 4 E / U ~ 12 times fewer global atomics for tet4; nodes interior to a patch could use
+//      plain stores, the REDs that remain are the patch-boundary nodes.
+// The sum order inside a patch is fixed, so two applies differ only in the order of the cross-patch REDs.
+// Index traffic: 2 * NXE * 2 B per element (local indices + incidence slots) + 6 B per unique node, against
+// NXE * 4 B of global indices -- the same bytes, all of them coalesced streams.
+//
+// Locality is the caller's: patches follow the element order. The reference reorders its meshes along a space-filling
+// curve before use (smesh::SFC::reorder); sfem_b200/mesh.py offers the same for the synthetic boxes.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200fem {
+
+struct PatchArrays {
+    ptrdiff_t ne, nchunks;
+    const uint16_t *lidx;      // [nchunks][NXE][E] local node index of every element corner
+    const int32_t *unodes;     // concatenated unique node ids of every patch
+    const int64_t *chunk_uoff; // [nchunks + 1] offsets into unodes
+    const uint16_t *nslot;     // [nchunks][NXE * E] incidence slots (corner * E + local element), grouped by node
+    const uint16_t *noff;      // per patch [U + 1] offsets into its nslot block; patch c starts at chunk_uoff[c] + c
+};
+
+struct PatchPlan {
+    int nxe = 0, E = 0, max_u = 0;
+    ptrdiff_t ne = 0, nchunks = 0;
+    double avg_u = 0;
+    DeviceArray<uint16_t> lidx, nslot, noff;
+    DeviceArray<int32_t> unodes;
+    DeviceArray<int64_t> chunk_uoff;
+    bool ready = false;
+
+    PatchArrays arrays() const { return PatchArrays{ne, nchunks, lidx.ptr, unodes.ptr, chunk_uoff.ptr, nslot.ptr, noff.ptr}; }
+
+    // elements: host SoA [nxe][ne]
+    int build(int nxe_, int E_, ptrdiff_t ne_, const int32_t *const *elements) {
+        nxe = nxe_;
+        E = E_;
+        ne = ne_;
+        nchunks = (ne + E - 1) / E;
+        if ((size_t)nxe * E > 65535) B2_FAIL("patch plan: NXE * E must fit 16 bits");
+        std::vector<uint16_t> h_lidx((size_t)nchunks * nxe * E, 0), h_nslot((size_t)nchunks * nxe * E, 0), h_noff;
+        std::vector<int32_t> h_unodes;
+        std::vector<int64_t> h_uoff((size_t)nchunks + 1, 0);
+        h_unodes.reserve((size_t)ne);
+        std::vector<int32_t> nodes, cnt;
+        max_u = 0;
+        for (ptrdiff_t c = 0; c < nchunks; ++c) {
+            const ptrdiff_t e0 = c * E, nel = std::min<ptrdiff_t>(E, ne - e0);
+            nodes.clear();
+            for (int v = 0; v < nxe; ++v) nodes.insert(nodes.end(), elements[v] + e0, elements[v] + e0 + nel);
+            std::sort(nodes.begin(), nodes.end());
+            nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+            const int U = (int)nodes.size();
+            if (U > 65535) B2_FAIL("patch plan: more than 65535 unique nodes in one patch");
+            max_u = std::max(max_u, U);
+            h_uoff[(size_t)c + 1] = h_uoff[(size_t)c] + U;
+            h_unodes.insert(h_unodes.end(), nodes.begin(), nodes.end());
+            // local indices and incidence counts
+            cnt.assign((size_t)U + 1, 0);
+            uint16_t *li = &h_lidx[(size_t)c * nxe * E];
+            for (int v = 0; v < nxe; ++v)
+                for (ptrdiff_t e = 0; e < nel; ++e) {
+                    const int j = (int)(std::lower_bound(nodes.begin(), nodes.end(), elements[v][e0 + e]) - nodes.begin());
+                    li[(size_t)v * E + e] = (uint16_t)j;
+                    cnt[(size_t)j + 1]++;
+                }
+            for (int j = 0; j < U; ++j) cnt[(size_t)j + 1] += cnt[(size_t)j];
+            const size_t nb = h_noff.size();
+            h_noff.resize(nb + (size_t)U + 1);
+            for (int j = 0; j <= U; ++j) h_noff[nb + (size_t)j] = (uint16_t)cnt[(size_t)j];
+            uint16_t *ns = &h_nslot[(size_t)c * nxe * E];
+            std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+            for (int v = 0; v < nxe; ++v)
+                for (ptrdiff_t e = 0; e < nel; ++e) {
+                    const int j = li[(size_t)v * E + e];
+                    ns[(size_t)fill[(size_t)j]++] = (uint16_t)(v * E + e);
+                }
+        }
+        avg_u = nchunks ? double(h_unodes.size()) / double(nchunks) : 0;
+        if (lidx.upload(h_lidx.data(), h_lidx.size()) || nslot.upload(h_nslot.data(), h_nslot.size()) ||
+            noff.upload(h_noff.data(), h_noff.size()) || unodes.upload(h_unodes.data(), h_unodes.size()) ||
+            chunk_uoff.upload(h_uoff.data(), h_uoff.size()))
+            return B200FEM_FAILURE;
+        ready = true;
+        return B200FEM_SUCCESS;
+    }
+
+    // streamed index bytes per apply
+    double index_bytes() const { return double(lidx.bytes() + nslot.bytes() + noff.bytes() + unodes.bytes() + chunk_uoff.bytes()); }
+    size_t smem_bytes(int bs, int real_size) const { return ((size_t)max_u * bs + (size_t)nxe * bs * E) * real_size; }
+};
+
+// Local: __device__ void operator()(ptrdiff_t e, const T (&uin)[NXE * BS], T (&out)[NXE * BS]) const
+// with uin / out ordered [corner][component]. EPT = elements per thread per patch = E / BT.
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+__global__ void __launch_bounds__(BT)
+    patch_apply_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
+    extern __shared__ __align__(16) unsigned char patch_smem[];
+    T *xs = reinterpret_cast<T *>(patch_smem);   // [max_u][BS]
+    T *contrib = xs + (size_t)max_u * BS;         // [BS][NXE][E]
+    const int tid = threadIdx.x;
+    for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
+        const int64_t u0 = p.chunk_uoff[c];
+        const int U = (int)(p.chunk_uoff[c + 1] - u0);
+        const ptrdiff_t e0 = c * E;
+        const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
+        // 1. stage the unique nodes' values
+        for (int j = tid; j < U; j += BT) {
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) xs[j * BS + a] = u[node * BS + a];
+        }
+        __syncthreads();
+        // 2. element operator from shared memory into per-element slots
+        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
+        for (int e = tid; e < nel; e += BT) {
+            T uin[NXE * BS], out[NXE * BS];
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) {
+                const int j = ldg_stream(&li[v * E + e]);
+#pragma unroll
+                for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[j * BS + a];
+            }
+            local(e0 + e, uin, out);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v)
+#pragma unroll
+                for (int a = 0; a < BS; ++a) contrib[(a * NXE + v) * E + e] = out[v * BS + a];
+        }
+        __syncthreads();
+        // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
+        const uint16_t *ns = p.nslot + (size_t)c * NXE * E;
+        const uint16_t *no = p.noff + u0 + c;
+        for (int j = tid; j < U; j += BT) {
+            const int b = no[j], eend = no[j + 1];
+            T acc[BS];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) acc[a] = T(0);
+            for (int s = b; s < eend; ++s) {
+                const int slot = ldg_stream(&ns[s]);
+#pragma unroll
+                for (int a = 0; a < BS; ++a) acc[a] += contrib[a * NXE * E + slot];
+            }
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], acc[a]);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+int launch_patch_apply(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
+    auto kern = patch_apply_kernel<T, NXE, BS, E, BT, Local>;
+    const size_t smem = plan.smem_bytes(BS, (int)sizeof(T));
+    static size_t configured = 0;
+    if (smem > configured) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (plan.nchunks == 0) return B200FEM_SUCCESS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+    const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);
+    kern<<<grid, BT, smem, s>>>(plan.arrays(), local, plan.max_u, x, y);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+}  // namespace b200fem

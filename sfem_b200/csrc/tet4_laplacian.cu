@@ -15,11 +15,13 @@
 // the 4 scatter-adds per element hit L2 (vectors are small next to 40 B/element of streams).
 // One thread per element; scatter = RED.ADD (B200FEM_SCATTER_ATOMIC) or element colouring.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
 #include "coloring.cuh"
 #include "common.cuh"
+#include "patch.cuh"
 
 namespace b200fem {
 
@@ -58,6 +60,26 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// element operator of the patch kernel (patch.cuh): same arithmetic as above
+template <typename T>
+struct Tet4LaplacianLocal {
+    const float *fff;  // SoA [6][ne]
+    ptrdiff_t ne;
+    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[4], T (&out)[4]) const {
+        T f[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+        const T d1 = uin[1] - uin[0], d2 = uin[2] - uin[0], d3 = uin[3] - uin[0];
+        const T w0 = f[0] * d1 + f[1] * d2 + f[2] * d3;
+        const T w1 = f[1] * d1 + f[3] * d2 + f[4] * d3;
+        const T w2 = f[2] * d1 + f[4] * d2 + f[5] * d3;
+        out[0] = -(w0 + w1 + w2);
+        out[1] = w0;
+        out[2] = w1;
+        out[3] = w2;
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     tet4_laplacian_diag_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements,
@@ -78,10 +100,15 @@ struct Tet4Laplacian final : OpBase {
     DeviceArray<int32_t> elements;  // [4][ne]
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
+    PatchPlan patch;
+    static constexpr int kPatchE = 1024;
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(1, sizeof(T)) <= 200 * 1024) {
+            return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+        }
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
@@ -118,6 +145,14 @@ struct Tet4Laplacian final : OpBase {
         int k = (scatter == B200FEM_SCATTER_COLORED && colors.ready) ? colors.ncolors() : 1;
         return k + (overwrite ? 1 : 0);
     }
+    double streamed_bytes(bool overwrite) const override {
+        const double idx = (scatter == B200FEM_SCATTER_PATCH && patch.ready) ? patch.index_bytes() : 16.0 * ne;
+        return idx + 24.0 * ne + double(nn) * real_type * (overwrite ? 2.0 : 3.0);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "patch_avg_unique_nodes")) { *value = (int)patch.avg_u; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
 };
 
 OpBase *make_tet4_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type) {
@@ -128,7 +163,7 @@ OpBase *make_tet4_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *el
     op->nn = nn;
     op->nxe = 4;
     op->geom_bytes_per_elem = 24;
-    op->scatter = B200FEM_SCATTER_ATOMIC;
+    op->scatter = B200FEM_SCATTER_PATCH;
     if (!check_indices(4, ne, nn, elements)) {
         set_error("tet4 laplacian: node index out of range");
         delete op;
@@ -140,7 +175,8 @@ OpBase *make_tet4_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *el
     std::vector<float> f((size_t)6 * ne);
     for (ptrdiff_t e = 0; e < ne; ++e)
         for (int k = 0; k < 6; ++k) f[(size_t)k * ne + e] = fff[e * 6 + k];
-    if (op->elements.upload(el.data(), el.size()) || op->fff.upload(f.data(), f.size())) {
+    if (op->patch.build(4, Tet4Laplacian::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
+        op->fff.upload(f.data(), f.size())) {
         delete op;
         return nullptr;
     }

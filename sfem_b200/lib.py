@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libb200fem.so")
 
 F32, F64 = 4, 8
 TET4, HEX8, SSHEX8 = 4, 8, 800
-SCATTER_AUTO, SCATTER_ATOMIC, SCATTER_COLORED = 0, 1, 2
+SCATTER_AUTO, SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_PATCH = 0, 1, 2, 3
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

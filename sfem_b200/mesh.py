@@ -329,3 +329,27 @@ def sshex8_face_nodes_macro(L: int, elements: np.ndarray, m_elements: np.ndarray
                 c[axis], c[a], c[b] = side * L, i, j
                 out.append(elements[sshex8_lidx(L, *c)][sel])
     return np.unique(np.concatenate(out)).astype(np.int32) if out else np.zeros(0, dtype=np.int32)
+
+
+def _morton3(ix, iy, iz, bits=10):
+    code = np.zeros(ix.shape, dtype=np.int64)
+    for b in range(bits):
+        code |= ((ix >> b) & 1) << (3 * b) | ((iy >> b) & 1) << (3 * b + 1) | ((iz >> b) & 1) << (3 * b + 2)
+    return code
+
+
+def sfc_reorder(elements: np.ndarray, points: np.ndarray, bits=10):
+    """Reorder nodes and elements along a Morton space-filling curve -- the step the reference applies to every mesh
+    before use (smesh::SFC::reorder; its source is not in the checkout, so this is the textbook Z-order on quantised
+    coordinates, not a restatement). Returns (elements, points, node_permutation old->new)."""
+    p = np.asarray(points, dtype=np.float64)
+    lo, hi = p.min(axis=1, keepdims=True), p.max(axis=1, keepdims=True)
+    q = np.minimum(((p - lo) / np.maximum(hi - lo, 1e-300) * (2**bits)).astype(np.int64), 2**bits - 1)
+    node_order = np.argsort(_morton3(q[0], q[1], q[2], bits), kind="stable")
+    new_id = np.empty(node_order.size, dtype=np.int64)
+    new_id[node_order] = np.arange(node_order.size)
+    el = new_id[np.asarray(elements, dtype=np.int64)]
+    cen = p[:, np.asarray(elements, dtype=np.int64)].mean(axis=1)  # [3][ne]
+    qc = np.minimum(((cen - lo) / np.maximum(hi - lo, 1e-300) * (2**bits)).astype(np.int64), 2**bits - 1)
+    el = el[:, np.argsort(_morton3(qc[0], qc[1], qc[2], bits), kind="stable")]
+    return np.ascontiguousarray(el.astype(idx_t)), np.ascontiguousarray(np.asarray(points)[:, node_order]), new_id

@@ -42,7 +42,7 @@ def _orc(oracles, real):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
-@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+@pytest.mark.parametrize("scatter", ["patch", "atomic", "colored"])
 def test_tet4_laplacian(oracles, real, scatter):
     torch = _torch()
     from sfem_b200 import lib, mesh
@@ -53,7 +53,8 @@ def test_tet4_laplacian(oracles, real, scatter):
     fff = orc.tet4_fff_fill(el, pts)
     nn = pts.shape[1]
     op = lib.laplacian(lib.TET4, el, fff, nn, _dt(real))
-    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    assert op.get_option("scatter") == lib.SCATTER_PATCH  # the default for tet4 (24 tets per node)
+    op.set_option("scatter", {"patch": lib.SCATTER_PATCH, "colored": lib.SCATTER_COLORED, "atomic": lib.SCATTER_ATOMIC}[scatter])
     for name, u in _fields(pts, 3).items():
         ref = orc.tet4_laplacian_apply_opt(el, fff, u)
         x = torch.from_numpy(u).to(_dt(real)).cuda()
@@ -77,7 +78,7 @@ def test_tet4_laplacian(oracles, real, scatter):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
-@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+@pytest.mark.parametrize("scatter", ["patch", "atomic", "colored"])
 def test_hex8_laplacian(oracles, real, scatter):
     torch = _torch()
     from sfem_b200 import lib, mesh
@@ -88,7 +89,8 @@ def test_hex8_laplacian(oracles, real, scatter):
     fff = orc.hex8_fff_fill(el, pts)
     nn = pts.shape[1]
     op = lib.laplacian(lib.HEX8, el, fff, nn, _dt(real))
-    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    assert op.get_option("scatter") == lib.SCATTER_ATOMIC  # the default for hex8
+    op.set_option("scatter", {"patch": lib.SCATTER_PATCH, "colored": lib.SCATTER_COLORED, "atomic": lib.SCATTER_ATOMIC}[scatter])
     for name, u in _fields(pts, 4).items():
         ref = orc.hex8_laplacian_apply_opt(el, fff, u)
         x = torch.from_numpy(u).to(_dt(real)).cuda()
@@ -101,7 +103,7 @@ def test_hex8_laplacian(oracles, real, scatter):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
-@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+@pytest.mark.parametrize("scatter", ["patch", "atomic", "colored"])
 def test_hex8_linear_elasticity(oracles, real, scatter):
     torch = _torch()
     from sfem_b200 import lib, mesh
@@ -113,7 +115,8 @@ def test_hex8_linear_elasticity(oracles, real, scatter):
     nn = pts.shape[1]
     mu, lam = 1.3, 0.7
     op = lib.linear_elasticity(lib.HEX8, el, adj, det, mu, lam, nn, _dt(real))
-    op.set_option("scatter", lib.SCATTER_COLORED if scatter == "colored" else lib.SCATTER_ATOMIC)
+    assert op.get_option("scatter") == lib.SCATTER_ATOMIC  # the default for hex8
+    op.set_option("scatter", {"patch": lib.SCATTER_PATCH, "colored": lib.SCATTER_COLORED, "atomic": lib.SCATTER_ATOMIC}[scatter])
     assert op.block_size == 3 and op.rows == nn * 3
     u = np.random.default_rng(5).uniform(-1, 1, nn * 3)
     ref = orc.hex8_linear_elasticity_apply(el, adj, det, mu, lam, u, nn)

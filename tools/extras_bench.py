@@ -53,43 +53,56 @@ def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "transfer",
 
     out = []
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")
+    SC = {"patch": lib.SCATTER_PATCH, "atomic": lib.SCATTER_ATOMIC}
     if "c1" in which:  # tet4 Laplacian fp64, 56^3 nodes (BASELINE config 1) and a 100x larger cube
         for n in (56, 260):
-            el, pts = mesh.box_tet4(n, n, n)
-            fff = lib.fff_fill(lib.TET4, el, pts)
-            nn = pts.shape[1]
-            for scatter in ("atomic",):
+            el0, pts0 = mesh.box_tet4(n, n, n)
+            for order in ("generator order", "SFC order"):
+                el, pts = (el0, pts0) if order == "generator order" else mesh.sfc_reorder(el0, pts0)[:2]
+                fff = lib.fff_fill(lib.TET4, el, pts)
+                nn = pts.shape[1]
                 op = lib.laplacian(lib.TET4, el, fff, nn, torch.float64)
                 x = torch.rand(nn, dtype=torch.float64, device="cuda")
                 y = torch.zeros_like(x)
-                ms = _time(lambda: op.apply_overwrite(x, y), torch, flush=flush if n == 56 else None)
-                out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, y = A x" + (", L2 flushed" if n == 56 else "") + ")",
-                                  nn, op.algorithmic_bytes, ms))
-                if n == 56:
-                    ms = _time(lambda: op.apply_overwrite(x, y), torch)
-                    out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, y = A x, L2-resident)", nn,
-                                      op.algorithmic_bytes, ms))
+                for scatter in ("patch", "atomic"):
+                    op.set_option("scatter", SC[scatter])
+                    extra = {"scatter": scatter, "order": order, "patch_avg_unique_nodes": op.get_option("patch_avg_unique_nodes")}
+                    ms = _time(lambda: op.apply_overwrite(x, y), torch, flush=flush if n == 56 else None)
+                    out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, {order}, y = A x" + (", L2 flushed" if n == 56 else "") + ")",
+                                      nn, op.algorithmic_bytes, ms, extra))
+                    if n == 56:
+                        ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                        out.append(_entry(f"C1 tet4 Laplacian f64 {n}^3 nodes ({scatter}, {order}, y = A x, L2-resident)", nn,
+                                          op.algorithmic_bytes, ms, extra))
                 del op
     if "c2" in which or "hex8lap" in which:
-        el, pts = mesh.box_hex8(129, 129, 129)
-        nn = pts.shape[1]
-        if "c2" in which:  # hex8 linear elasticity fp64, 128^3 elements (BASELINE config 2)
-            adj, det = lib.adjugate_and_det_fill(lib.HEX8, el, pts)
-            for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
-                op = lib.linear_elasticity(lib.HEX8, el, adj, det, 1.0, 1.0, nn, dt)
-                x = torch.rand(nn * 3, dtype=dt, device="cuda")
+        el0, pts0 = mesh.box_hex8(129, 129, 129)
+        for order in ("generator order", "SFC order"):
+            el, pts = (el0, pts0) if order == "generator order" else mesh.sfc_reorder(el0, pts0)[:2]
+            nn = pts.shape[1]
+            if "c2" in which:  # hex8 linear elasticity fp64, 128^3 elements (BASELINE config 2)
+                adj, det = lib.adjugate_and_det_fill(lib.HEX8, el, pts)
+                for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
+                    op = lib.linear_elasticity(lib.HEX8, el, adj, det, 1.0, 1.0, nn, dt)
+                    x = torch.rand(nn * 3, dtype=dt, device="cuda")
+                    y = torch.zeros_like(x)
+                    for scatter in ("patch", "atomic"):
+                        op.set_option("scatter", SC[scatter])
+                        ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                        out.append(_entry(f"C2 hex8 linear elasticity {rt} 128^3 ({scatter}, {order}, y = A x)", nn * 3,
+                                          op.algorithmic_bytes, ms, {"scatter": scatter, "order": order}))
+                    del op
+            if "hex8lap" in which:
+                fff = lib.fff_fill(lib.HEX8, el, pts)
+                op = lib.laplacian(lib.HEX8, el, fff, nn, torch.float64)
+                x = torch.rand(nn, dtype=torch.float64, device="cuda")
                 y = torch.zeros_like(x)
-                ms = _time(lambda: op.apply_overwrite(x, y), torch)
-                out.append(_entry(f"C2 hex8 linear elasticity {rt} 128^3 (y = A x)", nn * 3, op.algorithmic_bytes, ms))
+                for scatter in ("patch", "atomic"):
+                    op.set_option("scatter", SC[scatter])
+                    ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                    out.append(_entry(f"hex8 Laplacian f64 128^3 ({scatter}, {order}, y = A x)", nn, op.algorithmic_bytes, ms,
+                                      {"scatter": scatter, "order": order}))
                 del op
-        if "hex8lap" in which:
-            fff = lib.fff_fill(lib.HEX8, el, pts)
-            op = lib.laplacian(lib.HEX8, el, fff, nn, torch.float64)
-            x = torch.rand(nn, dtype=torch.float64, device="cuda")
-            y = torch.zeros_like(x)
-            ms = _time(lambda: op.apply_overwrite(x, y), torch)
-            out.append(_entry("hex8 Laplacian f64 128^3 (y = A x)", nn, op.algorithmic_bytes, ms))
-            del op
     if "c3f32" in which:
         m = mesh.sshex8_box(8, 64, 64, 64, with_points=False)
         fff = lib.fff_fill(lib.HEX8, m["m_elements"], m["m_points"])
