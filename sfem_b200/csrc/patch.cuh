@@ -106,6 +106,56 @@ struct PatchPlan {
 
 // Local: __device__ void operator()(ptrdiff_t e, const T (&uin)[NXE * BS], T (&out)[NXE * BS]) const
 // with uin / out ordered [corner][component]. EPT = elements per thread per patch = E / BT.
+// Variant without the incidence lists: results are accumulated with shared-memory atomics into one slot per unique
+// node (ATOMS, order not fixed), then one RED per (node, component). Streams 2 * NXE bytes per element less.
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+__global__ void __launch_bounds__(BT)
+    patch_apply_smem_atomic_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u,
+                                   T *__restrict__ y) {
+    extern __shared__ __align__(16) unsigned char patch_smem[];
+    T *xs = reinterpret_cast<T *>(patch_smem);  // [max_u][BS]
+    T *ys = xs + (size_t)max_u * BS;             // [max_u][BS]
+    const int tid = threadIdx.x;
+    for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
+        const int64_t u0 = p.chunk_uoff[c];
+        const int U = (int)(p.chunk_uoff[c + 1] - u0);
+        const ptrdiff_t e0 = c * E;
+        const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
+        for (int j = tid; j < U; j += BT) {
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) {
+                xs[j * BS + a] = u[node * BS + a];
+                ys[j * BS + a] = T(0);
+            }
+        }
+        __syncthreads();
+        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
+        for (int e = tid; e < nel; e += BT) {
+            T uin[NXE * BS], out[NXE * BS];
+            int jj[NXE];
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) {
+                jj[v] = ldg_stream(&li[v * E + e]);
+#pragma unroll
+                for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[jj[v] * BS + a];
+            }
+            local(e0 + e, uin, out);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v)
+#pragma unroll
+                for (int a = 0; a < BS; ++a) atomicAdd(&ys[jj[v] * BS + a], out[v * BS + a]);
+        }
+        __syncthreads();
+        for (int j = tid; j < U; j += BT) {
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], ys[j * BS + a]);
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T, int NXE, int BS, int E, int BT, class Local>
 __global__ void __launch_bounds__(BT)
     patch_apply_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
@@ -161,6 +211,23 @@ __global__ void __launch_bounds__(BT)
         }
         __syncthreads();
     }
+}
+
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+int launch_patch_apply_smem_atomic(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
+    auto kern = patch_apply_smem_atomic_kernel<T, NXE, BS, E, BT, Local>;
+    const size_t smem = (size_t)plan.max_u * BS * 2 * sizeof(T);
+    static size_t configured = 0;
+    if (smem > configured) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (plan.nchunks == 0) return B200FEM_SUCCESS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+    const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);
+    kern<<<grid, BT, smem, s>>>(plan.arrays(), local, plan.max_u, x, y);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
 }
 
 template <typename T, int NXE, int BS, int E, int BT, class Local>

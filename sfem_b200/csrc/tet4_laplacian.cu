@@ -101,12 +101,15 @@ struct Tet4Laplacian final : OpBase {
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
     PatchPlan patch;
+    int patch_smem_atomic = 0;  // 1 = shared-memory atomics instead of the incidence lists (order not fixed)
     static constexpr int kPatchE = 1024;
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(1, sizeof(T)) <= 200 * 1024) {
+            if (patch_smem_atomic)
+                return launch_patch_apply_smem_atomic<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         }
         if (scatter == B200FEM_SCATTER_COLORED) {
@@ -148,6 +151,10 @@ struct Tet4Laplacian final : OpBase {
     double streamed_bytes(bool overwrite) const override {
         const double idx = (scatter == B200FEM_SCATTER_PATCH && patch.ready) ? patch.index_bytes() : 16.0 * ne;
         return idx + 24.0 * ne + double(nn) * real_type * (overwrite ? 2.0 : 3.0);
+    }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "patch_smem_atomic")) { patch_smem_atomic = value; return B200FEM_SUCCESS; }
+        return OpBase::set_option(key, value);
     }
     int get_option(const char *key, int *value) override {
         if (!strcmp(key, "patch_avg_unique_nodes")) { *value = (int)patch.avg_u; return B200FEM_SUCCESS; }
