@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: overlap the halo gather with the ghost-independent elements (b200fem_op_apply_range). Off by "
+                         "default: measured on 2 GPUs it is slower (1.19 vs 1.10 ms per step) -- three launches of the "
+                         "persistent kernel and 8 reserved SMs cost more than the 0.12 ms exchange they hide")
     ap.add_argument("--no-solves", action="store_true", help="skip the CG / multigrid solve times (tools/solver_bench.py)")
     ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, vector kernels)")
     return ap.parse_args()
@@ -222,11 +226,25 @@ def run_b200(a):
     x = torch.from_numpy(u_host).to(dev)
     y = torch.zeros_like(x)
     halo = parallel.HaloExchange(lm, 1, device=dev) if lm is not None else None
+    overlapped = parallel.OverlappedApply(op, lm, halo, dev) if (halo is not None and a.overlap) else None
 
     def step():
+        if overlapped is not None:
+            overlapped.apply_overwrite(x, y)
+            return
         if halo is not None:
             halo.gather(x)
         op.apply_overwrite(x, y)
+
+    if overlapped is not None and overlapped.range:
+        # one-off check: the overlapped schedule computes what gather-then-apply computes (differences = RED order)
+        y_ref = torch.zeros_like(y)
+        halo.gather(x)
+        op.apply_overwrite(x, y_ref)
+        overlapped.apply_overwrite(x, y)
+        rel = float((y[:n_owned] - y_ref[:n_owned]).norm() / y_ref[:n_owned].norm())
+        assert rel < 1e-12, f"overlapped apply differs from gather-then-apply: {rel}"
+        del y_ref
 
     def barrier():
         if dist is not None:
@@ -306,7 +324,9 @@ def run_b200(a):
             "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair as one call (b200fem_op_apply_overwrite)",
             "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
             "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
-            "parallelism": f"z-slab x{world}, owned/ghost/aura, NCCL halo gather of x per step" if world > 1 else "single GPU",
+            "parallelism": (f"z-slab x{world}, owned/ghost/aura, NCCL halo gather of x per step"
+                            + (", overlapped with the ghost-independent elements" if overlapped is not None and overlapped.range else ""))
+            if world > 1 else "single GPU",
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -111,6 +111,14 @@ int b200fem_op_apply(b200fem_op_t op, const void *x, void *y, void *stream);
 /* y = A x : same result as zeros(y) followed by apply, without reading y where no other element
  * contributes. This is the fused form the device CG / Chebyshev below use. */
 int b200fem_op_apply_overwrite(b200fem_op_t op, const void *x, void *y, void *stream);
+/* The same over the element range [e_begin, e_end) only, for overlapping the halo exchange of a distributed apply
+ * with the elements that do not read ghost values ("order interface-adjacent elements last so
+ * interior elements can run while the halo is in flight"). mode 0: y += A_range x. mode 1: first part of an
+ * overwriting apply (zeroes what b200fem_op_apply_overwrite zeroes, then as mode 2). mode 2: continuation of an
+ * overwriting apply. The union of the ranges of one apply must be [0, nelements). Operators that do not implement
+ * ranges return B200FEM_FAILURE (the caller then uses the whole-mesh entry points). */
+int b200fem_op_apply_range(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_begin, ptrdiff_t e_end, int mode,
+                           void *stream);
 /* diag += diag(A)  (Op::hessian_diag, frontend/ops/sfem_Op.hpp:194; laplacian_diag,
  * operators/laplacian.cpp:156-195; affine_hex8_linear_elasticity_diag,
  * operators/hex8/hex8_linear_elasticity.cpp:1043) */

@@ -86,6 +86,11 @@ struct OpBase {
     int scatter = B200FEM_SCATTER_AUTO;
     virtual ~OpBase() {}
     virtual int apply(const void *x, void *y, bool overwrite, cudaStream_t s) = 0;
+    virtual int apply_range(const void *x, void *y, ptrdiff_t e0, ptrdiff_t e1, int mode, cudaStream_t s) {
+        (void)x; (void)y; (void)e0; (void)e1; (void)mode; (void)s;
+        set_error("apply_range not implemented for this operator");
+        return B200FEM_FAILURE;
+    }
     virtual int diag(void *d, cudaStream_t s) {
         (void)d; (void)s;
         set_error("diag not implemented for this operator");

@@ -261,6 +261,15 @@ int b200fem_op_apply_overwrite(b200fem_op_t op, const void *x, void *y, void *st
     return op->impl->apply(x, y, true, as_stream(stream));
 }
 
+int b200fem_op_apply_range(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_begin, ptrdiff_t e_end, int mode,
+                           void *stream) {
+    B2_OP_CHECK(op);
+    if (!x || !y) B2_FAIL("apply_range: NULL vector");
+    if (e_begin < 0 || e_end < e_begin || e_end > op->impl->ne) B2_FAIL("apply_range: element range out of bounds");
+    if (mode < 0 || mode > 2) B2_FAIL("apply_range: mode must be 0, 1 or 2");
+    return op->impl->apply_range(x, y, e_begin, e_end, mode, as_stream(stream));
+}
+
 int b200fem_op_diag(b200fem_op_t op, void *diag, void *stream) {
     B2_OP_CHECK(op);
     if (op->impl->ne == 0) return B200FEM_SUCCESS;

@@ -205,8 +205,14 @@ struct Sshex8Laplacian final : OpBase {
     int stream_cfg = 0;                 // which team shape / ring depth (see launch_stream)
     int use_stream = 1;                 // 0 = the batch kernel below (kept for explicit connectivity)
 
+    int reserve_sms = 0;
+    ptrdiff_t range_e0 = 0, range_e1 = -1;  // element range of the stream launch in flight (-1: the whole mesh)
+
     template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN>
     int launch_stream_cfg(const T *x, T *y, cudaStream_t s) {
+        const ptrdiff_t e_first = range_e1 < 0 ? 0 : range_e0;
+        const ptrdiff_t ne = (range_e1 < 0 ? this->ne : range_e1) - e_first;
+        const Sshex8Header *hdr = headers.ptr + e_first;
         using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
         auto kern = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, false>;
         auto tail = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, true>;
@@ -220,10 +226,12 @@ struct Sshex8Laplacian final : OpBase {
         const ptrdiff_t ngroups = ne / Cfg::EPT;
         const ptrdiff_t ne_main = ngroups * Cfg::EPT;
         if (ngroups > 0) {
-            const int grid = (int)std::min<ptrdiff_t>((ngroups + NTEAM - 1) / NTEAM, (ptrdiff_t)sm_count());
-            kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne_main, headers.ptr, x, y);
+            // `reserve_sms` SMs stay free for concurrently running kernels (the NCCL send / recv of an overlapped halo
+            // exchange): this kernel's CTAs hold a whole SM each until the launch ends
+            const int grid = (int)std::min<ptrdiff_t>((ngroups + NTEAM - 1) / NTEAM, (ptrdiff_t)std::max(1, sm_count() - reserve_sms));
+            kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne_main, hdr, x, y);
         }
-        if (ne_main < ne) tail<<<1, Cfg::threads, Cfg::smem_bytes, s>>>(ne - ne_main, headers.ptr + ne_main, x, y);
+        if (ne_main < ne) tail<<<1, Cfg::threads, Cfg::smem_bytes, s>>>(ne - ne_main, hdr + ne_main, x, y);
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
     }
@@ -338,6 +346,34 @@ struct Sshex8Laplacian final : OpBase {
         return launch<T, L, kModeExplicit, false, false>(x, y, s);
     }
 
+    template <typename T, int L>
+    int apply_range_L(const T *x, T *y, ptrdiff_t e0, ptrdiff_t e1, int mode, cudaStream_t s) {
+        if (mode == 1) {
+            if (interior_exclusive) {
+                if (zero_skeleton(y, s)) return B200FEM_FAILURE;
+            } else {
+                B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * sizeof(T), s));
+            }
+        }
+        if (e1 == e0) return B200FEM_SUCCESS;
+        range_e0 = e0;
+        range_e1 = e1;
+        const int rc = (mode != 0 && interior_exclusive) ? launch_stream<T, L, true>(x, y, s) : launch_stream<T, L, false>(x, y, s);
+        range_e1 = -1;
+        return rc;
+    }
+
+    int apply_range(const void *x, void *y, ptrdiff_t e0, ptrdiff_t e1, int mode, cudaStream_t s) override {
+        if (this->mode != kModeBoxes || !use_stream) B2_FAIL("apply_range: needs the boxes connectivity (stream kernel)");
+        const bool f64 = real_type == B200FEM_F64;
+        switch (level) {
+            case 2: return f64 ? apply_range_L<double, 2>((const double *)x, (double *)y, e0, e1, mode, s) : apply_range_L<float, 2>((const float *)x, (float *)y, e0, e1, mode, s);
+            case 4: return f64 ? apply_range_L<double, 4>((const double *)x, (double *)y, e0, e1, mode, s) : apply_range_L<float, 4>((const float *)x, (float *)y, e0, e1, mode, s);
+            case 8: return f64 ? apply_range_L<double, 8>((const double *)x, (double *)y, e0, e1, mode, s) : apply_range_L<float, 8>((const float *)x, (float *)y, e0, e1, mode, s);
+            default: B2_FAIL("sshex8 laplacian: level must be 2, 4 or 8");
+        }
+    }
+
     template <typename T>
     int apply_t(const T *x, T *y, bool overwrite, cudaStream_t s) {
         switch (level) {
@@ -385,6 +421,11 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "stream_cfg")) { stream_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_stream")) { use_stream = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_tma")) { use_tma = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "reserve_sms")) {
+            if (value < 0 || value >= sm_count()) B2_FAIL("reserve_sms out of range");
+            reserve_sms = value;
+            return B200FEM_SUCCESS;
+        }
         if (!strcmp(key, "tma_cfg")) { tma_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "explicit_index")) {
             if (value && mode == kModeBoxes) {

@@ -54,6 +54,7 @@ _SIG = {
     "b200fem_op_destroy": [vp],
     "b200fem_op_apply": [vp, vp, vp, vp],
     "b200fem_op_apply_overwrite": [vp, vp, vp, vp],
+    "b200fem_op_apply_range": [vp, vp, vp, ssz, ssz, i32, vp],
     "b200fem_op_diag": [vp, vp, vp],
     "b200fem_op_block_diag_sym": [vp, vp, vp],
     "b200fem_op_block_size": [vp],
@@ -238,6 +239,12 @@ class Op:
     def apply_overwrite(self, x, y):
         _vec(x, self.rows), _vec(y, self.rows)
         check(_lib.b200fem_op_apply_overwrite(self._h, _p(x), _p(y), _stream()), "op_apply_overwrite")
+        return y
+
+    def apply_range(self, x, y, e_begin: int, e_end: int, mode: int = 0):
+        """Elements [e_begin, e_end) only. mode 0: accumulate; 1 / 2: first part / continuation of an overwriting apply."""
+        _vec(x, self.rows), _vec(y, self.rows)
+        check(_lib.b200fem_op_apply_range(self._h, _p(x), _p(y), e_begin, e_end, mode, _stream()), "op_apply_range")
         return y
 
     def diag(self, d):

@@ -201,6 +201,55 @@ class HaloExchange:
         return x_local
 
 
+class OverlappedApply:
+    """y_local = A x_local with the halo gather of x overlapped with the elements that read no ghost value
+    (SURVEY section 8e). Element order is [ghost-dependent prefix | independent | ghost-dependent suffix] for the
+    slab meshes above (bottom macro layer, bulk, aura layer); anything else falls back to gather-then-apply.
+
+    Stream plan: the exchange (pack kernel + grouped NCCL send / recv) is enqueued FIRST on a side stream; the main
+    stream zeroes the shared rows and runs the independent range on `sm_count - reserve_sms` SMs (the apply kernel's
+    CTAs hold a whole SM until the launch ends, so NCCL's kernels need SMs of their own); after the exchange the two
+    dependent ranges follow."""
+
+    def __init__(self, op, lm: LocalMesh, halo: "HaloExchange", device, reserve_sms: int = 8):
+        import torch
+
+        self.torch, self.op, self.halo = torch, op, halo
+        self.ne = int(lm.elements.shape[1])
+        self.range = None
+        if halo.world > 1 and halo.peers:
+            dep = (lm.elements >= lm.n_owned).any(axis=0)
+            ind = np.flatnonzero(~dep)
+            if ind.size and not dep[ind[0]:ind[-1] + 1].any():
+                self.range = (int(ind[0]), int(ind[-1]) + 1)
+        self.reserve_sms = reserve_sms
+        self.comm = torch.cuda.Stream(device=device, priority=-1) if self.range else None
+
+    def apply_overwrite(self, x_local, y_local):
+        op, halo = self.op, self.halo
+        if self.range is None:
+            halo.gather(x_local)
+            return op.apply_overwrite(x_local, y_local)
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        self.comm.wait_stream(main)  # x_local is ready
+        with torch.cuda.stream(self.comm):
+            halo.gather(x_local)
+        e0, e1 = self.range
+        op.set_option("reserve_sms", self.reserve_sms)
+        op.apply_range(x_local, y_local, e0, e1, 1)
+        op.set_option("reserve_sms", 0)
+        main.wait_stream(self.comm)
+        if e0 > 0:
+            op.apply_range(x_local, y_local, 0, e0, 2)
+        if e1 < self.ne:
+            op.apply_range(x_local, y_local, e1, self.ne, 2)
+        return y_local
+
+    def launches(self):
+        return 1 + len(self.halo.send_idx) + (self.op.launches(True) + 2 if self.range else self.op.launches(True))
+
+
 class ParallelMatrixFreeOperator:
     """Operator<T> over the owned dofs: y = A x with halo gather (rows() = owned dofs,
     row_allocation_size() = local dofs), same contract as sfem::ParallelMatrixFreeOperator."""

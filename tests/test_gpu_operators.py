@@ -172,6 +172,41 @@ def test_sshex8_laplacian(oracles, real, level, path):
     assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
 
 
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_sshex8_laplacian_element_ranges(oracles, real):
+    """b200fem_op_apply_range: any split of [0, ne) into ranges gives the whole-mesh result, in both the accumulate
+    and the overwrite protocol (mode 1 then 2) -- what the overlapped distributed apply relies on."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    L = 8
+    m = mesh.sshex8_box(L, 3, 2, 3)
+    fff = orc.hex8_fff_fill(m["m_elements"], mesh.shear_points(m["m_points"]))
+    nn, ne = m["n_nodes"], m["elements"].shape[1]
+    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=L)
+    u = np.random.default_rng(3).uniform(-1, 1, nn)
+    ref = orc.sshex8_laplacian_apply(L, m["elements"], fff, u)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.full((nn,), 5.0, dtype=_dt(real), device="cuda")
+    op.set_option("reserve_sms", 8)
+    op.apply_range(x, y, 6, 13, 1)   # zeroes the shared rows, middle range first
+    op.set_option("reserve_sms", 0)
+    op.apply_range(x, y, 0, 6, 2)
+    op.apply_range(x, y, 13, ne, 2)
+    op.apply_range(x, y, 4, 4, 2)    # empty range
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    for a, b in ((0, 5), (5, 6), (6, ne)):
+        op.apply_range(x, y, a, b, 0)
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    with pytest.raises(lib.B200FemError):
+        op.apply_range(x, y, 3, ne + 1, 0)
+    tet_el, tet_pts = mesh.box_tet4(3, 3, 3)
+    tet = lib.laplacian(lib.TET4, tet_el, orc.tet4_fff_fill(tet_el, tet_pts), tet_pts.shape[1], _dt(real))
+    with pytest.raises(lib.B200FemError, match="not implemented"):
+        tet.apply_range(x[: tet_pts.shape[1]], y[: tet_pts.shape[1]], 0, 1, 0)
+
+
 def test_sshex8_laplacian_hierarchical_numbering(oracles):
     """Non-affine numbering (coarse lattices first) must take the explicit-index path and still match."""
     torch = _torch()
