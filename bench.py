@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: grouped ncclSend/ncclRecv instead of the symmetric-memory push")
     ap.add_argument("--overlap", action="store_true",
                     help="N > 1: overlap the halo gather with the ghost-independent elements (b200fem_op_apply_range). Off by "
                          "default: measured on 2 GPUs it is slower (1.19 vs 1.10 ms per step) -- three launches of the "
@@ -223,25 +224,48 @@ def run_b200(a):
     assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
 
     u_host = np.random.default_rng(42 + rank).uniform(-1, 1, n_local).astype(ndt)
-    x = torch.from_numpy(u_host).to(dev)
+    halo, halo_kind = None, None
+    if lm is not None:
+        if not a.nccl_halo:
+            try:  # owner-push over NVLink-mapped symmetric memory (sfem_b200.parallel.SymmetricHaloExchange)
+                halo = parallel.SymmetricHaloExchange(lm, 1, dtype=dt, device=dev)
+                halo_kind = "owner-push into the peers' ghost blocks over symmetric (NVLink-mapped) memory + stream-ordered signals"
+            except Exception as ex:  # no P2P mapping on this box: grouped ncclSend / ncclRecv
+                halo_kind = f"grouped ncclSend/ncclRecv (symmetric memory unavailable: {type(ex).__name__})"
+        if halo is None:
+            halo = parallel.HaloExchange(lm, 1, device=dev)
+            halo_kind = halo_kind or "grouped ncclSend/ncclRecv"
+    if isinstance(halo, parallel.SymmetricHaloExchange):
+        x = halo.local_vector()
+        x.copy_(torch.from_numpy(u_host))
+    else:
+        x = torch.from_numpy(u_host).to(dev)
     y = torch.zeros_like(x)
-    halo = parallel.HaloExchange(lm, 1, device=dev) if lm is not None else None
+    symmetric = isinstance(halo, parallel.SymmetricHaloExchange)
     overlapped = parallel.OverlappedApply(op, lm, halo, dev) if (halo is not None and a.overlap) else None
 
     def step():
         if overlapped is not None:
             overlapped.apply_overwrite(x, y)
+            if symmetric:
+                halo.release()
             return
         if halo is not None:
             halo.gather(x)
         op.apply_overwrite(x, y)
+        if symmetric:
+            halo.release()  # my ghost block may be overwritten again once this apply has run
 
     if overlapped is not None and overlapped.range:
         # one-off check: the overlapped schedule computes what gather-then-apply computes (differences = RED order)
         y_ref = torch.zeros_like(y)
         halo.gather(x)
         op.apply_overwrite(x, y_ref)
+        if symmetric:
+            halo.release()
         overlapped.apply_overwrite(x, y)
+        if symmetric:
+            halo.release()
         rel = float((y[:n_owned] - y_ref[:n_owned]).norm() / y_ref[:n_owned].norm())
         assert rel < 1e-12, f"overlapped apply differs from gather-then-apply: {rel}"
         del y_ref
@@ -284,6 +308,8 @@ def run_b200(a):
             if halo is not None:
                 halo.gather(x)
             op.apply_overwrite(x, y)
+            if symmetric:
+                halo.release()
             yh.copy_(y, non_blocking=True)
 
         k = max(3, min(a.steps, 5))
@@ -324,7 +350,7 @@ def run_b200(a):
             "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair as one call (b200fem_op_apply_overwrite)",
             "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
             "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
-            "parallelism": (f"z-slab x{world}, owned/ghost/aura, NCCL halo gather of x per step"
+            "parallelism": (f"z-slab x{world}, owned/ghost/aura, halo gather of x per step: {halo_kind}"
                             + (", overlapped with the ghost-independent elements" if overlapped is not None and overlapped.range else ""))
             if world > 1 else "single GPU",
         },

@@ -198,7 +198,7 @@ class Op:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.b200fem_op_destroy(h)
 
     @property
@@ -394,7 +394,7 @@ class Transfer:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _lib is not None:
             _lib.b200fem_transfer_destroy(h)
 
     @property
