@@ -29,6 +29,7 @@ REDUCE_CB = C.CFUNCTYPE(f64, vp, f64)
 _SIG = {
     "b200host_blas": (vp, [i32, REDUCE_CB, vp]),
     "b200host_blas_launches": (C.c_long, [vp]),
+    "b200host_blas_set_allocator": (i32, [vp, C.CFUNCTYPE(vp, vp, C.c_size_t), C.CFUNCTYPE(None, vp, vp), vp]),
     "b200host_function": (vp, [i32, ssz, i32]),
     "b200host_function_add_operator": (i32, [vp, vp]),
     "b200host_function_add_dirichlet": (i32, [vp, vp, ssz, i32, f64]),
@@ -102,6 +103,14 @@ class Blas(Handle):
 
     def launches(self) -> int:
         return _h.b200host_blas_launches(self.ptr)
+
+    def set_allocator(self, alloc, free):
+        """alloc(nbytes) -> device address of zero-filled memory, free(address): used for every vector a solver
+        allocates (work vectors with room for the ghost block / in symmetric memory for distributed solves)."""
+        a = C.CFUNCTYPE(vp, vp, C.c_size_t)(lambda _c, n: alloc(int(n)))
+        f = C.CFUNCTYPE(None, vp, vp)(lambda _c, p: free(p))
+        self.keep += [a, f, alloc, free]
+        _h.b200host_blas_set_allocator(self.ptr, a, f, None)
 
 
 class Function(Handle):

@@ -97,8 +97,20 @@ namespace b200fem {
         std::function<double(double)>   allreduce_sum;
         long                            n_launches{0};
 
+        /* Optional allocator: distributed solvers need work vectors with room for the ghost block
+         * (ParallelOperator::row_allocation_size(), algebra/parallel/sfem_ParallelOperator.hpp:13-25) and, for the
+         * owner-push halo exchange, vectors that live in NVLink-mapped symmetric memory. Must return zero-filled
+         * device memory of at least `bytes`. */
+        std::function<void *(std::size_t bytes)> alloc_hook;
+        std::function<void(void *)>              free_hook;
+
         T *allocate(const std::size_t n) override {
             void *p = nullptr;
+            if (alloc_hook) {
+                p = alloc_hook((n ? n : 1) * sizeof(T));
+                if (!p) ok_ = false;
+                return (T *)p;
+            }
             if (b200fem_malloc(&p, (n ? n : 1) * sizeof(T))) {
                 std::fprintf(stderr, "[b200fem] allocate(%zu) failed: %s\n", n, b200fem_last_error());
                 ok_ = false;
@@ -106,7 +118,12 @@ namespace b200fem {
             }
             return (T *)p;
         }
-        void destroy(void *a) override { b200fem_free(a); }
+        void destroy(void *a) override {
+            if (free_hook)
+                free_hook(a);
+            else
+                b200fem_free(a);
+        }
         void zeros(const std::size_t n, T *const x) override { track(b200fem_blas_zeros(RT, (ptrdiff_t)n, x, stream)); }
         void values(const std::size_t n, const T v, T *const x) override {
             track(b200fem_blas_values(RT, (ptrdiff_t)n, (double)v, x, stream));

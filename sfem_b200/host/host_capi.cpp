@@ -153,6 +153,23 @@ extern "C" {
 void *b200host_blas(int real_type, reduce_cb allreduce, void *ctx) {
     return DISPATCH(real_type, make_blas<double>(allreduce, ctx), make_blas<float>(allreduce, ctx));
 }
+/* custom allocator for the vectors the solvers allocate (see DeviceBLAS::alloc_hook) */
+typedef void *(*alloc_cb)(void *ctx, size_t bytes);
+typedef void (*free_cb)(void *ctx, void *ptr);
+int b200host_blas_set_allocator(void *blas, alloc_cb alloc, free_cb release, void *ctx) {
+    Box *b = (Box *)blas;
+    if (!b || b->kind != K_BLAS) return 1;
+    auto a = [alloc, ctx](std::size_t bytes) { return alloc(ctx, bytes); };
+    auto f = [release, ctx](void *p) { release(ctx, p); };
+    if (b->real_type == B200FEM_F64) {
+        blas_of<double>(b)->alloc_hook = a;
+        blas_of<double>(b)->free_hook  = f;
+    } else {
+        blas_of<float>(b)->alloc_hook = a;
+        blas_of<float>(b)->free_hook  = f;
+    }
+    return 0;
+}
 long b200host_blas_launches(void *blas) {
     Box *b = (Box *)blas;
     return DISPATCH(b->real_type, blas_of<double>(b)->n_launches, blas_of<float>(b)->n_launches);

@@ -222,42 +222,60 @@ class SymmetricHaloExchange(HaloExchange):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.dtype = dtype or torch.float64
-        grp = group or dist.group.WORLD
+        self._symm_mem, self._grp = symm_mem, group or dist.group.WORLD
         n = torch.tensor([self.n_local * self.bs], dtype=torch.int64, device=device)
-        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=grp)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self._grp)
         self.n_sym = int(n.item())
-        self.buf = symm_mem.empty(self.n_sym, dtype=self.dtype, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, grp.group_name)
-        self.buf.zero_()
         # where my values land on each peer: that peer's recv range for me
-        all_ranges = [None] * self.world
-        dist.all_gather_object(all_ranges, self.recv_ranges, group=grp)
-        self.remote = {}
+        self._all_ranges = [None] * self.world
+        dist.all_gather_object(self._all_ranges, self.recv_ranges, group=self._grp)
+        self.vectors = {}  # data_ptr -> (tensor, handle, {peer: remote ghost-block view})
+        self.buf = self.allocate()
+
+    def allocate(self):
+        """A new zero-filled symmetric vector (COLLECTIVE: every rank allocates in the same order). Any vector from
+        here can be handed to gather() / release(); solvers get their work vectors this way through
+        host.Blas.set_allocator."""
+        torch, dist = self.torch, self.dist
+        buf = self._symm_mem.empty(self.n_sym, dtype=self.dtype, device=self.device)
+        hdl = self._symm_mem.rendezvous(buf, self._grp.group_name)
+        buf.zero_()
+        remote = {}
         for q in self.send_idx:
-            a, b = all_ranges[q][self.rank]
+            a, b = self._all_ranges[q][self.rank]
             assert (b - a) == self.send_idx[q].numel()
-            self.remote[q] = self.hdl.get_buffer(q, ((b - a) * self.bs,), self.dtype, a * self.bs)
+            remote[q] = hdl.get_buffer(q, ((b - a) * self.bs,), self.dtype, a * self.bs)
+        self.vectors[buf.data_ptr()] = (buf, hdl, remote)
         torch.cuda.synchronize()
-        dist.barrier(group=grp)
-        self.release()  # every ghost block starts out free
+        dist.barrier(group=self._grp)
+        for p in self.recv_ranges:  # every ghost block starts out free
+            hdl.put_signal(p, channel=1)
+        return buf
+
+    def free(self, ptr):
+        self.vectors.pop(int(ptr), None)
 
     def local_vector(self):
         return self.buf[: self.n_local * self.bs]
 
-    def release(self):
+    def release(self, x_local=None):
+        ptr = self.buf.data_ptr() if x_local is None else (x_local if isinstance(x_local, int) else x_local.data_ptr())
+        hdl = self.vectors[ptr][1]
         for p in self.recv_ranges:
-            self.hdl.put_signal(p, channel=1)
+            hdl.put_signal(p, channel=1)
 
     def gather(self, x_local):
         from . import lib
 
-        assert x_local.data_ptr() == self.buf.data_ptr(), "gather() needs the symmetric vector of local_vector()"
+        ptr = x_local if isinstance(x_local, int) else x_local.data_ptr()
+        assert ptr in self.vectors, "gather() needs a vector from local_vector() / allocate()"
+        buf, hdl, remote = self.vectors[ptr]
         for q in self.send_idx:
-            self.hdl.wait_signal(q, channel=1)
-            lib.halo_pack(self.send_idx[q], self.bs, x_local, self.remote[q])
-            self.hdl.put_signal(q, channel=0)
+            hdl.wait_signal(q, channel=1)
+            lib.halo_pack(self.send_idx[q], self.bs, buf, remote[q])
+            hdl.put_signal(q, channel=0)
         for p in self.recv_ranges:
-            self.hdl.wait_signal(p, channel=0)
+            hdl.wait_signal(p, channel=0)
         return x_local
 
 

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--max-it", type=int, default=200)
     ap.add_argument("--rtol", type=float, default=1e-30)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="grouped ncclSend/ncclRecv instead of the symmetric-memory push")
     a = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -55,17 +56,34 @@ def main():
     # u = -1 / +1 on the x-faces (present on every rank of a z-stack), zero rhs
     f.add_dirichlet(mesh.sshex8_face_nodes_macro(L, lm.elements, m_el, m_pts, 0, 0.0), 0, -1.0)
     f.add_dirichlet(mesh.sshex8_face_nodes_macro(L, lm.elements, m_el, m_pts, 0, 1.0), 0, 1.0)
-    halo = parallel.HaloExchange(lm, 1, device=dev)
     n_owned, n_local = lm.n_owned, lm.n_local
-    xl = torch.zeros(n_local, dtype=dt, device=dev)
+    symmetric = world > 1 and not a.nccl_halo
+    if symmetric:  # owner-push over NVLink-mapped memory (parallel.SymmetricHaloExchange)
+        halo = parallel.SymmetricHaloExchange(lm, 1, dtype=dt, device=dev)
+        xl = halo.local_vector()
+    else:
+        halo = parallel.HaloExchange(lm, 1, device=dev)
+        xl = torch.zeros(n_local, dtype=dt, device=dev)
     yl = torch.zeros(n_local, dtype=dt, device=dev)
     raw = lib.raw()
     scal = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def apply_owned(x_addr, y_addr):  # y_owned = A x_owned
+    hraw = host.raw()
+
+    def apply_in_place(x_addr, y_addr):
+        # symmetric path: every solver vector is a symmetric vector with room for the ghost block (allocator hook
+        # below), so the exchange and the apply work on the solver's own vectors: no copies
+        halo.gather(x_addr)
+        rc = hraw.b200host_apply_overwrite(f.ptr, x_addr, y_addr)
+        halo.release(x_addr)
+        return rc
+
+    def apply_owned(x_addr, y_addr):  # y_owned = A x_owned through the local scratch vectors
         raw.b200fem_memcpy_d2d(xl.data_ptr(), x_addr, n_owned * 8, None)
         halo.gather(xl)
         host.apply_overwrite(f, xl, yl)
+        if symmetric:
+            halo.release()
         raw.b200fem_memcpy_d2d(y_addr, yl.data_ptr(), n_owned * 8, None)
         return 0
 
@@ -79,16 +97,21 @@ def main():
         dist.all_reduce(scal)
         return float(scal.item())
 
-    A = host.callback_op(dt, n_owned, n_owned, apply_owned_acc, overwrite=apply_owned)
+    A = host.callback_op(dt, n_owned, n_owned, apply_owned_acc, overwrite=apply_in_place if symmetric else apply_owned)
     blas = host.Blas(dt, allreduce=allreduce if world > 1 else None)
-    x = torch.zeros(n_owned, dtype=dt, device=dev)
+    if symmetric:
+        blas.set_allocator(lambda nbytes: halo.allocate().data_ptr(), halo.free)
+        x, x_warm = halo.allocate(), halo.allocate()
+    else:
+        x, x_warm = torch.zeros(n_owned, dtype=dt, device=dev), torch.zeros(n_owned, dtype=dt, device=dev)
     b = torch.zeros(n_owned, dtype=dt, device=dev)
     f.apply_constraints(xl)  # sets the Dirichlet values on the local vector; owned part is what the solver sees
-    x.copy_(xl[:n_owned])
+    x[:n_owned].copy_(xl[:n_owned])
+    x_warm[:n_owned].copy_(xl[:n_owned])
     b.copy_(xl[:n_owned])
     xl.zero_()
     cg = host.cg(blas, A, None, rtol=a.rtol, atol=1e-30, max_it=a.max_it)
-    host.apply(cg, b, x.clone())  # warm-up
+    host.apply(cg, b, x_warm)  # warm-up (allocates the work vectors)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
