@@ -303,21 +303,71 @@ def run_b200(a):
         xh = torch.from_numpy(u_host).pin_memory()
         yh = torch.empty_like(xh).pin_memory()
 
-        def e2e_step():
-            x.copy_(xh, non_blocking=True)
-            if halo is not None:
-                halo.gather(x)
-            op.apply_overwrite(x, y)
-            if symmetric:
-                halo.release()
-            yh.copy_(y, non_blocking=True)
+        # Double-buffered pipeline over three streams: the H2D copy of step k+1 and the D2H copy of step k-1 run
+        # while step k computes (PCIe is full duplex; one step moves 1.08 GB each way against 1 ms of kernel time).
+        # Every step still copies its whole input from pinned host memory and its whole result back.
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        if symmetric:
+            xb = [x, halo.allocate()[: x.numel()]]
+        else:
+            xb = [x, torch.empty_like(x)]
+        yb = [y, torch.empty_like(y)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_comp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        state = {"k": 0}
 
-        k = max(3, min(a.steps, 5))
-        ms_e2e = max_over_ranks(time_steps(e2e_step, k, 1, torch, barrier))
+        def e2e_step():
+            k = state["k"]
+            b = k % 2
+            state["k"] = k + 1
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_comp[b])  # the apply of step k-2 has consumed this x buffer
+                xb[b].copy_(xh, non_blocking=True)
+                ev_in[b].record(s_in)
+            main.wait_event(ev_in[b])
+            if k >= 2:
+                main.wait_event(ev_out[b])  # the D2H of step k-2 has drained this y buffer
+            if halo is not None:
+                halo.gather(xb[b])
+            op.apply_overwrite(xb[b], yb[b])
+            if symmetric:
+                halo.release(xb[b])
+            ev_comp[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[b])
+                yh.copy_(yb[b], non_blocking=True)
+                ev_out[b].record(s_out)
+
+        def e2e_run(nsteps):
+            state["k"] = 0
+            for _ in range(nsteps):
+                e2e_step()
+            main.wait_stream(s_out)  # the timed region ends when the last result is on the host
+
+        k = max(4, min(a.steps, 8))
+        e2e_run(2)  # warm-up
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(k)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1) / k)
+        # the result that reached the host is the apply of the host input
+        chk = float((yh[:n_owned].to(dev) - yb[(k - 1) % 2][:n_owned]).abs().max())
+        assert chk == 0.0, chk
         e2e = {"value": total_owned / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(n_local * x.element_size()), "d2h_bytes_per_step": int(n_local * x.element_size()),
                "ms_per_step": ms_e2e, "steps": k,
-               "note": "pinned host x -> device, y = A x through the C ABI, device y -> pinned host, every step"}
+               "note": "every step: pinned host x -> device, y = A x through the C ABI, device y -> pinned host; double-buffered "
+                       "over three streams so that the copies of neighbouring steps overlap (PCIe-bound: "
+                       f"{2 * n_local * x.element_size() / (ms_e2e * 1e-3) / 1e9:.1f} GB/s in + out)"}
+        del xb, yb
 
     if rank != 0:
         if dist is not None:
