@@ -19,6 +19,8 @@
 // curve before use (smesh::SFC::reorder); sfem_b200/mesh.py offers the same for the synthetic boxes.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -55,40 +57,64 @@ struct PatchPlan {
         std::vector<uint16_t> h_lidx((size_t)nchunks * nxe * E, 0), h_nslot((size_t)nchunks * nxe * E, 0), h_noff;
         std::vector<int32_t> h_unodes;
         std::vector<int64_t> h_uoff((size_t)nchunks + 1, 0);
-        h_unodes.reserve((size_t)ne);
-        std::vector<int32_t> nodes, cnt;
+        // patches are independent: build them on all host threads (a 7.4e7-tet plan takes ~2 s instead of ~15 s),
+        // each thread keeping the variable-length parts (unique nodes, CSR offsets) of its patches until the prefix sum
+        std::vector<std::vector<int32_t>> c_nodes((size_t)nchunks);
+        std::vector<std::vector<uint16_t>> c_noff((size_t)nchunks);
+        std::atomic<bool> too_many{false};
+        auto work = [&](ptrdiff_t c_begin, ptrdiff_t c_end) {
+            std::vector<int32_t> cnt, fill;
+            for (ptrdiff_t c = c_begin; c < c_end; ++c) {
+                const ptrdiff_t e0 = c * E, nel = std::min<ptrdiff_t>(E, ne - e0);
+                std::vector<int32_t> &nodes = c_nodes[(size_t)c];
+                for (int v = 0; v < nxe; ++v) nodes.insert(nodes.end(), elements[v] + e0, elements[v] + e0 + nel);
+                std::sort(nodes.begin(), nodes.end());
+                nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+                const int U = (int)nodes.size();
+                if (U > 65535) {
+                    too_many = true;
+                    return;
+                }
+                cnt.assign((size_t)U + 1, 0);
+                uint16_t *li = &h_lidx[(size_t)c * nxe * E];
+                for (int v = 0; v < nxe; ++v)
+                    for (ptrdiff_t e = 0; e < nel; ++e) {
+                        const int j = (int)(std::lower_bound(nodes.begin(), nodes.end(), elements[v][e0 + e]) - nodes.begin());
+                        li[(size_t)v * E + e] = (uint16_t)j;
+                        cnt[(size_t)j + 1]++;
+                    }
+                for (int j = 0; j < U; ++j) cnt[(size_t)j + 1] += cnt[(size_t)j];
+                c_noff[(size_t)c].resize((size_t)U + 1);
+                for (int j = 0; j <= U; ++j) c_noff[(size_t)c][(size_t)j] = (uint16_t)cnt[(size_t)j];
+                uint16_t *ns = &h_nslot[(size_t)c * nxe * E];
+                fill.assign(cnt.begin(), cnt.end() - 1);
+                for (int v = 0; v < nxe; ++v)
+                    for (ptrdiff_t e = 0; e < nel; ++e) {
+                        const int j = li[(size_t)v * E + e];
+                        ns[(size_t)fill[(size_t)j]++] = (uint16_t)(v * E + e);
+                    }
+            }
+        };
+        {
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const ptrdiff_t nthreads = std::max<ptrdiff_t>(1, std::min<ptrdiff_t>((ptrdiff_t)hw, nchunks / 64));
+            std::vector<std::thread> pool;
+            for (ptrdiff_t t = 1; t < nthreads; ++t) pool.emplace_back(work, nchunks * t / nthreads, nchunks * (t + 1) / nthreads);
+            work(0, nchunks / nthreads);
+            for (auto &th : pool) th.join();
+        }
+        if (too_many) B2_FAIL("patch plan: more than 65535 unique nodes in one patch");
         max_u = 0;
         for (ptrdiff_t c = 0; c < nchunks; ++c) {
-            const ptrdiff_t e0 = c * E, nel = std::min<ptrdiff_t>(E, ne - e0);
-            nodes.clear();
-            for (int v = 0; v < nxe; ++v) nodes.insert(nodes.end(), elements[v] + e0, elements[v] + e0 + nel);
-            std::sort(nodes.begin(), nodes.end());
-            nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
-            const int U = (int)nodes.size();
-            if (U > 65535) B2_FAIL("patch plan: more than 65535 unique nodes in one patch");
+            const int U = (int)c_nodes[(size_t)c].size();
             max_u = std::max(max_u, U);
             h_uoff[(size_t)c + 1] = h_uoff[(size_t)c] + U;
-            h_unodes.insert(h_unodes.end(), nodes.begin(), nodes.end());
-            // local indices and incidence counts
-            cnt.assign((size_t)U + 1, 0);
-            uint16_t *li = &h_lidx[(size_t)c * nxe * E];
-            for (int v = 0; v < nxe; ++v)
-                for (ptrdiff_t e = 0; e < nel; ++e) {
-                    const int j = (int)(std::lower_bound(nodes.begin(), nodes.end(), elements[v][e0 + e]) - nodes.begin());
-                    li[(size_t)v * E + e] = (uint16_t)j;
-                    cnt[(size_t)j + 1]++;
-                }
-            for (int j = 0; j < U; ++j) cnt[(size_t)j + 1] += cnt[(size_t)j];
-            const size_t nb = h_noff.size();
-            h_noff.resize(nb + (size_t)U + 1);
-            for (int j = 0; j <= U; ++j) h_noff[nb + (size_t)j] = (uint16_t)cnt[(size_t)j];
-            uint16_t *ns = &h_nslot[(size_t)c * nxe * E];
-            std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-            for (int v = 0; v < nxe; ++v)
-                for (ptrdiff_t e = 0; e < nel; ++e) {
-                    const int j = li[(size_t)v * E + e];
-                    ns[(size_t)fill[(size_t)j]++] = (uint16_t)(v * E + e);
-                }
+        }
+        h_unodes.resize((size_t)h_uoff[(size_t)nchunks]);
+        h_noff.resize((size_t)h_uoff[(size_t)nchunks] + (size_t)nchunks);
+        for (ptrdiff_t c = 0; c < nchunks; ++c) {
+            std::copy(c_nodes[(size_t)c].begin(), c_nodes[(size_t)c].end(), h_unodes.begin() + h_uoff[(size_t)c]);
+            std::copy(c_noff[(size_t)c].begin(), c_noff[(size_t)c].end(), h_noff.begin() + h_uoff[(size_t)c] + c);
         }
         avg_u = nchunks ? double(h_unodes.size()) / double(nchunks) : 0;
         if (lidx.upload(h_lidx.data(), h_lidx.size()) || nslot.upload(h_nslot.data(), h_nslot.size()) ||

@@ -64,6 +64,42 @@ def cg_poisson(torch, macro=64, level=8, max_it=200, peak_gbs=6470.5):
             "gdof_s_per_iteration": nn / (per_it * 1e-3) / 1e9, "vector_kernel_launches": blas.launches()}
 
 
+def cg_poisson_tet4(torch, n=232, max_it=200, peak_gbs=6470.5):
+    """One GPU's share of BASELINE config 4 (~100 M-node tet4 cube over 8 GPUs = 232^3 nodes, 7.4e7 tets per GPU):
+    poisson.exe.cpp pattern, u = -1 / +1 on the z-faces, zero rhs, unpreconditioned CG, fixed iteration count."""
+    from sfem_b200 import host, lib, mesh
+
+    dt = torch.float64
+    t0 = time.time()
+    el, pts = mesh.box_tet4(n, n, n)
+    nn = pts.shape[1]
+    fff = lib.fff_fill(lib.TET4, el, pts)
+    op = lib.laplacian(lib.TET4, el, fff, nn, dt)
+    f = host.Function(dt, nn, 1)
+    f.add_operator(op)
+    z = pts[2]
+    f.add_dirichlet(np.flatnonzero(z < 1e-6).astype(np.int32), 0, -1.0)
+    f.add_dirichlet(np.flatnonzero(z > 1 - 1e-6).astype(np.int32), 0, 1.0)
+    setup_s = time.time() - t0
+    blas = host.Blas(dt)
+    x = torch.zeros(nn, dtype=dt, device="cuda")
+    b = torch.zeros(nn, dtype=dt, device="cuda")
+    f.apply_constraints(x)
+    f.apply_constraints(b)
+    cg = host.cg(blas, f, None, rtol=1e-30, atol=1e-30, max_it=max_it)
+    host.apply(cg, b, x.clone())
+    rc, ms = _time_gpu(torch, lambda: host.apply(cg, b, x))
+    h = host.residual_history(cg)
+    it = host.iterations(cg)
+    per_it = ms / max(it, 1)
+    bytes_it = op.algorithmic_bytes + nn * 8 * 11
+    return {"name": f"CG Poisson, tet4 {n}^3 nodes ({el.shape[1]} tets; one GPU's share of config 4), f64, fixed {it} iterations",
+            "dofs": nn, "iterations": it, "ms_total": ms, "ms_per_iteration": per_it, "residual_0": float(h[0]),
+            "residual_end": float(h[-1]), "alg_GB_s": bytes_it / (per_it * 1e-3) / 1e9,
+            "frac_of_measured_hbm": bytes_it / (per_it * 1e-3) / 1e9 / peak_gbs, "gdof_s_per_iteration": nn / (per_it * 1e-3) / 1e9,
+            "setup_s": setup_s}
+
+
 def mg_elasticity(torch, macro=32, level=8, sweeps=30, max_cycles=40, tol=1e-9):
     from sfem_b200 import host, lib, mesh
 
@@ -124,9 +160,12 @@ def mg_elasticity(torch, macro=32, level=8, sweeps=30, max_cycles=40, tol=1e-9):
             "power_method_s": power_s, "setup_s": setup_s, "last_coarse_cg_iterations": host.iterations(coarse)}
 
 
-def run_solves(torch, cg_macro=64, mg_macro=32, peak_gbs=6470.5):
+def run_solves(torch, cg_macro=64, mg_macro=32, peak_gbs=6470.5, tet4_n=232):
     out = []
-    for fn, kw in ((cg_poisson, dict(macro=cg_macro, peak_gbs=peak_gbs)), (mg_elasticity, dict(macro=mg_macro))):
+    cases = [(cg_poisson, dict(macro=cg_macro, peak_gbs=peak_gbs)), (mg_elasticity, dict(macro=mg_macro))]
+    if tet4_n:
+        cases.append((cg_poisson_tet4, dict(n=tet4_n, peak_gbs=peak_gbs)))
+    for fn, kw in cases:
         try:
             out.append(fn(torch, **kw))
         except Exception as ex:  # report, do not hide the headline number
@@ -140,5 +179,6 @@ if __name__ == "__main__":
 
     cg_macro = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     mg_macro = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-    for r in run_solves(torch, cg_macro, mg_macro):
+    tet4_n = int(sys.argv[3]) if len(sys.argv) > 3 else 232
+    for r in run_solves(torch, cg_macro, mg_macro, tet4_n=tet4_n):
         print(json.dumps(r), flush=True)
