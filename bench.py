@@ -53,6 +53,7 @@ def parse_args():
                          "default: measured on 2 GPUs it is slower (1.19 vs 1.10 ms per step) -- three launches of the "
                          "persistent kernel and 8 reserved SMs cost more than the 0.12 ms exchange they hide")
     ap.add_argument("--no-solves", action="store_true", help="skip the CG / multigrid solve times (tools/solver_bench.py)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs 0 / 1 / 2-fp32 (tools/extras_bench.py)")
     ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, vector kernels)")
     return ap.parse_args()
 
@@ -431,6 +432,15 @@ def run_b200(a):
         del op, x, y
         torch.cuda.empty_cache()
         line["solves"] = run_solves(torch, cg_macro=a.macro, mg_macro=max(4, a.macro // 2), peak_gbs=peak)
+    if not a.no_other_configs and world == 1:
+        # the other single-GPU configurations of BASELINE.json beside the headline (config 0: tet4 Laplacian on the
+        # ~1 M-element cube; config 1: hex8 linear elasticity 128^3; config 2 in fp32), same timing rules
+        from tools.extras_bench import run_extras
+
+        try:
+            line["other_configs"] = run_extras(torch, which=("c1s", "c2", "c3f32"))
+        except Exception as ex:
+            line["other_configs"] = [{"error": repr(ex)}]
     if a.extras:
         from tools.extras_bench import run_extras
 

@@ -54,8 +54,8 @@ def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "transfer",
     out = []
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")
     SC = {"patch": lib.SCATTER_PATCH, "atomic": lib.SCATTER_ATOMIC}
-    if "c1" in which:  # tet4 Laplacian fp64, 56^3 nodes (BASELINE config 1) and a 100x larger cube
-        for n in (56, 260):
+    if "c1" in which or "c1s" in which:  # tet4 Laplacian fp64, 56^3 nodes (BASELINE config 1) and a 100x larger cube
+        for n in ((56, 260) if "c1" in which else (56,)):
             el0, pts0 = mesh.box_tet4(n, n, n)
             for order in ("generator order", "SFC order"):
                 el, pts = (el0, pts0) if order == "generator order" else mesh.sfc_reorder(el0, pts0)[:2]
