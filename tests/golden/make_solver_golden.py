@@ -30,6 +30,8 @@ def cases(orc):
         "mg2_poisson_L4": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), {}),
         "mg2_poisson_L8": (solver_cases.mg_two_level, lambda: problems.poisson_sshex8(orc, 8, 3, 2, 2, generic=True), dict(sweeps=10)),
         "mg2_elasticity_L4": (solver_cases.mg_two_level, lambda: problems.elasticity_sshex8(orc, 4, 3, 2, 2, generic=True), dict(sweeps=8, max_cycles=60)),
+        "mg4_poisson_L8": (solver_cases.mg_multilevel, lambda: problems.poisson_sshex8_multilevel(orc, 8, 2, 2, 2), dict(sweeps=3)),
+        "mg3_poisson_L4": (solver_cases.mg_multilevel, lambda: problems.poisson_sshex8_multilevel(orc, 4, 3, 2, 2), dict(sweeps=3)),
         "pcg_mg_poisson_L4": (solver_cases.pcg_mg, lambda: problems.poisson_sshex8(orc, 4, 3, 2, 2, generic=True), {}),
     }
 

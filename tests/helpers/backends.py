@@ -43,6 +43,13 @@ class RefBackend:
     def transfer(self, p):
         return P.ref_transfer_ops(self.rs, self.orc, p)
 
+    def level_op(self, p, i):
+        lv = p.levels[i]
+        return self.rs.make_op(p.ref_linear_op(p.ref_apply_level(i), lv["conditions"]), lv["n_nodes"])
+
+    def level_transfer(self, p, i):
+        return P.ref_level_transfer(self.rs, self.orc, p, i)
+
     def cg(self, op, precond=None, **kw):
         return self.rs.cg(op, precond, **kw)
 
@@ -103,7 +110,7 @@ class GpuBackend:
         return self.function(p, coarse)
 
     def apply_constraints(self, p, x):
-        self.function(p).apply_constraints(x)
+        (self.level_op(p, 0) if hasattr(p, "levels") else self.function(p)).apply_constraints(x)
 
     def diag(self, p):
         f = self.function(p)
@@ -111,6 +118,17 @@ class GpuBackend:
         f.hessian_diag(d)
         f.set_value_to_constrained_dofs(1.0, d)
         return d
+
+    def level_op(self, p, i):
+        key = (id(p), "level", i)
+        if key not in self._functions:
+            self._functions[key] = P.gpu_level_function(p, self.dtype, i)
+        return self._functions[key]
+
+    def level_transfer(self, p, i):
+        t = P.gpu_level_transfer(p, i)
+        return (self.host.restriction(self.dtype, t, 1, self.level_op(p, i + 1)),
+                self.host.prolongation(self.dtype, t, 1, self.level_op(p, i)))
 
     def transfer(self, p):
         t = P.gpu_transfer(p)

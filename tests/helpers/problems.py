@@ -122,6 +122,82 @@ def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0, generic=False
     return p
 
 
+def poisson_sshex8_multilevel(orc, L=8, mx=2, my=2, mz=2):
+    """The N-level hierarchy of create_ssgmg (ssmg/sfem_ssgmg.cpp, algebra/mg/sfem_GeometricMultigrid.cpp:12-78):
+    levels L, L/2, ..., 1 of one sheared macro mesh. Every level is its own sshex8 mesh (own compact numbering, so the
+    fast kernels apply on every level); level 1 is the hex8 macro mesh. Same Dirichlet faces on every level."""
+    levels = mesh.sshex8_derefinement_levels(L)[::-1]  # finest first
+    p = Problem(kind="sshex8_laplacian_multilevel", block_size=1, levels=[], rhs=None)
+    m0 = mesh.sshex8_box(1, mx, my, mz)
+    mpts = np.ascontiguousarray(mesh.shear_points(m0["m_points"]), dtype=np.float32)
+    fff = orc.hex8_fff_fill(m0["m_elements"], mpts)
+    p.fff = fff
+    for l in levels:
+        m = mesh.sshex8_box(l, mx, my, mz)
+        pts = m["points"]  # unsheared lattice coordinates: only used to find the faces
+        conds = [(_face_nodes(pts, 0, 0.0), 0, -1.0), (_face_nodes(pts, 0, 1.0), 0, 1.0)]
+        p.levels.append(dict(level=l, elements=m["elements"], n_nodes=m["n_nodes"], conditions=conds, m_elements=m["m_elements"]))
+    p.n_nodes = p.levels[0]["n_nodes"]
+    p.conditions = p.levels[0]["conditions"]
+    p.rhs = _rhs(p.n_nodes, 17)
+
+    def ref_apply_level(i):
+        lv = p.levels[i]
+        if lv["level"] == 1:
+            return lambda x: orc.hex8_laplacian_apply_opt(lv["m_elements"], fff, x)
+        return lambda x: orc.sshex8_laplacian_apply(lv["level"], lv["elements"], fff, x)
+
+    p.ref_apply_level = ref_apply_level
+    p.ref_apply = ref_apply_level(0)
+    return p
+
+
+def ref_level_transfer(rs, orc, p, i):
+    """(restriction, prolongation) between level i (fine) and i + 1 (coarse), each followed by apply_zero_constraints
+    on its target space (sfem_GeometricMultigrid.cpp:38-64); sshex8_restrict / sshex8_prolongate of the reference."""
+    fl, cl = p.levels[i], p.levels[i + 1]
+    count = orc.sshex8_element_node_incidence_count(fl["level"], 1, fl["elements"], fl["n_nodes"])
+    fine_cd = p.constrained_dofs(fl["conditions"])
+    coarse_cd = p.constrained_dofs(cl["conditions"])
+    nf, nc = fl["n_nodes"], cl["n_nodes"]
+
+    def restrict(frm, to):
+        if i == 0:
+            p.ref_restrict_calls += 1
+        to += orc.sshex8_restrict(fl["level"], 1, fl["elements"], count, cl["level"], 1, cl["elements"], 1,
+                                  np.array(frm, copy=True), nc)
+        to[coarse_cd] = 0
+
+    def prolong(frm, to):
+        to[:] = orc.sshex8_prolongate(cl["level"], 1, cl["elements"], fl["level"], 1, fl["elements"], 1,
+                                      np.array(frm, copy=True), nf)
+        to[fine_cd] = 0
+
+    return rs.make_op(restrict, nc, nf), rs.make_op(prolong, nf, nc)
+
+
+def gpu_level_function(p, dtype, i):
+    from sfem_b200 import host, lib
+
+    lv = p.levels[i]
+    f = host.Function(dtype, lv["n_nodes"], 1)
+    if lv["level"] == 1:
+        op = lib.laplacian(lib.HEX8, lv["m_elements"], p.fff, lv["n_nodes"], dtype)
+    else:
+        op = lib.laplacian(lib.SSHEX8, lv["elements"], p.fff, lv["n_nodes"], dtype, level=lv["level"])
+    f.add_operator(op)
+    for nodes, comp, val in lv["conditions"]:
+        f.add_dirichlet(nodes, comp, val)
+    return f
+
+
+def gpu_level_transfer(p, i):
+    from sfem_b200 import lib
+
+    fl, cl = p.levels[i], p.levels[i + 1]
+    return lib.Transfer(fl["level"], 1, fl["elements"], fl["n_nodes"], cl["level"], 1, cl["elements"], cl["n_nodes"])
+
+
 def level1_lattice(mel):
     """hex8 (VTK corner order) -> rows of a level-1 sshex8 lattice."""
     lat = np.zeros((8, mel.shape[1]), dtype=np.int32)

@@ -76,6 +76,35 @@ def mg_two_level(B, p, sweeps=3, tol=1e-9, max_cycles=40):
     return out
 
 
+def mg_multilevel(B, p, sweeps=3, tol=1e-9, max_cycles=40):
+    """create_ssgmg's N-level hierarchy (levels L, L/2, ..., 1) with mgsolve's Chebyshev3 smoother on every level but
+    the coarsest (power method from a seeded random vector) and CG on the coarsest."""
+    n = len(p.levels)
+    ops = [B.level_op(p, i) for i in range(n)]
+    mg = B.mg(max_it=max_cycles, atol=tol)
+    smoothers = []
+    transfers = [B.level_transfer(p, i) for i in range(n - 1)]
+    for i in range(n):
+        if i < n - 1:
+            guess = B.from_numpy(np.random.default_rng(100 + i).uniform(-0.5, 0.5, p.levels[i]["n_nodes"]))
+            sm = B.cheb3(ops[i], eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
+                         initial_guess_zero=False, init=guess)
+        else:
+            sm = B.cg(ops[i], None, rtol=1e-8, atol=1e-10, max_it=40000)
+        smoothers.append(sm)
+        restriction = transfers[i][0] if i < n - 1 else None
+        prolongation = transfers[i - 1][1] if i > 0 else None
+        B.mg_add_level(mg, ops[i], sm, prolongation, restriction)
+    x, b = _bvp_vectors(B, p)
+    p.ref_restrict_calls = 0
+    rc = B.apply(mg, b, x)
+    out = dict(rc=rc, x=B.to_numpy(x), eig_max=[B.cheb3_eig_max(s) for s in smoothers[:-1]],
+               last_coarse_iterations=B.iterations(smoothers[-1]))
+    it = B.iterations(mg)
+    out["iterations"] = it if it >= 0 else p.ref_restrict_calls
+    return out
+
+
 def pcg_mg(B, p, sweeps=3, rtol=1e-9):
     """SFEM_USE_MG_PRECONDITIONER (drivers/mgsolve.cpp:262-272): CG preconditioned by one multigrid cycle."""
     A, Ac = B.linear_op(p), B.linear_op(p, coarse=True)
