@@ -39,8 +39,19 @@ struct Sshex8LECfg {
     static constexpr int NXE = N * N * N;
     static constexpr int H = L / 2;            // micro elements per direction and colour
     static constexpr int TPE = H * H * H;      // threads per macro element
-    static constexpr int EPB = (L == 8) ? 4 : (L == 4 ? 16 : 64);  // macro elements per CTA batch
+    static constexpr int EPB = (L == 8) ? 6 : (L == 4 ? 16 : 64);  // macro elements per CTA batch
     static constexpr int BT = TPE * EPB;
+    // Shared-memory tile layout: index = z * PZ + y * N + xi(x) with the even x of a row first and the odd x behind
+    // them (xi(x) = (x & 1) * XE + x / 2) and PZ = N^2 padded to 2 (mod 8). The threads of a half-warp are the (i, k)
+    // pairs of one j (micro element (2i, 2j, 2k) + colour offset): consecutive i are consecutive doubles and k
+    // advances by 2 PZ = 4 (mod 16) doubles, so the 16 8-byte accesses of a half-warp fall on 16 different bank
+    // pairs. The dense layout with (i, j) half-warps put them on 2 (i + j): up to 6 wavefronts per request, and ncu
+    // showed the kernel MIO-bound (5 bank conflicts per shared load; 5.1 -> 3.7 ms with 2-way conflicts, see DESIGN).
+    static constexpr int XE = (N + 1) / 2;
+    static constexpr int PZ = (N * N + 5) / 8 * 8 + 2;
+    static constexpr int CS = N * PZ;  // component stride of a tile
+    static_assert(PZ >= N * N && PZ % 8 == 2, "plane stride");
+    __host__ __device__ static constexpr int xi(int x) { return (x & 1) * XE + (x >> 1); }
     static_assert(L % 2 == 0, "parity colouring needs an even level");
 };
 
@@ -51,7 +62,8 @@ __global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
                            const T lambda, const T *__restrict__ u, T *__restrict__ y) {
     using Cfg = Sshex8LECfg<L>;
     constexpr int N = Cfg::N, NXE = Cfg::NXE, H = Cfg::H, TPE = Cfg::TPE, EPB = Cfg::EPB, BT = Cfg::BT;
-    constexpr int ES = 3 * NXE;  // values per element tile
+    constexpr int PZ = Cfg::PZ, CS = Cfg::CS;
+    constexpr int ES = 3 * CS;  // values per element tile
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BoxDesc *sbox = reinterpret_cast<BoxDesc *>(smem_raw);
@@ -85,11 +97,12 @@ __global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
                 id = d.base + d.sx * x + d.sy * yy + d.sz * z;
             }
             const T *p = u + (ptrdiff_t)id * 3;
-            T *tu = tile_u + slot * ES + n, *to = tile_o + slot * ES + n;
+            const int tn = z * PZ + yy * N + Cfg::xi(x);
+            T *tu = tile_u + slot * ES + tn, *to = tile_o + slot * ES + tn;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                tu[c * NXE] = p[c];
-                to[c * NXE] = T(0);
+                tu[c * CS] = p[c];
+                to[c * CS] = T(0);
             }
         }
         __syncthreads();
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
         {
             const int slot = tid / TPE, t = tid - slot * TPE;
             const bool active = slot < nslots;
-            const int k = t / (H * H), j = (t - k * H * H) / H, i = t - k * H * H - j * H;
+            const int j = t / (H * H), k = (t - j * H * H) / H, i = t - j * H * H - k * H;  // half-warp = (i, k) pairs
             Hex8LEConsts<T> K;
             if (active) {
                 T A[9];
@@ -111,20 +124,22 @@ __global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
 #pragma unroll 1
             for (int colour = 0; colour < 8; ++colour) {
                 if (active) {
-                    const int base = ((2 * k + ((colour >> 2) & 1)) * N + 2 * j + ((colour >> 1) & 1)) * N + 2 * i + (colour & 1);
+                    const int x0 = 2 * i + (colour & 1);
+                    const int base = (2 * k + ((colour >> 2) & 1)) * PZ + (2 * j + ((colour >> 1) & 1)) * N;
+                    const int xo[2] = {Cfg::xi(x0), Cfg::xi(x0 + 1)};
                     T ul[3][8], ol[3][8];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
 #pragma unroll
                         for (int v = 0; v < 8; ++v)
-                            ul[c][v] = tu[c * NXE + base + ((v >> 2) & 1) * N * N + ((v >> 1) & 1) * N + (v & 1)];
+                            ul[c][v] = tu[c * CS + base + ((v >> 2) & 1) * PZ + ((v >> 1) & 1) * N + xo[v & 1]];
                     }
                     hex8_le_local_apply(K, ul, ol);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
 #pragma unroll
                         for (int v = 0; v < 8; ++v)
-                            to[c * NXE + base + ((v >> 2) & 1) * N * N + ((v >> 1) & 1) * N + (v & 1)] += ol[c][v];
+                            to[c * CS + base + ((v >> 2) & 1) * PZ + ((v >> 1) & 1) * N + xo[v & 1]] += ol[c][v];
                     }
                 }
                 __syncthreads();
@@ -147,13 +162,13 @@ __global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
                 plain = PLAIN_INTERIOR && b == 13;
             }
             T *p = y + (ptrdiff_t)id * 3;
-            const T *to = tile_o + slot * ES + n;
+            const T *to = tile_o + slot * ES + z * PZ + yy * N + Cfg::xi(x);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (plain)
-                    __stcs(&p[c], to[c * NXE]);
+                    __stcs(&p[c], to[c * CS]);
                 else
-                    red_add(&p[c], to[c * NXE]);
+                    red_add(&p[c], to[c * CS]);
             }
         }
         __syncthreads();
@@ -205,7 +220,7 @@ struct Sshex8LinearElasticity final : OpBase {
     template <typename T, int L, int MODE, bool PLAIN>
     int launch(const T *x, T *y, cudaStream_t s) {
         using Cfg = Sshex8LECfg<L>;
-        const size_t smem = (size_t)Cfg::EPB * 2 * 3 * Cfg::NXE * sizeof(T) + (MODE == kLEBoxes ? (size_t)Cfg::EPB * 27 * sizeof(BoxDesc) : 0);
+        const size_t smem = (size_t)Cfg::EPB * 2 * 3 * Cfg::CS * sizeof(T) + (MODE == kLEBoxes ? (size_t)Cfg::EPB * 27 * sizeof(BoxDesc) : 0);
         auto kern = sshex8_le_apply_kernel<T, L, MODE, PLAIN>;
         static bool configured = false;
         if (!configured) {
