@@ -124,10 +124,18 @@ def cpu_reference_run(a, elements, fff, nn, steps, warmup):
     from oracle.ref import Oracle, available
 
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if "TORCHELASTIC_RUN_ID" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+        # torchrun exports OMP_NUM_THREADS=1 for every rank; only rank 0 runs this leg and it gets all host cores
+        os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_PROC_BIND", "true")
     kind = "reference" if available("reference", a.real, fast=True) else "port"
     orc = Oracle(kind, a.real, fast=(kind == "reference"))
+    try:  # libgomp may have been initialised (by numpy / torch) before the variable was set
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+    except Exception:
+        pass
     u = np.random.default_rng(42).uniform(-1, 1, nn).astype(orc.rt)
     y = np.zeros(nn, dtype=orc.rt)
     for _ in range(warmup):
