@@ -313,9 +313,13 @@ __global__ void __launch_bounds__(NTEAM *TW * 32, 1)
     team_barrier<TW>(team);
 
     // ---- stream
-    const bool compute_lane = tl < EPT * N;
-    const int slot = compute_lane ? tl / N : 0;
-    const int yrow = compute_lane ? tl - slot * N : 0;
+    // Lanes beyond EPT * N (5 of 32 at L = 8) shadow the last row: they run the same arithmetic on the same shared-memory
+    // addresses and store the same values, so the compute section needs no divergent region (the FP64 pipe charges a
+    // warp instruction the same for 27 or 32 active lanes; reads of one address broadcast).
+    const int cl = tl < EPT * N ? tl : EPT * N - 1;
+    const bool compute_lane = true;
+    const int slot = cl / N;
+    const int yrow = cl - slot * N;
     Sshex8LaplacianRow<T, L> row;
 
     // Two forms of the same loop. fp32: z unrolled (static accumulator phases of the core: no register rotation, no
