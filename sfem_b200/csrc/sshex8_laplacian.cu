@@ -206,6 +206,12 @@ struct Sshex8Laplacian final : OpBase {
     int use_stream = 1;                 // 0 = the batch kernel below (kept for explicit connectivity)
 
     int reserve_sms = 0;
+    // Warp-specialised kernel (sshex8_laplacian_ws.cuh) where it applies: level 8, compact numbering, 16-byte aligned
+    // x. 1 = where it is the faster one (fp64: 0.90 against 0.97 - 1.04 ms at C3; at fp32 the z-unrolled plane-streaming
+    // kernel wins, 0.66 against 0.79 ms), 2 = whenever it applies, 0 = never. The plane-streaming kernel stays the path
+    // for everything else (and for the ne % 3 left-over elements).
+    int use_ws = 1;
+    int ws_cfg = 0;
     ptrdiff_t range_e0 = 0, range_e1 = -1;  // element range of the stream launch in flight (-1: the whole mesh)
 
     template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN>
@@ -232,6 +238,37 @@ struct Sshex8Laplacian final : OpBase {
             kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne_main, hdr, x, y);
         }
         if (ne_main < ne) tail<<<1, Cfg::threads, Cfg::smem_bytes, s>>>(ne - ne_main, hdr + ne_main, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+
+    template <typename T>
+    bool ws_applies(const T *x) const {
+        return (use_ws == 2 || (use_ws == 1 && sizeof(T) == 8)) && level == 8 && interior_exclusive && range_e1 < 0 && (((uintptr_t)x) & 15) == 0 &&
+               nn >= 64;
+    }
+
+    // warp-specialised kernel (sshex8_laplacian_ws.cu) over the full groups of 3 elements, the ne % 3 left-over
+    // elements in a clean-up launch of the plane-streaming kernel
+    template <typename T, bool PLAIN>
+    int launch_ws(const T *x, T *y, cudaStream_t s) {
+        constexpr int L = 8, EPT = 3;
+        const ptrdiff_t ne_main = (ne / EPT) * EPT;
+        if (ne_main > 0) {
+            const int max_ctas = std::max(1, sm_count() - reserve_sms);
+            if (sshex8_laplacian_ws_launch(sizeof(T) == 8 ? B200FEM_F64 : B200FEM_F32, PLAIN, ws_cfg, ne_main, nn, headers.ptr, x, y, max_ctas, s))
+                return B200FEM_FAILURE;
+        }
+        if (ne_main < ne) {
+            using SC = Sshex8StreamCfg<T, L, 1, 8, 3>;
+            auto tail = sshex8_laplacian_stream_kernel<T, L, 1, 8, 3, PLAIN, true>;
+            static bool tail_configured = false;
+            if (!tail_configured) {
+                B2_CUDA(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC::smem_bytes));
+                tail_configured = true;
+            }
+            tail<<<1, SC::threads, SC::smem_bytes, s>>>(ne - ne_main, headers.ptr + ne_main, x, y);
+        }
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
     }
@@ -266,6 +303,7 @@ struct Sshex8Laplacian final : OpBase {
     int launch_stream(const T *x, T *y, cudaStream_t s) {
         constexpr bool F64 = sizeof(T) == 8;
         if constexpr (L == 8) {
+            if (ws_applies(x)) return launch_ws<T, PLAIN>(x, y, s);
             switch (stream_cfg) {
                 default:
                 case 0:  // fp32 runs the z-unrolled loop, which wants the ring slots static (depth 3 divides N = 9)
@@ -421,6 +459,8 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "stream_cfg")) { stream_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_stream")) { use_stream = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_tma")) { use_tma = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_ws")) { use_ws = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "ws_cfg")) { ws_cfg = value; return B200FEM_SUCCESS; }
         if (!strcmp(key, "reserve_sms")) {
             if (value < 0 || value >= sm_count()) B2_FAIL("reserve_sms out of range");
             reserve_sms = value;
@@ -446,6 +486,7 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "stream_cfg")) { *value = stream_cfg; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_stream")) { *value = use_stream; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_tma")) { *value = use_tma; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "use_ws")) { *value = use_ws; return B200FEM_SUCCESS; }
         if (!strcmp(key, "tma_ok")) { *value = tma_ok ? 1 : 0; return B200FEM_SUCCESS; }
         return OpBase::get_option(key, value);
     }

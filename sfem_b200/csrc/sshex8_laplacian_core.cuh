@@ -194,6 +194,17 @@ struct Sshex8LaplacianRow {
             step_class<1>(plane, ystride);
     }
 
+    // rolled-loop form with a caller-supplied row loader (any shared-memory layout); pair with rotate()
+    template <class RowLoader>
+    B2_HD void step_with(const int zp, RowLoader &&load_row) {
+        if (zp == 0)
+            step_class_with<0, 1>(load_row);
+        else if (zp == L)
+            step_class_with<2, 1>(load_row);
+        else
+            step_class_with<1, 1>(load_row);
+    }
+
     // compile-time plane index: phase zp % 3, no register rotation (see `acc`)
     template <int ZP, class RowLoader>
     B2_HD void step_static(RowLoader &&load_row) {

@@ -1,0 +1,76 @@
+// Host side of the warp-specialised sshex8 Laplacian kernel (sshex8_laplacian_ws.cuh): tensor map + launch.
+#include <algorithm>
+
+#include "sshex8_laplacian_ws.cuh"
+
+namespace b200fem {
+
+// 1-D tensor map over the input vector (box = WsLayout<T>::BOX elements): what the interior-plane copies go through.
+// Encoded per call (the vector changes from call to call; ~1 us on the host).
+template <typename T>
+static int encode_vector_map(const T *x, ptrdiff_t nn, CUtensorMap *map) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    if (!encode) B2_FAIL("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[1] = {(cuuint64_t)nn};
+    const cuuint64_t strides[1] = {0};  // rank 1: no strides are read
+    const cuuint32_t box[1] = {(cuuint32_t)WsLayout<T>::BOX};
+    const cuuint32_t estr[1] = {1};
+    const CUresult r = encode(map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<T *>(x), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B2_FAIL("cuTensorMapEncodeTiled failed");
+    return B200FEM_SUCCESS;
+}
+
+template <typename T, int NC, int D, int S, bool PLAIN, bool PHASED = false>
+static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg) {
+    constexpr int L = 8;
+    using Cfg = Sshex8WsCfg<T, L, NC, D, S>;
+    auto kern = sshex8_laplacian_ws_kernel<T, L, NC, D, S, PLAIN, PHASED>;
+    static bool configured = false;
+    if (!configured) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+        configured = true;
+    }
+    const ptrdiff_t ngroups = ne / Cfg::EPT;
+    if (ngroups == 0) return B200FEM_SUCCESS;
+    alignas(64) CUtensorMap map;
+    if (encode_vector_map(x, nn, &map)) return B200FEM_FAILURE;
+    const int grid = (int)std::min<ptrdiff_t>((ngroups + NC - 1) / NC, (ptrdiff_t)max_ctas);
+    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ngroups * Cfg::EPT, headers, map, x, y, dbg);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+template <typename T, bool PLAIN>
+static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s) {
+    const int dbg = cfg >> 8;  // A/B switch (ws_cfg + 256): interior runs per node instead of TMA
+    switch (cfg & 255) {
+        default:
+        case 0: return launch_cfg<T, 8, 4, 2, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);  // measured best at C3
+        case 1: return launch_cfg<T, 8, 4, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 2: return launch_cfg<T, 8, 4, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 3: return launch_cfg<T, 8, 6, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 4: return launch_cfg<T, 8, 4, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // phase-unrolled z loop
+    }
+}
+
+int sshex8_laplacian_ws_launch(int real_type, bool plain, int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const void *x,
+                               void *y, int max_ctas, cudaStream_t s) {
+    if (real_type == B200FEM_F64)
+        return plain ? launch_t<double, true>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s)
+                     : launch_t<double, false>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s);
+    return plain ? launch_t<float, true>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s)
+                 : launch_t<float, false>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s);
+}
+
+}  // namespace b200fem

@@ -1,0 +1,472 @@
+// sshex8 Laplacian, warp-specialised plane-streaming kernel ("ws"): compute warps only read shared memory and
+// issue FMAs, mover warps own every global access. Same arithmetic (sshex8_laplacian_core.cuh), same element
+// headers and same plane ring as sshex8_laplacian_stream.cuh; what changes is who does what, and how the interior
+// of a plane travels.
+//
+// Why (ncu of the one-warp-does-everything kernel, profiles/r01e_ncu_sshex8_stream.details.txt):
+//   * 2 warps per scheduler at 250 registers, each alternating between a DFMA stream and the integer / LSU chains of
+//     its own copies: issue slots 41 % busy, FP64 pipe 37 % busy, 1.6 cycles of every 4.8 between two instructions of
+//     a warp spent in fixed-latency waits nobody covers;
+//   * the L1 data pipe is the busiest unit (71 %): an 8-byte LDGSTS costs one shared-memory wavefront per 32-byte
+//     SECTOR it fetches (52.5 M wavefronts for 191 M nodes, 4x what the bytes need), and the shared loads of the
+//     arithmetic pay 2.7-way bank conflicts between the element slots of a warp (layout [slot][y][x], 81 doubles
+//     per slot-plane).
+// Here
+//   * a CTA is NC compute warps + NC mover warps (one mover per compute warp; setmaxnreg moves the registers to the
+//     compute warps). Hand-off through mbarriers in shared memory, per compute warp: full[D] / empty[D] for the ring
+//     of input planes, sfull[S] / sempty[S] for the staged output planes. No CTA-wide barrier after the prologue;
+//   * for compact numberings (interior block of an element = one contiguous id run, x fastest) the (L-1)^2 interior
+//     values of a plane arrive as ONE 1-D tensor-map TMA copy per element (box of BOX elements starting at the
+//     16-byte boundary below the run; the over-fetch is at most 3 neighbours that sit in the same sectors anyway;
+//     out-of-range coordinates are zero-filled by the hardware). Only the 4 L skeleton
+//     positions of a plane (and the whole planes z = 0 and z = L) travel per node;
+//   * a slot-plane buffer is [interior run | skeleton: row y=0, row y=L, column x=0, column x=L] with per-slot offsets
+//     (WsLayout) chosen by exhaustive search so that the 27 shared loads of a z-step are nearly conflict-free.
+#pragma once
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "sshex8_laplacian_core.cuh"
+#include "sshex8_laplacian_stream.cuh"
+#include "sshex8_laplacian_tma.cuh"
+
+namespace b200fem {
+
+// Slot-plane buffer layout (elements): the interior run of plane z sits at offset k = g & (AL - 1), g = the node id
+// it starts with, AL = 16 / sizeof(T): the innermost tensor coordinate of a TMA copy must be a 16-byte multiple
+// (measured: tools/dev/tma1d_probe.cu -- odd fp64 coordinates raise "illegal instruction"), so the box starts at
+// g - k. Consecutive elements of a compact numbering have interior blocks of (L-1)^3 = 343 ids, i.e. k alternates
+// between the slots of a group -- which is exactly the skew that keeps the x-rows of neighbouring slots on disjoint
+// banks. The skeleton block of slot s starts at SK(s) (exhaustive search over the bank conflicts of the 27 loads of a
+// z-step: 75 wavefronts on average against the ideal 54 at fp64; the dense [slot][y][x] layout pays ~150).
+template <typename T>
+struct WsLayout;
+template <>
+struct WsLayout<double> {
+    static constexpr int BOX = 50;  // elements per TMA box (400 B) >= (L-1)^2 + AL - 1
+    __host__ __device__ static constexpr int SK(int s) { return s == 0 ? 56 : (s == 1 ? 58 : 56); }
+};
+template <>
+struct WsLayout<float> {
+    static constexpr int BOX = 52;  // 208 B
+    __host__ __device__ static constexpr int SK(int s) { return s == 0 ? 52 : (s == 1 ? 56 : 59); }
+};
+
+template <typename T, int L, int NC, int D, int S>
+struct Sshex8WsCfg {
+    static constexpr int N = L + 1;
+    static constexpr int NI = (L - 1) * (L - 1);  // interior positions of a plane
+    static constexpr int NSK = N * N - NI;        // skeleton positions of a plane (4 L)
+    static constexpr int EPT = 32 / N;            // elements per compute warp at a time
+    static constexpr int PS = 96;                 // elements per slot-plane buffer (128-byte multiple for 4 and 8 B)
+    static constexpr int PLANE = EPT * PS;
+    static constexpr size_t ring_bytes = (size_t)D * PLANE * sizeof(T);
+    static constexpr size_t stage_bytes = (size_t)S * PLANE * sizeof(T);
+    static constexpr size_t hdr_bytes = (size_t)3 * EPT * sizeof(Sshex8Header);
+    static constexpr size_t bar_bytes = (size_t)(2 * D + 2 * S) * sizeof(uint64_t);
+    static constexpr size_t warp_bytes = ((ring_bytes + stage_bytes + hdr_bytes + bar_bytes + 127) / 128) * 128;
+    static constexpr size_t smem_bytes = warp_bytes * NC;
+    static constexpr int threads = 2 * NC * 32;
+    static_assert(L == 8, "the ws kernel is built for level 8 (EPT = 3, 32 skeleton positions per plane)");
+    static_assert(NSK == 32, "one skeleton position per lane and slot");
+    static_assert(WsLayout<T>::BOX * sizeof(T) % 16 == 0, "TMA box must be a multiple of 16 bytes");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on `bar` once all cp.async copies this thread has issued so far have landed (counts against the init count)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const CUtensorMap *tmap, int c0, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// offset of a skeleton position of slot i relative to the same position of slot 0
+template <typename T>
+__device__ __forceinline__ constexpr int ws_slot_shift(const int i) {
+    return i * 96 + WsLayout<T>::SK(i) - WsLayout<T>::SK(0);
+}
+
+// element offset of lattice position (x, yy) inside the buffer of slot s (interior positions: before the per-plane
+// alignment offset k is added)
+template <typename T, int L>
+__device__ __forceinline__ int ws_offset(const int s, const int x, const int yy) {
+    constexpr int PS = 96;
+    constexpr int k = 0;
+    const int sk = (s == 0) ? WsLayout<T>::SK(0) : (s == 1 ? WsLayout<T>::SK(1) : WsLayout<T>::SK(2));
+    // (yy may come in unclamped: rows below 0 / above L are the boundary rows. Written with <= / >= on purpose:
+    // ptxas 12.9 folded a clamp followed by `== L` into the predicate output of VIMNMX and took the `yy == L`
+    // branch for every lane.)
+    int o;
+    if (yy <= 0)
+        o = sk + x;
+    else if (yy >= L)
+        o = sk + (L + 1) + x;
+    else if (x == 0)
+        o = sk + 2 * (L + 1) + (yy - 1);
+    else if (x == L)
+        o = sk + 2 * (L + 1) + (L - 1) + (yy - 1);
+    else
+        o = k + (yy - 1) * (L - 1) + (x - 1);
+    return s * PS + o;
+}
+
+template <typename T, int L, int NC, int D, int S, bool PLAIN_INTERIOR, bool PHASED>
+__global__ void __launch_bounds__(2 * NC * 32, 1)
+    sshex8_laplacian_ws_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers, const __grid_constant__ CUtensorMap tmap_u,
+                               const T *__restrict__ u, T *__restrict__ y, const int dbg) {
+    using Cfg = Sshex8WsCfg<T, L, NC, D, S>;
+    using Lay = WsLayout<T>;
+    constexpr int N = Cfg::N, NI = Cfg::NI, EPT = Cfg::EPT, PS = Cfg::PS, PLANE = Cfg::PLANE;
+    constexpr int HSZ = (int)sizeof(Sshex8Header);
+    constexpr int HBUF = EPT * HSZ;
+    constexpr uint32_t TX_BYTES = (uint32_t)(EPT * Lay::BOX * sizeof(T));
+    constexpr int AL = 16 / (int)sizeof(T);  // elements per 16 bytes
+    // register budgets: 2 NC warps start with 65536 / (64 NC) each
+    constexpr int REG_MOVER = 88;
+    constexpr int REG_COMPUTE = (65536 / 32 - NC * REG_MOVER) / NC / 8 * 8;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, tl = threadIdx.x & 31;
+    const bool is_mover = warp >= NC;
+    const int cw = is_mover ? warp - NC : warp;  // the compute warp this warp is, or serves
+    unsigned char *wbase = smem_raw + (size_t)cw * Cfg::warp_bytes;
+    T *ring = reinterpret_cast<T *>(wbase);                                      // [D][EPT][PS]
+    T *stage = ring + (size_t)D * PLANE;                                         // [S][EPT][PS]
+    unsigned char *hdr_bytes = wbase + Cfg::ring_bytes + Cfg::stage_bytes;       // [3][EPT] headers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hdr_bytes + Cfg::hdr_bytes);
+    uint64_t *full = bars, *empty = bars + D, *sfull = bars + 2 * D, *sempty = bars + 2 * D + S;
+
+    // ---- work of this warp pair: groups gteam, gteam + nteams, ... (ne is a multiple of EPT: the host sends the rest
+    // to the clean-up launch of the streaming kernel)
+    const int ngroups = (int)(ne / EPT);  // element ids are int32 (idx_t)
+    const int nteams = (int)gridDim.x * NC;
+    const int gteam = (int)blockIdx.x * NC + cw;
+    const int my_groups = gteam < ngroups ? (ngroups - gteam + nteams - 1) / nteams : 0;
+    const int T_steps = my_groups * N;
+
+    if (!is_mover && tl == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            mbar_init(full + i, 33);  // 32 cp.async-triggered arrivals + the elected lane's (expect_tx) arrival
+            mbar_init(empty + i, 1);
+        }
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            mbar_init(sfull + i, 1);
+            mbar_init(sempty + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    auto group_of = [&](int g_local) -> int { return gteam + g_local * nteams; };
+
+    if (is_mover) {
+        // =========================================================================================== mover warp
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_MOVER));
+        if (my_groups == 0) return;
+
+        // skeleton item i: slot i, plane position NI + tl (interior-first order of plane_pos_to_xy)
+        int sk_x, sk_y;
+        plane_pos_to_xy<L>(NI + tl, sk_x, sk_y);
+        const int sk_cxy = ((sk_x == 0) ? 0 : (sk_x == L ? 2 : 1)) + 3 * ((sk_y == 0) ? 0 : (sk_y == L ? 2 : 1));
+        const int sk_off0 = ws_offset<T, L>(0, sk_x, sk_y);  // slot i: + ws_slot_shift<T>(i)
+        // interior items of slot s: run positions q = tl (always) and q = 32 + tl (lanes below NI - 32); the slot is a
+        // compile-time index, so per plane and slot there is one base id / base offset and the items are one add away
+        const bool in_second = tl < NI - 32;
+        const int q1 = in_second ? 32 + tl : 0;
+        const int x0 = 1 + tl % (L - 1), y0 = 1 + tl / (L - 1), x1 = 1 + q1 % (L - 1), y1 = 1 + q1 / (L - 1);
+
+        auto issue_headers = [&](int g_local) {
+            if (g_local >= my_groups) return;
+            const int4 *src = reinterpret_cast<const int4 *>(headers + (size_t)group_of(g_local) * EPT);
+            int4 *dst = reinterpret_cast<int4 *>(hdr_bytes + (g_local % 3) * HBUF);
+            for (int i = tl; i < EPT * 29; i += 32) cp_async_16(dst + i, src + i);
+        };
+        // skeleton ids of the z-interior planes of a group: id(z) = I + S z; interior run of plane z starts at B + NI z
+        auto plane_set = [&](const unsigned char *hb, int (&I)[EPT], int (&Sz)[EPT], int (&B)[EPT]) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int4 d = *reinterpret_cast<const int4 *>(hb + i * HSZ + (9 + sk_cxy) * 16);
+                I[i] = d.x + d.y * sk_x + d.z * sk_y;
+                Sz[i] = d.w;
+                const int4 c = *reinterpret_cast<const int4 *>(hb + i * HSZ + 13 * 16);
+                B[i] = c.x + c.y + c.z;  // id(1, 1, z) = B + sz z with the canonical strides (1, L-1, (L-1)^2)
+            }
+        };
+        // node id on a boundary plane (cz = 0 / 2): the position's own box descriptor
+        auto boundary_id = [&](const unsigned char *hb, int slot, int x, int yy, int cxy, int z) -> int {
+            const int4 d = *reinterpret_cast<const int4 *>(hb + slot * HSZ + ((z == 0 ? 0 : 18) + cxy) * 16);
+            return d.x + d.y * x + d.z * yy + d.w * z;
+        };
+        auto put = [&](T *p, const T v, auto plain_tag) {  // streaming store or RED, chosen at compile time
+            if constexpr (decltype(plain_tag)::value) {
+                if constexpr (sizeof(T) == 8)
+                    asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(v));
+                else
+                    asm volatile("st.global.cs.f32 [%0], %1;\n" ::"l"(p), "f"(v));
+            } else {
+                if constexpr (sizeof(T) == 8)
+                    asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(p), "d"(v));
+                else
+                    asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(p), "f"(v));
+            }
+        };
+        using PlainT = std::integral_constant<bool, PLAIN_INTERIOR>;
+        using RedT = std::integral_constant<bool, false>;
+
+        int ldI[EPT], ldS[EPT], ldB[EPT];  // set of the group whose planes are being gathered
+        int scI[EPT], scS[EPT], scB[EPT];  // set of the group whose planes are being scattered
+
+        // gather plane zp of the group with header buffer hb into ring slot `rs` (the slot is free)
+        auto issue_plane = [&](const int rs, const unsigned char *hb, const int zp) {
+            uint64_t *bar = full + rs;
+            T *dst = ring + (size_t)rs * PLANE;
+            if (zp == 0) {
+                // headers of this group were issued N commit groups ago
+                cp_async_wait<N - 2>();
+                __syncwarp();
+                plane_set(hb, ldI, ldS, ldB);
+            }
+            if (zp == 0 || zp == L) {
+                if (tl == 0) mbar_arrive(bar);
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = (ldB[i] + NI * zp) & (AL - 1);
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + boundary_id(hb, i, sk_x, sk_y, sk_cxy, zp));
+                    cp_async_value(dst + (i * PS + k + tl), u + boundary_id(hb, i, x0, y0, 4, zp));
+                    if (in_second) cp_async_value(dst + (i * PS + k + q1), u + boundary_id(hb, i, x1, y1, 4, zp));
+                    asm volatile("" ::: "memory");  // one slot at a time: small register budget
+                }
+            } else if (dbg & 1) {  // A/B switch: interior runs per node as well (no TMA)
+                if (tl == 0) mbar_arrive(bar);
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int g = ldB[i] + NI * zp, k = g & (AL - 1);
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + (ldI[i] + ldS[i] * zp));
+                    cp_async_value(dst + (i * PS + k + tl), u + (g + tl));
+                    if (in_second) cp_async_value(dst + (i * PS + k + q1), u + (g + q1));
+                }
+            } else {
+                if (tl == 0) {
+                    mbar_arrive_expect_tx(bar, TX_BYTES);
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const int g = ldB[i] + NI * zp;
+                        tma_load_1d(dst + i * PS, &tmap_u, g - (g & (AL - 1)), bar);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + (ldI[i] + ldS[i] * zp));
+            }
+            cp_async_mbar_arrive_noinc(bar);
+        };
+
+        // output plane z of the group with header buffer hb, staged in slot ss (phase parity sp); the staging slot is
+        // handed back after the last value has been read
+        auto scatter_plane = [&](const int ss, const uint32_t sp, const unsigned char *hb, const int z) {
+            const T *src = stage + (size_t)ss * PLANE;
+            mbar_wait(sfull + ss, sp);
+            if (z == 0 || z == L) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = (scB[i] + NI * z) & (AL - 1);
+                    put(y + boundary_id(hb, i, sk_x, sk_y, sk_cxy, z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
+                    put(y + boundary_id(hb, i, x0, y0, 4, z), src[i * PS + k + tl], RedT{});
+                    if (in_second) put(y + boundary_id(hb, i, x1, y1, 4, z), src[i * PS + k + q1], RedT{});
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int g = scB[i] + NI * z, k = g & (AL - 1);
+                    put(y + (scI[i] + scS[i] * z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
+                    put(y + (g + tl), src[i * PS + k + tl], PlainT{});
+                    if (in_second) put(y + (g + q1), src[i * PS + k + q1], PlainT{});
+                }
+            }
+            __syncwarp();
+            if (tl == 0) mbar_arrive(sempty + ss);
+        };
+
+        // ---- prologue: headers of groups 0 and 1, planes 0 .. D-1
+        issue_headers(0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        issue_headers(1);
+#pragma unroll 1
+        for (int s = 0; s < D; ++s) {
+            if (s < T_steps) issue_plane(s, hdr_bytes, s);  // D <= N: all in group 0
+            cp_async_commit();
+        }
+        // ---- stream. Counters instead of divisions: (gn, zn, hn) = group, plane and header buffer of step t + D;
+        // (zp, hs) = plane and header buffer of step t; rs / re = ring slot and `empty` parity of step t + D;
+        // ss / sp = staging slot and `sfull` parity of the next output plane.
+        int gn = 0, zn = D, hn = 0, rs = 0;
+        uint32_t re = 0;
+        if (zn == N) { zn = 0; gn = 1; hn = 1; }
+        int zp = 0, hs = 0, ss = 0;
+        uint32_t sp = 0;
+        static_assert(D <= N, "ring deeper than a group");
+#pragma unroll 1
+        for (int t = 0; t < T_steps; ++t) {
+            if (t + D < T_steps) {
+                mbar_wait(empty + rs, re);
+                if (zn == 0) issue_headers(gn + 1);  // headers of group g+2 travel with the first plane of g+1
+                issue_plane(rs, hdr_bytes + hn * HBUF, zn);
+            }
+            cp_async_commit();
+            if (++rs == D) { rs = 0; re ^= 1u; }
+            if (++zn == N) { zn = 0; ++gn; hn = (hn == 2) ? 0 : hn + 1; }
+
+            const unsigned char *hb = hdr_bytes + hs * HBUF;
+            if (zp == 0) plane_set(hb, scI, scS, scB);
+            if (zp > 0) {
+                scatter_plane(ss, sp, hb, zp - 1);
+                if (++ss == S) { ss = 0; sp ^= 1u; }
+            }
+            if (zp == L) {
+                scatter_plane(ss, sp, hb, L);
+                if (++ss == S) { ss = 0; sp ^= 1u; }
+            }
+            if (++zp == N) { zp = 0; hs = (hs == 2) ? 0 : hs + 1; }
+        }
+        cp_async_wait<0>();
+    } else {
+        // ========================================================================================= compute warp
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_COMPUTE));
+        if (my_groups == 0) return;
+        // lanes beyond EPT * N shadow the last row (same addresses, same values: no divergent region)
+        const int cl = tl < EPT * N ? tl : EPT * N - 1;
+        const int slot = cl / N;
+        const int yrow = cl - slot * N;
+        // the three rows this lane reads: offsets of x = 0, x = 1 (x = 1 .. L-1 are contiguous) and x = L
+        int a0[3], am[3], aL[3];
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const int yy = yrow + iy - 1;  // unclamped, see ws_offset
+            a0[iy] = ws_offset<T, L>(slot, 0, yy);
+            am[iy] = ws_offset<T, L>(slot, 1, yy);
+            aL[iy] = ws_offset<T, L>(slot, L, yy);
+        }
+        // rows of the interior block carry the per-plane alignment offset of the run (see WsLayout)
+        bool rint[3];
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const int yy = yrow + iy - 1;
+            rint[iy] = (yy >= 1 && yy <= L - 1);
+        }
+        int Bs = 0;  // id of lattice node (1, 1, 0) of this lane's element: the interior run of plane z starts at Bs + NI z
+        Sshex8LaplacianRow<T, L> row;
+
+        auto emit = [&](int o, int z, const T(&vals)[N]) {  // stage output plane z (number o overall), this lane's row
+            if (o >= S) mbar_wait(sempty + (o % S), (uint32_t)(((o / S) - 1) & 1));
+            T *dst = stage + (size_t)(o % S) * PLANE;
+            const int m = am[1] + (rint[1] ? ((Bs + NI * z) & (AL - 1)) : 0);
+            dst[a0[1]] = vals[0];
+#pragma unroll
+            for (int x = 1; x < L; ++x) dst[m + x - 1] = vals[x];
+            dst[aL[1]] = vals[L];
+            __syncwarp();
+            if (tl == 0) mbar_arrive(sfull + (o % S));
+        };
+
+        // One z-step with compile-time plane class ZC (0: z = 0, 1: interior, 2: z = L) and accumulator phase P = zp % 3
+        // (plane z accumulates in row.acc[z % 3]: no register rotation; N = 9 is a multiple of 3, so the phase pattern
+        // is the same for every group).
+        auto z_step = [&](auto zc_tag, auto p_tag, const int g_local, const int zp) {
+            constexpr int ZC = decltype(zc_tag)::value, P = decltype(p_tag)::value;
+            const int t = g_local * N + zp;
+            const T *plane = ring + (size_t)(t % D) * PLANE;
+            mbar_wait(full + (t % D), (uint32_t)((t / D) & 1));
+            if constexpr (ZC == 0) {
+                const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
+                T f[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                row.init(f, yrow);
+                Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
+            }
+            const int kin = (Bs + NI * zp) & (AL - 1);
+            row.template step_class_with<ZC, P>([&](const int iy, T(&r)[N]) {
+                const int m = am[iy] + (rint[iy] ? kin : 0);
+                r[0] = plane[a0[iy]];
+#pragma unroll
+                for (int x = 1; x < L; ++x) r[x] = plane[m + x - 1];
+                r[L] = plane[aL[iy]];
+            });
+            __syncwarp();
+            if (tl == 0) mbar_arrive(empty + (t % D));
+            if constexpr (ZC != 0) {  // output plane zp - 1 is final; its registers become the accumulator of plane zp + 2
+                emit(t - 1, zp - 1, row.acc[(P + 2) % 3]);
+#pragma unroll
+                for (int x = 0; x < N; ++x) row.acc[(P + 2) % 3][x] = T(0);
+            }
+            if constexpr (ZC == 2) emit(t, L, row.acc[P % 3]);
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        static_assert(N % 3 == 0, "phase pattern assumes N % 3 == 0");
+        if constexpr (!PHASED) {
+            // rolled form: one loop body, accumulators rotated through the registers after every step
+            int g_local = 0, zp = 0;
+#pragma unroll 1
+            for (int t = 0; t < T_steps; ++t) {
+                const T *plane = ring + (size_t)(t % D) * PLANE;
+                mbar_wait(full + (t % D), (uint32_t)((t / D) & 1));
+                if (zp == 0) {
+                    const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
+                    T f[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                    row.init(f, yrow);
+                    Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
+                }
+                const int kin = (Bs + NI * zp) & (AL - 1);
+                row.step_with(zp, [&](const int iy, T(&r)[N]) {
+                    const int m = am[iy] + (rint[iy] ? kin : 0);
+                    r[0] = plane[a0[iy]];
+#pragma unroll
+                    for (int x = 1; x < L; ++x) r[x] = plane[m + x - 1];
+                    r[L] = plane[aL[iy]];
+                });
+                __syncwarp();
+                if (tl == 0) mbar_arrive(empty + (t % D));
+                if (zp > 0) emit(g_local * N + zp - 1, zp - 1, row.acc[0]);
+                row.rotate();
+                if (zp == L) emit(g_local * N + L, L, row.acc[0]);
+                if (++zp == N) {
+                    zp = 0;
+                    ++g_local;
+                }
+            }
+            return;
+        }
+#pragma unroll 1
+        for (int g_local = 0; g_local < my_groups; ++g_local) {
+            z_step(I0{}, I0{}, g_local, 0);
+#pragma unroll 1
+            for (int zz = 0; zz < N; zz += 3) {
+                if (zz > 0) z_step(I1{}, I0{}, g_local, zz);
+                z_step(I1{}, I1{}, g_local, zz + 1);
+                if (zz + 2 < L)
+                    z_step(I1{}, I2{}, g_local, zz + 2);
+                else
+                    z_step(I2{}, I2{}, g_local, L);
+            }
+        }
+    }
+}
+
+}  // namespace b200fem

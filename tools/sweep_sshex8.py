@@ -16,6 +16,8 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--tma_cfg", type=int, default=0)
 ap.add_argument("--tma", default="0", help="comma list of use_tma values to sweep (0 = plane-streaming, 1 = entity-box TMA kernel)")
+ap.add_argument("--ws", default="1", help="comma list of use_ws values (1 = warp-specialised kernel, 0 = plane-streaming kernel)")
+ap.add_argument("--ws_cfgs", default="0")
 a = ap.parse_args()
 
 m = mesh.sshex8_box(a.level, a.macro, a.macro, a.macro, with_points=False)
@@ -32,8 +34,15 @@ for real in a.reals.split(","):
         yref = torch.zeros_like(x)
         op.apply_overwrite(x, yref)
         op.set_option("use_stream", 1)
-    for tma, cfg in [(t, c) for t in [int(v) for v in a.tma.split(",")] for c in ([int(c) for c in a.cfgs.split(",")] if t == 0 else [0])]:
-        op.set_option("stream_cfg", cfg)
+    combos = []
+    for ws in [int(v) for v in a.ws.split(",")]:
+        if ws:
+            combos += [(1, 0, c) for c in [int(c) for c in a.ws_cfgs.split(",")]]
+        else:
+            combos += [(0, t, c) for t in [int(v) for v in a.tma.split(",")] for c in ([int(c) for c in a.cfgs.split(",")] if t == 0 else [0])]
+    for ws, tma, cfg in combos:
+        op.set_option("use_ws", 2 if ws else 0)
+        op.set_option("ws_cfg" if ws else "stream_cfg", cfg)
         op.set_option("use_tma", tma)
         op.set_option("tma_cfg", a.tma_cfg)
         res = {}
@@ -54,7 +63,7 @@ for real in a.reals.split(","):
             op.apply_overwrite(x, y)
             err = float((y - yref).norm() / yref.norm())
         alg = op.algorithmic_bytes
-        print(json.dumps({"real": real, "tma": tma, "cfg": cfg, "ms_overwrite": round(res["overwrite"], 4), "ms_accumulate": round(res["accumulate"], 4),
+        print(json.dumps({"real": real, "ws": ws, "tma": tma, "cfg": cfg, "ms_overwrite": round(res["overwrite"], 4), "ms_accumulate": round(res["accumulate"], 4),
                           "gdofs_overwrite": round(nn / res["overwrite"] / 1e6, 1), "alg_GBs_overwrite": round(alg / res["overwrite"] / 1e6, 1),
                           "rel_vs_batch_kernel": err}), flush=True)
     del op
