@@ -100,11 +100,14 @@ class GpuBackend:
     def to_numpy(self, v):
         return v.detach().cpu().numpy().astype(np.float64)
 
+    # The cache is keyed by id(p), so it must keep p alive: this backend is module-scoped, the problems are per test,
+    # and CPython hands the id of a collected problem to the next one -- which then got the previous problem's
+    # operator (intermittent "MG does not converge" failures in the full suite, never in isolation).
     def function(self, p, coarse=False):
         key = (id(p), coarse)
         if key not in self._functions:
-            self._functions[key] = P.gpu_function(p, self.dtype, coarse)
-        return self._functions[key]
+            self._functions[key] = (p, P.gpu_function(p, self.dtype, coarse))
+        return self._functions[key][1]
 
     def linear_op(self, p, coarse=False):
         return self.function(p, coarse)
@@ -122,8 +125,8 @@ class GpuBackend:
     def level_op(self, p, i):
         key = (id(p), "level", i)
         if key not in self._functions:
-            self._functions[key] = P.gpu_level_function(p, self.dtype, i)
-        return self._functions[key]
+            self._functions[key] = (p, P.gpu_level_function(p, self.dtype, i))
+        return self._functions[key][1]
 
     def level_transfer(self, p, i):
         t = P.gpu_level_transfer(p, i)
