@@ -248,29 +248,12 @@ struct Sshex8Laplacian final : OpBase {
                nn >= 64;
     }
 
-    // warp-specialised kernel (sshex8_laplacian_ws.cu) over the full groups of 3 elements, the ne % 3 left-over
-    // elements in a clean-up launch of the plane-streaming kernel
+    // warp-specialised kernel (sshex8_laplacian_ws.cu); a partial last group of 3 reads the padding headers (copies of
+    // the last element, see make_sshex8_laplacian) and scatters only its valid slots
     template <typename T, bool PLAIN>
     int launch_ws(const T *x, T *y, cudaStream_t s) {
-        constexpr int L = 8, EPT = 3;
-        const ptrdiff_t ne_main = (ne / EPT) * EPT;
-        if (ne_main > 0) {
-            const int max_ctas = std::max(1, sm_count() - reserve_sms);
-            if (sshex8_laplacian_ws_launch(sizeof(T) == 8 ? B200FEM_F64 : B200FEM_F32, PLAIN, ws_cfg, ne_main, nn, headers.ptr, x, y, max_ctas, s))
-                return B200FEM_FAILURE;
-        }
-        if (ne_main < ne) {
-            using SC = Sshex8StreamCfg<T, L, 1, 8, 3>;
-            auto tail = sshex8_laplacian_stream_kernel<T, L, 1, 8, 3, PLAIN, true>;
-            static bool tail_configured = false;
-            if (!tail_configured) {
-                B2_CUDA(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC::smem_bytes));
-                tail_configured = true;
-            }
-            tail<<<1, SC::threads, SC::smem_bytes, s>>>(ne - ne_main, headers.ptr + ne_main, x, y);
-        }
-        B2_CHECK_LAUNCH();
-        return B200FEM_SUCCESS;
+        const int max_ctas = std::max(1, sm_count() - reserve_sms);
+        return sshex8_laplacian_ws_launch(sizeof(T) == 8 ? B200FEM_F64 : B200FEM_F32, PLAIN, ws_cfg, ne, nn, headers.ptr, x, y, max_ctas, s);
     }
 
     template <typename T, int L, bool PLAIN>
@@ -576,6 +559,11 @@ OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32
             }
             for (int k = 0; k < 6; ++k) h.fff[k] = fff[e * 6 + k];
             h.pad[0] = h.pad[1] = 0.f;
+        }
+        // two padding headers (copies of the last element): the ws kernel fetches headers by groups of 3
+        if (ne > 0) {
+            hdrs.push_back(hdrs.back());
+            hdrs.push_back(hdrs.back());
         }
         rc |= op->headers.upload(hdrs.data(), hdrs.size());
         // TMA headers: every box must be a contiguous id run

@@ -36,7 +36,8 @@ struct Sshex8Header {   // 464 B, 16-byte aligned
 };
 static_assert(sizeof(Sshex8Header) == 29 * 16, "header must be 29 x 16 B");
 
-// Warp-specialised level-8 kernel (sshex8_laplacian_ws.cu / .cuh): `ne` must be a multiple of 3; compact numbering
+// Warp-specialised level-8 kernel (sshex8_laplacian_ws.cu / .cuh): `headers` must be readable up to the next multiple
+// of 3 elements (padding = copies of the last element; only valid slots are scattered); compact numbering
 // (interior block of an element = one contiguous id run, x fastest) and 16-byte aligned x required. real_type is
 // B200FEM_F64 / B200FEM_F32; `plain` = interior nodes are stored, not added (overwriting apply).
 int sshex8_laplacian_ws_launch(int real_type, bool plain, int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const void *x,

@@ -41,12 +41,12 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
         configured = true;
     }
-    const ptrdiff_t ngroups = ne / Cfg::EPT;
+    const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;  // the last group may be partial (padded headers)
     if (ngroups == 0) return B200FEM_SUCCESS;
     alignas(64) CUtensorMap map;
     if (encode_vector_map(x, nn, &map)) return B200FEM_FAILURE;
     const int grid = (int)std::min<ptrdiff_t>((ngroups + NC - 1) / NC, (ptrdiff_t)max_ctas);
-    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ngroups * Cfg::EPT, headers, map, x, y, dbg);
+    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers, map, x, y, dbg);
     B2_CHECK_LAUNCH();
     return B200FEM_SUCCESS;
 }

@@ -144,9 +144,10 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
     uint64_t *bars = reinterpret_cast<uint64_t *>(hdr_bytes + Cfg::hdr_bytes);
     uint64_t *full = bars, *empty = bars + D, *sfull = bars + 2 * D, *sempty = bars + 2 * D + S;
 
-    // ---- work of this warp pair: groups gteam, gteam + nteams, ... (ne is a multiple of EPT: the host sends the rest
-    // to the clean-up launch of the streaming kernel)
-    const int ngroups = (int)(ne / EPT);  // element ids are int32 (idx_t)
+    // ---- work of this warp pair: groups gteam, gteam + nteams, ... The last group may hold fewer than EPT elements: its
+    // missing slots read the padding headers (copies of the last element: same loads, same arithmetic) and are not
+    // scattered.
+    const int ngroups = (int)((ne + EPT - 1) / EPT);  // element ids are int32 (idx_t)
     const int nteams = (int)gridDim.x * NC;
     const int gteam = (int)blockIdx.x * NC + cw;
     const int my_groups = gteam < ngroups ? (ngroups - gteam + nteams - 1) / nteams : 0;
@@ -273,12 +274,13 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 
         // output plane z of the group with header buffer hb, staged in slot ss (phase parity sp); the staging slot is
         // handed back after the last value has been read
-        auto scatter_plane = [&](const int ss, const uint32_t sp, const unsigned char *hb, const int z) {
+        auto scatter_plane = [&](const int ss, const uint32_t sp, const unsigned char *hb, const int z, const int nv) {
             const T *src = stage + (size_t)ss * PLANE;
             mbar_wait(sfull + ss, sp);
             if (z == 0 || z == L) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
+                    if (i >= nv) break;
                     const int k = (scB[i] + NI * z) & (AL - 1);
                     put(y + boundary_id(hb, i, sk_x, sk_y, sk_cxy, z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
                     put(y + boundary_id(hb, i, x0, y0, 4, z), src[i * PS + k + tl], RedT{});
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             } else {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
+                    if (i >= nv) break;
                     const int g = scB[i] + NI * z, k = g & (AL - 1);
                     put(y + (scI[i] + scS[i] * z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
                     put(y + (g + tl), src[i * PS + k + tl], PlainT{});
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         int gn = 0, zn = D, hn = 0, rs = 0;
         uint32_t re = 0;
         if (zn == N) { zn = 0; gn = 1; hn = 1; }
-        int zp = 0, hs = 0, ss = 0;
+        int zp = 0, hs = 0, ss = 0, gs = 0, nv = EPT;
         uint32_t sp = 0;
         static_assert(D <= N, "ring deeper than a group");
 #pragma unroll 1
@@ -330,16 +333,20 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             if (++zn == N) { zn = 0; ++gn; hn = (hn == 2) ? 0 : hn + 1; }
 
             const unsigned char *hb = hdr_bytes + hs * HBUF;
-            if (zp == 0) plane_set(hb, scI, scS, scB);
+            if (zp == 0) {
+                plane_set(hb, scI, scS, scB);
+                const int left = (int)ne - group_of(gs) * EPT;  // valid slots of the group being scattered
+                nv = left < EPT ? left : EPT;
+            }
             if (zp > 0) {
-                scatter_plane(ss, sp, hb, zp - 1);
+                scatter_plane(ss, sp, hb, zp - 1, nv);
                 if (++ss == S) { ss = 0; sp ^= 1u; }
             }
             if (zp == L) {
-                scatter_plane(ss, sp, hb, L);
+                scatter_plane(ss, sp, hb, L, nv);
                 if (++ss == S) { ss = 0; sp ^= 1u; }
             }
-            if (++zp == N) { zp = 0; hs = (hs == 2) ? 0 : hs + 1; }
+            if (++zp == N) { zp = 0; ++gs; hs = (hs == 2) ? 0 : hs + 1; }
         }
         cp_async_wait<0>();
     } else {
