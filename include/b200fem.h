@@ -136,6 +136,9 @@ double b200fem_op_algorithmic_bytes(b200fem_op_t op);
 /* Bytes the plan actually streams per apply (compressed connectivity, y read when accumulating). */
 double b200fem_op_streamed_bytes(b200fem_op_t op, int overwrite);
 int b200fem_op_gpu_launches_per_apply(b200fem_op_t op, int overwrite);
+/* Tuning switches (all optional; defaults are the measured best). Common: "scatter" (B200FEM_SCATTER_*).
+ * sshex8 Laplacian: "use_ws" (1 = warp-specialised level-8 kernel where it is the faster one [fp64], 2 = wherever it
+ * applies, 0 = never), "ws_cfg" (ring / staging depth variant), "stream_cfg", "use_tma", "explicit_index". */
 int b200fem_op_set_option(b200fem_op_t op, const char *key, int value);
 int b200fem_op_get_option(b200fem_op_t op, const char *key, int *value);
 
