@@ -39,19 +39,24 @@ namespace b200fem {
 // (measured: tools/dev/tma1d_probe.cu -- odd fp64 coordinates raise "illegal instruction"), so the box starts at
 // g - k. Consecutive elements of a compact numbering have interior blocks of (L-1)^3 = 343 ids, i.e. k alternates
 // between the slots of a group -- which is exactly the skew that keeps the x-rows of neighbouring slots on disjoint
-// banks. The skeleton block of slot s starts at SK(s) (exhaustive search over the bank conflicts of the 27 loads of a
-// z-step: 75 wavefronts on average against the ideal 54 at fp64; the dense [slot][y][x] layout pays ~150).
+// banks. The skeleton block of slot s starts at SK(s) + DK(s) k: with a fixed start one of the two parity patterns of
+// a group, (k0, k1, k2) = (1, 0, 1), costs 89 wavefronts for the 27 loads of a z-step and 35 for the 9 stores (ideal
+// 54 / 18; ncu: 2.8 wavefronts per LDS.64); the k-dependent start brings both patterns to 60 / 20 (exhaustive search,
+// same model).
 template <typename T>
 struct WsLayout;
 template <>
 struct WsLayout<double> {
     static constexpr int BOX = 50;  // elements per TMA box (400 B) >= (L-1)^2 + AL - 1
-    __host__ __device__ static constexpr int SK(int s) { return s == 0 ? 56 : (s == 1 ? 58 : 56); }
+    // skeleton block of slot s at SK(s) + DK(s) * k, k = the alignment offset of that slot's interior run in this plane
+    __host__ __device__ static constexpr int SK(int s) { return s == 0 ? 56 : (s == 1 ? 57 : 53); }
+    __host__ __device__ static constexpr int DK(int s) { return s == 0 ? 0 : (s == 1 ? 1 : -1); }
 };
 template <>
 struct WsLayout<float> {
     static constexpr int BOX = 52;  // 208 B
     __host__ __device__ static constexpr int SK(int s) { return s == 0 ? 52 : (s == 1 ? 56 : 59); }
+    __host__ __device__ static constexpr int DK(int) { return 0; }
 };
 
 template <typename T, int L, int NC, int D, int S>
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     const int k = (ldB[i] + NI * zp) & (AL - 1);
-                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + boundary_id(hb, i, sk_x, sk_y, sk_cxy, zp));
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k), u + boundary_id(hb, i, sk_x, sk_y, sk_cxy, zp));
                     cp_async_value(dst + (i * PS + k + tl), u + boundary_id(hb, i, x0, y0, 4, zp));
                     if (in_second) cp_async_value(dst + (i * PS + k + q1), u + boundary_id(hb, i, x1, y1, 4, zp));
                     asm volatile("" ::: "memory");  // one slot at a time: small register budget
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     const int g = ldB[i] + NI * zp, k = g & (AL - 1);
-                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + (ldI[i] + ldS[i] * zp));
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k), u + (ldI[i] + ldS[i] * zp));
                     cp_async_value(dst + (i * PS + k + tl), u + (g + tl));
                     if (in_second) cp_async_value(dst + (i * PS + k + q1), u + (g + q1));
                 }
@@ -267,7 +272,10 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < EPT; ++i) cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i)), u + (ldI[i] + ldS[i] * zp));
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = (ldB[i] + NI * zp) & (AL - 1);
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k), u + (ldI[i] + ldS[i] * zp));
+                }
             }
             cp_async_mbar_arrive_noinc(bar);
         };
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 for (int i = 0; i < EPT; ++i) {
                     if (i >= nv) break;
                     const int k = (scB[i] + NI * z) & (AL - 1);
-                    put(y + boundary_id(hb, i, sk_x, sk_y, sk_cxy, z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
+                    put(y + boundary_id(hb, i, sk_x, sk_y, sk_cxy, z), src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
                     put(y + boundary_id(hb, i, x0, y0, 4, z), src[i * PS + k + tl], RedT{});
                     if (in_second) put(y + boundary_id(hb, i, x1, y1, 4, z), src[i * PS + k + q1], RedT{});
                     asm volatile("" ::: "memory");
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 for (int i = 0; i < EPT; ++i) {
                     if (i >= nv) break;
                     const int g = scB[i] + NI * z, k = g & (AL - 1);
-                    put(y + (scI[i] + scS[i] * z), src[sk_off0 + ws_slot_shift<T>(i)], RedT{});
+                    put(y + (scI[i] + scS[i] * z), src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
                     put(y + (g + tl), src[i * PS + k + tl], PlainT{});
                     if (in_second) put(y + (g + q1), src[i * PS + k + q1], PlainT{});
                 }
@@ -373,17 +381,20 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             const int yy = yrow + iy - 1;
             rint[iy] = (yy >= 1 && yy <= L - 1);
         }
+        const int dk = (slot == 0) ? Lay::DK(0) : (slot == 1 ? Lay::DK(1) : Lay::DK(2));  // skeleton block moves by dk * k
         int Bs = 0;  // id of lattice node (1, 1, 0) of this lane's element: the interior run of plane z starts at Bs + NI z
         Sshex8LaplacianRow<T, L> row;
 
         auto emit = [&](int o, int z, const T(&vals)[N]) {  // stage output plane z (number o overall), this lane's row
             if (o >= S) mbar_wait(sempty + (o % S), (uint32_t)(((o / S) - 1) & 1));
             T *dst = stage + (size_t)(o % S) * PLANE;
-            const int m = am[1] + (rint[1] ? ((Bs + NI * z) & (AL - 1)) : 0);
-            dst[a0[1]] = vals[0];
+            const int k = (Bs + NI * z) & (AL - 1);
+            T *ds = dst + dk * k;                        // skeleton positions
+            T *dm = (rint[1] ? dst + k : ds) + am[1];    // x = 1 .. L-1 of this lane's row
+            ds[a0[1]] = vals[0];
 #pragma unroll
-            for (int x = 1; x < L; ++x) dst[m + x - 1] = vals[x];
-            dst[aL[1]] = vals[L];
+            for (int x = 1; x < L; ++x) dm[x - 1] = vals[x];
+            ds[aL[1]] = vals[L];
             __syncwarp();
             if (tl == 0) mbar_arrive(sfull + (o % S));
         };
@@ -405,12 +416,13 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
             }
             const int kin = (Bs + NI * zp) & (AL - 1);
+            const T *pk = plane + kin, *ps = plane + dk * kin;  // interior rows / skeleton positions
             row.template step_class_with<ZC, P>([&](const int iy, T(&r)[N]) {
-                const int m = am[iy] + (rint[iy] ? kin : 0);
-                r[0] = plane[a0[iy]];
+                const T *pm = (rint[iy] ? pk : ps) + am[iy];
+                r[0] = ps[a0[iy]];
 #pragma unroll
-                for (int x = 1; x < L; ++x) r[x] = plane[m + x - 1];
-                r[L] = plane[aL[iy]];
+                for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
+                r[L] = ps[aL[iy]];
             });
             __syncwarp();
             if (tl == 0) mbar_arrive(empty + (t % D));
@@ -441,12 +453,13 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
                 }
                 const int kin = (Bs + NI * zp) & (AL - 1);
+                const T *pk = plane + kin, *ps = plane + dk * kin;  // interior rows / skeleton positions
                 row.step_with(zp, [&](const int iy, T(&r)[N]) {
-                    const int m = am[iy] + (rint[iy] ? kin : 0);
-                    r[0] = plane[a0[iy]];
+                    const T *pm = (rint[iy] ? pk : ps) + am[iy];
+                    r[0] = ps[a0[iy]];
 #pragma unroll
-                    for (int x = 1; x < L; ++x) r[x] = plane[m + x - 1];
-                    r[L] = plane[aL[iy]];
+                    for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
+                    r[L] = ps[aL[iy]];
                 });
                 __syncwarp();
                 if (tl == 0) mbar_arrive(empty + (t % D));
