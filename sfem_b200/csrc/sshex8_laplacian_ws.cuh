@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
     constexpr uint32_t TX_BYTES = (uint32_t)(EPT * Lay::BOX * sizeof(T));
     constexpr int AL = 16 / (int)sizeof(T);  // elements per 16 bytes
     // register budgets: 2 NC warps start with 65536 / (64 NC) each
-    constexpr int REG_MOVER = 88;
+    constexpr int REG_MOVER = 80;
     constexpr int REG_COMPUTE = (65536 / 32 - NC * REG_MOVER) / NC / 8 * 8;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -365,14 +365,13 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         const int cl = tl < EPT * N ? tl : EPT * N - 1;
         const int slot = cl / N;
         const int yrow = cl - slot * N;
-        // the three rows this lane reads: offsets of x = 0, x = 1 (x = 1 .. L-1 are contiguous) and x = L
-        int a0[3], am[3], aL[3];
+        // the three rows this lane reads: offsets of x = 0 and x = 1 (x = 1 .. L-1 are contiguous; x = L follows from x = 0)
+        int a0[3], am[3];
 #pragma unroll
         for (int iy = 0; iy < 3; ++iy) {
             const int yy = yrow + iy - 1;  // unclamped, see ws_offset
             a0[iy] = ws_offset<T, L>(slot, 0, yy);
             am[iy] = ws_offset<T, L>(slot, 1, yy);
-            aL[iy] = ws_offset<T, L>(slot, L, yy);
         }
         // rows of the interior block carry the per-plane alignment offset of the run (see WsLayout)
         bool rint[3];
@@ -394,7 +393,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             ds[a0[1]] = vals[0];
 #pragma unroll
             for (int x = 1; x < L; ++x) dm[x - 1] = vals[x];
-            ds[aL[1]] = vals[L];
+            ds[a0[1] + (rint[1] ? L - 1 : L)] = vals[L];
             __syncwarp();
             if (tl == 0) mbar_arrive(sfull + (o % S));
         };
@@ -422,7 +421,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 r[0] = ps[a0[iy]];
 #pragma unroll
                 for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
-                r[L] = ps[aL[iy]];
+                r[L] = ps[a0[iy] + (rint[iy] ? L - 1 : L)];  // x = L sits L-1 (column block) or L (boundary row) after x = 0
             });
             __syncwarp();
             if (tl == 0) mbar_arrive(empty + (t % D));
@@ -459,7 +458,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     r[0] = ps[a0[iy]];
 #pragma unroll
                     for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
-                    r[L] = ps[aL[iy]];
+                    r[L] = ps[a0[iy] + (rint[iy] ? L - 1 : L)];  // x = L sits L-1 (column block) or L (boundary row) after x = 0
                 });
                 __syncwarp();
                 if (tl == 0) mbar_arrive(empty + (t % D));
