@@ -181,6 +181,10 @@ int b200fem_blas_dot_async(int real_type, ptrdiff_t n, const void *x, const void
  * rtr is returned on the host (synchronises the stream). */
 int b200fem_cg_update_x_r_rtr(int real_type, ptrdiff_t n, double alpha, const void *p, const void *Ap, void *x,
                               void *r, double *rtr_host, void *stream);
+/* The same update with the reduction left in DEVICE memory (one double) and no synchronisation: the distributed CG
+ * sums it over the ranks on the device (b200fem_comm_sum_to_host) and reads one scalar per iteration. */
+int b200fem_cg_update_x_r_rtr_async(int real_type, ptrdiff_t n, double alpha, const void *p, const void *Ap, void *x,
+                                    void *r, double *rtr_dev, void *stream);
 int b200fem_cg_update_p(int real_type, ptrdiff_t n, double beta, const void *z, void *p, void *stream);
 /* p = beta p - rhs + Ax ; x -= alpha p   (chebyshev3_host_::iteration_update) */
 int b200fem_cheb3_update(int real_type, ptrdiff_t n, double alpha, double beta, const void *rhs, const void *Ax,
@@ -199,6 +203,56 @@ int b200fem_halo_pack(int real_type, ptrdiff_t n, const int32_t *idx, int block_
                       void *stream);
 int b200fem_halo_unpack_add(int real_type, ptrdiff_t n, const int32_t *idx, int block_size, const void *src,
                             void *dst, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Communicator and halo exchange: the distributed half of the path, one process per GPU.
+ * Replaces what the reference takes from smesh (source unavailable): Communicator::sum behind every dot product of
+ * ParallelConjugateGradient (algebra/parallel/sfem_parallel_cg.hpp:169-172, 238, 290) and Exchange::gather in
+ * ParallelMatrixFreeOperator::apply (frontend/sfem_ParallelMatrixFreeOperator.cpp:78-105).
+ *   b200fem_comm_unique_id : rank 0 creates the 128-byte id (ncclGetUniqueId) and the launcher hands it to every rank
+ *                            (MPI_Bcast in the reference's world; a torchrun store / broadcast in bench.py).
+ *   b200fem_comm_create    : ncclCommInitRank on the CURRENT device; world == 1 needs no id and never touches NCCL.
+ *   b200fem_comm_sum_to_host : allreduce(SUM) of n <= 64 DEVICE doubles, then ONE device->host read (synchronises
+ *                            `stream`); values_dev is left untouched. This is comm->sum() of the reference with the
+ *                            local reduction already on the device.
+ *   b200fem_comm_allreduce_sum : the same in place on the device, asynchronous.
+ * Halo plan: local nodes are [owned | ghosts], the ghosts received from one peer are a contiguous range
+ * [recv_begin, recv_begin + recv_count) (ghosts sorted by owner); send_idx lists the OWNED local ids each peer
+ * needs, in the order of that peer's range (CSR over send_peers through send_offsets). gather(x) fills the ghost
+ * block of the device vector x ([n_local * block_size], any allocation) from the owners, stream-ordered.
+ * Transports: PUSH = the owner's pack kernel stores straight into the peer's receive block over NVLink (cudaIpc-mapped),
+ * flags with acquire / release at system scope, every spin bounded by B200FEM_COMM_TIMEOUT_S (default 60 s; a time-out
+ * raises b200fem_comm_error and fails the next reduction instead of hanging the GPU); NCCL = pack + grouped
+ * ncclSend / ncclRecv into the ghost ranges. AUTO takes PUSH when every rank can map its peers.
+ * create / destroy are collective over the communicator.
+ * ---------------------------------------------------------------------------------------- */
+#define B200FEM_UNIQUE_ID_BYTES 128
+#define B200FEM_HALO_AUTO 0
+#define B200FEM_HALO_PUSH 1
+#define B200FEM_HALO_NCCL 2
+#define B200FEM_REDUCE_SUM 0
+#define B200FEM_REDUCE_MAX 1
+typedef struct b200fem_comm_s *b200fem_comm_t;
+typedef struct b200fem_halo_s *b200fem_halo_t;
+int b200fem_comm_unique_id(void *id_out /* [B200FEM_UNIQUE_ID_BYTES] */);
+int b200fem_comm_create(b200fem_comm_t *comm, int world, int rank, const void *unique_id);
+int b200fem_comm_destroy(b200fem_comm_t comm);
+int b200fem_comm_rank(b200fem_comm_t comm);
+int b200fem_comm_size(b200fem_comm_t comm);
+int b200fem_comm_error(b200fem_comm_t comm); /* 1 after a halo wait timed out */
+int b200fem_comm_allreduce_sum(b200fem_comm_t comm, double *values_dev, int n, void *stream);
+int b200fem_comm_sum_to_host(b200fem_comm_t comm, const double *values_dev, int n, double *values_host, void *stream);
+int b200fem_comm_allreduce_host(b200fem_comm_t comm, double *values_host, int n, int op, void *stream);
+int b200fem_comm_barrier(b200fem_comm_t comm, void *stream);
+int b200fem_halo_create(b200fem_halo_t *halo, b200fem_comm_t comm, int real_type, int block_size, ptrdiff_t n_owned,
+                        ptrdiff_t n_local, int n_send_peers, const int *send_peers, const ptrdiff_t *send_offsets,
+                        const int32_t *send_idx, int n_recv_peers, const int *recv_peers, const ptrdiff_t *recv_begin,
+                        const ptrdiff_t *recv_count, int transport);
+int b200fem_halo_destroy(b200fem_halo_t halo);
+int b200fem_halo_gather(b200fem_halo_t halo, void *x_local, void *stream);
+int b200fem_halo_transport(b200fem_halo_t halo); /* the transport in use */
+ptrdiff_t b200fem_halo_values_sent(b200fem_halo_t halo);
+int b200fem_halo_launches_per_gather(b200fem_halo_t halo);
 
 /* ------------------------------------------------------------------------------------------
  * Multigrid transfer between two lattices of one semi-structured macro mesh.
@@ -221,6 +275,10 @@ int b200fem_transfer_destroy(b200fem_transfer_t t);
 ptrdiff_t b200fem_transfer_fine_nodes(b200fem_transfer_t t);
 ptrdiff_t b200fem_transfer_coarse_nodes(b200fem_transfer_t t);
 int b200fem_transfer_incidence_count(b200fem_transfer_t t, uint16_t *count_host /* [n_fine_nodes] */);
+/* Distributed meshes: the plan counts over the LOCAL elements, which is the global count for owned nodes only (every
+ * element touching an owned node is local); the caller completes the ghost entries from their owners and hands the
+ * full table back. */
+int b200fem_transfer_set_incidence_count(b200fem_transfer_t t, const uint16_t *count_host /* [n_fine_nodes] */);
 int b200fem_transfer_restrict(b200fem_transfer_t t, int real_type, int vec_size, const void *from, void *to,
                               void *stream);
 int b200fem_transfer_prolongate(b200fem_transfer_t t, int real_type, int vec_size, const void *from, void *to,

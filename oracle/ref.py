@@ -179,6 +179,37 @@ class Oracle:
                    C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
+    def hex8_laplacian_diag(self, elements, points, nnodes):
+        """hex8_laplacian_diag (operators/hex8/hex8_laplacian.hpp:36; geometry from the fp32 points, in scalar_t)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        self._call("hex8_laplacian_diag", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def hex8_linear_elasticity_diag(self, elements, points, mu, lam, nnodes):
+        """affine_hex8_linear_elasticity_diag (operators/hex8/hex8_linear_elasticity.cpp:1043); AoS [nnodes*3]."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 3, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("affine_hex8_linear_elasticity_diag", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
+    def hex8_linear_elasticity_block_diag_sym(self, elements, points, mu, lam, nnodes):
+        """affine_hex8_linear_elasticity_block_diag_sym (hex8_linear_elasticity.cpp:1100-1200); AoS [nnodes*6]."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 6, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(6)]
+        self._call("affine_hex8_linear_elasticity_block_diag_sym", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(6), *op)
+        return out
+
     def sshex8_linear_elasticity_diag(self, level, elements, points, mu, lam, nnodes):
         """affine_sshex8_linear_elasticity_diag (operators/sshex8/sshex8_linear_elasticity.cpp:971);
         `points` is SoA fp32 [3][nnodes] indexed by sshex8 node id (only the macro corners are read)."""

@@ -396,6 +396,21 @@ static int dot_sync_t(ptrdiff_t n, const T *x, const T *y, double *result_host, 
 }
 
 template <typename T>
+static int cg_xr_async_t(ptrdiff_t n, T alpha, const T *p, const T *Ap, T *x, T *r, double *rtr_dev, cudaStream_t s) {
+    ReduceWorkspace *w;
+    if (get_workspace(s, &w)) return B200FEM_FAILURE;
+    if (n <= 0) {
+        B2_CUDA(cudaMemsetAsync(rtr_dev, 0, sizeof(double), s));
+        return B200FEM_SUCCESS;
+    }
+    const bool vec = aligned16(p) && aligned16(Ap) && aligned16(x) && aligned16(r);
+    cg_xr_kernel<T><<<grid_for(n, (vec ? Vec<T>::N : 1) * 2), kThreads, 0, s>>>(n, vec, alpha, p, Ap, x, r, w->partials,
+                                                                                 w->ticket, rtr_dev);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+template <typename T>
 static int cg_xr_t(ptrdiff_t n, T alpha, const T *p, const T *Ap, T *x, T *r, double *rtr_host, cudaStream_t s) {
     ReduceWorkspace *w;
     if (get_workspace(s, &w)) return B200FEM_FAILURE;
@@ -403,10 +418,7 @@ static int cg_xr_t(ptrdiff_t n, T alpha, const T *p, const T *Ap, T *x, T *r, do
         *rtr_host = 0;
         return B200FEM_SUCCESS;
     }
-    const bool vec = aligned16(p) && aligned16(Ap) && aligned16(x) && aligned16(r);
-    cg_xr_kernel<T><<<grid_for(n, (vec ? Vec<T>::N : 1) * 2), kThreads, 0, s>>>(n, vec, alpha, p, Ap, x, r, w->partials,
-                                                                                 w->ticket, w->result);
-    B2_CHECK_LAUNCH();
+    if (cg_xr_async_t<T>(n, alpha, p, Ap, x, r, w->result, s)) return B200FEM_FAILURE;
     B2_CUDA(cudaMemcpyAsync(w->host_slot, w->result, sizeof(double), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *rtr_host = *w->host_slot;
@@ -545,6 +557,14 @@ int b200fem_cg_update_x_r_rtr(int rt, ptrdiff_t n, double alpha, const void *p, 
     B2_REAL_DISPATCH(
         rt, cg_xr_t<double>(n, alpha, (const double *)p, (const double *)Ap, (double *)x, (double *)r, rtr_host, as_stream(stream)),
         cg_xr_t<float>(n, (float)alpha, (const float *)p, (const float *)Ap, (float *)x, (float *)r, rtr_host, as_stream(stream)));
+}
+
+int b200fem_cg_update_x_r_rtr_async(int rt, ptrdiff_t n, double alpha, const void *p, const void *Ap, void *x, void *r,
+                                    double *rtr_dev, void *stream) {
+    if (!rtr_dev) B2_FAIL("cg_update_x_r_rtr_async: NULL result");
+    B2_REAL_DISPATCH(
+        rt, cg_xr_async_t<double>(n, alpha, (const double *)p, (const double *)Ap, (double *)x, (double *)r, rtr_dev, as_stream(stream)),
+        cg_xr_async_t<float>(n, (float)alpha, (const float *)p, (const float *)Ap, (float *)x, (float *)r, rtr_dev, as_stream(stream)));
 }
 
 int b200fem_cg_update_p(int rt, ptrdiff_t n, double beta, const void *z, void *p, void *stream) {

@@ -246,6 +246,12 @@ int b200fem_transfer_incidence_count(b200fem_transfer_t t, uint16_t *count_host)
     return B200FEM_SUCCESS;
 }
 
+int b200fem_transfer_set_incidence_count(b200fem_transfer_t t, const uint16_t *count_host) {
+    if (!t || !count_host) B2_FAIL("invalid transfer handle");
+    if (t->t.count.n) B2_CUDA(cudaMemcpy(t->t.count.ptr, count_host, t->t.count.bytes(), cudaMemcpyHostToDevice));
+    return B200FEM_SUCCESS;
+}
+
 }  // extern "C"
 
 template <bool RESTRICT>

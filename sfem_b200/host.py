@@ -54,6 +54,24 @@ _SIG = {
     "b200host_cheb3_set_initial_guess_zero": (i32, [vp, i32]),
     "b200host_mg": (vp, [vp, i32, f64, i32, i32]),
     "b200host_mg_add_level": (i32, [vp, vp, vp, vp, vp]),
+    "b200host_comm_unique_id": (i32, [vp]),
+    "b200host_comm": (vp, [i32, i32, vp]),
+    "b200host_comm_rank": (i32, [vp]),
+    "b200host_comm_size": (i32, [vp]),
+    "b200host_comm_sum": (f64, [vp, f64]),
+    "b200host_comm_max": (f64, [vp, f64]),
+    "b200host_comm_error": (i32, [vp]),
+    "b200host_comm_barrier": (None, [vp]),
+    "b200host_halo": (vp, [vp, i32, i32, ssz, ssz, i32, vp, vp, vp, i32, vp, vp, vp, i32]),
+    "b200host_halo_gather": (i32, [vp, vp]),
+    "b200host_halo_transport": (i32, [vp]),
+    "b200host_halo_values_sent": (ssz, [vp]),
+    "b200host_halo_launches_per_gather": (i32, [vp]),
+    "b200host_parallel_op": (vp, [vp, vp, ssz, ssz]),
+    "b200host_blas_set_comm": (i32, [vp, vp]),
+    "b200host_blas_reserve_allocation": (i32, [vp, ssz, ssz]),
+    "b200host_blas_reductions": (C.c_long, [vp]),
+    "b200host_blas_dot": (f64, [vp, ssz, vp, vp]),
     "b200host_apply": (i32, [vp, vp, vp]),
     "b200host_apply_overwrite": (i32, [vp, vp, vp]),
     "b200host_rows": (ssz, [vp]),
@@ -104,6 +122,20 @@ class Blas(Handle):
     def launches(self) -> int:
         return _h.b200host_blas_launches(self.ptr)
 
+    def reductions(self) -> int:
+        return _h.b200host_blas_reductions(self.ptr)
+
+    def set_comm(self, comm: "Communicator"):
+        """dots / norms / fused CG reductions become device-side sums over the communicator's ranks"""
+        self.keep.append(comm)
+        _l.check(_h.b200host_blas_set_comm(self.ptr, comm.ptr), "blas_set_comm")
+
+    def reserve_allocation(self, n_owned: int, n_local: int):
+        _l.check(_h.b200host_blas_reserve_allocation(self.ptr, n_owned, n_local), "blas_reserve_allocation")
+
+    def dot(self, n: int, x, y) -> float:
+        return _h.b200host_blas_dot(self.ptr, n, _p(x), _p(y))
+
     def set_allocator(self, alloc, free):
         """alloc(nbytes) -> device address of zero-filled memory, free(address): used for every vector a solver
         allocates (work vectors with room for the ghost block / in symmetric memory for distributed solves)."""
@@ -111,6 +143,81 @@ class Blas(Handle):
         f = C.CFUNCTYPE(None, vp, vp)(lambda _c, p: free(p))
         self.keep += [a, f, alloc, free]
         _h.b200host_blas_set_allocator(self.ptr, a, f, None)
+
+
+class Communicator(Handle):
+    """b200fem::Communicator (NCCL, one process per GPU). `broadcast_bytes(bytes | None) -> bytes` is the launcher's way
+    of handing rank 0's unique id to every rank (a torch.distributed broadcast under torchrun, MPI_Bcast elsewhere)."""
+
+    def __init__(self, world: int, rank: int, broadcast_bytes=None):
+        uid = None
+        if world > 1:
+            buf = C.create_string_buffer(_l.UNIQUE_ID_BYTES)
+            if rank == 0:
+                _l.check(_h.b200host_comm_unique_id(buf), "comm_unique_id")
+            uid = broadcast_bytes(bytes(buf.raw) if rank == 0 else None)
+            assert len(uid) == _l.UNIQUE_ID_BYTES
+        self.world, self.rank = world, rank
+        super().__init__(_h.b200host_comm(world, rank, uid))
+
+    def sum(self, v: float) -> float:
+        return _h.b200host_comm_sum(self.ptr, float(v))
+
+    def max(self, v: float) -> float:
+        return _h.b200host_comm_max(self.ptr, float(v))
+
+    def barrier(self):
+        _h.b200host_comm_barrier(self.ptr)
+
+    def error(self) -> int:
+        return _h.b200host_comm_error(self.ptr)
+
+
+def torch_broadcast_bytes(group=None):
+    """broadcast_bytes for Communicator under torchrun: rank 0's bytes to everyone through torch.distributed."""
+    import torch.distributed as dist
+
+    def bc(payload):
+        box = [payload]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return box[0]
+
+    return bc
+
+
+class Halo(Handle):
+    """b200fem::HaloExchange from a plan dict (sfem_b200.parallel.halo_plan); COLLECTIVE over the communicator."""
+
+    def __init__(self, comm: Communicator, dtype, block_size: int, plan: dict, transport: int = 0):
+        ci = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        cp = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        sp, so, si = ci(plan["send_peers"]), cp(plan["send_offsets"]), ci(plan["send_idx"])
+        rp, rb, rc = ci(plan["recv_peers"]), cp(plan["recv_begin"]), cp(plan["recv_count"])
+        self.n_owned, self.n_local, self.bs = int(plan["n_owned"]), int(plan["n_local"]), block_size
+        ptr = _h.b200host_halo(comm.ptr, _l._rt(dtype), block_size, self.n_owned, self.n_local, sp.size, sp.ctypes.data,
+                               so.ctypes.data, si.ctypes.data if si.size else None, rp.size, rp.ctypes.data, rb.ctypes.data,
+                               rc.ctypes.data, transport)
+        super().__init__(ptr, keep=[comm])
+
+    def gather(self, x_local):
+        _l.check(_h.b200host_halo_gather(self.ptr, _p(x_local)), "halo_gather")
+
+    @property
+    def transport(self) -> str:
+        return {1: "push", 2: "nccl"}.get(_h.b200host_halo_transport(self.ptr), "?")
+
+    @property
+    def values_sent(self) -> int:
+        return _h.b200host_halo_values_sent(self.ptr)
+
+    @property
+    def launches_per_gather(self) -> int:
+        return _h.b200host_halo_launches_per_gather(self.ptr)
+
+
+def parallel_op(local_op: Handle, in_halo: Halo, owned_rows: int, owned_cols: int) -> Handle:
+    """ParallelMatrixFreeOperator: gather the ghost block of x (input space), then the local operator."""
+    return Handle(_h.b200host_parallel_op(local_op.ptr, in_halo.ptr, owned_rows, owned_cols), keep=[local_op, in_halo])
 
 
 class Function(Handle):

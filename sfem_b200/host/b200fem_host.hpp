@@ -12,6 +12,9 @@
  *   StationaryIteration<T>                         algebra/sfem_Stationary.hpp:18-80
  *   ShiftableJacobi<T>, ShiftableBlockSymJacobi<T> algebra/sfem_ShiftableJacobi.hpp:17-144
  *   Multigrid<T>                                   algebra/sfem_Multigrid.hpp:26-346
+ *   Communicator, ParallelOperator<T>              algebra/parallel/sfem_ParallelOperator.hpp:13-25 (smesh::Communicator)
+ *   ParallelMatrixFreeOperator<T>                  frontend/sfem_ParallelMatrixFreeOperator.cpp:35-105
+ *   ParallelConjugateGradient<T>                   algebra/parallel/sfem_parallel_cg.hpp:257-400
  *
  * Everything here is orchestration: every vector and every operator action runs in the CUDA kernels behind the
  * C ABI. There is no host arithmetic on vectors and no CPU fallback. Device-side differences from the reference
@@ -28,6 +31,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -96,6 +100,27 @@ namespace b200fem {
         void                           *stream{nullptr};
         std::function<double(double)>   allreduce_sum;
         long                            n_launches{0};
+        long                            n_reductions{0};
+
+        /* Distributed reductions without leaving C++: every dot / norm / fused CG reduction stays on the device, is
+         * summed over the ranks there (ncclAllReduce on one double) and read back once. Takes precedence over
+         * `allreduce_sum`. */
+        b200fem_comm_t comm{nullptr};
+        ~DeviceBLAS() override {
+            if (scalar_dev_) b200fem_free(scalar_dev_);
+        }
+        bool distributed() const { return comm && b200fem_comm_size(comm) > 1; }
+
+        /* ParallelOperator::row_allocation_size(): a vector of `n_owned` entries is allocated with `n_local` entries
+         * so that the halo gather can fill its ghost block in place (multigrid levels register one pair each). */
+        void reserve_allocation(std::size_t n_owned, std::size_t n_local) {
+            auto it = alloc_size_.find(n_owned);
+            if (it == alloc_size_.end() || it->second < n_local) alloc_size_[n_owned] = n_local;
+        }
+        std::size_t allocation_size(std::size_t n) const {
+            auto it = alloc_size_.find(n);
+            return (it == alloc_size_.end() || it->second < n) ? n : it->second;
+        }
 
         /* Optional allocator: distributed solvers need work vectors with room for the ghost block
          * (ParallelOperator::row_allocation_size(), algebra/parallel/sfem_ParallelOperator.hpp:13-25) and, for the
@@ -104,8 +129,9 @@ namespace b200fem {
         std::function<void *(std::size_t bytes)> alloc_hook;
         std::function<void(void *)>              free_hook;
 
-        T *allocate(const std::size_t n) override {
-            void *p = nullptr;
+        T *allocate(const std::size_t n_requested) override {
+            void             *p = nullptr;
+            const std::size_t n = allocation_size(n_requested);
             if (alloc_hook) {
                 p = alloc_hook((n ? n : 1) * sizeof(T));
                 if (!p) ok_ = false;
@@ -131,6 +157,10 @@ namespace b200fem {
         void copy(const ptrdiff_t n, const T *const s, T *const d) override { track(b200fem_blas_copy(RT, n, s, d, stream)); }
         T    dot(const ptrdiff_t n, const T *const l, const T *const r) override {
             double v = 0;
+            if (distributed()) {
+                track(b200fem_blas_dot_async(RT, n, l, r, scalar_dev(), stream));
+                return (T)sum_over_ranks();
+            }
             track(b200fem_blas_dot(RT, n, l, r, &v, stream));
             return (T)reduce(v);
         }
@@ -145,6 +175,7 @@ namespace b200fem {
             track(b200fem_blas_reciprocal(RT, n, (double)a, x, stream));
         }
         T norm2(const ptrdiff_t n, const T *const x) override {
+            if (distributed()) return (T)std::sqrt((double)dot(n, x, x));
             if (!allreduce_sum) {
                 double v = 0;
                 track(b200fem_blas_norm2(RT, n, x, &v, stream));
@@ -164,6 +195,10 @@ namespace b200fem {
 
         T cg_update_x_r_and_rtr(const ptrdiff_t n, const T alpha, const T *p, const T *Ap, T *x, T *r) override {
             double v = 0;
+            if (distributed()) {
+                track(b200fem_cg_update_x_r_rtr_async(RT, n, (double)alpha, p, Ap, x, r, scalar_dev(), stream));
+                return (T)sum_over_ranks();
+            }
             track(b200fem_cg_update_x_r_rtr(RT, n, (double)alpha, p, Ap, x, r, &v, stream));
             return (T)reduce(v);
         }
@@ -176,7 +211,26 @@ namespace b200fem {
         }
 
     private:
-        bool   ok_{true};
+        bool                               ok_{true};
+        double                            *scalar_dev_{nullptr};
+        std::map<std::size_t, std::size_t> alloc_size_;
+        double                            *scalar_dev() {
+            if (!scalar_dev_) {
+                void *p = nullptr;
+                if (b200fem_malloc(&p, 64 * sizeof(double))) ok_ = false;
+                scalar_dev_ = (double *)p;
+            }
+            return scalar_dev_;
+        }
+        double sum_over_ranks() {
+            double v = 0;
+            n_reductions++;
+            if (b200fem_comm_sum_to_host(comm, scalar_dev_, 1, &v, stream)) {
+                std::fprintf(stderr, "[b200fem] distributed reduction failed: %s\n", b200fem_last_error());
+                ok_ = false;
+            }
+            return v;
+        }
         double reduce(double v) const { return allreduce_sum ? allreduce_sum(v) : v; }
         void   track(int rc) {
             n_launches++;
@@ -904,6 +958,124 @@ namespace b200fem {
         };
         /* the prolongation kernel writes every fine node: the same callable serves as the overwriting form */
         return make_op<T>(rows, cols, fn, fn);
+    }
+
+    /* ---------------------------------------------------------------------------------------------------- */
+    /* Distributed layer: one process per GPU                                                               */
+    /* ---------------------------------------------------------------------------------------------------- */
+    /* smesh::Communicator as far as the path uses it: rank / size / sum. Owns the NCCL communicator. */
+    class Communicator {
+    public:
+        /* `unique_id`: B200FEM_UNIQUE_ID_BYTES from b200fem_comm_unique_id on rank 0, handed round by the launcher */
+        static std::shared_ptr<Communicator> create(int world, int rank, const void *unique_id) {
+            b200fem_comm_t c = nullptr;
+            if (b200fem_comm_create(&c, world, rank, unique_id)) {
+                std::fprintf(stderr, "[b200fem] Communicator::create failed: %s\n", b200fem_last_error());
+                return nullptr;
+            }
+            return std::shared_ptr<Communicator>(new Communicator(c));
+        }
+        ~Communicator() { b200fem_comm_destroy(c_); }
+        int            rank() const { return b200fem_comm_rank(c_); }
+        int            size() const { return b200fem_comm_size(c_); }
+        b200fem_comm_t get() const { return c_; }
+        double         sum(double v) const {
+            b200fem_comm_allreduce_host(c_, &v, 1, B200FEM_REDUCE_SUM, nullptr);
+            return v;
+        }
+        double max(double v) const {
+            b200fem_comm_allreduce_host(c_, &v, 1, B200FEM_REDUCE_MAX, nullptr);
+            return v;
+        }
+        void barrier() const { b200fem_comm_barrier(c_, nullptr); }
+
+    private:
+        explicit Communicator(b200fem_comm_t c) : c_(c) {}
+        b200fem_comm_t c_;
+    };
+
+    /* algebra/parallel/sfem_ParallelOperator.hpp:13-25: rows() / cols() count OWNED dofs, vectors are allocated
+     * with *_allocation_size() entries (owned + ghosts) */
+    template <typename T>
+    class ParallelOperator : public Operator<T> {
+    public:
+        virtual std::shared_ptr<Communicator> comm() const                = 0;
+        virtual std::ptrdiff_t                row_allocation_size() const = 0;
+        virtual std::ptrdiff_t                col_allocation_size() const = 0;
+    };
+
+    /* Halo plan of one space (smesh::Exchange): owns the b200fem_halo_t */
+    class HaloExchange {
+    public:
+        HaloExchange(b200fem_halo_t h, std::shared_ptr<Communicator> comm) : h_(h), comm_(std::move(comm)) {}
+        ~HaloExchange() { b200fem_halo_destroy(h_); }
+        HaloExchange(const HaloExchange &)            = delete;
+        HaloExchange &operator=(const HaloExchange &) = delete;
+        int  gather(void *x_local, void *stream = nullptr) const { return b200fem_halo_gather(h_, x_local, stream); }
+        b200fem_halo_t                get() const { return h_; }
+        std::shared_ptr<Communicator> comm() const { return comm_; }
+
+    private:
+        b200fem_halo_t                h_;
+        std::shared_ptr<Communicator> comm_;
+    };
+
+    /* y(owned rows) = A x: gather the ghost block of x from the owners, then the local operator over the owned + aura
+     * elements; interface rows are completed by the redundant aura computation, there is no reverse scatter
+     * (frontend/sfem_ParallelMatrixFreeOperator.cpp:78-105). The reference stages x and y through scratch vectors of
+     * local size; here the caller's vectors already have col_/row_allocation_size() entries (DeviceBLAS::
+     * reserve_allocation), so the exchange and the kernels work in place and the ghost block of x is scratch that
+     * every apply overwrites. Rows >= rows() of y hold partial sums and are never read. `in_halo` exchanges the
+     * input space (it differs from the output space for the level transfers). */
+    template <typename T>
+    class ParallelMatrixFreeOperator final : public ParallelOperator<T> {
+    public:
+        ParallelMatrixFreeOperator(std::shared_ptr<Operator<T>> local, std::shared_ptr<HaloExchange> in_halo,
+                                   std::ptrdiff_t owned_rows, std::ptrdiff_t owned_cols, void *stream = nullptr)
+            : local_(std::move(local)), halo_(std::move(in_halo)), rows_(owned_rows), cols_(owned_cols), stream_(stream) {}
+
+        int apply(const T *const x, T *const y) override {
+            B200FEM_TRY(halo_->gather(const_cast<T *>(x), stream_));
+            return local_->apply(x, y);
+        }
+        /* local operators without an overwriting form (the restriction) get their whole local output zeroed here:
+         * the solvers only zero the owned rows, and the ghost rows would otherwise pile up partial sums */
+        bool can_overwrite() const override { return true; }
+        int  apply_overwrite(const T *const x, T *const y) override {
+            B200FEM_TRY(halo_->gather(const_cast<T *>(x), stream_));
+            if (local_->can_overwrite()) return local_->apply_overwrite(x, y);
+            B200FEM_TRY(b200fem_blas_zeros(RealType<T>::value, local_->rows(), y, stream_));
+            return local_->apply(x, y);
+        }
+        std::ptrdiff_t                rows() const override { return rows_; }
+        std::ptrdiff_t                cols() const override { return cols_; }
+        std::ptrdiff_t                row_allocation_size() const override { return local_->rows(); }
+        std::ptrdiff_t                col_allocation_size() const override { return local_->cols(); }
+        std::shared_ptr<Communicator> comm() const override { return halo_->comm(); }
+        void reserve(DeviceBLAS<T> &blas) const {
+            blas.reserve_allocation((std::size_t)rows_, (std::size_t)local_->rows());
+            blas.reserve_allocation((std::size_t)cols_, (std::size_t)local_->cols());
+        }
+
+    private:
+        std::shared_ptr<Operator<T>>  local_;
+        std::shared_ptr<HaloExchange> halo_;
+        std::ptrdiff_t                rows_, cols_;
+        void                         *stream_;
+    };
+
+    /* algebra/parallel/sfem_parallel_cg.hpp:257-400 is ConjugateGradient with every reduction followed by comm->sum and
+     * vectors of row_allocation_size(): the same recurrences and stopping rule, so it is the same class here, bound to a
+     * ParallelOperator and a DeviceBLAS whose reductions run over the communicator. */
+    template <typename T>
+    std::shared_ptr<ConjugateGradient<T>> make_parallel_cg(const std::shared_ptr<ParallelOperator<T>> &op,
+                                                           const std::shared_ptr<DeviceBLAS<T>>       &blas) {
+        auto cg = std::make_shared<ConjugateGradient<T>>();
+        blas->comm = op->comm() ? op->comm()->get() : nullptr;
+        blas->reserve_allocation((std::size_t)op->rows(), (std::size_t)op->row_allocation_size());
+        cg->blas = blas;
+        cg->set_op(op);
+        return cg;
     }
 
 }  // namespace b200fem

@@ -18,7 +18,15 @@ namespace {
         std::shared_ptr<void> blas;      /* shared_ptr<DeviceBLAS<T>> */
         int                   kind{0};
     };
-    enum { K_OP = 1, K_CG, K_JACOBI, K_BJACOBI, K_STATIONARY, K_CHEB, K_MG, K_FUNCTION, K_BLAS };
+    enum { K_OP = 1, K_CG, K_JACOBI, K_BJACOBI, K_STATIONARY, K_CHEB, K_MG, K_FUNCTION, K_BLAS, K_COMM, K_HALO };
+
+    /* distributed objects are not templated on the scalar type: boxed through `obj` as shared_ptr<void> */
+    std::shared_ptr<Communicator> comm_of(void *b) {
+        return (b && ((Box *)b)->kind == K_COMM) ? std::static_pointer_cast<Communicator>(((Box *)b)->obj) : nullptr;
+    }
+    std::shared_ptr<HaloExchange> halo_of(void *b) {
+        return (b && ((Box *)b)->kind == K_HALO) ? std::static_pointer_cast<HaloExchange>(((Box *)b)->obj) : nullptr;
+    }
 
     template <typename T>
     std::shared_ptr<Operator<T>> op_of(void *b) {
@@ -231,6 +239,87 @@ int b200host_function_launches_per_apply(void *f, int overwrite) {
 void *b200host_callback_op(int real_type, ptrdiff_t rows, ptrdiff_t cols, apply_cb apply, apply_cb overwrite, void *ctx) {
     return DISPATCH(real_type, make_callback_op<double>(rows, cols, apply, overwrite, ctx),
                     make_callback_op<float>(rows, cols, apply, overwrite, ctx));
+}
+
+/* ---- distributed layer (Communicator, HaloExchange, ParallelMatrixFreeOperator, parallel CG) ---------------------- */
+int b200host_comm_unique_id(void *id_out) { return b200fem_comm_unique_id(id_out); }
+void *b200host_comm(int world, int rank, const void *unique_id) {
+    auto c = Communicator::create(world, rank, unique_id);
+    if (!c) return nullptr;
+    auto b  = new Box();
+    b->obj  = c;
+    b->kind = K_COMM;
+    return b;
+}
+int    b200host_comm_rank(void *c) { return comm_of(c)->rank(); }
+int    b200host_comm_size(void *c) { return comm_of(c)->size(); }
+double b200host_comm_sum(void *c, double v) { return comm_of(c)->sum(v); }
+double b200host_comm_max(void *c, double v) { return comm_of(c)->max(v); }
+int    b200host_comm_error(void *c) { return b200fem_comm_error(comm_of(c)->get()); }
+void   b200host_comm_barrier(void *c) { comm_of(c)->barrier(); }
+
+/* halo plan of one space; arguments as b200fem_halo_create (collective) */
+void *b200host_halo(void *comm, int real_type, int block_size, ptrdiff_t n_owned, ptrdiff_t n_local, int n_send_peers,
+                    const int *send_peers, const ptrdiff_t *send_offsets, const int32_t *send_idx, int n_recv_peers,
+                    const int *recv_peers, const ptrdiff_t *recv_begin, const ptrdiff_t *recv_count, int transport) {
+    auto c = comm_of(comm);
+    if (!c) return nullptr;
+    b200fem_halo_t h = nullptr;
+    if (b200fem_halo_create(&h, c->get(), real_type, block_size, n_owned, n_local, n_send_peers, send_peers, send_offsets, send_idx,
+                            n_recv_peers, recv_peers, recv_begin, recv_count, transport))
+        return nullptr;
+    auto b       = new Box();
+    b->real_type = real_type;
+    b->obj       = std::make_shared<HaloExchange>(h, c);
+    b->kind      = K_HALO;
+    return b;
+}
+int b200host_halo_gather(void *halo, void *x_local) { return halo_of(halo)->gather(x_local); }
+int b200host_halo_transport(void *halo) { return b200fem_halo_transport(halo_of(halo)->get()); }
+ptrdiff_t b200host_halo_values_sent(void *halo) { return b200fem_halo_values_sent(halo_of(halo)->get()); }
+int b200host_halo_launches_per_gather(void *halo) { return b200fem_halo_launches_per_gather(halo_of(halo)->get()); }
+
+/* ParallelMatrixFreeOperator over any local operator box (Function, restriction, prolongation): rows / cols = OWNED
+ * dofs of the output / input space, `in_halo` exchanges the input space */
+void *b200host_parallel_op(void *local_op, void *in_halo, ptrdiff_t owned_rows, ptrdiff_t owned_cols) {
+    Box *o = (Box *)local_op;
+    auto h = halo_of(in_halo);
+    if (!o || !h) return nullptr;
+    if (o->real_type == B200FEM_F64)
+        return box<double>(std::make_shared<ParallelMatrixFreeOperator<double>>(op_of<double>(o), h, owned_rows, owned_cols), K_OP, nullptr);
+    return box<float>(std::make_shared<ParallelMatrixFreeOperator<float>>(op_of<float>(o), h, owned_rows, owned_cols), K_OP, nullptr);
+}
+/* reductions of this BLAS run over the communicator (device-side sum + ncclAllReduce + one host read) */
+int b200host_blas_set_comm(void *blas, void *comm) {
+    Box *b = (Box *)blas;
+    auto c = comm_of(comm);
+    if (!b || b->kind != K_BLAS || !c) return 1;
+    if (b->real_type == B200FEM_F64)
+        blas_of<double>(b)->comm = c->get();
+    else
+        blas_of<float>(b)->comm = c->get();
+    b->function = c; /* keeps the communicator alive as long as the BLAS */
+    return 0;
+}
+/* vectors of n_owned entries are allocated with n_local entries (ParallelOperator::row_allocation_size) */
+int b200host_blas_reserve_allocation(void *blas, ptrdiff_t n_owned, ptrdiff_t n_local) {
+    Box *b = (Box *)blas;
+    if (!b || b->kind != K_BLAS) return 1;
+    if (b->real_type == B200FEM_F64)
+        blas_of<double>(b)->reserve_allocation((size_t)n_owned, (size_t)n_local);
+    else
+        blas_of<float>(b)->reserve_allocation((size_t)n_owned, (size_t)n_local);
+    return 0;
+}
+long b200host_blas_reductions(void *blas) {
+    Box *b = (Box *)blas;
+    return DISPATCH(b->real_type, blas_of<double>(b)->n_reductions, blas_of<float>(b)->n_reductions);
+}
+/* BLAS calls on raw device vectors through a BLAS box (drivers: distributed norms / dots of their own vectors) */
+double b200host_blas_dot(void *blas, ptrdiff_t n, const void *x, const void *y) {
+    Box *b = (Box *)blas;
+    return DISPATCH(b->real_type, (double)blas_of<double>(b)->dot(n, (const double *)x, (const double *)y),
+                    (double)blas_of<float>(b)->dot(n, (const float *)x, (const float *)y));
 }
 
 /* level transfer operators; `constraints_function` (may be NULL) zeroes the constrained dofs of the result */

@@ -19,6 +19,8 @@ LIB_PATH = os.path.join(HERE, "libb200fem.so")
 F32, F64 = 4, 8
 TET4, HEX8, SSHEX8 = 4, 8, 800
 SCATTER_AUTO, SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_PATCH = 0, 1, 2, 3
+UNIQUE_ID_BYTES = 128
+HALO_AUTO, HALO_PUSH, HALO_NCCL = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -79,12 +81,29 @@ _SIG = {
     "b200fem_blas_norm2": [i32, ssz, vp, C.POINTER(f64), vp],
     "b200fem_blas_dot_async": [i32, ssz, vp, vp, vp, vp],
     "b200fem_cg_update_x_r_rtr": [i32, ssz, f64, vp, vp, vp, vp, C.POINTER(f64), vp],
+    "b200fem_cg_update_x_r_rtr_async": [i32, ssz, f64, vp, vp, vp, vp, vp, vp],
     "b200fem_cg_update_p": [i32, ssz, f64, vp, vp, vp],
     "b200fem_cheb3_update": [i32, ssz, f64, f64, vp, vp, vp, vp, vp],
     "b200fem_sshex8_transfer_create": [C.POINTER(vp), ssz, i32, i32, c_idx_pp, ssz, i32, i32, c_idx_pp, ssz],
     "b200fem_transfer_destroy": [vp],
     "b200fem_transfer_incidence_count": [vp, C.POINTER(C.c_uint16)],
+    "b200fem_transfer_set_incidence_count": [vp, C.POINTER(C.c_uint16)],
     "b200fem_transfer_restrict": [vp, i32, i32, vp, vp, vp],
+    "b200fem_comm_unique_id": [vp],
+    "b200fem_comm_create": [C.POINTER(vp), i32, i32, vp],
+    "b200fem_comm_destroy": [vp],
+    "b200fem_comm_rank": [vp],
+    "b200fem_comm_size": [vp],
+    "b200fem_comm_error": [vp],
+    "b200fem_comm_allreduce_sum": [vp, vp, i32, vp],
+    "b200fem_comm_sum_to_host": [vp, vp, i32, C.POINTER(f64), vp],
+    "b200fem_comm_allreduce_host": [vp, C.POINTER(f64), i32, i32, vp],
+    "b200fem_comm_barrier": [vp, vp],
+    "b200fem_halo_create": [C.POINTER(vp), vp, i32, i32, ssz, ssz, i32, vp, vp, vp, i32, vp, vp, vp, i32],
+    "b200fem_halo_destroy": [vp],
+    "b200fem_halo_gather": [vp, vp, vp],
+    "b200fem_halo_transport": [vp],
+    "b200fem_halo_launches_per_gather": [vp],
     "b200fem_transfer_prolongate": [vp, i32, i32, vp, vp, vp],
     "b200fem_block_sym_jacobi_setup": [i32, ssz, vp, vp, vp, f64, vp, vp],
     "b200fem_block_jacobi_apply": [i32, ssz, vp, vp, vp, vp],
@@ -98,7 +117,7 @@ _lib.b200fem_op_rows.argtypes = [vp]
 _lib.b200fem_op_rows.restype = ssz
 _lib.b200fem_op_algorithmic_bytes.argtypes = [vp]
 _lib.b200fem_op_algorithmic_bytes.restype = f64
-for _name in ("b200fem_transfer_fine_nodes", "b200fem_transfer_coarse_nodes"):
+for _name in ("b200fem_transfer_fine_nodes", "b200fem_transfer_coarse_nodes", "b200fem_halo_values_sent"):
     getattr(_lib, _name).argtypes = [vp]
     getattr(_lib, _name).restype = ssz
 _lib.b200fem_op_streamed_bytes.argtypes = [vp, i32]
@@ -405,6 +424,12 @@ class Transfer:
         out = np.zeros(self.n_fine, dtype=np.uint16)
         check(_lib.b200fem_transfer_incidence_count(self._h, out.ctypes.data_as(C.POINTER(C.c_uint16))), "incidence_count")
         return out
+
+    def set_incidence_count(self, count: np.ndarray):
+        """Distributed meshes: hand the globally completed table back (ghost entries from their owners)."""
+        c = np.ascontiguousarray(count, dtype=np.uint16)
+        assert c.size == self.n_fine
+        check(_lib.b200fem_transfer_set_incidence_count(self._h, c.ctypes.data_as(C.POINTER(C.c_uint16))), "set_incidence_count")
 
     def restrict(self, frm, to, vec_size=1):
         """to[coarse] += R from[fine] (the caller zeroes `to`, like the reference)."""

@@ -106,7 +106,7 @@ def sshex8_box_lattice_keys(L: int, mx: int, my: int, elements: np.ndarray, n_no
     return gid, izl
 
 
-def sshex8_slab(level: int, mx: int, my: int, mz: int, rank: int, world: int) -> LocalMesh:
+def sshex8_slab(level: int, mx: int, my: int, mz: int, rank: int, world: int, extent=(1.0, 1.0, 1.0)) -> LocalMesh:
     """Weak-scaling fixture: the global mesh is a stack of `world` blocks of mx*my*mz macro elements along
     z, refined to `level`; this builds rank `rank`'s LocalMesh directly (its block plus the aura layer of
     the block above), without ever materialising the global mesh. Interface planes belong to the lower rank.
@@ -119,6 +119,8 @@ def sshex8_slab(level: int, mx: int, my: int, mz: int, rank: int, world: int) ->
     z0 = rank * mz  # first macro layer of this rank in the global stack
     m_el, m_pts = mesh.box_hex8(mx + 1, my + 1, mz_loc + 1, 1.0, 1.0, float(mz_loc) / mz)
     m_pts[2] += np.float32(float(z0) / mz)
+    if tuple(extent) != (1.0, 1.0, 1.0):  # one rank's block spans `extent` instead of the unit cube
+        m_pts = (m_pts.astype(np.float64) * np.asarray(extent, dtype=np.float64)[:, None]).astype(np.float32)
     el, nn, istart, _ = mesh.sshex8_from_hex8(L, m_el, None)
     gid, izl = sshex8_box_lattice_keys(L, mx, my, el, nn, z0)
     owner = np.clip((izl + mz * L - 1) // (mz * L) - 1, 0, world - 1).astype(np.int32)
@@ -126,6 +128,114 @@ def sshex8_slab(level: int, mx: int, my: int, mz: int, rank: int, world: int) ->
     return LocalMesh(elements=np.ascontiguousarray(lel), n_owned_elements=mx * my * mz, n_owned=n_owned, n_local=nn,
                      global_ids=gids, owner=own, rank=rank, world=world,
                      extra=dict(level=L, m_elements=m_el, m_points=m_pts))
+
+
+def tet4_slab(nx: int, ny: int, nz: int, rank: int, world: int, w=1.0, h=1.0, t=1.0) -> LocalMesh:
+    """Rank `rank`'s share of the nx*ny*nz-node tet4 box of mesh.box_tet4 (STRONG scaling: the global mesh is fixed),
+    built directly without materialising the global mesh. The box numbering x*nz + y*nz*nx + z has y slowest, so the cut
+    is along y: the ny-1 cell layers are split into `world` chunks, interface node planes belong to the lower rank, the
+    aura is the first cell layer of the rank above. Coordinates are slices of the global fp32 linspace, i.e. bit-identical
+    to the one-piece mesh."""
+    from . import mesh
+
+    nc = ny - 1
+    bounds = np.linspace(0, nc, world + 1).astype(np.int64)
+    c0, c1 = int(bounds[rank]), int(bounds[rank + 1])
+    has_aura = rank < world - 1
+    cl = c1 - c0 + (1 if has_aura else 0)           # local cell layers
+    nyl = cl + 1
+    el, _ = mesh.box_tet4(nx, nyl, nz)
+    gx = np.linspace(0, w, num=nx, dtype=mesh.geom_t)
+    gy = np.linspace(0, h, num=ny, dtype=mesh.geom_t)[c0:c0 + nyl]
+    gz = np.linspace(0, t, num=nz, dtype=mesh.geom_t)
+    pts = np.stack([np.broadcast_to(gx[None, :, None], (nyl, nx, nz)).reshape(-1),
+                    np.broadcast_to(gy[:, None, None], (nyl, nx, nz)).reshape(-1),
+                    np.broadcast_to(gz[None, None, :], (nyl, nx, nz)).reshape(-1)]).astype(mesh.geom_t)
+    plane = nx * nz
+    nn = nyl * plane
+    yl = np.arange(nn, dtype=np.int64) // plane       # local node layer
+    gid = np.arange(nn, dtype=np.int64) + c0 * plane
+    gyl = yl + c0                                     # global node layer; owner = rank whose (b_r, b_r+1] holds it
+    owner = np.clip(np.searchsorted(bounds, gyl, side="left") - 1, 0, world - 1).astype(np.int32)
+    n_own_e = el.shape[1]
+    if has_aura:  # cells are z-major in box_tet4: move the aura layer's tets behind the owned ones (stable)
+        cells_per_z = (nx - 1) * (nyl - 1)
+        cell = np.arange(el.shape[1] // 6, dtype=np.int64)
+        yi = (cell % cells_per_z) // (nx - 1)
+        is_aura = np.repeat(yi == cl - 1, 6)          # box_tet4: element id = cell * 6 + k
+        n_own_e = int(is_aura.size - is_aura.sum())
+        el = np.concatenate([el[:, ~is_aura], el[:, is_aura]], axis=1)
+        del is_aura
+    lel, gids, own, n_owned = renumber_owned_first(el, gid, owner, rank)
+    # renumber_owned_first is a stable partition by (owned first, then owner): rebuild it for the coordinates
+    key = np.where(owner == rank, -1, owner).astype(np.int64)
+    perm = np.argsort(key, kind="stable")
+    return LocalMesh(elements=np.ascontiguousarray(lel), n_owned_elements=n_own_e, n_owned=n_owned, n_local=nn,
+                     global_ids=gids, owner=own, rank=rank, world=world, extra=dict(points=np.ascontiguousarray(pts[:, perm])))
+
+
+def coarse_space(lm: LocalMesh, corner_rows) -> tuple[LocalMesh, np.ndarray]:
+    """FunctionSpace::derefine for a distributed sshex8 mesh: the coarse (macro hex8) LocalMesh whose nodes are the
+    lattice corners of `lm`, numbered in the order of their fine local ids -- which keeps [owned | ghosts by owner].
+    Returns (coarse mesh, fine local id of every coarse node)."""
+    corners = lm.elements[np.asarray(corner_rows)]
+    fine_of_coarse = np.unique(corners)
+    coarse_of_fine = np.full(lm.n_local, -1, dtype=np.int64)
+    coarse_of_fine[fine_of_coarse] = np.arange(fine_of_coarse.size)
+    cel = coarse_of_fine[corners].astype(idx_t)
+    n_owned = int((fine_of_coarse < lm.n_owned).sum())
+    cm = LocalMesh(elements=np.ascontiguousarray(cel), n_owned_elements=lm.n_owned_elements, n_owned=n_owned,
+                   n_local=int(fine_of_coarse.size), global_ids=lm.global_ids[fine_of_coarse], owner=lm.owner[fine_of_coarse],
+                   rank=lm.rank, world=lm.world)
+    return cm, fine_of_coarse
+
+
+def halo_plan(lm: LocalMesh, all_gather_object=None) -> dict:
+    """The exchange plan of one space in the form b200fem_halo_create takes it (include/b200fem.h): per peer the
+    contiguous ghost range I receive and the owned local ids I send, in the order of the peer's range.
+    `all_gather_object(obj) -> [obj of every rank]` is the launcher's collective (setup only)."""
+    plan = dict(n_owned=lm.n_owned, n_local=lm.n_local, send_peers=[], send_offsets=[0], send_idx=np.zeros(0, np.int32),
+                recv_peers=[], recv_begin=[], recv_count=[])
+    if lm.world == 1:
+        return plan
+    ghost_owner = lm.owner[lm.n_owned:]
+    ghost_gid = lm.global_ids[lm.n_owned:]
+    need = {}
+    for p in np.unique(ghost_owner):
+        sel = np.flatnonzero(ghost_owner == p)
+        assert sel.size == sel[-1] - sel[0] + 1, "ghosts must be sorted by owner"
+        plan["recv_peers"].append(int(p))
+        plan["recv_begin"].append(lm.n_owned + int(sel[0]))
+        plan["recv_count"].append(int(sel.size))
+        need[int(p)] = ghost_gid[sel]
+    all_need = all_gather_object(need)
+    owned_gid = lm.global_ids[:lm.n_owned]
+    sorter = np.argsort(owned_gid, kind="stable")
+    chunks = []
+    for q, nd in enumerate(all_need):
+        if q == lm.rank or lm.rank not in nd:
+            continue
+        want = nd[lm.rank]
+        pos = np.searchsorted(owned_gid, want, sorter=sorter)
+        loc = sorter[np.clip(pos, 0, sorter.size - 1)]
+        assert np.array_equal(owned_gid[loc], want), "a peer asked for a node this rank does not own"
+        plan["send_peers"].append(q)
+        plan["send_offsets"].append(plan["send_offsets"][-1] + int(loc.size))
+        chunks.append(loc.astype(np.int32))
+    plan["send_idx"] = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
+    return plan
+
+
+def torch_all_gather_object(group=None):
+    """all_gather_object for halo_plan under torchrun (gloo in the CPU tests, NCCL on the GPUs)."""
+    import torch.distributed as dist
+
+    def ag(obj):
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, obj, group=group)
+        return out
+
+    return ag
 
 
 class HaloExchange:
@@ -142,28 +252,13 @@ class HaloExchange:
         self.peers, self.recv_ranges, self.send_idx = [], {}, {}
         if self.world == 1:
             return
-        # what I need: ghosts are sorted by owner, so each peer's block is contiguous
-        ghost_owner = lm.owner[lm.n_owned:]
-        ghost_gid = lm.global_ids[lm.n_owned:]
-        need = {}
-        for p in np.unique(ghost_owner):
-            sel = np.flatnonzero(ghost_owner == p)
-            assert sel.size == sel[-1] - sel[0] + 1
-            self.recv_ranges[int(p)] = (lm.n_owned + int(sel[0]), lm.n_owned + int(sel[-1]) + 1)
-            need[int(p)] = ghost_gid[sel]
-        # tell every owner which of its nodes I need (setup only: pickled through all_gather_object)
-        all_need = [None] * self.world
-        dist.all_gather_object(all_need, need, group=group)
-        owned_gid = lm.global_ids[:lm.n_owned]
-        sorter = np.argsort(owned_gid, kind="stable")
-        for q, nd in enumerate(all_need):
-            if q == self.rank or self.rank not in nd:
-                continue
-            want = nd[self.rank]
-            pos = np.searchsorted(owned_gid, want, sorter=sorter)
-            loc = sorter[np.clip(pos, 0, sorter.size - 1)]
-            assert np.array_equal(owned_gid[loc], want), "a peer asked for a node this rank does not own"
-            self.send_idx[q] = torch.from_numpy(loc.astype(np.int32)).to(device) if device is not None else torch.from_numpy(loc.astype(np.int32))
+        # the same plan the C++ layer takes (b200fem_halo_create through host.Halo)
+        self.plan = plan = halo_plan(lm, torch_all_gather_object(group))
+        for p, b, c in zip(plan["recv_peers"], plan["recv_begin"], plan["recv_count"]):
+            self.recv_ranges[p] = (b, b + c)
+        for j, q in enumerate(plan["send_peers"]):
+            loc = torch.from_numpy(plan["send_idx"][plan["send_offsets"][j]:plan["send_offsets"][j + 1]].copy())
+            self.send_idx[q] = loc.to(device) if device is not None else loc
         self.peers = sorted(set(self.recv_ranges) | set(self.send_idx))
         self.send_buf = {}
         self.bytes_sent_per_gather = sum(int(v.numel()) for v in self.send_idx.values())

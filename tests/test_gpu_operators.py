@@ -383,3 +383,45 @@ def test_golden_vectors_on_gpu(real):
         nn = g["u"].size
         op = lib.laplacian(lib.SSHEX8, g["elements"], g["fff"], nn, dt, level=L)
         assert _rel(run(op, g["u"]), g[f"y_lap_{real}"]) < TOL[real], L
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_hex8_diagonals(oracles, real):
+    """hex8 Laplacian diag, hex8 linear-elasticity diag and symmetric block diagonal against the reference's
+    hex8_laplacian_diag / affine_hex8_linear_elasticity_diag / _block_diag_sym (operators/hex8/hex8_laplacian.hpp:36,
+    hex8_linear_elasticity.cpp:1043-1200). Those take the points; the geometry here is dyadic (unit spacing, dyadic shear),
+    so the fp32 FFF / adjugates of the plan are exactly what the reference derives."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("needs the reference build for the diagonal oracles")
+    el, pts = mesh.box_hex8(6, 5, 7, 5.0, 4.0, 6.0)
+    pts = mesh.shear_points(pts, 0.25, 0.5, 0.125)
+    nn = pts.shape[1]
+    dt = _dt(real)
+    fff = orc.hex8_fff_fill(el, pts)
+    op = lib.laplacian(lib.HEX8, el, fff, nn, dt)
+    d = torch.zeros(nn, dtype=dt, device="cuda")
+    op.diag(d)
+    assert _rel(d.cpu().numpy(), orc.hex8_laplacian_diag(el, pts, nn)) < TOL[real]
+    op.diag(d)  # diag accumulates like Op::hessian_diag
+    assert _rel(d.cpu().numpy(), 2 * orc.hex8_laplacian_diag(el, pts, nn)) < TOL[real]
+    mu, lam = 1.3, 0.7
+    adj, det = orc.hex8_adjugate_and_det_fill(el, pts)
+    le = lib.linear_elasticity(lib.HEX8, el, adj, det, mu, lam, nn, dt)
+    d3 = torch.zeros(nn * 3, dtype=dt, device="cuda")
+    le.diag(d3)
+    assert _rel(d3.cpu().numpy(), orc.hex8_linear_elasticity_diag(el, pts, mu, lam, nn)) < TOL[real]
+    b6 = torch.zeros(nn * 6, dtype=dt, device="cuda")
+    le.block_diag_sym(b6)
+    assert _rel(b6.cpu().numpy(), orc.hex8_linear_elasticity_block_diag_sym(el, pts, mu, lam, nn)) < TOL[real]
+    # the diagonal is what unit applies see
+    if real == "f64":
+        for i in (0, nn * 3 // 2 + 1, nn * 3 - 1):
+            e = torch.zeros(nn * 3, dtype=dt, device="cuda")
+            e[i] = 1.0
+            y = torch.zeros_like(e)
+            le.apply(e, y)
+            assert abs(float(y[i]) - float(d3[i])) < 1e-12 * abs(float(d3[i]))

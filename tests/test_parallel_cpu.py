@@ -58,6 +58,23 @@ def _worker(rank, world, port, case):
                 lambda x: orc.tet4_laplacian_apply_opt(lm.elements, lfff, x))
             u_of_gid = lambda g: u[g]
             ref_of_gid = lambda g: ref[g]
+        elif case == "tet4_slab":  # per-rank generation of the strong-scaling tet4 box (config 4) against the one-piece box
+            nx, ny, nz = 5, 9, 4
+            el, pts = mesh.box_tet4(nx, ny, nz)
+            u = mesh.quadratic_field(pts)
+            ref = orc.tet4_laplacian_apply_opt(el, orc.tet4_fff_fill(el, pts), u)
+            lm = parallel.tet4_slab(nx, ny, nz, rank, world)
+            lpts = lm.extra["points"]
+            assert np.array_equal(lpts, pts[:, lm.global_ids]), "slab coordinates differ from the one-piece box"
+            assert lm.n_owned_elements == 6 * (nx - 1) * (nz - 1) * (np.linspace(0, ny - 1, world + 1).astype(int)[rank + 1]
+                                                                      - np.linspace(0, ny - 1, world + 1).astype(int)[rank])
+            if rank < world - 1:
+                assert lm.elements.shape[1] == lm.n_owned_elements + 6 * (nx - 1) * (nz - 1), "aura layer missing"
+            # owned elements reference no node of the layer above the interface plane
+            lfff = orc.tet4_fff_fill(lm.elements, lpts)
+            apply = lambda x: orc.tet4_laplacian_apply_opt(lm.elements, lfff, x)
+            u_of_gid = lambda g: u[g]
+            ref_of_gid = lambda g: ref[g]
         else:  # sshex8 slab (weak-scaling fixture) against the serial mesh of the whole stack
             L, mx, my, mz = 4, 3, 2, 2
             lm = parallel.sshex8_slab(L, mx, my, mz, rank, world)
@@ -91,14 +108,29 @@ def _worker(rank, world, port, case):
         d = torch.tensor([float(x_local[: lm.n_owned].numpy() @ y_local[: lm.n_owned])], dtype=torch.float64)
         dist.all_reduce(d)
         tot = int(cnt.item())
-        gids = np.arange(tot) if case in ("hex8", "tet4") else None
+        gids = np.arange(tot) if case in ("hex8", "tet4", "tet4_slab") else None
+        if case == "sshex8":
+            # FunctionSpace::derefine of the distributed mesh: the macro corners as their own [owned | ghosts] space,
+            # its exchange plan, and a gather on it
+            corner_rows = [mesh.sshex8_lidx(L, cx * L, cy * L, cz * L) for cx, cy, cz in mesh.HEX8_CORNERS]
+            cm, fine_of_coarse = parallel.coarse_space(lm, corner_rows)
+            assert cm.n_owned == int((fine_of_coarse < lm.n_owned).sum()) and cm.n_local == fine_of_coarse.size
+            assert np.all(np.diff(np.where(cm.owner == rank, -1, cm.owner)) >= 0), "coarse ghosts not sorted by owner"
+            cex = parallel.HaloExchange(cm)
+            xc = torch.zeros(cm.n_local, dtype=torch.float64)
+            xc[: cm.n_owned] = torch.from_numpy(u_of_gid(cm.global_ids[: cm.n_owned]))
+            cex.gather(xc)
+            assert np.array_equal(xc.numpy(), u_of_gid(cm.global_ids)), "coarse ghost values differ from the owners'"
+            nc = torch.tensor([cm.n_owned], dtype=torch.int64)
+            dist.all_reduce(nc)
+            assert int(nc.item()) == (mx + 1) * (my + 1) * (mz * world + 1)
         if gids is not None:
             assert abs(d.item() - float(u_of_gid(gids) @ ref_of_gid(gids))) < 1e-9 * max(1.0, abs(d.item()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2)])
+@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2), ("tet4_slab", 2), ("tet4_slab", 3)])
 def test_distributed_apply_matches_serial(case, world, oracles):
     import torch.multiprocessing as mp
 

@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""BASELINE configs 4 and 5 on N GPUs of one box, one rank per GPU, entirely through the C++ host layer
+(sfem_b200/host/b200fem_host.hpp: Communicator, HaloExchange, ParallelMatrixFreeOperator, ConjugateGradient with
+device-side reductions over NCCL, Chebyshev3, Multigrid) -- Python only builds the per-rank mesh and wires the objects:
+
+    torchrun --nproc-per-node N tools/dist_solve.py c4 [--n 465] [--rtol 1e-6]
+    torchrun --nproc-per-node N tools/dist_solve.py c5 [--macro 87] [--layers 11] [--sweeps 30]
+
+  c4  drivers/simulations/poisson.exe.cpp:14-41,122-129: matrix-free CG (rtol 1e-6, atol 1e-16, max_it 20000) on a tet4
+      cube of n^3 nodes (465^3 = 1.005e8), u = -1 on z = 0 and +1 on z = top, zero rhs. STRONG scaling: the global mesh
+      is fixed and cut along y into N element slabs (the reference's partitioner lives in smesh, which is not in the
+      checkout, METIS is neither there nor installed: this is a coordinate partition, named as such in the output).
+  c5  drivers/mgsolve.cpp:61-131,175-241 with SFEM_USE_CHEB=1: 2-level multigrid, sshex8 L8 linear elasticity with
+      Chebyshev3 smoothing (30 sweeps, notebook/SOLVERS.md:16; eig scale 1.02, power-method tol 1e-5) on the fine level,
+      CG (rtol 1e-8, atol 1e-10, max_it 40000) on the derefined hex8 operator, hierarchical restriction / prolongation with
+      zeroed constraints, (-1,0,0) / (1,0,0) on the x-faces, tol 1e-9. WEAK scaling: every rank holds a block of
+      macro x macro x layers macro elements, the blocks stack along z; 87 x 87 x 11 per GPU on 8 GPUs is 87 x 87 x 88 macro
+      elements = 1.03e9 dofs. Halo gathers on both levels, distributed restriction / prolongation (gather of the input
+      space, then the element-local kernel), coarse CG with allreduce.
+With --check (small sizes) rank 0 also solves the same global problem on one GPU and compares iteration / cycle counts and
+residual histories: the reference's own parity criterion for its distributed path
+(frontend/tests/mpi/sfem_ParallelLaplacianApplyTest.cpp:133-141) extended to the solvers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+
+class Dist:
+    """rank / world / device + the C++ communicator; torch.distributed only hands the NCCL unique id and the setup-time
+    plan objects round."""
+
+    def __init__(self, torch, backend=None):
+        import torch.distributed as dist
+
+        from sfem_b200 import host, parallel
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.own_group = False
+        if self.world > 1 and not dist.is_initialized():
+            # gloo: setup traffic only (pickled plans, the unique id); every solver-time collective is ours
+            dist.init_process_group(backend or "gloo")
+            self.own_group = True
+        self.comm = host.Communicator(self.world, self.rank, host.torch_broadcast_bytes() if self.world > 1 else None)
+        self.all_gather_object = parallel.torch_all_gather_object() if self.world > 1 else (lambda o: [o])
+
+    def close(self):
+        self.comm = None
+        if self.own_group:
+            self.dist.destroy_process_group()
+
+
+def _timed(torch, comm, fn):
+    """fn() bracketed by barrier + synchronize on both sides, CUDA events, max over ranks (ms)."""
+    torch.cuda.synchronize()
+    comm.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, comm.max(e0.elapsed_time(e1))
+
+
+def cg_poisson_tet4(d: Dist, n=465, rtol=1e-6, max_it=20000, peak_gbs=6470.5, check=False):
+    from sfem_b200 import host, lib, mesh, parallel
+
+    torch, dt = d.torch, d.torch.float64
+    t0 = time.time()
+    lm = parallel.tet4_slab(n, n, n, d.rank, d.world)
+    pts = lm.extra["points"]
+    fff = lib.fff_fill(lib.TET4, lm.elements, pts)
+    op = lib.laplacian(lib.TET4, lm.elements, fff, lm.n_local, dt)
+    f = host.Function(dt, lm.n_local, 1)
+    f.add_operator(op)
+    z = pts[2]
+    f.add_dirichlet(np.flatnonzero(z < 1e-6).astype(np.int32), 0, -1.0)
+    f.add_dirichlet(np.flatnonzero(z > 1 - 1e-6).astype(np.int32), 0, 1.0)
+    halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object))
+    A = host.parallel_op(f, halo, lm.n_owned, lm.n_owned)
+    blas = host.Blas(dt)
+    blas.set_comm(d.comm)
+    blas.reserve_allocation(lm.n_owned, lm.n_local)
+    x = torch.zeros(lm.n_local, dtype=dt, device=d.dev)
+    b = torch.zeros(lm.n_local, dtype=dt, device=d.dev)
+    f.apply_constraints(x)
+    f.apply_constraints(b)
+    setup_s = time.time() - t0
+    ne_owned, alg = lm.n_owned_elements, op.algorithmic_bytes
+    del fff, pts, z
+    warm = host.cg(blas, A, None, rtol=rtol, atol=1e-16, max_it=3)
+    host.apply(warm, b, x.clone())  # warm-up: allocates nothing that the timed solve reuses, loads the kernels
+    del warm
+    cg = host.cg(blas, A, None, rtol=rtol, atol=1e-16, max_it=max_it)
+    rc, ms = _timed(torch, d.comm, lambda: host.apply(cg, b, x))
+    hist, it = host.residual_history(cg), host.iterations(cg)
+    n_it = max(len(hist) - 1, 1)  # applies in the loop
+    dofs, tets = int(d.comm.sum(lm.n_owned)), int(d.comm.sum(ne_owned))
+    bytes_it = d.comm.sum(alg + lm.n_local * 8 * 11)
+    per_it = ms / n_it
+    out = {"name": f"C4: CG Poisson (poisson.exe), tet4 {n}^3 nodes, f64, rtol {rtol:g}, {d.world} GPU(s), coordinate slabs along y",
+           "config": "C4", "n_gpus": d.world, "dofs": dofs, "tets": tets, "rc": rc, "iterations": it, "ms_total": ms,
+           "solve_s": ms * 1e-3, "ms_per_iteration": per_it, "residual_0": float(hist[0]), "residual_end": float(hist[-1]),
+           "gdof_s_per_iteration": dofs / (per_it * 1e-3) / 1e9, "alg_GB_s_all_gpus": bytes_it / (per_it * 1e-3) / 1e9,
+           "frac_of_measured_hbm": bytes_it / (per_it * 1e-3) / 1e9 / (peak_gbs * d.world), "setup_s": setup_s,
+           "halo": {"transport": halo.transport, "values_sent_rank0": halo.values_sent, "launches_per_gather": halo.launches_per_gather},
+           "reductions": blas.reductions(), "partition": "coordinate slabs (y), interface planes owned by the lower rank"}
+    if check:
+        out["check"] = _check_serial_c4(d, n, rtol, max_it, it, rc, hist)
+    return out
+
+
+def _check_serial_c4(d, n, rtol, max_it, it, rc, hist):
+    from sfem_b200 import host, lib, mesh
+
+    if d.rank != 0:
+        return None
+    torch, dt = d.torch, d.torch.float64
+    el, pts = mesh.box_tet4(n, n, n)
+    nn = pts.shape[1]
+    op = lib.laplacian(lib.TET4, el, lib.fff_fill(lib.TET4, el, pts), nn, dt)
+    f = host.Function(dt, nn, 1)
+    f.add_operator(op)
+    f.add_dirichlet(np.flatnonzero(pts[2] < 1e-6).astype(np.int32), 0, -1.0)
+    f.add_dirichlet(np.flatnonzero(pts[2] > 1 - 1e-6).astype(np.int32), 0, 1.0)
+    x = torch.zeros(nn, dtype=dt, device=d.dev)
+    b = torch.zeros(nn, dtype=dt, device=d.dev)
+    f.apply_constraints(x)
+    f.apply_constraints(b)
+    cg = host.cg(host.Blas(dt), f, None, rtol=rtol, atol=1e-16, max_it=max_it)
+    rc1 = host.apply(cg, b, x)
+    h1 = host.residual_history(cg)
+    res = {"serial_iterations": host.iterations(cg), "serial_rc": rc1,
+           "max_rel_residual_history_diff": float(np.max(np.abs(h1 - hist) / np.maximum(np.abs(h1), 1e-300))) if len(h1) == len(hist) else None}
+    assert res["serial_iterations"] == it and rc1 == rc, (res, it, rc)
+    return res
+
+
+def _mg_problem(d, lm, level, dt, side_x, distributed=True):
+    """Objects of the 2-level mgsolve configuration on one LocalMesh (world 1: the plain single-GPU problem)."""
+    from sfem_b200 import host, lib, mesh, parallel
+
+    torch = d.torch
+    L = level
+    m_el, m_pts = lm.extra["m_elements"], lm.extra["m_points"]
+    corner_rows = [mesh.sshex8_lidx(L, cx * L, cy * L, cz * L) for cx, cy, cz in mesh.HEX8_CORNERS]
+    cm, fine_of_coarse = parallel.coarse_space(lm, corner_rows)
+    coarse_of_fine = np.full(lm.n_local, -1, dtype=np.int64)
+    coarse_of_fine[fine_of_coarse] = np.arange(fine_of_coarse.size)
+    adj, det = lib.adjugate_and_det_fill(lib.HEX8, m_el, m_pts)
+    fine_op = lib.linear_elasticity(lib.SSHEX8, lm.elements, adj, det, 1.0, 1.0, lm.n_local, dt, level=L)
+    coarse_op = lib.linear_elasticity(lib.HEX8, cm.elements, adj, det, 1.0, 1.0, cm.n_local, dt)
+    left = mesh.sshex8_face_nodes_macro(L, lm.elements, m_el, m_pts, 0, 0.0)
+    right = mesh.sshex8_face_nodes_macro(L, lm.elements, m_el, m_pts, 0, side_x)
+    conds = [(left, 0, -1.0), (left, 1, 0.0), (left, 2, 0.0), (right, 0, 1.0), (right, 1, 0.0), (right, 2, 0.0)]
+    f, fc = host.Function(dt, lm.n_local, 3), host.Function(dt, cm.n_local, 3)
+    f.add_operator(fine_op)
+    fc.add_operator(coarse_op)
+    for nodes, comp, val in conds:
+        f.add_dirichlet(nodes, comp, val)
+        c = coarse_of_fine[nodes]
+        fc.add_dirichlet(c[c >= 0].astype(np.int32), comp, val)
+    lat = np.zeros((8, cm.elements.shape[1]), dtype=np.int32)
+    for k, (cx, cy, cz) in enumerate(mesh.HEX8_CORNERS):
+        lat[mesh.sshex8_lidx(1, cx, cy, cz)] = cm.elements[k]
+    tr = lib.Transfer(L, 1, lm.elements, lm.n_local, 1, 1, lat, cm.n_local)
+    blas = host.Blas(dt)
+    R, P = host.restriction(dt, tr, 3, fc), host.prolongation(dt, tr, 3, f)
+    keep = [tr, fine_op, coarse_op]
+    if not distributed:
+        return dict(f=f, fc=fc, A=f, Ac=fc, R=R, P=P, blas=blas, lm=lm, cm=cm, keep=keep, halo=None)
+    plan_f, plan_c = parallel.halo_plan(lm, d.all_gather_object), parallel.halo_plan(cm, d.all_gather_object)
+    halo_f, halo_c = host.Halo(d.comm, dt, 3, plan_f), host.Halo(d.comm, dt, 3, plan_c)
+    if d.world > 1:
+        # node -> element incidence of the fine lattice: the local count is the global one for owned nodes only
+        h1 = host.Halo(d.comm, dt, 1, plan_f)
+        cnt = torch.from_numpy(tr.incidence_count().astype(np.float64)).to(d.dev)
+        h1.gather(cnt)
+        tr.set_incidence_count(cnt.cpu().numpy().astype(np.uint16))
+        del h1, cnt
+    blas.set_comm(d.comm)
+    blas.reserve_allocation(lm.n_owned * 3, lm.n_local * 3)
+    blas.reserve_allocation(cm.n_owned * 3, cm.n_local * 3)
+    A = host.parallel_op(f, halo_f, lm.n_owned * 3, lm.n_owned * 3)
+    Ac = host.parallel_op(fc, halo_c, cm.n_owned * 3, cm.n_owned * 3)
+    Rp = host.parallel_op(R, halo_f, cm.n_owned * 3, lm.n_owned * 3)
+    Pp = host.parallel_op(P, halo_c, lm.n_owned * 3, cm.n_owned * 3)
+    return dict(f=f, fc=fc, A=A, Ac=Ac, R=Rp, P=Pp, blas=blas, lm=lm, cm=cm, keep=keep + [R, P], halo=halo_f)
+
+
+def _mg_solve(d, pr, dt, sweeps, max_cycles, tol, seed):
+    from sfem_b200 import host
+
+    torch = d.torch
+    f, blas, lm = pr["f"], pr["blas"], pr["lm"]
+    nl = lm.n_local * 3
+    t0 = time.time()
+    # power method from a seeded random vector (Chebyshev3::init_with_random): from the ones vector of mgsolve.cpp:183 the
+    # interior rows of A 1 vanish and the iteration stops at the eigenvalue 1 of the Dirichlet rows
+    guess = torch.from_numpy(np.random.default_rng(seed).uniform(-0.5, 0.5, nl)).to(d.dev)
+    smoother = host.cheb3(blas, pr["A"], eig_tol=1e-5, eig_max_it=1000, scale_eig_max=1.02, scale_eig_min=0.06, max_it=sweeps,
+                          init=guess)
+    del guess
+    torch.cuda.synchronize()
+    power_s = time.time() - t0
+    coarse = host.cg(blas, pr["Ac"], None, rtol=1e-8, atol=1e-10, max_it=40000)
+    mg = host.mg(blas, max_it=max_cycles, atol=tol)
+    host.mg_add_level(mg, pr["A"], smoother, None, pr["R"])
+    host.mg_add_level(mg, None, coarse, pr["P"], None)
+    x = torch.zeros(nl, dtype=dt, device=d.dev)
+    b = torch.zeros(nl, dtype=dt, device=d.dev)
+    f.apply_constraints(x)
+    f.apply_constraints(b)
+    rc, ms = _timed(torch, d.comm, lambda: host.apply(mg, b, x))
+    return dict(rc=rc, ms=ms, hist=host.residual_history(mg), cycles=host.iterations(mg), eig_max=host.cheb3_eig_max(smoother),
+                pm_it=host.cheb3_power_method_iterations(smoother), power_s=power_s, coarse_it=host.iterations(coarse), x=x)
+
+
+def mg_elasticity(d: Dist, macro=87, layers=11, level=8, sweeps=30, max_cycles=40, tol=1e-9, check=False):
+    from sfem_b200 import parallel
+
+    torch, dt = d.torch, d.torch.float64
+    t0 = time.time()
+    # micro-elements of size 1 (see tools/solver_bench.py: on the unit cube the identity rows of the Dirichlet dofs
+    # dominate the spectrum and the Chebyshev interval misses the operator)
+    ext = (float(macro * level), float(macro * level), float(layers * level))
+    lm = parallel.sshex8_slab(level, macro, macro, layers, d.rank, d.world, extent=ext)
+    pr = _mg_problem(d, lm, level, dt, ext[0])
+    setup_s = time.time() - t0
+    s = _mg_solve(d, pr, dt, sweeps, max_cycles, tol, seed=5 + d.rank)
+    dofs, cdofs = int(d.comm.sum(lm.n_owned * 3)), int(d.comm.sum(pr["cm"].n_owned * 3))
+    out = {"name": f"C5: 2-level multigrid (mgsolve, SFEM_USE_CHEB=1), sshex8 L{level} linear elasticity, {macro}x{macro}x{layers} macro "
+                   f"per GPU x {d.world} GPU(s) (z-stack), f64, Chebyshev3 x{sweeps} / coarse CG",
+           "config": "C5", "n_gpus": d.world, "dofs": dofs, "coarse_dofs": cdofs, "rc": s["rc"], "cycles": s["cycles"],
+           "ms_total": s["ms"], "solve_s": s["ms"] * 1e-3, "ms_per_cycle": s["ms"] / max(s["cycles"], 1),
+           "residual_history": [float(v) for v in s["hist"]], "eig_max": s["eig_max"], "power_method_iterations": s["pm_it"],
+           "power_method_s": s["power_s"], "setup_s": setup_s, "solve_plus_power_method_s": s["ms"] * 1e-3 + s["power_s"],
+           "last_coarse_cg_iterations": s["coarse_it"], "reductions": pr["blas"].reductions(),
+           "halo": {"transport": pr["halo"].transport if pr["halo"] else None,
+                    "values_sent_rank0": pr["halo"].values_sent if pr["halo"] else 0}}
+    if check and d.rank == 0:
+        # the same global stack on one GPU
+        ext1 = (ext[0], ext[1], ext[2] * d.world)
+        one = Dist.__new__(Dist)
+        one.torch, one.rank, one.world, one.dev, one.comm = torch, 0, 1, d.dev, _SerialComm()
+        one.all_gather_object = lambda o: [o]
+        lm1 = parallel.sshex8_slab(level, macro, macro, layers * d.world, 0, 1, extent=ext1)
+        pr1 = _mg_problem(one, lm1, level, dt, ext1[0], distributed=False)
+        s1 = _mg_solve(one, pr1, dt, sweeps, max_cycles, tol, seed=5)
+        out["check"] = {"serial_cycles": s1["cycles"], "serial_rc": s1["rc"], "serial_eig_max": s1["eig_max"],
+                        "serial_residual_history": [float(v) for v in s1["hist"]]}
+        assert s1["cycles"] == s["cycles"] and s1["rc"] == s["rc"], (s1["cycles"], s["cycles"])
+    return out
+
+
+class _SerialComm:
+    def barrier(self):
+        pass
+
+    def max(self, v):
+        return v
+
+    def sum(self, v):
+        return v
+
+
+def main():
+    import torch
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("case", choices=["c4", "c5"])
+    ap.add_argument("--n", type=int, default=465)
+    ap.add_argument("--rtol", type=float, default=1e-6)
+    ap.add_argument("--max-it", type=int, default=20000)
+    ap.add_argument("--macro", type=int, default=87)
+    ap.add_argument("--layers", type=int, default=11)
+    ap.add_argument("--level", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=30)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    d = Dist(torch)
+    if a.case == "c4":
+        out = cg_poisson_tet4(d, a.n, a.rtol, a.max_it, check=a.check)
+    else:
+        out = mg_elasticity(d, a.macro, a.layers, a.level, a.sweeps, check=a.check)
+    if d.rank == 0:
+        print(json.dumps(out), flush=True)
+    d.comm.barrier()
+    d.close()
+
+
+if __name__ == "__main__":
+    main()
