@@ -584,7 +584,7 @@ int b200fem_cheb3_update(int rt, ptrdiff_t n, double alpha, double beta, const v
 int b200fem_constraint_nodes_copy_vec(int rt, ptrdiff_t n, const int32_t *idx, int bs, int comp, const void *src,
                                       void *dst, void *stream) {
     if (n <= 0) return B200FEM_SUCCESS;
-    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    const int grid = (int)std::min<ptrdiff_t>((n + 255) / 256, (ptrdiff_t)sm_count() * 8);
     if (rt == B200FEM_F64)
         constraint_copy_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(n, idx, bs, comp, (const double *)src, (double *)dst);
     else if (rt == B200FEM_F32)
@@ -598,7 +598,7 @@ int b200fem_constraint_nodes_copy_vec(int rt, ptrdiff_t n, const int32_t *idx, i
 int b200fem_constraint_nodes_to_value_vec(int rt, ptrdiff_t n, const int32_t *idx, int bs, int comp, double value,
                                           void *values, void *stream) {
     if (n <= 0) return B200FEM_SUCCESS;
-    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    const int grid = (int)std::min<ptrdiff_t>((n + 255) / 256, (ptrdiff_t)sm_count() * 8);
     if (rt == B200FEM_F64)
         constraint_value_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(n, idx, bs, comp, value, (double *)values);
     else if (rt == B200FEM_F32)

@@ -4,6 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "b200fem.h"
@@ -28,7 +29,29 @@ bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();  // cached SM count of the current device
+int sm_count();  // SM count of the current device (per-device cache, thread-safe)
+
+// The dynamic shared-memory opt-in (cudaFuncAttributeMaxDynamicSharedMemorySize) is a per-device attribute of a kernel:
+// one record per launch site remembers, per device, the largest size already granted. Safe across host threads (a
+// racing duplicate cudaFuncSetAttribute is harmless).
+struct SmemOptIn {
+    static constexpr int kMaxDevices = 64;
+    std::atomic<size_t> granted[kMaxDevices];
+    SmemOptIn() {
+        for (auto &g : granted) g.store(0);
+    }
+    template <typename K>
+    int ensure(K kernel, size_t smem) {
+        int dev = 0;
+        B2_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1, granted[dev].store(0);  // no caching beyond the table
+        if (smem > granted[dev].load(std::memory_order_acquire)) {
+            B2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            granted[dev].store(smem, std::memory_order_release);
+        }
+        return B200FEM_SUCCESS;
+    }
+};
 
 // fire-and-forget global add: compiles to RED.E.ADD.F64/F32 (no return value requested)
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }

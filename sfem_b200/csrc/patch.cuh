@@ -243,11 +243,8 @@ template <typename T, int NXE, int BS, int E, int BT, class Local>
 int launch_patch_apply_smem_atomic(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
     auto kern = patch_apply_smem_atomic_kernel<T, NXE, BS, E, BT, Local>;
     const size_t smem = (size_t)plan.max_u * BS * 2 * sizeof(T);
-    static size_t configured = 0;
-    if (smem > configured) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
     if (plan.nchunks == 0) return B200FEM_SUCCESS;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
     const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);
@@ -260,11 +257,8 @@ template <typename T, int NXE, int BS, int E, int BT, class Local>
 int launch_patch_apply(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
     auto kern = patch_apply_kernel<T, NXE, BS, E, BT, Local>;
     const size_t smem = plan.smem_bytes(BS, (int)sizeof(T));
-    static size_t configured = 0;
-    if (smem > configured) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
     if (plan.nchunks == 0) return B200FEM_SUCCESS;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
     const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);

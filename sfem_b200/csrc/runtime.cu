@@ -21,16 +21,17 @@ bool cuda_ok(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 int sm_count() {
-    static int cached_dev = -1, cached = 0;
+    static std::atomic<int> cached[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached = n;
-        cached_dev = dev;
+    if (dev >= 0 && dev < 64) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
     }
-    return cached;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
+    return n;
 }
 
 int OpBase::set_option(const char *key, int value) {

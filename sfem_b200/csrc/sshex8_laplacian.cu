@@ -222,12 +222,8 @@ struct Sshex8Laplacian final : OpBase {
         using Cfg = Sshex8StreamCfg<T, L, TW, NTEAM, D>;
         auto kern = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, false>;
         auto tail = sshex8_laplacian_stream_kernel<T, L, TW, NTEAM, D, PLAIN, true>;
-        static bool configured = false;
-        if (!configured) {
-            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-            B2_CUDA(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-            configured = true;
-        }
+        static SmemOptIn opt_main, opt_tail;
+        if (opt_main.ensure(kern, Cfg::smem_bytes) || opt_tail.ensure(tail, Cfg::smem_bytes)) return B200FEM_FAILURE;
         // full groups in the main launch, the ne % EPT left-over elements in a one-CTA clean-up launch
         const ptrdiff_t ngroups = ne / Cfg::EPT;
         const ptrdiff_t ne_main = ngroups * Cfg::EPT;
@@ -262,11 +258,8 @@ struct Sshex8Laplacian final : OpBase {
         using Cfg = Sshex8TmaCfg<T, L, NWARP>;
         auto kern = tma_cfg == 1 ? sshex8_laplacian_tma_kernel<T, L, NWARP, PLAIN, false>
                                  : sshex8_laplacian_tma_kernel<T, L, NWARP, PLAIN, true>;
-        static bool configured[2] = {false, false};
-        if (!configured[tma_cfg == 1]) {
-            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-            configured[tma_cfg == 1] = true;
-        }
+        static SmemOptIn opt[2];
+        if (opt[tma_cfg == 1].ensure(kern, Cfg::smem_bytes)) return B200FEM_FAILURE;
         const ptrdiff_t ngroups = (ne + Cfg::EPW - 1) / Cfg::EPW;
         if (ngroups == 0) return B200FEM_SUCCESS;
         const int grid = (int)std::min<ptrdiff_t>((ngroups + NWARP - 1) / NWARP, (ptrdiff_t)sm_count());
@@ -325,11 +318,8 @@ struct Sshex8Laplacian final : OpBase {
         constexpr int EPB = BT / N;
         const size_t smem = (size_t)EPB * N * N * N * sizeof(T) + (MODE == kModeBoxes ? (size_t)EPB * 27 * sizeof(BoxDesc) : 0);
         auto kern = sshex8_laplacian_kernel<T, L, BT, MODE, OVERWRITE, IE>;
-        static bool configured = false;
-        if (!configured) {
-            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        static SmemOptIn opt;
+        if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
         const ptrdiff_t nbatches = (ne + EPB - 1) / EPB;
         const int grid = (int)std::min<ptrdiff_t>(nbatches, (ptrdiff_t)sm_count() * ctas_per_sm);
         kern<<<grid, BT, smem, s>>>(ne, idx_aos.ptr, boxes.ptr, fff.ptr, x, y);
@@ -525,6 +515,10 @@ static bool build_tma_headers(int level, ptrdiff_t ne, const std::vector<BoxDesc
 
 OpBase *make_sshex8_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff,
                               int real_type) {
+    if (level != 2 && level != 4 && level != 8) {  // the levels the apply kernels are instantiated for
+        set_error("sshex8 laplacian: level must be 2, 4 or 8");
+        return nullptr;
+    }
     const int N = level + 1, nxe = N * N * N;
     for (int v = 0; v < nxe; ++v)
         for (ptrdiff_t e = 0; e < ne; ++e)

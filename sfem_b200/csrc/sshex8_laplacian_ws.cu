@@ -36,11 +36,8 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     constexpr int L = 8;
     using Cfg = Sshex8WsCfg<T, L, NC, D, S>;
     auto kern = sshex8_laplacian_ws_kernel<T, L, NC, D, S, PLAIN, PHASED>;
-    static bool configured = false;
-    if (!configured) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-        configured = true;
-    }
+    static SmemOptIn opt;
+    if (opt.ensure(kern, Cfg::smem_bytes)) return B200FEM_FAILURE;
     const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;  // the last group may be partial (padded headers)
     if (ngroups == 0) return B200FEM_SUCCESS;
     alignas(64) CUtensorMap map;

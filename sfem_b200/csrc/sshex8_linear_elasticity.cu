@@ -222,11 +222,8 @@ struct Sshex8LinearElasticity final : OpBase {
         using Cfg = Sshex8LECfg<L>;
         const size_t smem = (size_t)Cfg::EPB * 2 * 3 * Cfg::CS * sizeof(T) + (MODE == kLEBoxes ? (size_t)Cfg::EPB * 27 * sizeof(BoxDesc) : 0);
         auto kern = sshex8_le_apply_kernel<T, L, MODE, PLAIN>;
-        static bool configured = false;
-        if (!configured) {
-            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        static SmemOptIn opt;
+        if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
         const ptrdiff_t nbatches = (ne + Cfg::EPB - 1) / Cfg::EPB;
         const int per_sm = std::max(1, (int)((size_t)220 * 1024 / (smem + 1024)));
         const int grid = (int)std::min<ptrdiff_t>(nbatches, (ptrdiff_t)sm_count() * per_sm);

@@ -271,6 +271,10 @@ class HaloExchange:
             self.send_buf[(q, like.dtype)] = b
         return b
 
+    def release(self, x_local=None):
+        """Called after the local apply that consumed the ghost block has been enqueued. Nothing to do for the
+        send/recv transport; the symmetric-memory transport raises "ghost block free" towards its writers."""
+
     def gather(self, x_local):
         """x_local: [n_local * block_size]; on return its ghost block holds the owners' values."""
         if self.world == 1 or not self.peers:
@@ -402,7 +406,9 @@ class OverlappedApply:
         op, halo = self.op, self.halo
         if self.range is None:
             halo.gather(x_local)
-            return op.apply_overwrite(x_local, y_local)
+            out = op.apply_overwrite(x_local, y_local)
+            halo.release(x_local)
+            return out
         torch = self.torch
         main = torch.cuda.current_stream()
         self.comm.wait_stream(main)  # x_local is ready
@@ -417,6 +423,7 @@ class OverlappedApply:
             op.apply_range(x_local, y_local, 0, e0, 2)
         if e1 < self.ne:
             op.apply_range(x_local, y_local, e1, self.ne, 2)
+        halo.release(x_local)
         return y_local
 
     def launches(self):
@@ -445,6 +452,7 @@ class ParallelMatrixFreeOperator:
         xl[: self.owned_dofs].copy_(x_owned)
         self.ex.gather(xl)
         self.op.apply_overwrite(xl, yl)
+        self.ex.release(xl)
         y_owned.copy_(yl[: self.owned_dofs])
         return y_owned
 
@@ -452,3 +460,4 @@ class ParallelMatrixFreeOperator:
         """Same, for callers that keep their vectors at local size (x in self.x_local, y in self.y_local)."""
         self.ex.gather(self.x_local)
         self.op.apply_overwrite(self.x_local, self.y_local)
+        self.ex.release(self.x_local)

@@ -39,7 +39,7 @@ def _run(world, args, timeout=600):
 
 
 def test_distributed_cg_tet4_matches_serial():
-    out = _run(2, ["c4", "--n", "33", "--rtol", "1e-8", "--check"])
+    out = _run(2, ["c4", "--side", "33", "--rtol", "1e-8", "--check"])
     assert out["rc"] == 0 and out["check"]["serial_iterations"] == out["iterations"]
     assert out["check"]["max_rel_residual_history_diff"] < 1e-6, out["check"]
     assert out["halo"]["transport"] in ("push", "nccl")
@@ -53,6 +53,6 @@ def test_distributed_mg_elasticity_matches_serial():
 
 def test_single_rank_goes_through_the_same_layer():
     """world 1: Communicator / Halo / ParallelMatrixFreeOperator degenerate to the plain solve (no NCCL call)."""
-    out = _run(1, ["c4", "--n", "25", "--check"])
+    out = _run(1, ["c4", "--side", "25", "--check"])
     assert out["rc"] == 0 and out["check"]["serial_iterations"] == out["iterations"]
-    assert out["check"]["max_rel_residual_history_diff"] == 0.0
+    assert out["check"]["max_rel_residual_history_diff"] < 1e-10  # RED order only

@@ -3,7 +3,7 @@
 (sfem_b200/host/b200fem_host.hpp: Communicator, HaloExchange, ParallelMatrixFreeOperator, ConjugateGradient with
 device-side reductions over NCCL, Chebyshev3, Multigrid) -- Python only builds the per-rank mesh and wires the objects:
 
-    torchrun --nproc-per-node N tools/dist_solve.py c4 [--n 465] [--rtol 1e-6]
+    torchrun --nproc-per-node N tools/dist_solve.py c4 [--side 465] [--rtol 1e-6]
     torchrun --nproc-per-node N tools/dist_solve.py c5 [--macro 87] [--layers 11] [--sweeps 30]
 
   c4  drivers/simulations/poisson.exe.cpp:14-41,122-129: matrix-free CG (rtol 1e-6, atol 1e-16, max_it 20000) on a tet4
@@ -281,7 +281,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("case", choices=["c4", "c5"])
-    ap.add_argument("--n", type=int, default=465)
+    ap.add_argument("--side", type=int, default=465)
     ap.add_argument("--rtol", type=float, default=1e-6)
     ap.add_argument("--max-it", type=int, default=20000)
     ap.add_argument("--macro", type=int, default=87)
@@ -292,7 +292,7 @@ def main():
     a = ap.parse_args()
     d = Dist(torch)
     if a.case == "c4":
-        out = cg_poisson_tet4(d, a.n, a.rtol, a.max_it, check=a.check)
+        out = cg_poisson_tet4(d, a.side, a.rtol, a.max_it, check=a.check)
     else:
         out = mg_elasticity(d, a.macro, a.layers, a.level, a.sweeps, check=a.check)
     if d.rank == 0:
