@@ -9,8 +9,11 @@ What is timed is  y = A x  -- the pair `zeros(y); Op::apply(x, y)` every solver 
 
 With N > 1 ranks (torchrun, one process per GPU) the global mesh is an N-long stack of such blocks along z
 (weak scaling). Every rank holds its block plus the aura layer of the block above
-(sfem_b200/parallel.py, the reference's owned/ghost/aura scheme) and every step starts with the NCCL halo
-gather of x. `value` counts the dofs all ranks own.
+(sfem_b200/parallel.py, the reference's owned/ghost/aura scheme) and every step is one apply of the C++ host
+layer's ParallelMatrixFreeOperator (halo gather of x: owner-push over NVLink-mapped memory, else grouped ncclSend /
+ncclRecv; then the local kernel). `value` counts the dofs all ranks own. The solver rows of BASELINE.json ride in
+`solves`: config 4 (tet4 CG, strong scaling over the ranks) and config 5 (sshex8 multigrid elasticity, weak scaling:
+87 x 87 x 11 macro elements per GPU = 1.03e9 dofs on 8), both through tools/dist_solve.py.
 
 Prints ONE JSON line (DESIGN.md "Measurement" explains every field). `--impl reference` times the
 reference's own OpenMP kernel (oracle/_ref, else the oracle port) on the host cores instead.
@@ -47,11 +50,10 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: grouped ncclSend/ncclRecv instead of the symmetric-memory push")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: overlap the halo gather with the ghost-independent elements (b200fem_op_apply_range). Off by "
-                         "default: measured on 2 GPUs it is slower (1.19 vs 1.10 ms per step) -- three launches of the "
-                         "persistent kernel and 8 reserved SMs cost more than the 0.12 ms exchange they hide")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: grouped ncclSend/ncclRecv instead of the owner-push transport")
+    ap.add_argument("--c4-side", type=int, default=465, help="nodes per side of the config-4 tet4 cube (strong scaling)")
+    ap.add_argument("--c5-macro", type=int, default=87, help="config 5: macro elements per x / y side")
+    ap.add_argument("--c5-layers", type=int, default=11, help="config 5: macro layers per GPU (z-stack)")
     ap.add_argument("--no-solves", action="store_true", help="skip the CG / multigrid solve times (tools/solver_bench.py)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs 0 / 1 / 2-fp32 (tools/extras_bench.py)")
     ap.add_argument("--extras", action="store_true", help="also time the other configs (C1, C2, fp32, vector kernels)")
@@ -129,7 +131,16 @@ def cpu_reference_run(a, elements, fff, nn, steps, warmup):
         os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_PROC_BIND", "true")
     kind = "reference" if available("reference", a.real, fast=True) else "port"
-    orc = Oracle(kind, a.real, fast=(kind == "reference"))
+    isa = "avx2+fma"
+    orc = None
+    if kind == "reference" and "avx512f" in cpu_flags():
+        try:  # the reference builds with -march=native; the box's ISA is not known at build time, so two builds travel
+            orc = Oracle(kind, a.real, fast="avx512")
+            isa = "x86-64-v4 (avx512)"
+        except Exception:
+            orc = None
+    if orc is None:
+        orc = Oracle(kind, a.real, fast=(kind == "reference"))
     try:  # libgomp may have been initialised (by numpy / torch) before the variable was set
         import ctypes
 
@@ -148,7 +159,53 @@ def cpu_reference_run(a, elements, fff, nn, steps, warmup):
     return {"value": nn / dt / 1e9, "unit": UNIT, "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": kind,
             "sample": f"the full workload ({nn} dofs), {steps} x (zero y + apply) after {warmup} warm-up, wall clock, "
                       f"OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}",
+            "cpu_model": cpu_model(), "isa": isa if kind == "reference" else "-O2 port",
+            "host_GB_s": nn * (2 * orc.rt().itemsize) / dt / 1e9 + elements.size * 4 / dt / 1e9,
             "ms_per_step": dt * 1e3}
+
+
+def host_memory_gb():
+    """memory this process may still take: MemAvailable capped by the cgroup limit"""
+    avail = 0.0
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = float(ln.split()[1]) / 1e6
+    except Exception:
+        return 0.0
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v != "max":
+                used = 0.0
+                try:
+                    used = float(open(path.replace("memory.max", "memory.current").replace("limit_in_bytes", "usage_in_bytes")).read())
+                except Exception:
+                    pass
+                avail = min(avail, (float(v) - used) / 1e9)
+        except Exception:
+            pass
+    return avail
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_flags():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                return set(ln.split(":", 1)[1].split())
+    except Exception:
+        pass
+    return set()
 
 
 def run_reference(a):
@@ -160,15 +217,15 @@ def run_reference(a):
     m = mesh.sshex8_box(a.level, a.macro, a.macro, a.macro, with_points=False)
     kind = "reference" if available("reference", "f64") else "port"
     fff = Oracle(kind, "f64").hex8_fff_fill(m["m_elements"], m["m_points"])
-    steps = max(1, min(a.steps, 20))
-    warm = max(1, min(a.warmup, 3))
+    steps, warm = max(1, a.steps), max(0, a.warmup)  # the caller's counts: one step = 0.4 s on 16 cores
     cb = cpu_reference_run(a, m["elements"], fff, m["n_nodes"], steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.real, "data": "synthetic",
-        "config": {"workload": workload_name(a) + " -- reference OpenMP kernel on the host cores (one rank's block)"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": workload_name(a),
+                   "arm": "the reference's OpenMP kernel (oracle/_ref) on the host cores of rank 0, one rank's block"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "isa", "host_GB_s")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -196,10 +253,35 @@ def time_steps(fn, steps, warmup, torch, barrier=None):
     return ev0.elapsed_time(ev1) / steps  # ms per step
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's host threads (and with them the first-touch placement of its pinned e2e buffers) to the NUMA node
+    its GPU hangs off: with every rank's buffers on node 0 the 8-GPU e2e copies all cross one socket."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(a):
     import torch
 
-    from sfem_b200 import lib, mesh, parallel
+    from sfem_b200 import host, lib, mesh, parallel
+    from tools.dist_solve import Dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,11 +289,13 @@ def run_b200(a):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # setup plumbing (unique id, plan objects) and the driver's NCCL check
+    d = Dist(torch)  # the C++ communicator every timed collective goes through
 
     dt = torch.float64 if a.real == "f64" else torch.float32
     ndt = np.float64 if a.real == "f64" else np.float32
@@ -233,62 +317,29 @@ def run_b200(a):
     assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
 
     u_host = np.random.default_rng(42 + rank).uniform(-1, 1, n_local).astype(ndt)
-    halo, halo_kind = None, None
-    if lm is not None:
-        if not a.nccl_halo:
-            try:  # owner-push over NVLink-mapped symmetric memory (sfem_b200.parallel.SymmetricHaloExchange)
-                halo = parallel.SymmetricHaloExchange(lm, 1, dtype=dt, device=dev)
-                halo_kind = "owner-push into the peers' ghost blocks over symmetric (NVLink-mapped) memory + stream-ordered signals"
-            except Exception as ex:  # no P2P mapping on this box: grouped ncclSend / ncclRecv
-                halo_kind = f"grouped ncclSend/ncclRecv (symmetric memory unavailable: {type(ex).__name__})"
-        if halo is None:
-            halo = parallel.HaloExchange(lm, 1, device=dev)
-            halo_kind = halo_kind or "grouped ncclSend/ncclRecv"
-    if isinstance(halo, parallel.SymmetricHaloExchange):
-        x = halo.local_vector()
-        x.copy_(torch.from_numpy(u_host))
-    else:
-        x = torch.from_numpy(u_host).to(dev)
+    x = torch.from_numpy(u_host).to(dev)
     y = torch.zeros_like(x)
-    symmetric = isinstance(halo, parallel.SymmetricHaloExchange)
-    overlapped = parallel.OverlappedApply(op, lm, halo, dev) if (halo is not None and a.overlap) else None
+    halo, halo_kind, A = None, None, None
+    if lm is not None:
+        # ParallelMatrixFreeOperator of the C++ host layer: halo gather of x (in place, into its ghost block) + local apply
+        f = host.Function(dt, n_local, 1)
+        f.add_operator(op)
+        halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object),
+                         transport=lib.HALO_NCCL if a.nccl_halo else lib.HALO_AUTO)
+        A = host.parallel_op(f, halo, n_owned, n_owned)
+        halo_kind = {"push": "owner-push: the owner's pack kernel stores into the peer's receive block over NVLink (cudaIpc-mapped), "
+                             "acquire / release epoch flags, a second kernel waits and copies into the ghost block",
+                     "nccl": "pack kernel + grouped ncclSend / ncclRecv into the ghost block"}[halo.transport]
 
     def step():
-        if overlapped is not None:
-            overlapped.apply_overwrite(x, y)
-            if symmetric:
-                halo.release()
-            return
-        if halo is not None:
-            halo.gather(x)
-        op.apply_overwrite(x, y)
-        if symmetric:
-            halo.release()  # my ghost block may be overwritten again once this apply has run
+        if A is not None:
+            rc = host.apply_overwrite(A, x, y)
+            assert rc == 0
+        else:
+            op.apply_overwrite(x, y)
 
-    if overlapped is not None and overlapped.range:
-        # one-off check: the overlapped schedule computes what gather-then-apply computes (differences = RED order)
-        y_ref = torch.zeros_like(y)
-        halo.gather(x)
-        op.apply_overwrite(x, y_ref)
-        if symmetric:
-            halo.release()
-        overlapped.apply_overwrite(x, y)
-        if symmetric:
-            halo.release()
-        rel = float((y[:n_owned] - y_ref[:n_owned]).norm() / y_ref[:n_owned].norm())
-        assert rel < 1e-12, f"overlapped apply differs from gather-then-apply: {rel}"
-        del y_ref
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier = d.comm.barrier if world > 1 else None
+    max_over_ranks = d.comm.max
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -296,11 +347,7 @@ def run_b200(a):
     ms = max_over_ranks(time_steps(step, a.steps, a.warmup, torch, barrier))
     clocks = sampler.stop() if rank == 0 else None
 
-    total_owned = n_owned
-    if dist is not None:
-        t = torch.tensor([n_owned], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        total_owned = int(t.item())
+    total_owned = int(d.comm.sum(n_owned))
 
     # the dominant kernel alone (no halo): overwrite form = [memset of the skeleton ranges + stream kernel]
     ms_kernel = time_steps(lambda: op.apply_overwrite(x, y), a.steps, 2, torch)
@@ -317,10 +364,7 @@ def run_b200(a):
         # Every step still copies its whole input from pinned host memory and its whole result back.
         main = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        if symmetric:
-            xb = [x, halo.allocate()[: x.numel()]]
-        else:
-            xb = [x, torch.empty_like(x)]
+        xb = [x, torch.empty_like(x)]
         yb = [y, torch.empty_like(y)]
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_comp = [torch.cuda.Event() for _ in range(2)]
@@ -339,11 +383,10 @@ def run_b200(a):
             main.wait_event(ev_in[b])
             if k >= 2:
                 main.wait_event(ev_out[b])  # the D2H of step k-2 has drained this y buffer
-            if halo is not None:
-                halo.gather(xb[b])
-            op.apply_overwrite(xb[b], yb[b])
-            if symmetric:
-                halo.release(xb[b])
+            if A is not None:
+                host.apply_overwrite(A, xb[b], yb[b])
+            else:
+                op.apply_overwrite(xb[b], yb[b])
             ev_comp[b].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_comp[b])
@@ -359,13 +402,15 @@ def run_b200(a):
         k = max(4, min(a.steps, 8))
         e2e_run(2)  # warm-up
         torch.cuda.synchronize()
-        barrier()
+        if barrier:
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         e2e_run(k)
         e1.record()
         torch.cuda.synchronize()
-        barrier()
+        if barrier:
+            barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1) / k)
         # the result that reached the host is the apply of the host input
         chk = float((yh[:n_owned].to(dev) - yb[(k - 1) % 2][:n_owned]).abs().max())
@@ -378,44 +423,79 @@ def run_b200(a):
                        f"{2 * n_local * x.element_size() / (ms_e2e * 1e-3) / 1e9:.1f} GB/s in + out)"}
         del xb, yb
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None  # dram__bytes_read + dram__bytes_write of the dominant kernel, from the committed ncu capture
+    alg, streamed, op_launches = op.algorithmic_bytes, op.streamed_bytes(True), op.launches(True)
+    halo_launches = halo.launches_per_gather if halo is not None else 0
+    n_elements = int(elements.shape[1])
+
+    # the solver rows of BASELINE.json (configs 4 and 5) on all ranks, through the C++ distributed layer
+    solves = None
+    if not a.no_solves:
+        from tools import dist_solve, solver_bench
+
+        del op, x, y, A, halo
+        if lm is not None:
+            del f
+        torch.cuda.empty_cache()
+        solves = []
+
+        def attempt(fn, *args, **kw):
+            try:
+                solves.append(fn(*args, **kw))
+            except Exception as ex:  # report, do not hide the headline number
+                solves.append({"name": getattr(fn, "__name__", "solve"), "error": repr(ex)})
+            torch.cuda.empty_cache()
+
+        if world == 1:
+            attempt(solver_bench.cg_poisson, torch, macro=a.macro, peak_gbs=peak)
+        # config 4, STRONG scaling: the 465^3-node cube cut into `world` slabs. One GPU holds it too (6e8 tets: 24 GB of
+        # connectivity + FFF) when the host has the memory to generate it; else its 1/8 share (233^3) is reported
+        side = a.c4_side
+        if world == 1 and host_memory_gb() < 160:
+            side = (a.c4_side + 1) // 2
+        attempt(dist_solve.cg_poisson_tet4, d, n=side, peak_gbs=peak)
+        # config 5, WEAK scaling: 87 x 87 x 11 macro elements per GPU (1.03e9 dofs on 8 GPUs)
+        attempt(dist_solve.mg_elasticity, d, macro=a.c5_macro, layers=a.c5_layers)
+
+    if rank != 0:
+        d.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    traffic, traffic_source = None, None  # dram__bytes_read + dram__bytes_write of the dominant kernel (ncu --set full)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if a.real == "f64" and a.macro == 64 and a.level == 8:
+        if a.real == "f64" and a.macro == 64 and a.level == 8 and world == 1:
             traffic = tr["dram_bytes_per_launch"]
+            traffic_source = "committed capture: " + tr.get("source", "profiles/traffic.json")
     except Exception:
         pass
-    alg = op.algorithmic_bytes
     achieved = alg / (ms_kernel * 1e-3) / 1e9
-    launches_per_step = op.launches(True) + (len(halo.send_idx) if halo is not None else 0)
+    launches_per_step = op_launches + halo_launches
     line = {
         "metric": METRIC, "value": total_owned / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.real, "data": "synthetic",
         "config": {
             "workload": workload_name(a), "dofs_owned_total": total_owned, "dofs_local_rank0": n_local,
-            "macro_elements_rank0": int(elements.shape[1]),
+            "macro_elements_rank0": n_elements,
             "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair as one call (b200fem_op_apply_overwrite)",
             "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
             "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
-            "parallelism": (f"z-slab x{world}, owned/ghost/aura, halo gather of x per step: {halo_kind}"
-                            + (", overlapped with the ghost-independent elements" if overlapped is not None and overlapped.range else ""))
+            "parallelism": (f"z-slab x{world}, owned/ghost/aura; every step = ParallelMatrixFreeOperator::apply of the C++ host "
+                            f"layer: halo gather of x ({halo_kind}), then the local kernel"
+                            + (f"; rank 0 bound to NUMA node {numa_node}" if numa_node is not None else ""))
             if world > 1 else "single GPU",
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "algorithmic_bytes": alg, "streamed_bytes": op.streamed_bytes(True),
+            "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg, "streamed_bytes": streamed,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
             "kernel": ("sshex8_laplacian_ws_kernel" if (a.real == "f64" and a.level == 8) else "sshex8_laplacian_stream_kernel")
             + " (+ the memsets of the skeleton ranges that belong to the call)",
@@ -432,15 +512,11 @@ def run_b200(a):
     if not a.no_cpu_baseline and world == 1:
         try:
             cb = cpu_reference_run(a, elements, fff, n_local, 20, 2)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "isa", "host_GB_s")}
         except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
-    if not a.no_solves and world == 1:
-        from tools.solver_bench import run_solves
-
-        del op, x, y
-        torch.cuda.empty_cache()
-        line["solves"] = run_solves(torch, cg_macro=a.macro, mg_macro=max(4, a.macro // 2), peak_gbs=peak)
+    if solves is not None:
+        line["solves"] = solves
     if not a.no_other_configs and world == 1:
         # the other single-GPU configurations of BASELINE.json beside the headline (config 0: tet4 Laplacian on the
         # ~1 M-element cube; config 1: hex8 linear elasticity 128^3; config 2 in fp32), same timing rules
@@ -455,6 +531,7 @@ def run_b200(a):
 
         line["extras"] = run_extras(torch)
     print(json.dumps(line), flush=True)
+    d.close()
     if dist is not None:
         dist.destroy_process_group()
 

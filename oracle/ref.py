@@ -36,22 +36,24 @@ def _soa_ptrs(arr: np.ndarray, ctype):
     return ptrs
 
 
-def lib_path(kind: str, real: str, fast: bool = False) -> str:
+def lib_path(kind: str, real: str, fast=False) -> str:
+    """fast: False = the -O2 parity build, True = the reference's Release flags with -mavx2 -mfma, "avx512" = the same
+    with -march=x86-64-v4 (the reference builds -march=native; the GPU box's ISA is not known when this is compiled)."""
     if kind == "reference":
-        return os.path.join(HERE, "_ref", f"libsfem_ref_{real}{'_fast' if fast else ''}.so")
+        return os.path.join(HERE, "_ref", f"libsfem_ref_{real}{('_fast_avx512' if fast == 'avx512' else '_fast') if fast else ''}.so")
     if kind == "port":
         return os.path.join(HERE, f"liboracle_port_{real}.so")
     raise ValueError(kind)
 
 
-def available(kind: str, real: str = "f64", fast: bool = False) -> bool:
+def available(kind: str, real: str = "f64", fast=False) -> bool:
     return os.path.exists(lib_path(kind, real, fast))
 
 
 class Oracle:
     """Thin numpy front for one oracle library (one real type)."""
 
-    def __init__(self, kind: str = "reference", real: str = "f64", fast: bool = False):
+    def __init__(self, kind: str = "reference", real: str = "f64", fast=False):
         self.kind, self.real = kind, real
         self.rt = np.float64 if real == "f64" else np.float32
         self.crt = C.c_double if real == "f64" else C.c_float
