@@ -43,8 +43,8 @@ extern "C" {
 #define B200FEM_SCATTER_AUTO 0
 #define B200FEM_SCATTER_ATOMIC 1  /* red.global.add on every element dof                        */
 #define B200FEM_SCATTER_COLORED 2 /* element colouring, plain read-modify-write, one launch/colour */
-#define B200FEM_SCATTER_PATCH 3   /* element patches staged in shared memory, fixed-order sums, one red per
-                                     (patch, node): the default of the tet4 / hex8 operators              */
+#define B200FEM_SCATTER_PATCH 3   /* element patches staged in shared memory, fixed-order sums, one red per (patch, node):
+                                     the default of tet4 Laplacian and hex8 linear elasticity (hex8 Laplacian: ATOMIC) */
 
 typedef struct b200fem_op_s *b200fem_op_t; /* opaque operator plan (device connectivity + geometry) */
 
@@ -137,6 +137,7 @@ double b200fem_op_algorithmic_bytes(b200fem_op_t op);
 double b200fem_op_streamed_bytes(b200fem_op_t op, int overwrite);
 int b200fem_op_gpu_launches_per_apply(b200fem_op_t op, int overwrite);
 /* Tuning switches (all optional; defaults are the measured best). Common: "scatter" (B200FEM_SCATTER_*).
+ * hex8 linear elasticity: "patch_elements" (128 [default] | 256 | 512 elements per patch; the plan is rebuilt on the next apply).
  * sshex8 Laplacian: "use_ws" (1 = warp-specialised level-8 kernel where it is the faster one [fp64], 2 = wherever it
  * applies, 0 = never), "ws_cfg" (ring / staging depth variant), "stream_cfg", "use_tma", "explicit_index". */
 int b200fem_op_set_option(b200fem_op_t op, const char *key, int value);

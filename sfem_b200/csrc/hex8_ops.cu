@@ -20,10 +20,13 @@
 // layout the reference Op caches for HEX8, frontend/ops/sfem_LinearElasticity.cpp:275-277),
 // determinant fp32 [ne]; all coalesced over elements and streamed once. Vectors: scalar [nn] or AoS
 // [nn*3]; gathers/scatters go through L2.
+#include <string.h>
+
 #include <vector>
 
 #include "coloring.cuh"
 #include "common.cuh"
+#include "hex8_le_core.cuh"
 #include "hex8_local.cuh"
 #include "patch.cuh"
 
@@ -119,35 +122,24 @@ __global__ void __launch_bounds__(128)
         for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
         const T det = (T)ldg_stream(&determinant[e]);
 
-        T c[3][8];
+        // element vector from the gradient-moment form of hex8_le_core.cuh (h = 1: the element is its own macro element):
+        // 444 fp64 operations against the ~840 of the per-(a, b) coefficient form this kernel started with
+        T c[3][8], O[3][8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             const T *p = &u[(ptrdiff_t)ev[v] * 3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) c[a][kVtkToLex[v]] = p[a];
         }
+        Hex8LEConsts<T> K;
+        K.init(A, det, T(1), mu, lambda);
+        hex8_le_local_apply(K, c, O);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) haar_forward(c[a]);
-
-        T AAt_mu[6], lam_idet, mu_idet;
-        le_prepare(A, det, mu, lambda, AAt_mu, lam_idet, mu_idet);
-
+        for (int v = 0; v < 8; ++v) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            T O[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) O[k] = T(0);
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                T t[3][3];
-                le_coeff(A, AAt_mu, lam_idet, mu_idet, a, b, t);
-                haar_grad_grad(t, c[b], O);
-            }
-            haar_inverse_unscaled(O);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
+            for (int a = 0; a < 3; ++a) {
                 T *dst = &y[(ptrdiff_t)ev[v] * 3 + a];
-                const T val = T(0.125) * O[kVtkToLex[v]];
+                const T val = O[a][kVtkToLex[v]];
                 if (COLORED)
                     *dst += val;
                 else
@@ -230,30 +222,18 @@ struct Hex8LinearElasticityLocal {
 #pragma unroll
         for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
         const T det = (T)ldg_stream(&determinant[e]);
-        T c[3][8];
+        T c[3][8], O[3][8];
 #pragma unroll
         for (int v = 0; v < 8; ++v)
 #pragma unroll
             for (int a = 0; a < 3; ++a) c[a][kVtkToLex[v]] = uin[v * 3 + a];
+        Hex8LEConsts<T> K;
+        K.init(A, det, T(1), mu, lambda);
+        hex8_le_local_apply(K, c, O);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) haar_forward(c[a]);
-        T AAt_mu[6], lam_idet, mu_idet;
-        le_prepare(A, det, mu, lambda, AAt_mu, lam_idet, mu_idet);
+        for (int v = 0; v < 8; ++v)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            T O[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) O[k] = T(0);
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                T t[3][3];
-                le_coeff(A, AAt_mu, lam_idet, mu_idet, a, b, t);
-                haar_grad_grad(t, c[b], O);
-            }
-            haar_inverse_unscaled(O);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) out[v * 3 + a] = T(0.125) * O[kVtkToLex[v]];
-        }
+            for (int a = 0; a < 3; ++a) out[v * 3 + a] = O[a][kVtkToLex[v]];
     }
 };
 
@@ -267,8 +247,8 @@ struct Hex8Laplacian final : OpBase {
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
-        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(1, sizeof(T)) <= 200 * 1024)
-            return launch_patch_apply<T, 8, 1, kPatchE, 256>(patch, Hex8LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) <= 200 * 1024)
+            return launch_patch_apply_direct<T, 8, 1, kPatchE, 256>(patch, Hex8LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
@@ -311,14 +291,43 @@ struct Hex8LinearElasticity final : OpBase {
     double mu = 1, lambda = 1;
     ColorPlan colors;
     PatchPlan patch;
-    static constexpr int kPatchE = 256;
+    std::vector<int32_t> host_el;  // SoA copy for the lazily built plans (patch / colours)
+    int patch_elements = 256;      // elements per patch: 128, 256 (3 CTAs of 128 threads per SM) or 512
+
+    int ensure_patch() {
+        if (patch.ready && patch.E == patch_elements) return B200FEM_SUCCESS;
+        if (host_el.empty() && ne > 0) B2_FAIL("hex8 linear elasticity: connectivity no longer on the host");
+        std::vector<const int32_t *> rows(8);
+        for (int v = 0; v < 8; ++v) rows[v] = host_el.data() + (size_t)v * ne;
+        patch.ready = false;
+        return patch.build(8, patch_elements, ne, rows.data());
+    }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "patch_elements")) {
+            if (value != 128 && value != 256 && value != 512) B2_FAIL("patch_elements must be 128, 256 or 512");
+            patch_elements = value;
+            return B200FEM_SUCCESS;
+        }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "patch_elements")) { *value = patch_elements; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "patch_avg_unique_nodes")) { *value = patch.ready ? (int)patch.avg_u : 0; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
-        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(3, sizeof(T)) <= 200 * 1024)
-            return launch_patch_apply<T, 8, 3, kPatchE, 128>(
-                patch, Hex8LinearElasticityLocal<T>{adjugate.ptr, determinant.ptr, ne, (T)mu, (T)lambda}, x, y, s);
+        if (scatter == B200FEM_SCATTER_PATCH) {
+            if (ensure_patch()) return B200FEM_FAILURE;
+            const Hex8LinearElasticityLocal<T> local{adjugate.ptr, determinant.ptr, ne, (T)mu, (T)lambda};
+            if (patch.smem_bytes(3, sizeof(T)) <= 200 * 1024) {
+                if (patch.E == 128) return launch_patch_apply<T, 8, 3, 128, 128>(patch, local, x, y, s);
+                if (patch.E == 256) return launch_patch_apply<T, 8, 3, 256, 128>(patch, local, x, y, s);
+                return launch_patch_apply<T, 8, 3, 512, 256>(patch, local, x, y, s);
+            }
+        }
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
@@ -412,9 +421,10 @@ OpBase *make_hex8_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     op->nn = nn;
     op->nxe = 8;
     op->geom_bytes_per_elem = 40;
-    // measured at 128^3 (profiles/r01f_extras_patch.jsonl): with 8 elements per node the patch kernel does not beat
-    // RED.ADD for hex8 in fp64 (0.354 vs 0.303 ms elasticity, 0.112 vs 0.105 ms Laplacian); it stays selectable
-    op->scatter = B200FEM_SCATTER_ATOMIC;
+    // measured at 128^3 (profiles/r02d_c2_sweep.jsonl): the staged patch kernel with 128-element patches beats RED.ADD in
+    // both element orders (fp64 0.167 vs 0.243 ms in SFC order, 0.264 vs 0.297 ms in generator order; fp32 0.114 vs 0.181)
+    op->scatter = B200FEM_SCATTER_PATCH;
+    op->patch_elements = 128;
     op->mu = mu;
     op->lambda = lambda;
     std::vector<int32_t> el;
@@ -422,8 +432,8 @@ OpBase *make_hex8_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     soa_copy(8, ne, elements, el);
     aos_to_soa(9, ne, adjugate, a);
     op->colors.keep(8, ne, elements);
-    if (op->patch.build(8, Hex8LinearElasticity::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
-        op->adjugate.upload(a.data(), a.size()) ||
+    op->host_el = el;  // the patch plan is built on first use (scatter = PATCH)
+    if (op->elements.upload(el.data(), el.size()) || op->adjugate.upload(a.data(), a.size()) ||
         op->determinant.upload(determinant, (size_t)ne)) {
         delete op;
         return nullptr;

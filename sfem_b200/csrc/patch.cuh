@@ -30,10 +30,12 @@ namespace b200fem {
 struct PatchArrays {
     ptrdiff_t ne, nchunks;
     const uint16_t *lidx;      // [nchunks][NXE][E] local node index of every element corner
-    const int32_t *unodes;     // concatenated unique node ids of every patch
-    const int64_t *chunk_uoff; // [nchunks + 1] offsets into unodes
+    const int32_t *unodes;     // unique node ids: patch c owns the block [chunk_uoff[c], chunk_uoff[c + 1]) of
+                               // roundup8(U_c + 1) entries (16-byte aligned for cp.async), the first U_c in use
+    const int64_t *chunk_uoff; // [nchunks + 1] block offsets (multiples of 8), shared by unodes and noff
+    const int32_t *chunk_u;    // [nchunks] U_c
     const uint16_t *nslot;     // [nchunks][NXE * E] incidence slots (corner * E + local element), grouped by node
-    const uint16_t *noff;      // per patch [U + 1] offsets into its nslot block; patch c starts at chunk_uoff[c] + c
+    const uint16_t *noff;      // per patch U_c + 1 offsets into its nslot block, in the same blocks as unodes
 };
 
 struct PatchPlan {
@@ -41,11 +43,14 @@ struct PatchPlan {
     ptrdiff_t ne = 0, nchunks = 0;
     double avg_u = 0;
     DeviceArray<uint16_t> lidx, nslot, noff;
-    DeviceArray<int32_t> unodes;
+    DeviceArray<int32_t> unodes, chunk_u;
     DeviceArray<int64_t> chunk_uoff;
     bool ready = false;
 
-    PatchArrays arrays() const { return PatchArrays{ne, nchunks, lidx.ptr, unodes.ptr, chunk_uoff.ptr, nslot.ptr, noff.ptr}; }
+    PatchArrays arrays() const {
+        return PatchArrays{ne, nchunks, lidx.ptr, unodes.ptr, chunk_uoff.ptr, chunk_u.ptr, nslot.ptr, noff.ptr};
+    }
+    int max_u_pad() const { return (max_u + 1 + 7) / 8 * 8; }
 
     // elements: host SoA [nxe][ne]
     int build(int nxe_, int E_, ptrdiff_t ne_, const int32_t *const *elements) {
@@ -105,29 +110,41 @@ struct PatchPlan {
         }
         if (too_many) B2_FAIL("patch plan: more than 65535 unique nodes in one patch");
         max_u = 0;
+        std::vector<int32_t> h_u((size_t)nchunks, 0);
+        size_t total_u = 0;
         for (ptrdiff_t c = 0; c < nchunks; ++c) {
             const int U = (int)c_nodes[(size_t)c].size();
             max_u = std::max(max_u, U);
-            h_uoff[(size_t)c + 1] = h_uoff[(size_t)c] + U;
+            h_u[(size_t)c] = U;
+            total_u += (size_t)U;
+            h_uoff[(size_t)c + 1] = h_uoff[(size_t)c] + (U + 1 + 7) / 8 * 8;
         }
-        h_unodes.resize((size_t)h_uoff[(size_t)nchunks]);
-        h_noff.resize((size_t)h_uoff[(size_t)nchunks] + (size_t)nchunks);
+        h_unodes.assign((size_t)h_uoff[(size_t)nchunks], 0);
+        h_noff.assign((size_t)h_uoff[(size_t)nchunks], 0);
         for (ptrdiff_t c = 0; c < nchunks; ++c) {
             std::copy(c_nodes[(size_t)c].begin(), c_nodes[(size_t)c].end(), h_unodes.begin() + h_uoff[(size_t)c]);
-            std::copy(c_noff[(size_t)c].begin(), c_noff[(size_t)c].end(), h_noff.begin() + h_uoff[(size_t)c] + c);
+            std::copy(c_noff[(size_t)c].begin(), c_noff[(size_t)c].end(), h_noff.begin() + h_uoff[(size_t)c]);
         }
-        avg_u = nchunks ? double(h_unodes.size()) / double(nchunks) : 0;
+        avg_u = nchunks ? double(total_u) / double(nchunks) : 0;
         if (lidx.upload(h_lidx.data(), h_lidx.size()) || nslot.upload(h_nslot.data(), h_nslot.size()) ||
             noff.upload(h_noff.data(), h_noff.size()) || unodes.upload(h_unodes.data(), h_unodes.size()) ||
-            chunk_uoff.upload(h_uoff.data(), h_uoff.size()))
+            chunk_u.upload(h_u.data(), h_u.size()) || chunk_uoff.upload(h_uoff.data(), h_uoff.size()))
             return B200FEM_FAILURE;
         ready = true;
         return B200FEM_SUCCESS;
     }
 
     // streamed index bytes per apply
-    double index_bytes() const { return double(lidx.bytes() + nslot.bytes() + noff.bytes() + unodes.bytes() + chunk_uoff.bytes()); }
-    size_t smem_bytes(int bs, int real_size) const { return ((size_t)max_u * bs + (size_t)nxe * bs * E) * real_size; }
+    double index_bytes() const {
+        return double(lidx.bytes() + nslot.bytes() + noff.bytes() + unodes.bytes() + chunk_uoff.bytes() + chunk_u.bytes());
+    }
+    // one index stage of the pipelined kernel: unodes (4 B) + noff (2 B) per padded node, lidx + nslot (2 B each) per corner
+    size_t idx_stage_bytes() const { return (size_t)max_u_pad() * 6 + (size_t)nxe * E * 4; }
+    // 3 index stages + 2 value stages + the per-element result slots
+    size_t smem_bytes(int bs, int real_size) const {
+        return 3 * idx_stage_bytes() + ((size_t)2 * max_u_pad() * bs + (size_t)nxe * bs * E) * real_size;
+    }
+    size_t smem_bytes_direct(int bs, int real_size) const { return ((size_t)max_u * bs + (size_t)nxe * bs * E) * real_size; }
 };
 
 // Local: __device__ void operator()(ptrdiff_t e, const T (&uin)[NXE * BS], T (&out)[NXE * BS]) const
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(BT)
     const int tid = threadIdx.x;
     for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
         const int64_t u0 = p.chunk_uoff[c];
-        const int U = (int)(p.chunk_uoff[c + 1] - u0);
+        const int U = p.chunk_u[c];
         const ptrdiff_t e0 = c * E;
         const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
         for (int j = tid; j < U; j += BT) {
@@ -182,16 +199,20 @@ __global__ void __launch_bounds__(BT)
     }
 }
 
+// The direct form: index lists read from global memory inside the phases, 36 KB (tet4) of shared memory per CTA. Lower
+// latency tolerance per CTA, but 5 CTAs per SM: for the light operators (tet4 / hex8 Laplacian, ~45 - 90 flop per element,
+// the FFF stream is 60 % of the bytes and is read by the element phase itself) the extra CTAs keep more bytes in flight
+// than the staged kernel below does with its 2 CTAs, and it measures faster there (tet4 260^3: 1.56 against 2.07 ms).
 template <typename T, int NXE, int BS, int E, int BT, class Local>
 __global__ void __launch_bounds__(BT)
-    patch_apply_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
+    patch_apply_direct_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
     extern __shared__ __align__(16) unsigned char patch_smem[];
     T *xs = reinterpret_cast<T *>(patch_smem);   // [max_u][BS]
     T *contrib = xs + (size_t)max_u * BS;         // [BS][NXE][E]
     const int tid = threadIdx.x;
     for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
         const int64_t u0 = p.chunk_uoff[c];
-        const int U = (int)(p.chunk_uoff[c + 1] - u0);
+        const int U = p.chunk_u[c];
         const ptrdiff_t e0 = c * E;
         const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
         // 1. stage the unique nodes' values
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(BT)
         __syncthreads();
         // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
         const uint16_t *ns = p.nslot + (size_t)c * NXE * E;
-        const uint16_t *no = p.noff + u0 + c;
+        const uint16_t *no = p.noff + u0;
         for (int j = tid; j < U; j += BT) {
             const int b = no[j], eend = no[j + 1];
             T acc[BS];
@@ -235,6 +256,136 @@ __global__ void __launch_bounds__(BT)
 #pragma unroll
             for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], acc[a]);
         }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void patch_cp16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void patch_cp_value(T *smem, const T *gmem) {
+    if (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+// Software-pipelined patch kernel. The first version of this kernel read its index lists (local corner indices, incidence
+// slots, CSR offsets) straight from global memory inside the compute and summation phases: every unique node walked its
+// incidence list through a chain of dependent global loads (8 for hex8, ~24 for tet4), three CTA-wide barriers per
+// patch exposed that latency, and with 3 CTAs per SM nothing covered it (ncu of the hex8 elasticity patch kernel: 8.5
+// long-scoreboard stall cycles per issue, L2 at 21 %, 349 us against 296 us for plain REDs). Here a persistent CTA keeps
+//   * the index lists of patches k, k+1, k+2 in three shared-memory stages (16-byte cp.async of the padded blocks),
+//   * the unique-node values of patches k and k+1 in two stages (8-byte cp.async gathers issued one patch ahead, from
+//     the node list that is already in shared memory),
+// so phases 2 and 3 of patch k touch shared memory only and every global access of patches k+1 / k+2 is in flight
+// behind them. One wait + barrier per patch.
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+__global__ void __launch_bounds__(BT)
+    patch_apply_kernel(const PatchArrays p, const Local local, const int up, const T *__restrict__ u, T *__restrict__ y) {
+    extern __shared__ __align__(16) unsigned char patch_smem[];
+    constexpr int NC = NXE * E;                       // corners per patch
+    const size_t idx_bytes = (size_t)up * 6 + (size_t)NC * 4;  // multiple of 16: up % 8 == 0, NC * 2 % 16 == 0
+    static_assert((NC * 2) % 16 == 0, "corner lists must be 16-byte multiples");
+    auto st_unodes = [&](int s) { return reinterpret_cast<int32_t *>(patch_smem + (size_t)s * idx_bytes); };
+    auto st_noff = [&](int s) { return reinterpret_cast<uint16_t *>(patch_smem + (size_t)s * idx_bytes + (size_t)up * 4); };
+    auto st_lidx = [&](int s) { return reinterpret_cast<uint16_t *>(patch_smem + (size_t)s * idx_bytes + (size_t)up * 6); };
+    auto st_nslot = [&](int s) { return st_lidx(s) + NC; };
+    T *xs_base = reinterpret_cast<T *>(patch_smem + 3 * idx_bytes);  // [2][up][BS]
+    T *contrib = xs_base + (size_t)2 * up * BS;                       // [BS][NXE][E]
+    const int tid = threadIdx.x;
+    const ptrdiff_t stride = gridDim.x;
+
+    auto issue_idx = [&](const ptrdiff_t c, const int s) {
+        if (c >= p.nchunks) return;
+        const int64_t u0 = p.chunk_uoff[c];
+        const int U = p.chunk_u[c];
+        const int4 *g_un = reinterpret_cast<const int4 *>(p.unodes + u0);
+        const int4 *g_no = reinterpret_cast<const int4 *>(p.noff + u0);
+        const int4 *g_li = reinterpret_cast<const int4 *>(p.lidx + (size_t)c * NC);
+        const int4 *g_ns = reinterpret_cast<const int4 *>(p.nslot + (size_t)c * NC);
+        int4 *s_un = reinterpret_cast<int4 *>(st_unodes(s)), *s_no = reinterpret_cast<int4 *>(st_noff(s));
+        int4 *s_li = reinterpret_cast<int4 *>(st_lidx(s)), *s_ns = reinterpret_cast<int4 *>(st_nslot(s));
+        for (int i = tid; i < (U * 4 + 15) / 16; i += BT) patch_cp16(s_un + i, g_un + i);
+        for (int i = tid; i < ((U + 1) * 2 + 15) / 16; i += BT) patch_cp16(s_no + i, g_no + i);
+        for (int i = tid; i < NC * 2 / 16; i += BT) {
+            patch_cp16(s_li + i, g_li + i);
+            patch_cp16(s_ns + i, g_ns + i);
+        }
+    };
+    auto issue_x = [&](const ptrdiff_t c, const int s_idx, const int s_x) {  // node list of c is in stage s_idx
+        if (c >= p.nchunks) return;
+        const int U = p.chunk_u[c];
+        const int32_t *un = st_unodes(s_idx);
+        T *xs = xs_base + (size_t)s_x * up * BS;
+        for (int j = tid; j < U; j += BT) {
+            const ptrdiff_t node = un[j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) patch_cp_value(&xs[j * BS + a], &u[node * BS + a]);
+        }
+    };
+    auto commit = [] { asm volatile("cp.async.commit_group;\n" ::: "memory"); };
+    auto wait_all = [] { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); };
+
+    const ptrdiff_t c0 = blockIdx.x;
+    issue_idx(c0, 0);
+    issue_idx(c0 + stride, 1);
+    commit();
+    wait_all();
+    __syncthreads();
+    issue_x(c0, 0, 0);
+    commit();
+    wait_all();
+    __syncthreads();
+
+    int k = 0;
+    for (ptrdiff_t c = c0; c < p.nchunks; c += stride, ++k) {
+        const int si = k % 3, sx = k & 1;
+        issue_idx(c + 2 * stride, (k + 2) % 3);
+        issue_x(c + stride, (k + 1) % 3, (k + 1) & 1);
+        commit();
+
+        const int U = p.chunk_u[c];
+        const ptrdiff_t e0 = c * E;
+        const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
+        const T *xs = xs_base + (size_t)sx * up * BS;
+        // 2. element operator from shared memory into per-element slots
+        const uint16_t *li = st_lidx(si);
+        for (int e = tid; e < nel; e += BT) {
+            T uin[NXE * BS], out[NXE * BS];
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) {
+                const int j = li[v * E + e];
+#pragma unroll
+                for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[j * BS + a];
+            }
+            local(e0 + e, uin, out);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v)
+#pragma unroll
+                for (int a = 0; a < BS; ++a) contrib[(a * NXE + v) * E + e] = out[v * BS + a];
+        }
+        __syncthreads();
+        // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
+        const uint16_t *ns = st_nslot(si);
+        const uint16_t *no = st_noff(si);
+        const int32_t *un = st_unodes(si);
+        for (int j = tid; j < U; j += BT) {
+            const int b = no[j], eend = no[j + 1];
+            T acc[BS];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) acc[a] = T(0);
+            for (int s = b; s < eend; ++s) {
+                const int slot = ns[s];
+#pragma unroll
+                for (int a = 0; a < BS; ++a) acc[a] += contrib[a * NXE * E + slot];
+            }
+            const ptrdiff_t node = un[j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], acc[a]);
+        }
+        wait_all();  // index lists of patch k + 2, values of patch k + 1
         __syncthreads();
     }
 }
@@ -254,15 +405,29 @@ int launch_patch_apply_smem_atomic(const PatchPlan &plan, const Local &local, co
 }
 
 template <typename T, int NXE, int BS, int E, int BT, class Local>
-int launch_patch_apply(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
-    auto kern = patch_apply_kernel<T, NXE, BS, E, BT, Local>;
-    const size_t smem = plan.smem_bytes(BS, (int)sizeof(T));
+int launch_patch_apply_direct(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
+    auto kern = patch_apply_direct_kernel<T, NXE, BS, E, BT, Local>;
+    const size_t smem = ((size_t)plan.max_u * BS + (size_t)NXE * BS * E) * sizeof(T);
     static SmemOptIn opt;
     if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
     if (plan.nchunks == 0) return B200FEM_SUCCESS;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
     const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);
     kern<<<grid, BT, smem, s>>>(plan.arrays(), local, plan.max_u, x, y);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+template <typename T, int NXE, int BS, int E, int BT, class Local>
+int launch_patch_apply(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
+    auto kern = patch_apply_kernel<T, NXE, BS, E, BT, Local>;
+    const size_t smem = plan.smem_bytes(BS, (int)sizeof(T));
+    static SmemOptIn opt;
+    if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
+    if (plan.nchunks == 0) return B200FEM_SUCCESS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / BT, (220 * 1024) / (smem + 1024)));
+    const int grid = (int)std::min<ptrdiff_t>(plan.nchunks, (ptrdiff_t)sm_count() * per_sm);
+    kern<<<grid, BT, smem, s>>>(plan.arrays(), local, plan.max_u_pad(), x, y);
     B2_CHECK_LAUNCH();
     return B200FEM_SUCCESS;
 }

@@ -101,16 +101,18 @@ struct Tet4Laplacian final : OpBase {
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
     PatchPlan patch;
+    int patch_pipelined = 0;    // 1 = the staged / software-pipelined patch kernel (slower for this light operator)
     int patch_smem_atomic = 0;  // 1 = shared-memory atomics instead of the incidence lists (order not fixed)
     static constexpr int kPatchE = 1024;
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
-        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes(1, sizeof(T)) <= 200 * 1024) {
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) <= 200 * 1024) {
             if (patch_smem_atomic)
                 return launch_patch_apply_smem_atomic<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
-            return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            if (patch_pipelined) return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            return launch_patch_apply_direct<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         }
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
@@ -154,6 +156,7 @@ struct Tet4Laplacian final : OpBase {
     }
     int set_option(const char *key, int value) override {
         if (!strcmp(key, "patch_smem_atomic")) { patch_smem_atomic = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "patch_pipelined")) { patch_pipelined = value; return B200FEM_SUCCESS; }
         return OpBase::set_option(key, value);
     }
     int get_option(const char *key, int *value) override {

@@ -98,10 +98,16 @@ def test_c2_hex8_linear_elasticity_full_size(oracles):
     op.apply_overwrite(rot, y)
     # only up to the fp32 rounding of the cached adjugates (geom_t), which breaks exact skew-symmetry of the gradient
     assert float(y.abs().max()) < 1e-7
-    # patch and atomic scatter agree
-    op.set_option("scatter", lib.SCATTER_PATCH)
+    # atomic scatter and the other patch sizes agree with the default (staged patch kernel, 128-element patches)
+    assert op.get_option("scatter") == lib.SCATTER_PATCH
+    op.set_option("scatter", lib.SCATTER_ATOMIC)
     op.apply_overwrite(u, y)
     assert _rel(y, Au) < 1e-13
+    for pe in (256, 512):
+        op.set_option("patch_elements", pe)
+        op.set_option("scatter", lib.SCATTER_PATCH)
+        op.apply_overwrite(u, y)
+        assert _rel(y, Au) < 1e-13
     orc = oracles.get(("reference", "f64")) or oracles[("port", "f64")]
     ref = orc.hex8_linear_elasticity_apply(el, adj, det, 1.0, 1.0, u.cpu().numpy(), nn)
     assert np.linalg.norm(Au.cpu().numpy() - ref) < 1e-12 * np.linalg.norm(ref)

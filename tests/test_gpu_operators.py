@@ -115,7 +115,7 @@ def test_hex8_linear_elasticity(oracles, real, scatter):
     nn = pts.shape[1]
     mu, lam = 1.3, 0.7
     op = lib.linear_elasticity(lib.HEX8, el, adj, det, mu, lam, nn, _dt(real))
-    assert op.get_option("scatter") == lib.SCATTER_ATOMIC  # the default for hex8
+    assert op.get_option("scatter") == lib.SCATTER_PATCH  # hex8 elasticity: the staged patch kernel, 128-element patches
     op.set_option("scatter", {"patch": lib.SCATTER_PATCH, "colored": lib.SCATTER_COLORED, "atomic": lib.SCATTER_ATOMIC}[scatter])
     assert op.block_size == 3 and op.rows == nn * 3
     u = np.random.default_rng(5).uniform(-1, 1, nn * 3)
@@ -416,7 +416,9 @@ def test_hex8_diagonals(oracles, real):
     assert _rel(d3.cpu().numpy(), orc.hex8_linear_elasticity_diag(el, pts, mu, lam, nn)) < TOL[real]
     b6 = torch.zeros(nn * 6, dtype=dt, device="cuda")
     le.block_diag_sym(b6)
-    assert _rel(b6.cpu().numpy(), orc.hex8_linear_elasticity_block_diag_sym(el, pts, mu, lam, nn)) < TOL[real]
+    # the reference's generated block-diagonal code is itself off by 1.4e-11 (relative, uniformly): on this dyadic geometry the
+    # closed form is exact (6.00703125 at node 52, the reference returns 6.007031249918575)
+    assert _rel(b6.cpu().numpy(), orc.hex8_linear_elasticity_block_diag_sym(el, pts, mu, lam, nn)) < (1e-10 if real == "f64" else TOL[real])
     # the diagonal is what unit applies see
     if real == "f64":
         for i in (0, nn * 3 // 2 + 1, nn * 3 - 1):
