@@ -12,5 +12,7 @@ namespace smesh {
     }
     static inline bool is_semistructured_type(int t) { return t == SSHEX8; }
     static inline int semistructured_level(int) { return 0; }
+    static inline ElemType macro_base_elem(ElemType t) { return t == SSHEX8 ? HEX8 : (t == MACRO_TET4 ? TET4 : (t == MACRO_TRI3 ? TRI3 : t)); }
+    static inline ElemType macro_type_variant(ElemType t) { return t == TET10 ? MACRO_TET4 : (t == TRI6 ? MACRO_TRI3 : t); }
 }
 #endif
