@@ -116,7 +116,10 @@ def test_sshex8_linear_elasticity_diagonals(oracles, level):
     op.block_diag_sym(b)
     e_b = _rel(b.cpu().numpy(), orc.sshex8_linear_elasticity_block_diag_sym(level, m["elements"], pts, mu, lam, nn))
     print(f"sshex8 LE block diag L{level}: rel-L2 vs oracle = {e_b:.3e}")
-    assert e_b < 1e-12, e_b
+    # the reference's generated block-diagonal routine carries a uniform 1.36e-11 relative error (the same one its hex8 twin
+    # shows: tests/test_gpu_operators.py::test_hex8_diagonals; its plain diagonal agrees to 1e-16 above)
+    assert e_b < 1e-10, e_b
+    assert _rel(b.view(nn, 6)[:, [0, 3, 5]].reshape(-1).cpu().numpy(), d.cpu().numpy()) < 1e-14
     # the diagonal is what unit applies see
     for i in (0, nn * 3 // 2, nn * 3 - 1):
         e = torch.zeros(nn * 3, dtype=torch.float64, device="cuda")
