@@ -161,6 +161,11 @@ void *refsolv_cg(void *op, void *precond, double rtol, double atol, int max_it, 
     return o;
 }
 
+/* verbose = the reference's own monitor() lines on stdout ("<it>: residual abs: ..., rel: ..."), sfem_cg.hpp:184-199 */
+void refsolv_cg_set_verbose(void *cg, int val) {
+    std::static_pointer_cast<ConjugateGradient<real_t>>(((Obj *)cg)->op)->verbose = val != 0;
+}
+
 void refsolv_cg_set_host_fusion(void *cg, int val) {
     std::static_pointer_cast<ConjugateGradient<real_t>>(((Obj *)cg)->op)->set_host_fusion(val != 0);
 }

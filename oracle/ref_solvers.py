@@ -120,6 +120,12 @@ class RefSolvers:
         return Handle(self, self.lib.refsolv_cg(op.ptr, precond.ptr if precond else None, rtol, atol, max_it, es),
                       keep=[op, precond])
 
+    def cg_set_verbose(self, cg: Handle, val: bool):
+        """the reference's own monitor() output (one line per iteration on stdout); pair with capture_stdout()"""
+        self.lib.refsolv_cg_set_verbose.argtypes = [C.c_void_p, C.c_int]
+        self.lib.refsolv_cg_set_verbose.restype = None
+        self.lib.refsolv_cg_set_verbose(cg.ptr, int(val))
+
     def cg_set_host_fusion(self, cg: Handle, val: bool):
         self.lib.refsolv_cg_set_host_fusion(cg.ptr, int(val))
 
@@ -177,3 +183,46 @@ class RefSolvers:
     def power_method(self, op: Handle, max_it: int, tol: float, eigen_vector: np.ndarray, work: np.ndarray) -> float:
         return self.lib.refsolv_power_method(op.ptr, max_it, tol, eigen_vector.size, eigen_vector.ctypes.data,
                                              work.ctypes.data, HOST)
+
+
+class capture_stdout:
+    """fd-level capture of what the reference's solvers printf (their residual monitors): `with capture_stdout() as c: ...;
+    c.text` afterwards."""
+
+    def __enter__(self):
+        import os
+        import sys
+        import tempfile
+
+        sys.stdout.flush()
+        C.CDLL(None).fflush(None)
+        self._saved = os.dup(1)
+        self._tmp = tempfile.TemporaryFile(mode="w+b")
+        os.dup2(self._tmp.fileno(), 1)
+        self.text = ""
+        return self
+
+    def __exit__(self, *exc):
+        import os
+
+        C.CDLL(None).fflush(None)
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        self._tmp.seek(0)
+        self.text = self._tmp.read().decode(errors="replace")
+        self._tmp.close()
+        return False
+
+
+def parse_cg_monitor(text: str):
+    """[(iteration, abs residual)] from the reference's CG monitor lines."""
+    import re
+
+    return [(int(m.group(1)), float(m.group(2))) for m in re.finditer(r"^(\d+): residual abs: ([-+0-9.eEinfa]+)", text, flags=re.M)]
+
+
+def parse_mg_monitor(text: str):
+    """[abs residual per cycle] from the reference's Multigrid monitor lines (sfem_Multigrid.hpp:274-296)."""
+    import re
+
+    return [float(m.group(2)) for m in re.finditer(r"^(\d+)\t([-+0-9.eE]+)", text, flags=re.M)]

@@ -100,15 +100,21 @@ def poisson_sshex8(orc, L=4, mx=3, my=2, mz=2, generic=False):
     return p
 
 
-def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0, generic=False):
-    m = mesh.sshex8_box(L, mx, my, mz)
+def elasticity_sshex8(orc, L=4, mx=3, my=2, mz=2, mu=1.0, lam=1.0, generic=False, scale=None):
+    """scale: edge length of one MACRO element (default: the unit cube split into mx x my x mz)."""
+    if scale is None:
+        m = mesh.sshex8_box(L, mx, my, mz)
+        wx = 1.0
+    else:
+        m = mesh.sshex8_box(L, mx, my, mz, mx * scale, my * scale, mz * scale)
+        wx = mx * scale
     mpts = np.ascontiguousarray(m["m_points"], dtype=np.float32)
     if generic:
         mpts = np.ascontiguousarray(mesh.shear_points(mpts), dtype=np.float32)
     adj, det = orc.hex8_adjugate_and_det_fill(m["m_elements"], mpts)
     nn = m["n_nodes"]
     pts = m["points"]
-    left, right = _face_nodes(pts, 0, 0.0), _face_nodes(pts, 0, 1.0)
+    left, right = _face_nodes(pts, 0, 0.0), _face_nodes(pts, 0, wx, eps=1e-4 * wx)
     conds = [(left, 0, -1.0), (left, 1, 0.0), (left, 2, 0.0), (right, 0, 1.0), (right, 1, 0.0), (right, 2, 0.0)]
     p = Problem(kind="sshex8_linear_elasticity", block_size=3, n_nodes=nn, level=L, elements=m["elements"], adj=adj, det=det,
                 mu=mu, lam=lam, m=m, points=pts, conditions=conds, rhs=_rhs(nn * 3, 13) if generic else None)
