@@ -103,6 +103,36 @@ int b200fem_laplacian_create(b200fem_op_t *op, int element_type, int level, ptrd
 int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements,
                                      ptrdiff_t nnodes, const int32_t *const *elements, const float *adjugate,
                                      const float *determinant, double mu, double lambda, int real_type);
+/* The reference's non-default paths that take the node coordinates (fp32 SoA `points[3][nnodes]`, HOST) instead of cached
+ * geometry factors:
+ *   laplacian, TET4   <- tet4_laplacian_apply (operators/tet4/tet4_laplacian.cpp:70-135): FFF recomputed per element from
+ *                        the points in the vector precision (used when the Op has no FFF cache, sfem_Laplacian.cpp:43-49);
+ *   laplacian, SSHEX8 <- sshex8_laplacian_apply (operators/sshex8/sshex8_laplacian.cpp:39-182): trilinear (non-affine) macro
+ *                        elements, FFF at the 6 face-centre quadrature points of every micro element; `points` is indexed by
+ *                        sshex8 node id, only the 8 macro corners of each element are read;
+ *   linear elasticity, HEX8 <- hex8_linear_elasticity_apply (operators/hex8/hex8_linear_elasticity.cpp:86-324): the
+ *                        isoparametric variant of SFEM_HEX8_ASSUME_AFFINE=0, Jacobian at each of the 2x2x2 Gauss points. */
+int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements, ptrdiff_t nnodes,
+                                         const int32_t *const *elements, const float *const *points, int real_type);
+int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements,
+                                                 ptrdiff_t nnodes, const int32_t *const *elements, const float *const *points,
+                                                 double mu, double lambda, int real_type);
+/* Stored-element-matrix ("EM") semi-structured operators: ss:em:Laplacian / ss:em:LinearElasticity
+ * (frontend/ops/sfem_SemiStructuredEMLaplacian.cpp, sfem_SemiStructuredEMLinearElasticity.cpp; kernels
+ * operators/stencil/sshex8_stencil_element_matrix_apply.cpp:10-160, GPU twins GPUEMOp / GPUEMWarpOp over
+ * operators/sshex8/cuda/cu_sshex8_elemental_matrix.cu:226-1053). `element_matrix` is HOST memory of `real_type`,
+ * [nelements][(8 bs)^2] row-major, VTK corner order, components blocked [c0 x 8 | c1 x 8 | c2 x 8]; applied to every micro
+ * element of the macro element as out_j += sum_i u_i M[i][j] (operators/sshex8/sshex8.hpp:44-86). block_size 1 or 3.
+ * The two builders replace sshex8_laplacian_element_matrix (operators/sshex8/sshex8_laplacian.cpp:595-634; from the macro FFF,
+ * scaled by h = 1/level) and sshex8_linear_elasticity_element_matrix (sshex8_linear_elasticity.cpp:1258-1310; from the macro
+ * adjugate / determinant); with the first one the EM operator is affine_sshex8_laplacian_apply (sshex8_laplacian.cpp:184-331),
+ * the element-matrix formulation of the affine Laplacian. `values_host`: [nelements * 64] / [nelements * 576] of real_type. */
+int b200fem_sshex8_em_create(b200fem_op_t *op, int level, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
+                             int block_size, const void *element_matrix, int real_type);
+int b200fem_sshex8_laplacian_element_matrix(int level, ptrdiff_t nelements, const float *fff, int real_type, void *values_host);
+int b200fem_sshex8_linear_elasticity_element_matrix(int level, ptrdiff_t nelements, const float *adjugate,
+                                                    const float *determinant, double mu, double lambda, int real_type,
+                                                    void *values_host);
 int b200fem_op_destroy(b200fem_op_t op);
 
 /* y += A x  (sfem::Op::apply(x, h, out), frontend/ops/sfem_Op.hpp:214; Operator<T>::apply,
@@ -299,6 +329,12 @@ int b200fem_block_sym_jacobi_setup(int real_type, ptrdiff_t n_blocks, const void
                                    const void *constraints_mask, double relaxation, void *inv_diag9, void *stream);
 int b200fem_block_jacobi_apply(int real_type, ptrdiff_t n_blocks, const void *inv_diag9, const void *x, void *y,
                                void *stream);
+/* MixedPrecisionShiftableBlockSymJacobi<double, float> (algebra/sfem_MixedPrecisionShiftableBlockSymJacobi.hpp:13-108): the
+ * fp64 block diagonal is converted to fp32, masked, inverted and scaled in fp32; the apply reads fp32 blocks (36 B per node
+ * instead of 72 B) with fp64 vectors. */
+int b200fem_block_sym_jacobi_setup_mixed(ptrdiff_t n_blocks, const double *sym_diag6, const double *shift6,
+                                         const void *constraints_mask, double relaxation, float *inv_diag9, void *stream);
+int b200fem_block_jacobi_apply_mixed(ptrdiff_t n_blocks, const float *inv_diag9, const double *x, double *y, void *stream);
 
 #ifdef __cplusplus
 }

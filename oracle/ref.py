@@ -181,6 +181,76 @@ class Oracle:
                    C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
+    # ---- non-default paths that take the points (operators/tet4/tet4_laplacian.cpp:70, hex8_linear_elasticity.cpp:86,
+    #      sshex8_laplacian.cpp:39 / :184) and the stored-element-matrix operators
+    def tet4_laplacian_apply_points(self, elements, points, u, nnodes):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        self._call("tet4_laplacian_apply", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), pu, out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def hex8_linear_elasticity_apply_isoparametric(self, elements, points, mu, lam, u, nnodes):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        u, _ = self._r(u)
+        out = np.zeros_like(u)
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("hex8_linear_elasticity_apply", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3),
+                   op[0], op[1], op[2])
+        return out
+
+    def sshex8_laplacian_apply_points(self, level, elements, points, u, affine=False):
+        """sshex8_laplacian_apply (non-affine, q6) or affine_sshex8_laplacian_apply (element-matrix formulation);
+        `points` is SoA fp32 [3][nnodes] by sshex8 node id (only the macro corners are read)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        self._call("affine_sshex8_laplacian_apply" if affine else "sshex8_laplacian_apply", C.c_int(level), C.c_ssize_t(el.shape[1]),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), pu, out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def sshex8_laplacian_element_matrix(self, level, macro_elements, macro_points):
+        """[ne, 64] (sshex8_laplacian_element_matrix, sshex8_laplacian.cpp:595); scalar_t = real_t in this build"""
+        el = np.ascontiguousarray(macro_elements, dtype=np.int32)
+        pts = np.ascontiguousarray(macro_points, dtype=np.float32)
+        out = np.zeros((el.shape[1], 64), dtype=self.rt)
+        self._call("sshex8_laplacian_element_matrix", C.c_int(level), C.c_ssize_t(el.shape[1]), C.c_ssize_t(pts.shape[1]),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def sshex8_linear_elasticity_element_matrix(self, level, macro_elements, macro_points, mu, lam):
+        el = np.ascontiguousarray(macro_elements, dtype=np.int32)
+        pts = np.ascontiguousarray(macro_points, dtype=np.float32)
+        out = np.zeros((el.shape[1], 576), dtype=self.rt)
+        self._call("sshex8_linear_elasticity_element_matrix", C.c_int(level), C.c_ssize_t(el.shape[1]), C.c_ssize_t(pts.shape[1]),
+                   _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam),
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def sshex8_em_apply(self, level, elements, element_matrix, u, block_size=1):
+        """sshex8_stencil_element_matrix_apply / _apply3 (operators/stencil/sshex8_stencil_element_matrix_apply.cpp)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        m = np.ascontiguousarray(element_matrix, dtype=self.rt)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        if block_size == 1:
+            self._call("sshex8_stencil_element_matrix_apply", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32),
+                       m.ctypes.data_as(C.POINTER(self.crt)), pu, out.ctypes.data_as(C.POINTER(self.crt)))
+            return out
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("sshex8_stencil_element_matrix_apply3", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32),
+                   m.ctypes.data_as(C.POINTER(self.crt)), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
     def hex8_laplacian_diag(self, elements, points, nnodes):
         """hex8_laplacian_diag (operators/hex8/hex8_laplacian.hpp:36; geometry from the fp32 points, in scalar_t)."""
         el = np.ascontiguousarray(elements, dtype=np.int32)

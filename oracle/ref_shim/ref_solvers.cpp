@@ -24,6 +24,7 @@
 #include "sfem_aliases.hpp"
 
 #include "sfem_Chebyshev3.hpp"
+#include "sfem_MixedPrecisionShiftableBlockSymJacobi.hpp"
 #include "sfem_Multigrid.hpp"
 #include "sfem_ShiftableJacobi.hpp"
 #include "sfem_Stationary.hpp"
@@ -194,6 +195,20 @@ void *refsolv_block_sym_jacobi(real_t *diag6, ptrdiff_t n_blocks, mask_t *mask, 
     o->op  = j;
     return o;
 }
+
+#ifndef ORACLE_REAL_FLOAT32
+/* MixedPrecisionShiftableBlockSymJacobi<double, float> (algebra/sfem_MixedPrecisionShiftableBlockSymJacobi.hpp), host only */
+void *refsolv_mixed_block_sym_jacobi(real_t *diag6, ptrdiff_t n_blocks, mask_t *mask, ptrdiff_t mask_bytes, double relaxation) {
+    auto j = std::make_shared<MixedPrecisionShiftableBlockSymJacobi<double, float>>();
+    j->default_init();
+    j->relaxation_parameter = relaxation;
+    j->constraints_mask     = Buffer<mask_t>::wrap(mask_bytes, mask);
+    j->set_diag(Buffer<double>::wrap(n_blocks * 6, diag6));
+    auto o = new Obj();
+    o->op  = j;
+    return o;
+}
+#endif
 
 void *refsolv_stationary(void *op, void *precond, int max_it, int es) {
     auto s              = std::make_shared<StationaryIteration<real_t>>();

@@ -142,6 +142,15 @@ class RefSolvers:
         return Handle(self, self.lib.refsolv_block_sym_jacobi(diag6.ctypes.data, diag6.size // 6, mask.ctypes.data,
                                                               mask.size, relaxation), keep=[diag6, mask])
 
+    def mixed_block_sym_jacobi(self, diag6, mask: np.ndarray, relaxation: float) -> Handle:
+        """MixedPrecisionShiftableBlockSymJacobi<double, float> (f64 build only)"""
+        diag6 = np.ascontiguousarray(diag6, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        fn = self.lib.refsolv_mixed_block_sym_jacobi
+        fn.restype = C.c_void_p
+        fn.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_double]
+        return Handle(self, fn(diag6.ctypes.data, diag6.size // 6, mask.ctypes.data, mask.size, relaxation), keep=[diag6, mask])
+
     def stationary(self, op: Handle, precond: Handle, max_it: int, es=HOST) -> Handle:
         return Handle(self, self.lib.refsolv_stationary(op.ptr, precond.ptr, max_it, es), keep=[op, precond])
 

@@ -144,6 +144,18 @@ OpBase *make_sshex8_linear_elasticity(int level, ptrdiff_t ne, ptrdiff_t nn, con
                                       const float *adjugate, const float *determinant, double mu, double lambda,
                                       int real_type);
 
+OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
+                                        int real_type);
+OpBase *make_hex8_le_isoparametric(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
+                                   double lambda, int real_type);
+OpBase *make_sshex8_nonaffine_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                                        const float *const *points, int real_type);
+OpBase *make_sshex8_em(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, int block_size,
+                       const void *element_matrix, int real_type);
+int sshex8_laplacian_element_matrix_build(int level, ptrdiff_t ne, const float *fff, int real_type, void *values_host);
+int sshex8_le_element_matrix_build(int level, ptrdiff_t ne, const float *adjugate, const float *determinant, double mu, double lambda,
+                                   int real_type, void *values_host);
+
 // Greedy element colouring on the host (nodes shared => different colour). Returns the element
 // permutation grouped by colour and the colour offsets.
 void color_elements(ptrdiff_t ne, ptrdiff_t nn, int nxe, const int32_t *const *elements, std::string *err,

@@ -1,0 +1,229 @@
+// Operators that take the node coordinates instead of cached geometry factors -- the reference's non-default paths:
+//
+//   tet4_laplacian_apply (operators/tet4/tet4_laplacian.cpp:70-135): FFF of every element recomputed from the fp32 points
+//     in scalar_t (tet4_fff_s, operators/tet4/tet4_inline_cpu.hpp:168-222), used when the Op holds no FFF cache
+//     (frontend/ops/sfem_Laplacian.cpp:43-49);
+//   hex8_linear_elasticity_apply (operators/hex8/hex8_linear_elasticity.cpp:86-324): the isoparametric variant selected by
+//     SFEM_HEX8_ASSUME_AFFINE=0 -- trilinear geometry, Jacobian at each of the 2x2x2 Gauss points (1-D tables :55-71).
+//
+// Both are one thread per element with RED.ADD scatter: they are fallbacks, the cached-geometry plans are the fast path.
+#include <algorithm>
+#include <vector>
+
+#include "coloring.cuh"
+#include "common.cuh"
+#include "hex8_le_core.cuh"
+#include "hex8_local.cuh"
+
+namespace b200fem {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    tet4_laplacian_points_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements,
+                                 const float *__restrict__ points, const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        // J[r][c] = x_r(vertex c + 1) - x_r(vertex 0); adj = det J^-1; FFF = adj adj^T / (6 det)
+        T J[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const T p0 = (T)points[(size_t)r * nn + ev[0]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[r * 3 + c] = (T)points[(size_t)r * nn + ev[c + 1]] - p0;
+        }
+        T A[9];
+        A[0] = J[4] * J[8] - J[5] * J[7];
+        A[1] = J[2] * J[7] - J[1] * J[8];
+        A[2] = J[1] * J[5] - J[2] * J[4];
+        A[3] = J[5] * J[6] - J[3] * J[8];
+        A[4] = J[0] * J[8] - J[2] * J[6];
+        A[5] = J[2] * J[3] - J[0] * J[5];
+        A[6] = J[3] * J[7] - J[4] * J[6];
+        A[7] = J[1] * J[6] - J[0] * J[7];
+        A[8] = J[0] * J[4] - J[1] * J[3];
+        const T det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+        const T sc = T(1) / (T(6) * det);
+        T f[6];
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j) f[k++] = (A[i * 3] * A[j * 3] + A[i * 3 + 1] * A[j * 3 + 1] + A[i * 3 + 2] * A[j * 3 + 2]) * sc;
+        const T u0 = u[ev[0]];
+        const T d1 = u[ev[1]] - u0, d2 = u[ev[2]] - u0, d3 = u[ev[3]] - u0;
+        const T w0 = f[0] * d1 + f[1] * d2 + f[2] * d3;
+        const T w1 = f[1] * d1 + f[3] * d2 + f[4] * d3;
+        const T w2 = f[2] * d1 + f[4] * d2 + f[5] * d3;
+        red_add(&y[ev[0]], -(w0 + w1 + w2));
+        red_add(&y[ev[1]], w0);
+        red_add(&y[ev[2]], w1);
+        red_add(&y[ev[3]], w2);
+    }
+}
+
+// isoparametric Q1 hex, 2x2x2 Gauss on [0,1]^3 (weights 1/8): out_i^a += sum_q w sum_c P[a][c] dN_i/dxi_c,
+// P = sigma(H) adj^T, H = G adj / det, G[b][c] = sum_i u_i^b dN_i/dxi_c, sigma = lambda tr(H) I + mu (H + H^T)
+template <typename T>
+__global__ void __launch_bounds__(128)
+    hex8_le_isoparametric_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements,
+                                 const float *__restrict__ points, const T mu, const T lambda, const T *__restrict__ u,
+                                 T *__restrict__ y) {
+    // 1-D shape values at the two Gauss points: hex8_q2_shape_1d (hex8_linear_elasticity.cpp:55-61)
+    const T s_lo = T(0.78867513459481287), s_hi = T(0.21132486540518708);
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[8];  // lexicographic corners
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ev[kVtkToLex[v]] = ldg_stream(&elements[v * ne + e]);
+        T X[3][8], U[3][8], O[3][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                X[d][i] = (T)points[(size_t)d * nn + ev[i]];
+                U[d][i] = u[(ptrdiff_t)ev[i] * 3 + d];
+                O[d][i] = T(0);
+            }
+        }
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const int qx = q & 1, qy = (q >> 1) & 1, qz = (q >> 2) & 1;
+            // shape value of corner bit b at Gauss point index g: (b == g) ? s_lo : s_hi  (point 0 sits near corner 0)
+            T gx[8], gy[8], gz[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int bx = i & 1, by = (i >> 1) & 1, bz = (i >> 2) & 1;
+                const T sx = (bx == qx) ? s_lo : s_hi, sy = (by == qy) ? s_lo : s_hi, sz = (bz == qz) ? s_lo : s_hi;
+                gx[i] = (bx ? T(1) : T(-1)) * sy * sz;
+                gy[i] = sx * (by ? T(1) : T(-1)) * sz;
+                gz[i] = sx * sy * (bz ? T(1) : T(-1));
+            }
+            T J[9], G[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) J[k] = G[k] = T(0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    J[r * 3 + 0] = le_fma(X[r][i], gx[i], J[r * 3 + 0]);
+                    J[r * 3 + 1] = le_fma(X[r][i], gy[i], J[r * 3 + 1]);
+                    J[r * 3 + 2] = le_fma(X[r][i], gz[i], J[r * 3 + 2]);
+                    G[r * 3 + 0] = le_fma(U[r][i], gx[i], G[r * 3 + 0]);
+                    G[r * 3 + 1] = le_fma(U[r][i], gy[i], G[r * 3 + 1]);
+                    G[r * 3 + 2] = le_fma(U[r][i], gz[i], G[r * 3 + 2]);
+                }
+            }
+            T A[9];  // adj[c][k] = det * d xi_c / d x_k
+            A[0] = J[4] * J[8] - J[5] * J[7];
+            A[1] = J[2] * J[7] - J[1] * J[8];
+            A[2] = J[1] * J[5] - J[2] * J[4];
+            A[3] = J[5] * J[6] - J[3] * J[8];
+            A[4] = J[0] * J[8] - J[2] * J[6];
+            A[5] = J[2] * J[3] - J[0] * J[5];
+            A[6] = J[3] * J[7] - J[4] * J[6];
+            A[7] = J[1] * J[6] - J[0] * J[7];
+            A[8] = J[0] * J[4] - J[1] * J[3];
+            const T det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+            const T idet = T(1) / det;
+            T Hm[9];  // H[b][k] = sum_c G[b][c] adj[c][k] / det
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Hm[b * 3 + k] = (G[b * 3] * A[k] + G[b * 3 + 1] * A[3 + k] + G[b * 3 + 2] * A[6 + k]) * idet;
+            const T ltr = lambda * (Hm[0] + Hm[4] + Hm[8]);
+            T S[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) S[a * 3 + k] = mu * (Hm[a * 3 + k] + Hm[k * 3 + a]) + (a == k ? ltr : T(0));
+            const T w = T(0.125);
+            T P[9];  // P[a][c] = w sum_k S[a][k] adj[c][k]   (the determinant of dV cancels the 1 / det of the test gradient)
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P[a * 3 + c] = w * (S[a * 3] * A[c * 3] + S[a * 3 + 1] * A[c * 3 + 1] + S[a * 3 + 2] * A[c * 3 + 2]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) O[a][i] += P[a * 3] * gx[i] + P[a * 3 + 1] * gy[i] + P[a * 3 + 2] * gz[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) red_add(&y[(ptrdiff_t)ev[i] * 3 + a], O[a][i]);
+    }
+}
+
+struct PointsOp final : OpBase {
+    DeviceArray<int32_t> elements;  // SoA [nxe][ne]
+    DeviceArray<float> points;      // [3][nn]
+    double mu = 1, lambda = 1;
+    bool elasticity = false;
+
+    template <typename T>
+    int apply_t(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        if (elasticity) {
+            const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+            hex8_le_isoparametric_kernel<T><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, (T)mu, (T)lambda, x, y);
+        } else {
+            const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+            tet4_laplacian_points_kernel<T><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, x, y);
+        }
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * block_size * real_type, s));
+        return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, s) : apply_t<float>((const float *)x, (float *)y, s);
+    }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+};
+
+static OpBase *make_points_op(int nxe, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
+                              int real_type, const char *what) {
+    if (!check_indices(nxe, ne, nn, elements)) {
+        set_error(std::string(what) + ": node index out of range");
+        return nullptr;
+    }
+    auto *op = new PointsOp();
+    op->real_type = real_type;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = nxe;
+    op->geom_bytes_per_elem = nxe * 3 * 4;  // the corner coordinates an element reads
+    std::vector<int32_t> el((size_t)nxe * ne);
+    for (int v = 0; v < nxe; ++v) std::copy(elements[v], elements[v] + ne, el.begin() + (size_t)v * ne);
+    bool bad = op->elements.upload(el.data(), el.size()) != 0 || op->points.alloc((size_t)3 * nn) != 0;
+    for (int d = 0; d < 3 && !bad; ++d)
+        bad = cudaMemcpy(op->points.ptr + (size_t)d * nn, points[d], (size_t)nn * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess;
+    if (bad) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
+                                        int real_type) {
+    OpBase *op = make_points_op(4, ne, nn, elements, points, real_type, "tet4 laplacian (from points)");
+    if (op) op->elem_type = B200FEM_TET4;
+    return op;
+}
+
+OpBase *make_hex8_le_isoparametric(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
+                                   double lambda, int real_type) {
+    OpBase *op = make_points_op(8, ne, nn, elements, points, real_type, "hex8 linear elasticity (isoparametric)");
+    if (op) {
+        auto *p = static_cast<PointsOp *>(op);
+        p->elem_type = B200FEM_HEX8;
+        p->block_size = 3;
+        p->elasticity = true;
+        p->mu = mu;
+        p->lambda = lambda;
+    }
+    return op;
+}
+
+}  // namespace b200fem

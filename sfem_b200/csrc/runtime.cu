@@ -233,6 +233,58 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
     return B200FEM_SUCCESS;
 }
 
+int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t ne, ptrdiff_t nn,
+                                         const int32_t *const *elements, const float *const *points, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
+    OpBase *impl = nullptr;
+    switch (element_type) {
+        case B200FEM_TET4: impl = make_tet4_laplacian_from_points(ne, nn, elements, points, real_type); break;
+        case B200FEM_SSHEX8: impl = make_sshex8_nonaffine_laplacian(level, ne, nn, elements, points, real_type); break;
+        default: B2_FAIL("laplacian from points: tet4 (tet4_laplacian_apply) and sshex8 (sshex8_laplacian_apply) only");
+    }
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t ne, ptrdiff_t nn,
+                                                 const int32_t *const *elements, const float *const *points, double mu,
+                                                 double lambda, int real_type) {
+    (void)level;
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
+    if (element_type != B200FEM_HEX8) B2_FAIL("linear elasticity from points: hex8 (hex8_linear_elasticity_apply, isoparametric) only");
+    OpBase *impl = make_hex8_le_isoparametric(ne, nn, elements, points, mu, lambda, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_sshex8_em_create(b200fem_op_t *op, int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                             int block_size, const void *element_matrix, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (ne > 0 && !element_matrix) B2_FAIL("element_matrix is NULL");
+    OpBase *impl = make_sshex8_em(level, ne, nn, elements, block_size, element_matrix, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_sshex8_laplacian_element_matrix(int level, ptrdiff_t ne, const float *fff, int real_type, void *values_host) {
+    if (real_type != B200FEM_F32 && real_type != B200FEM_F64) B2_FAIL("real_type must be B200FEM_F32 or B200FEM_F64");
+    if (level < 1 || ne < 0 || (ne > 0 && (!fff || !values_host))) B2_FAIL("sshex8_laplacian_element_matrix: bad arguments");
+    return sshex8_laplacian_element_matrix_build(level, ne, fff, real_type, values_host);
+}
+
+int b200fem_sshex8_linear_elasticity_element_matrix(int level, ptrdiff_t ne, const float *adjugate, const float *determinant,
+                                                    double mu, double lambda, int real_type, void *values_host) {
+    if (real_type != B200FEM_F32 && real_type != B200FEM_F64) B2_FAIL("real_type must be B200FEM_F32 or B200FEM_F64");
+    if (level < 1 || ne < 0 || (ne > 0 && (!adjugate || !determinant || !values_host)))
+        B2_FAIL("sshex8_linear_elasticity_element_matrix: bad arguments");
+    return sshex8_le_element_matrix_build(level, ne, adjugate, determinant, mu, lambda, real_type, values_host);
+}
+
 int b200fem_op_destroy(b200fem_op_t op) {
     if (op) {
         delete op->impl;

@@ -162,6 +162,58 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// MixedPrecisionShiftableBlockSymJacobi<HP, LP> (algebra/sfem_MixedPrecisionShiftableBlockSymJacobi.hpp): the block
+// diagonal arrives in HP, is converted to LP (sym_diag_to_diag), masked, inverted and scaled in LP
+// (algebra/openmp/sfem_openmp_ShiftableJacobi.hpp:31-98, 227-243), and the apply mixes LP blocks with HP vectors.
+template <typename HP, typename LP>
+__global__ void __launch_bounds__(256)
+    block_sym_jacobi_setup_mixed_kernel(const ptrdiff_t n_blocks, const HP *__restrict__ sym6, const HP *__restrict__ shift6,
+                                        const unsigned char *__restrict__ mask, const LP relaxation, LP *__restrict__ inv9) {
+    for (ptrdiff_t b = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (ptrdiff_t)gridDim.x * blockDim.x) {
+        LP d[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            d[k] = (LP)sym6[b * 6 + k];                 // sym_diag_to_diag<HP, LP>
+            if (shift6) d[k] += (LP)shift6[b * 6 + k];  // add_sym_diag_to_diag<HP, LP>
+        }
+        LP m[9] = {d[0], d[1], d[2], d[1], d[3], d[4], d[2], d[4], d[5]};
+        if (mask) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const ptrdiff_t i = b * 3 + r;
+                if ((mask[i >> 3] >> (i & 7)) & 1) {
+                    m[r * 3 + 0] = m[r * 3 + 1] = m[r * 3 + 2] = LP(0);
+                    m[r * 3 + r] = LP(1);
+                }
+            }
+        }
+        const LP x0 = m[4] * m[8], x1 = m[5] * m[7], x2 = m[1] * m[5], x3 = m[1] * m[8], x4 = m[2] * m[4];
+        const LP x5 = LP(1) / (m[0] * x0 - m[0] * x1 + m[2] * m[3] * m[7] - m[3] * x3 + m[6] * x2 - m[6] * x4);
+        LP *o = inv9 + b * 9;
+        o[0] = relaxation * (x5 * (x0 - x1));
+        o[1] = relaxation * (x5 * (m[2] * m[7] - x3));
+        o[2] = relaxation * (x5 * (x2 - x4));
+        o[3] = relaxation * (x5 * (-m[3] * m[8] + m[5] * m[6]));
+        o[4] = relaxation * (x5 * (m[0] * m[8] - m[2] * m[6]));
+        o[5] = relaxation * (x5 * (-m[0] * m[5] + m[2] * m[3]));
+        o[6] = relaxation * (x5 * (m[3] * m[7] - m[4] * m[6]));
+        o[7] = relaxation * (x5 * (-m[0] * m[7] + m[1] * m[6]));
+        o[8] = relaxation * (x5 * (m[0] * m[4] - m[1] * m[3]));
+    }
+}
+
+template <typename HP, typename LP>
+__global__ void __launch_bounds__(256)
+    block_jacobi_apply_mixed_kernel(const ptrdiff_t n_blocks, const LP *__restrict__ inv9, const HP *__restrict__ x, HP *__restrict__ y) {
+    for (ptrdiff_t b = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (ptrdiff_t)gridDim.x * blockDim.x) {
+        const LP *d = inv9 + b * 9;
+        const HP x0 = x[b * 3 + 0], x1 = x[b * 3 + 1], x2 = x[b * 3 + 2];
+        y[b * 3 + 0] += (HP)d[0] * x0 + (HP)d[1] * x1 + (HP)d[2] * x2;
+        y[b * 3 + 1] += (HP)d[3] * x0 + (HP)d[4] * x1 + (HP)d[5] * x2;
+        y[b * 3 + 2] += (HP)d[6] * x0 + (HP)d[7] * x1 + (HP)d[8] * x2;
+    }
+}
+
 }  // namespace b200fem
 
 using namespace b200fem;
@@ -303,6 +355,28 @@ int b200fem_block_sym_jacobi_setup(int real_type, ptrdiff_t n_blocks, const void
             n_blocks, (const float *)sym_diag6, (const float *)shift6, (const unsigned char *)constraints_mask, (float)relaxation, (float *)inv_diag9);
     else
         B2_FAIL("real_type must be B200FEM_F32 or B200FEM_F64");
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_block_sym_jacobi_setup_mixed(ptrdiff_t n_blocks, const double *sym_diag6, const double *shift6, const void *constraints_mask,
+                                         double relaxation, float *inv_diag9, void *stream) {
+    if (n_blocks < 0) B2_FAIL("negative size");
+    if (n_blocks == 0) return B200FEM_SUCCESS;
+    if (!sym_diag6 || !inv_diag9) B2_FAIL("block_sym_jacobi_setup_mixed: NULL array");
+    const int grid = (int)std::min<ptrdiff_t>((n_blocks + 255) / 256, (ptrdiff_t)sm_count() * 8);
+    block_sym_jacobi_setup_mixed_kernel<double, float><<<grid, 256, 0, as_stream(stream)>>>(
+        n_blocks, sym_diag6, shift6, (const unsigned char *)constraints_mask, (float)relaxation, inv_diag9);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_block_jacobi_apply_mixed(ptrdiff_t n_blocks, const float *inv_diag9, const double *x, double *y, void *stream) {
+    if (n_blocks < 0) B2_FAIL("negative size");
+    if (n_blocks == 0) return B200FEM_SUCCESS;
+    if (!inv_diag9 || !x || !y) B2_FAIL("block_jacobi_apply_mixed: NULL array");
+    const int grid = (int)std::min<ptrdiff_t>((n_blocks + 255) / 256, (ptrdiff_t)sm_count() * 8);
+    block_jacobi_apply_mixed_kernel<double, float><<<grid, 256, 0, as_stream(stream)>>>(n_blocks, inv_diag9, x, y);
     B2_CHECK_LAUNCH();
     return B200FEM_SUCCESS;
 }

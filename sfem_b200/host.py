@@ -45,6 +45,7 @@ _SIG = {
     "b200host_cg": (vp, [vp, vp, vp, f64, f64, i32]),
     "b200host_jacobi": (vp, [vp, vp, ssz, f64]),
     "b200host_block_sym_jacobi": (vp, [vp, vp, ssz, vp, f64]),
+    "b200host_mixed_block_sym_jacobi": (vp, [vp, ssz, vp, f64]),
     "b200host_stationary": (vp, [vp, vp, vp, i32]),
     "b200host_cheb3": (vp, [vp, vp, f64, i32, f64, f64, i32, i32]),
     "b200host_cheb3_init_with_ones": (i32, [vp]),
@@ -291,6 +292,11 @@ def jacobi(blas: Blas, diag, relaxation: float) -> Handle:
 def block_sym_jacobi(blas: Blas, diag6, mask, relaxation: float) -> Handle:
     return Handle(_h.b200host_block_sym_jacobi(blas.ptr, _p(diag6), diag6.numel() // 6, _p(mask), relaxation),
                   keep=[blas, diag6, mask])
+
+
+def mixed_block_sym_jacobi(diag6, mask, relaxation: float) -> Handle:
+    """MixedPrecisionShiftableBlockSymJacobi<double, float>: fp64 block diagonal in, fp32 inverted blocks kept."""
+    return Handle(_h.b200host_mixed_block_sym_jacobi(_p(diag6), diag6.numel() // 6, _p(mask), relaxation), keep=[diag6, mask])
 
 
 def stationary(blas: Blas, op: Handle, precond: Handle, max_it: int) -> Handle:

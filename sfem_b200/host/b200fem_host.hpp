@@ -630,6 +630,40 @@ namespace b200fem {
         std::ptrdiff_t cols() const override { return n_blocks * 3; }
     };
 
+    /* MixedPrecisionShiftableBlockSymJacobi<double, float> (algebra/sfem_MixedPrecisionShiftableBlockSymJacobi.hpp): fp64
+     * vectors and block diagonal, the inverted blocks kept in fp32 */
+    class MixedPrecisionShiftableBlockSymJacobi final : public Operator<double> {
+    public:
+        void         *stream{nullptr};
+        const double *diag{nullptr};
+        const void   *constraints_mask{nullptr};
+        ptrdiff_t     n_blocks{0};
+        double        relaxation_parameter{1. / 3};
+        ~MixedPrecisionShiftableBlockSymJacobi() override {
+            if (inv_diag_) b200fem_free(inv_diag_);
+        }
+        int set_diag(const double *sym_diag6, ptrdiff_t n_blocks_) {
+            diag     = sym_diag6;
+            n_blocks = n_blocks_;
+            if (inv_diag_) b200fem_free(inv_diag_);
+            void *p = nullptr;
+            B200FEM_TRY(b200fem_malloc(&p, (size_t)(n_blocks ? n_blocks : 1) * 9 * sizeof(float)));
+            inv_diag_ = (float *)p;
+            return b200fem_block_sym_jacobi_setup_mixed(n_blocks, diag, nullptr, constraints_mask, relaxation_parameter, inv_diag_, stream);
+        }
+        int shift(const double *shift6) {
+            return b200fem_block_sym_jacobi_setup_mixed(n_blocks, diag, shift6, constraints_mask, relaxation_parameter, inv_diag_, stream);
+        }
+        int apply(const double *const x, double *const y) override {
+            return b200fem_block_jacobi_apply_mixed(n_blocks, inv_diag_, x, y, stream);
+        }
+        std::ptrdiff_t rows() const override { return n_blocks * 3; }
+        std::ptrdiff_t cols() const override { return n_blocks * 3; }
+
+    private:
+        float *inv_diag_{nullptr};
+    };
+
     /* x <- x + P (b - A x), max_it times (StationaryIteration::apply, sfem_Stationary.hpp:50-80) */
     template <typename T>
     class StationaryIteration final : public MatrixFreeLinearSolver<T> {

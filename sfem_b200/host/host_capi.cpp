@@ -344,6 +344,14 @@ void *b200host_block_sym_jacobi(void *blas, const void *diag6_dev, ptrdiff_t n_b
     return DISPATCH(((Box *)blas)->real_type, make_bjacobi<double>(blas, diag6_dev, n_blocks, mask_dev, relaxation),
                     make_bjacobi<float>(blas, diag6_dev, n_blocks, mask_dev, relaxation));
 }
+/* MixedPrecisionShiftableBlockSymJacobi<double, float>: fp64 only */
+void *b200host_mixed_block_sym_jacobi(const void *diag6_dev, ptrdiff_t n_blocks, const void *mask_dev, double relaxation) {
+    auto j                  = std::make_shared<MixedPrecisionShiftableBlockSymJacobi>();
+    j->relaxation_parameter = relaxation;
+    j->constraints_mask     = mask_dev;
+    if (j->set_diag((const double *)diag6_dev, n_blocks)) return nullptr;
+    return box<double>(j, K_BJACOBI, nullptr);
+}
 void *b200host_stationary(void *blas, void *op, void *precond, int max_it) {
     return DISPATCH(((Box *)blas)->real_type, make_stationary<double>(blas, op, precond, max_it),
                     make_stationary<float>(blas, op, precond, max_it));

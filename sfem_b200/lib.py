@@ -53,6 +53,11 @@ _SIG = {
     "b200fem_laplacian_create": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32],
     "b200fem_linear_elasticity_create": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), f64, f64, i32],
+    "b200fem_laplacian_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
+    "b200fem_linear_elasticity_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, f64, f64, i32],
+    "b200fem_sshex8_em_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, i32, vp, i32],
+    "b200fem_sshex8_laplacian_element_matrix": [i32, ssz, C.POINTER(C.c_float), i32, vp],
+    "b200fem_sshex8_linear_elasticity_element_matrix": [i32, ssz, C.POINTER(C.c_float), C.POINTER(C.c_float), f64, f64, i32, vp],
     "b200fem_op_destroy": [vp],
     "b200fem_op_apply": [vp, vp, vp, vp],
     "b200fem_op_apply_overwrite": [vp, vp, vp, vp],
@@ -107,6 +112,8 @@ _SIG = {
     "b200fem_transfer_prolongate": [vp, i32, i32, vp, vp, vp],
     "b200fem_block_sym_jacobi_setup": [i32, ssz, vp, vp, vp, f64, vp, vp],
     "b200fem_block_jacobi_apply": [i32, ssz, vp, vp, vp, vp],
+    "b200fem_block_sym_jacobi_setup_mixed": [ssz, vp, vp, vp, f64, vp, vp],
+    "b200fem_block_jacobi_apply_mixed": [ssz, vp, vp, vp, vp],
 }
 for _name, _args in _SIG.items():
     _fn = getattr(_lib, _name)
@@ -296,6 +303,64 @@ def linear_elasticity(element_type: int, elements: np.ndarray, adjugate: np.ndar
                                                 _soa_ptrs(el, C.c_int32), a.ctypes.data_as(C.POINTER(C.c_float)),
                                                 d.ctypes.data_as(C.POINTER(C.c_float)), mu, lam, _rt(dtype)),
           "linear_elasticity_create")
+    return Op(h, nnodes)
+
+
+def _np_rt(dtype):
+    return np.float64 if _rt(dtype) == F64 else np.float32
+
+
+def laplacian_from_points(element_type: int, elements: np.ndarray, points: np.ndarray, nnodes: int, dtype, level: int = 0) -> Op:
+    """TET4: tet4_laplacian_apply (FFF from the points per element); SSHEX8: sshex8_laplacian_apply (non-affine, q6)."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_laplacian_create_from_points(C.byref(h), element_type, level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
+                                                    _soa_ptrs(pts, C.c_float), _rt(dtype)), "laplacian_create_from_points")
+    return Op(h, nnodes)
+
+
+def linear_elasticity_from_points(element_type: int, elements: np.ndarray, points: np.ndarray, mu: float, lam: float, nnodes: int,
+                                  dtype, level: int = 0) -> Op:
+    """HEX8: hex8_linear_elasticity_apply, the isoparametric variant (Jacobian per Gauss point)."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_linear_elasticity_create_from_points(C.byref(h), element_type, level, el.shape[1], nnodes,
+                                                            _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), mu, lam, _rt(dtype)),
+          "linear_elasticity_create_from_points")
+    return Op(h, nnodes)
+
+
+def sshex8_laplacian_element_matrix(level: int, fff: np.ndarray, dtype) -> np.ndarray:
+    """[ne, 64] element matrices of ss:em:Laplacian from the macro FFF (sshex8_laplacian_element_matrix)."""
+    f = np.ascontiguousarray(fff, dtype=np.float32).reshape(-1, 6)
+    out = np.zeros((f.shape[0], 64), dtype=_np_rt(dtype))
+    check(_lib.b200fem_sshex8_laplacian_element_matrix(level, f.shape[0], f.ctypes.data_as(C.POINTER(C.c_float)), _rt(dtype),
+                                                       out.ctypes.data), "sshex8_laplacian_element_matrix")
+    return out
+
+
+def sshex8_linear_elasticity_element_matrix(level: int, adjugate: np.ndarray, determinant: np.ndarray, mu: float, lam: float,
+                                            dtype) -> np.ndarray:
+    """[ne, 576] element matrices of ss:em:LinearElasticity (sshex8_linear_elasticity_element_matrix)."""
+    a = np.ascontiguousarray(adjugate, dtype=np.float32).reshape(-1, 9)
+    d = np.ascontiguousarray(determinant, dtype=np.float32)
+    out = np.zeros((a.shape[0], 576), dtype=_np_rt(dtype))
+    check(_lib.b200fem_sshex8_linear_elasticity_element_matrix(level, a.shape[0], a.ctypes.data_as(C.POINTER(C.c_float)),
+                                                               d.ctypes.data_as(C.POINTER(C.c_float)), mu, lam, _rt(dtype),
+                                                               out.ctypes.data), "sshex8_linear_elasticity_element_matrix")
+    return out
+
+
+def sshex8_em(level: int, elements: np.ndarray, element_matrix: np.ndarray, block_size: int, nnodes: int, dtype) -> Op:
+    """Stored-element-matrix operator (ss:em:Laplacian / ss:em:LinearElasticity): one (8 bs)^2 matrix per macro element."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    m = np.ascontiguousarray(element_matrix, dtype=_np_rt(dtype))
+    assert m.size == el.shape[1] * (8 * block_size) ** 2
+    h = vp()
+    check(_lib.b200fem_sshex8_em_create(C.byref(h), level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32), block_size, m.ctypes.data,
+                                        _rt(dtype)), "sshex8_em_create")
     return Op(h, nnodes)
 
 

@@ -1,0 +1,185 @@
+"""GPU parity of the reference's non-default formulations on the path and of the stored-element-matrix
+("EM") semi-structured operators (section 8f rank 1), through the C ABI against the oracle on the same inputs:
+
+  tet4_laplacian_apply            FFF recomputed from the points           operators/tet4/tet4_laplacian.cpp:70-135
+  hex8_linear_elasticity_apply    isoparametric (SFEM_HEX8_ASSUME_AFFINE=0) operators/hex8/hex8_linear_elasticity.cpp:86-324
+  sshex8_laplacian_apply          non-affine macro elements, q6            operators/sshex8/sshex8_laplacian.cpp:39-182
+  affine_sshex8_laplacian_apply   element-matrix formulation               operators/sshex8/sshex8_laplacian.cpp:184-331
+  ss:em:Laplacian / ss:em:LinearElasticity   sshex8_*_element_matrix + sshex8_stencil_element_matrix_apply(3)
+Bars: 1e-12 (fp64) / 1e-5 (fp32)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = {"f64": 1e-12, "f32": 1e-5}
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _dt(real):
+    torch = _torch()
+    return torch.float64 if real == "f64" else torch.float32
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _orc(oracles, real):
+    o = oracles.get(("reference", real))
+    if o is None:
+        pytest.skip("needs the reference build (oracle/_ref)")
+    return o
+
+
+def _apply(op, u, dt, n_out=None):
+    torch = _torch()
+    x = torch.from_numpy(np.asarray(u)).to(dt).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    return x, y
+
+
+def _sshex8_points(mesh, m, mpts, L):
+    nn = m["n_nodes"]
+    pts = np.zeros((3, nn), dtype=np.float32)
+    corners = [mesh.sshex8_lidx(L, cx * L, cy * L, cz * L) for cx, cy, cz in mesh.HEX8_CORNERS]
+    for k, c in enumerate(corners):
+        pts[:, m["elements"][c]] = mpts[:, m["m_elements"][k]]
+    return pts
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_tet4_laplacian_from_points(oracles, real):
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    el, pts = mesh.box_tet4(9, 7, 8)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    op = lib.laplacian_from_points(lib.TET4, el, pts, nn, _dt(real))
+    for seed in (0, 1):
+        u = np.random.default_rng(seed).uniform(-1, 1, nn)
+        x, y = _apply(op, u, _dt(real))
+        assert _rel(y.cpu().numpy(), orc.tet4_laplacian_apply_points(el, pts, u, nn)) < TOL[real]
+    # constants are in the kernel; empty mesh; overwrite form
+    x, y = _apply(op, np.ones(nn), _dt(real))
+    assert float(y.abs().max()) < (1e-12 if real == "f64" else 1e-4)
+    op.apply_overwrite(x, y)
+    assert float(y.abs().max()) < (1e-12 if real == "f64" else 1e-4)
+    empty = lib.laplacian_from_points(lib.TET4, el[:, :0], pts, nn, _dt(real))
+    y.fill_(3.0)
+    empty.apply_overwrite(x, y)
+    assert float(y.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_hex8_linear_elasticity_isoparametric(oracles, real):
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    el, pts = mesh.box_hex8(6, 5, 7)
+    pts = mesh.warp_points(pts)  # genuinely trilinear elements: the affine operator does not apply here
+    nn = pts.shape[1]
+    mu, lam = 1.3, 0.7
+    op = lib.linear_elasticity_from_points(lib.HEX8, el, pts, mu, lam, nn, _dt(real))
+    assert op.block_size == 3
+    u = np.random.default_rng(5).uniform(-1, 1, nn * 3)
+    x, y = _apply(op, u, _dt(real))
+    ref = orc.hex8_linear_elasticity_apply_isoparametric(el, pts, mu, lam, u, nn)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    # on this warped mesh the affine operator is a different (approximate) one -- the isoparametric path is not an alias
+    adj, det = orc.hex8_adjugate_and_det_fill(el, pts)
+    assert _rel(orc.hex8_linear_elasticity_apply(el, adj, det, mu, lam, u, nn), ref) > 1e-4
+    # rigid translations are in the kernel
+    x, y = _apply(op, np.tile(np.array([0.3, -1.2, 0.5]), nn), _dt(real))
+    assert float(y.abs().max()) < (1e-12 if real == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level", [2, 4, 8])
+def test_sshex8_laplacian_nonaffine(oracles, real, level):
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    m = mesh.sshex8_box(level, 3, 2, 2)
+    mpts = mesh.warp_points(m["m_points"])  # trilinear macro elements
+    nn = m["n_nodes"]
+    pts = _sshex8_points(mesh, m, mpts, level)
+    op = lib.laplacian_from_points(lib.SSHEX8, m["elements"], pts, nn, _dt(real), level=level)
+    u = np.random.default_rng(level).uniform(-1, 1, nn)
+    x, y = _apply(op, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.sshex8_laplacian_apply_points(level, m["elements"], pts, u)) < TOL[real]
+    op.apply(x, y)  # accumulates
+    assert _rel(y.cpu().numpy(), 2 * orc.sshex8_laplacian_apply_points(level, m["elements"], pts, u)) < TOL[real]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level", [2, 4, 8])
+def test_sshex8_em_laplacian(oracles, real, level):
+    """ss:em:Laplacian: builder == sshex8_laplacian_element_matrix, apply == sshex8_stencil_element_matrix_apply, and the
+    same operator == affine_sshex8_laplacian_apply (the element-matrix formulation of the affine Laplacian)."""
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    m = mesh.sshex8_box(level, 3, 2, 2, 3.0, 2.0, 2.0)
+    mpts = mesh.shear_points(m["m_points"], 0.25, 0.5, 0.125)  # dyadic: the fp32 FFF we hand over are exact
+    nn = m["n_nodes"]
+    fff = orc.hex8_fff_fill(m["m_elements"], mpts)
+    M = lib.sshex8_laplacian_element_matrix(level, fff, _dt(real))
+    M_ref = orc.sshex8_laplacian_element_matrix(level, m["m_elements"], mpts)
+    assert _rel(M, M_ref) < TOL[real]
+    op = lib.sshex8_em(level, m["elements"], M_ref, 1, nn, _dt(real))  # the reference's matrices in, like the reference's Op
+    u = np.random.default_rng(7).uniform(-1, 1, nn)
+    x, y = _apply(op, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.sshex8_em_apply(level, m["elements"], M_ref, u)) < TOL[real]
+    pts = _sshex8_points(mesh, m, mpts, level)
+    assert _rel(y.cpu().numpy(), orc.sshex8_laplacian_apply_points(level, m["elements"], pts, u, affine=True)) < TOL[real]
+    # and the default (stencil / FFF) operator computes the same thing
+    default = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=level)
+    _, yd = _apply(default, u, _dt(real))
+    assert _rel(y.cpu().numpy(), yd.cpu().numpy()) < TOL[real]
+    # diagonal = what unit applies see
+    torch = _torch()
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    dd = torch.zeros_like(d)
+    default.diag(dd)
+    assert _rel(d.cpu().numpy(), dd.cpu().numpy()) < TOL[real]
+    # an arbitrary (non-FFF) symmetric matrix is applied as given: the operator is not tied to the Laplacian
+    rng = np.random.default_rng(8)
+    R = rng.uniform(-1, 1, (m["elements"].shape[1], 8, 8))
+    R = (R + R.transpose(0, 2, 1)).reshape(-1, 64)
+    op2 = lib.sshex8_em(level, m["elements"], R, 1, nn, _dt(real))
+    _, y2 = _apply(op2, u, _dt(real))
+    assert _rel(y2.cpu().numpy(), orc.sshex8_em_apply(level, m["elements"], R, u)) < (1e-11 if real == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level", [2, 4, 8])
+def test_sshex8_em_linear_elasticity(oracles, real, level):
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    m = mesh.sshex8_box(level, 2, 3, 2, 2.0, 3.0, 2.0)
+    mpts = mesh.shear_points(m["m_points"], 0.25, 0.5, 0.125)
+    nn = m["n_nodes"]
+    mu, lam = 1.3, 0.7
+    adj, det = orc.hex8_adjugate_and_det_fill(m["m_elements"], mpts)
+    K = lib.sshex8_linear_elasticity_element_matrix(level, adj, det, mu, lam, _dt(real))
+    K_ref = orc.sshex8_linear_elasticity_element_matrix(level, m["m_elements"], mpts, mu, lam)
+    assert _rel(K, K_ref) < TOL[real]
+    op = lib.sshex8_em(level, m["elements"], K_ref, 3, nn, _dt(real))
+    assert op.block_size == 3
+    u = np.random.default_rng(9).uniform(-1, 1, nn * 3)
+    x, y = _apply(op, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.sshex8_em_apply(level, m["elements"], K_ref, u, 3)) < TOL[real]
+    # == the matrix-free macro-adjugate operator
+    assert _rel(y.cpu().numpy(), orc.sshex8_linear_elasticity_apply(level, m["elements"], adj, det, mu, lam, u, nn)) < (
+        1e-11 if real == "f64" else 1e-4)

@@ -236,3 +236,42 @@ def test_block_sym_jacobi(real):
     lib.block_jacobi_apply(inv9, torch.from_numpy(x).to(_dt(real)).cuda(), y)
     ref = y0 + np.einsum("bij,bj->bi", inv, x.reshape(nb, 3)).reshape(-1)
     assert _rel(y.cpu().numpy(), ref) < (1e-12 if real == "f64" else 1e-4)
+
+
+def test_mixed_precision_block_sym_jacobi(oracles):
+    """MixedPrecisionShiftableBlockSymJacobi<double, float> (algebra/sfem_MixedPrecisionShiftableBlockSymJacobi.hpp): fp64
+    vectors, fp32 inverted blocks. Against the reference's own class (oracle/_ref solver build) when it is on this box,
+    and against the fp64 smoother to fp32 accuracy."""
+    torch = _torch()
+    from sfem_b200 import host
+
+    rng = np.random.default_rng(4)
+    nb = 2000
+    a = rng.uniform(-1, 1, (nb, 3, 3))
+    spd = a @ a.transpose(0, 2, 1) + 3 * np.eye(3)
+    sym6 = np.stack([spd[:, 0, 0], spd[:, 0, 1], spd[:, 0, 2], spd[:, 1, 1], spd[:, 1, 2], spd[:, 2, 2]], axis=1).reshape(-1)
+    mask_bits = rng.uniform(size=nb * 3) < 0.1
+    mask = np.packbits(mask_bits, bitorder="little")
+    relax = 1.0 / 3.0
+    x = rng.uniform(-1, 1, nb * 3)
+    y0 = rng.uniform(-1, 1, nb * 3)
+    d6 = torch.from_numpy(sym6).cuda()
+    mk = torch.from_numpy(mask).cuda()
+    j = host.mixed_block_sym_jacobi(d6, mk, relax)
+    y = torch.from_numpy(y0).cuda()
+    assert host.apply(j, torch.from_numpy(x).cuda(), y) == 0
+    # fp64 smoother of the same blocks: equal to fp32 accuracy, but NOT to fp64 accuracy (the blocks really are fp32)
+    j64 = host.block_sym_jacobi(host.Blas(torch.float64), d6, mk, relax)
+    y64 = torch.from_numpy(y0).cuda()
+    host.apply(j64, torch.from_numpy(x).cuda(), y64)
+    diff = float((y - y64).norm() / (y64 - torch.from_numpy(y0).cuda()).norm())
+    assert 1e-10 < diff < 1e-5, diff
+    from oracle import ref_solvers
+
+    if ref_solvers.available("f64"):
+        rs = ref_solvers.RefSolvers("f64")
+        jr = rs.mixed_block_sym_jacobi(sym6, mask, relax)
+        yr = y0.copy()
+        assert rs.apply(jr, np.ascontiguousarray(x), yr) == 0
+        # same fp32 operations on both sides; the only freedom is fp32 contraction / evaluation order inside the 3x3 inverse
+        assert np.linalg.norm(y.cpu().numpy() - yr) < 2e-6 * np.linalg.norm(yr - y0)
