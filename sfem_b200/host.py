@@ -73,6 +73,18 @@ _SIG = {
     "b200host_blas_reserve_allocation": (i32, [vp, ssz, ssz]),
     "b200host_blas_reductions": (C.c_long, [vp]),
     "b200host_blas_dot": (f64, [vp, ssz, vp, vp]),
+    "b200host_mesh_last_error": (C.c_char_p, []),
+    "b200host_mesh_read": (vp, [C.c_char_p]),
+    "b200host_mesh_destroy": (None, [vp]),
+    "b200host_mesh_n_elements": (ssz, [vp]),
+    "b200host_mesh_n_nodes": (ssz, [vp]),
+    "b200host_mesh_nxe": (i32, [vp]),
+    "b200host_mesh_dim": (i32, [vp]),
+    "b200host_mesh_element_type": (C.c_char_p, [vp]),
+    "b200host_mesh_elements": (C.POINTER(C.c_int32), [vp, i32]),
+    "b200host_mesh_points": (C.POINTER(C.c_float), [vp, i32]),
+    "b200host_mesh_write": (i32, [C.c_char_p, C.c_char_p, i32, ssz, ssz, i32, C.POINTER(C.POINTER(C.c_int32)),
+                                  C.POINTER(C.POINTER(C.c_float))]),
     "b200host_apply": (i32, [vp, vp, vp]),
     "b200host_apply_overwrite": (i32, [vp, vp, vp]),
     "b200host_rows": (ssz, [vp]),
@@ -365,3 +377,32 @@ def constraints_mask(n_dofs: int, block_size: int, conditions) -> np.ndarray:
         dof = np.asarray(nodes, dtype=np.int64) * block_size + comp
         np.bitwise_or.at(m, dof // 8, (1 << (dof % 8)).astype(np.uint8))
     return m
+
+
+def read_mesh(folder: str) -> dict:
+    """A mesh folder in the reference's on-disk format (x/y/z.raw fp32, i<k>.raw int32, meta.yaml) through the C++ reader
+    (sfem_b200/host/b200fem_mesh_io.hpp): {"element_type", "elements" [nxe][ne] int32, "points" [dim][nn] fp32}."""
+    m = _h.b200host_mesh_read(folder.encode())
+    if not m:
+        raise _l.B200FemError("read_mesh: " + _h.b200host_mesh_last_error().decode())
+    try:
+        ne, nn = _h.b200host_mesh_n_elements(m), _h.b200host_mesh_n_nodes(m)
+        nxe, dim = _h.b200host_mesh_nxe(m), _h.b200host_mesh_dim(m)
+        if ne:
+            el = np.stack([np.ctypeslib.as_array(_h.b200host_mesh_elements(m, k), shape=(ne,)).copy() for k in range(nxe)])
+        else:
+            el = np.zeros((nxe, 0), np.int32)
+        pts = np.stack([np.ctypeslib.as_array(_h.b200host_mesh_points(m, d), shape=(nn,)).copy() for d in range(dim)])
+        return {"element_type": _h.b200host_mesh_element_type(m).decode(), "elements": el, "points": pts}
+    finally:
+        _h.b200host_mesh_destroy(m)
+
+
+def write_mesh(folder: str, element_type: str, elements: np.ndarray, points: np.ndarray):
+    os.makedirs(folder, exist_ok=True)
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    rc = _h.b200host_mesh_write(folder.encode(), element_type.encode(), el.shape[0], el.shape[1], pts.shape[1], pts.shape[0],
+                                _l._soa_ptrs(el, C.c_int32), _l._soa_ptrs(pts, C.c_float))
+    if rc:
+        raise _l.B200FemError("write_mesh: " + _h.b200host_mesh_last_error().decode())

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "b200fem_host.hpp"
+#include "b200fem_mesh_io.hpp"
 
 using namespace b200fem;
 
@@ -414,6 +415,35 @@ int b200host_mg_add_level(void *mg, void *op, void *smoother, void *prolongation
         std::static_pointer_cast<Multigrid<float>>(b->obj)->add_level(op_of<float>(op), op_of<float>(smoother),
                                                                       op_of<float>(prolongation), op_of<float>(restriction));
     return 0;
+}
+
+/* ---- mesh folders in the reference's on-disk format (b200fem_mesh_io.hpp) ----------------------------------------- */
+static thread_local std::string g_mesh_error;
+const char *b200host_mesh_last_error() { return g_mesh_error.c_str(); }
+void *b200host_mesh_read(const char *folder) {
+    auto m = new RawMesh();
+    if (read_mesh(folder, *m, &g_mesh_error)) {
+        delete m;
+        return nullptr;
+    }
+    return m;
+}
+void        b200host_mesh_destroy(void *m) { delete (RawMesh *)m; }
+ptrdiff_t   b200host_mesh_n_elements(void *m) { return ((RawMesh *)m)->n_elements(); }
+ptrdiff_t   b200host_mesh_n_nodes(void *m) { return ((RawMesh *)m)->n_nodes(); }
+int         b200host_mesh_nxe(void *m) { return ((RawMesh *)m)->nxe(); }
+int         b200host_mesh_dim(void *m) { return (int)((RawMesh *)m)->points.size(); }
+const char *b200host_mesh_element_type(void *m) { return ((RawMesh *)m)->element_type.c_str(); }
+const int32_t *b200host_mesh_elements(void *m, int corner) { return ((RawMesh *)m)->elements[(size_t)corner].data(); }
+const float   *b200host_mesh_points(void *m, int d) { return ((RawMesh *)m)->points[(size_t)d].data(); }
+int b200host_mesh_write(const char *folder, const char *element_type, int nxe, ptrdiff_t ne, ptrdiff_t nn, int dim,
+                        const int32_t *const *elements, const float *const *points) {
+    RawMesh m;
+    m.element_type      = element_type;
+    m.spatial_dimension = dim;
+    for (int k = 0; k < nxe; ++k) m.elements.emplace_back(elements[k], elements[k] + ne);
+    for (int d = 0; d < dim; ++d) m.points.emplace_back(points[d], points[d] + nn);
+    return write_mesh(folder, m, &g_mesh_error);
 }
 
 /* run any object: solvers take (b, x) and update x in place; operators accumulate y += A x */
