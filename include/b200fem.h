@@ -71,7 +71,8 @@ int b200fem_device_synchronize(void);
 /* ------------------------------------------------------------------------------------------
  * Geometry caches (setup path). Replace tet4_fff_fill (operators/tet4/tet4_fff.cpp:4-27),
  * hex8_fff_fill (operators/hex8/hex8_fff.cpp:5-37) and hex8_adjugate_and_det_fill
- * (operators/hex8/hex8_jacobian.cpp:5-38). Host in, host out; the work runs on the device.
+ * (operators/hex8/hex8_jacobian.cpp:5-38; TET4: tet4_adjugate_and_det, operators/tet4/tet4_inline_cpu.hpp:285-380).
+ * Host in, host out; the work runs on the device.
  * For B200FEM_SSHEX8 pass the 8 macro corners as `elements` (rows of the level-L lattice corners).
  * ---------------------------------------------------------------------------------------- */
 int b200fem_fff_fill(int element_type, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
@@ -89,7 +90,8 @@ int b200fem_adjugate_and_det_fill(int element_type, ptrdiff_t nelements, ptrdiff
  *                                 affine_sshex8_laplacian_stencil_apply_fff
  *                                 (operators/sshex8/sshex8_laplacian.cpp:698); GPU twin being superseded:
  *                                 cu_laplacian_apply (frontend/cuda/sfem_Function_incore_cuda.cpp:683-697).
- *   b200fem_linear_elasticity_create <- HEX8: affine_hex8_linear_elasticity_apply_adjugate_soa
+ *   b200fem_linear_elasticity_create <- TET4: tet4_linear_elasticity_apply_opt (operators/tet4/tet4_linear_elasticity.cpp:237-300),
+ *                                 HEX8: affine_hex8_linear_elasticity_apply_adjugate_soa
  *                                 (operators/hex8/hex8_linear_elasticity.cpp:625), SSHEX8:
  *                                 affine_sshex8_linear_elasticity_apply_macro_adjugate
  *                                 (operators/sshex8/sshex8_linear_elasticity.cpp:275).
@@ -110,6 +112,8 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
  *   laplacian, SSHEX8 <- sshex8_laplacian_apply (operators/sshex8/sshex8_laplacian.cpp:39-182): trilinear (non-affine) macro
  *                        elements, FFF at the 6 face-centre quadrature points of every micro element; `points` is indexed by
  *                        sshex8 node id, only the 8 macro corners of each element are read;
+ *   linear elasticity, TET4 <- tet4_linear_elasticity_apply / _diag (operators/tet4/tet4_linear_elasticity.cpp:86-230): the
+ *                        reference's only tet4 elasticity path (its cached-adjugate twin is declared but not defined);
  *   linear elasticity, HEX8 <- hex8_linear_elasticity_apply (operators/hex8/hex8_linear_elasticity.cpp:86-324): the
  *                        isoparametric variant of SFEM_HEX8_ASSUME_AFFINE=0, Jacobian at each of the 2x2x2 Gauss points. */
 int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements, ptrdiff_t nnodes,

@@ -72,8 +72,26 @@ class Oracle:
         a = np.ascontiguousarray(a, dtype=np.float32)
         return a, a.ctypes.data_as(C.POINTER(C.c_float))
 
+    def _symbol(self, name):
+        """C symbol, or the Itanium-mangled C++ one (a few reference headers carry no extern "C": tet4_linear_elasticity.hpp)"""
+        try:
+            return getattr(self.lib, name)
+        except AttributeError:
+            pass
+        if not hasattr(self, "_mangled"):
+            import subprocess
+
+            out = subprocess.run(["nm", "-D", "--defined-only", self.lib._name], capture_output=True, text=True).stdout
+            self._mangled = [ln.split()[-1] for ln in out.splitlines() if ln.split()[-1].startswith("_Z")]
+        prefix = f"_Z{len(name)}{name}"
+        hits = [m for m in self._mangled if m.startswith(prefix) and not m[len(prefix)].isalnum() or m.startswith(prefix + "l")]
+        hits = [m for m in self._mangled if m.startswith(prefix) and (len(m) == len(prefix) or not m[len(prefix)].islower() or m[len(prefix)] in "lv")]
+        if len(hits) != 1:
+            raise AttributeError(f"{name}: {len(hits)} mangled candidates in {self.lib._name}")
+        return getattr(self.lib, hits[0])
+
     def _call(self, name, *args):
-        fn = getattr(self.lib, name)
+        fn = self._symbol(name)
         fn.restype = C.c_int
         rc = fn(*args)
         if rc != 0:
@@ -249,6 +267,31 @@ class Oracle:
         op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
         self._call("sshex8_stencil_element_matrix_apply3", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32),
                    m.ctypes.data_as(C.POINTER(self.crt)), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
+    def tet4_linear_elasticity_apply_points(self, elements, points, mu, lam, u, nnodes):
+        """tet4_linear_elasticity_apply (operators/tet4/tet4_linear_elasticity.cpp:86-160): adjugate from the points in scalar_t"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        u, _ = self._r(u)
+        out = np.zeros_like(u)
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("tet4_linear_elasticity_apply", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3),
+                   op[0], op[1], op[2])
+        return out
+
+    def tet4_linear_elasticity_diag_points(self, elements, points, mu, lam, nnodes):
+        """tet4_linear_elasticity_diag (:162-230)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 3, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call("tet4_linear_elasticity_diag", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
     def hex8_laplacian_diag(self, elements, points, nnodes):

@@ -144,8 +144,12 @@ OpBase *make_sshex8_linear_elasticity(int level, ptrdiff_t ne, ptrdiff_t nn, con
                                       const float *adjugate, const float *determinant, double mu, double lambda,
                                       int real_type);
 
+OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
+                                    const float *determinant, double mu, double lambda, int real_type);
 OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
                                         int real_type);
+OpBase *make_tet4_le_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
+                                 double lambda, int real_type);
 OpBase *make_hex8_le_isoparametric(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
                                    double lambda, int real_type);
 OpBase *make_sshex8_nonaffine_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,

@@ -155,6 +155,203 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// tet4 linear elasticity from the cached adjugate / determinant: tet4_linear_elasticity_apply_opt
+// (operators/tet4/tet4_linear_elasticity.cpp:237-300; local kernel tet4_linear_elasticity_apply_adj,
+// tet4_linear_elasticity_inline_cpu.hpp:8-90). Constant strain: H = G adj / det with G[b][c] = u_b(v_{c+1}) - u_b(v_0),
+// P = (lambda tr(H) I + mu (H + H^T)) adj^T / 6, out_b(v_{c+1}) = P[b][c], out_b(v_0) = -sum_c P[b][c].
+template <typename T>
+__device__ __forceinline__ void tet4_le_local(const T A[9], const T det, const T mu, const T lambda, const T (&u)[4][3], T (&o)[4][3]) {
+    const T idet = T(1) / det;
+    T H[9];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const T g0 = u[1][b] - u[0][b], g1 = u[2][b] - u[0][b], g2 = u[3][b] - u[0][b];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) H[b * 3 + k] = idet * (A[k] * g0 + A[3 + k] * g1 + A[6 + k] * g2);
+    }
+    const T sixth = T(1.0 / 6.0);
+    const T ltr = lambda * (H[0] + H[4] + H[8]);
+    T S[9];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) S[b * 3 + k] = sixth * (mu * (H[b * 3 + k] + H[k * 3 + b]) + (b == k ? ltr : T(0)));
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        T sum = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const T p = A[c * 3] * S[b * 3] + A[c * 3 + 1] * S[b * 3 + 1] + A[c * 3 + 2] * S[b * 3 + 2];
+            o[c + 1][b] = p;
+            sum += p;
+        }
+        o[0][b] = -sum;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    tet4_le_apply_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ adjugate,
+                         const float *__restrict__ determinant, const T mu, const T lambda, const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
+        const T det = (T)ldg_stream(&determinant[e]);
+        T ul[4][3], ol[4][3];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) ul[v][b] = u[(ptrdiff_t)ev[v] * 3 + b];
+        tet4_le_local(A, det, mu, lambda, ul, ol);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) red_add(&y[(ptrdiff_t)ev[v] * 3 + b], ol[v][b]);
+    }
+}
+
+// diagonal: row (v, b) of the 12 x 12 element matrix applied to its own unit vector
+template <typename T>
+__global__ void __launch_bounds__(256)
+    tet4_le_diag_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ adjugate,
+                        const float *__restrict__ determinant, const T mu, const T lambda, T *__restrict__ diag) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)adjugate[k * ne + e];
+        const T det = (T)determinant[e];
+        for (int v = 0; v < 4; ++v) {
+            for (int b = 0; b < 3; ++b) {
+                T ul[4][3], ol[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) ul[i][c] = T(0);
+                ul[v][b] = T(1);
+                tet4_le_local(A, det, mu, lambda, ul, ol);
+                red_add(&diag[(ptrdiff_t)elements[v * ne + e] * 3 + b], ol[v][b]);
+            }
+        }
+    }
+}
+
+// tet4_linear_elasticity_apply / _diag (operators/tet4/tet4_linear_elasticity.cpp:86-160, 162-230): adjugate and determinant
+// recomputed from the points in the vector precision (tet4_adjugate_and_det_s), then the same local operator
+template <typename T, bool DIAG>
+__global__ void __launch_bounds__(256)
+    tet4_le_points_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                          const T mu, const T lambda, const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        T J[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const T p0 = (T)points[(size_t)r * nn + ev[0]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[r * 3 + c] = (T)points[(size_t)r * nn + ev[c + 1]] - p0;
+        }
+        T A[9];
+        A[0] = J[4] * J[8] - J[5] * J[7];
+        A[1] = J[2] * J[7] - J[1] * J[8];
+        A[2] = J[1] * J[5] - J[2] * J[4];
+        A[3] = J[5] * J[6] - J[3] * J[8];
+        A[4] = J[0] * J[8] - J[2] * J[6];
+        A[5] = J[2] * J[3] - J[0] * J[5];
+        A[6] = J[3] * J[7] - J[4] * J[6];
+        A[7] = J[1] * J[6] - J[0] * J[7];
+        A[8] = J[0] * J[4] - J[1] * J[3];
+        const T det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+        T ul[4][3], ol[4][3];
+        if (DIAG) {
+            for (int v = 0; v < 4; ++v) {
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) ul[i][c] = T(0);
+                    ul[v][b] = T(1);
+                    tet4_le_local(A, det, mu, lambda, ul, ol);
+                    red_add(&y[(ptrdiff_t)ev[v] * 3 + b], ol[v][b]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) ul[v][b] = u[(ptrdiff_t)ev[v] * 3 + b];
+            tet4_le_local(A, det, mu, lambda, ul, ol);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) red_add(&y[(ptrdiff_t)ev[v] * 3 + b], ol[v][b]);
+        }
+    }
+}
+
+struct Tet4LinearElasticity final : OpBase {
+    DeviceArray<int32_t> elements;  // [4][ne]
+    DeviceArray<float> adjugate;    // SoA [9][ne]
+    DeviceArray<float> determinant;
+    double mu = 1, lambda = 1;
+    template <typename T>
+    int apply_t(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        tet4_le_apply_kernel<T><<<grid, 256, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (T)mu, (T)lambda, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * 3 * real_type, s));
+        return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, s) : apply_t<float>((const float *)x, (float *)y, s);
+    }
+    int diag(void *d, cudaStream_t s) override {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        if (real_type == B200FEM_F64)
+            tet4_le_diag_kernel<double><<<grid, 256, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, mu, lambda, (double *)d);
+        else
+            tet4_le_diag_kernel<float><<<grid, 256, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (float)mu, (float)lambda, (float *)d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+};
+
+OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
+                                    const float *determinant, double mu, double lambda, int real_type) {
+    if (!check_indices(4, ne, nn, elements)) {
+        set_error("tet4 linear elasticity: node index out of range");
+        return nullptr;
+    }
+    auto *op = new Tet4LinearElasticity();
+    op->elem_type = B200FEM_TET4;
+    op->real_type = real_type;
+    op->block_size = 3;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = 4;
+    op->geom_bytes_per_elem = 40;
+    op->mu = mu;
+    op->lambda = lambda;
+    std::vector<int32_t> el((size_t)4 * ne);
+    for (int v = 0; v < 4; ++v) std::copy(elements[v], elements[v] + ne, el.begin() + (size_t)v * ne);
+    std::vector<float> a((size_t)9 * ne);
+    for (ptrdiff_t e = 0; e < ne; ++e)
+        for (int k = 0; k < 9; ++k) a[(size_t)k * ne + e] = adjugate[e * 9 + k];
+    if (op->elements.upload(el.data(), el.size()) || op->adjugate.upload(a.data(), a.size()) || op->determinant.upload(determinant, (size_t)ne)) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
 struct PointsOp final : OpBase {
     DeviceArray<int32_t> elements;  // SoA [nxe][ne]
     DeviceArray<float> points;      // [3][nn]
@@ -164,7 +361,10 @@ struct PointsOp final : OpBase {
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         if (ne == 0) return B200FEM_SUCCESS;
-        if (elasticity) {
+        if (elasticity && nxe == 4) {
+            const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+            tet4_le_points_kernel<T, false><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (T)mu, (T)lambda, x, y);
+        } else if (elasticity) {
             const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
             hex8_le_isoparametric_kernel<T><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, (T)mu, (T)lambda, x, y);
         } else {
@@ -177,6 +377,17 @@ struct PointsOp final : OpBase {
     int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
         if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * block_size * real_type, s));
         return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, s) : apply_t<float>((const float *)x, (float *)y, s);
+    }
+    int diag(void *d, cudaStream_t s) override {
+        if (!(elasticity && nxe == 4)) return OpBase::diag(d, s);
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        if (real_type == B200FEM_F64)
+            tet4_le_points_kernel<double, true><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, mu, lambda, nullptr, (double *)d);
+        else
+            tet4_le_points_kernel<float, true><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float)mu, (float)lambda, nullptr, (float *)d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
     }
     int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
 };
@@ -209,6 +420,20 @@ OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_
                                         int real_type) {
     OpBase *op = make_points_op(4, ne, nn, elements, points, real_type, "tet4 laplacian (from points)");
     if (op) op->elem_type = B200FEM_TET4;
+    return op;
+}
+
+OpBase *make_tet4_le_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
+                                 double lambda, int real_type) {
+    OpBase *op = make_points_op(4, ne, nn, elements, points, real_type, "tet4 linear elasticity (from points)");
+    if (op) {
+        auto *p = static_cast<PointsOp *>(op);
+        p->elem_type = B200FEM_TET4;
+        p->block_size = 3;
+        p->elasticity = true;
+        p->mu = mu;
+        p->lambda = lambda;
+    }
     return op;
 }
 

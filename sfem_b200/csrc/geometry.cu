@@ -101,6 +101,30 @@ __global__ void hex8_adjugate_kernel(const ptrdiff_t ne, const int32_t *__restri
     }
 }
 
+// tet4_adjugate_and_det (operators/tet4/tet4_inline_cpu.hpp:285-380): J[r][c] = x_r(v_{c+1}) - x_r(v_0), adjugate = det J^-1
+__global__ void tet4_adjugate_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ px,
+                                     const float *__restrict__ py, const float *__restrict__ pz, float *__restrict__ adjugate,
+                                     float *__restrict__ determinant) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = elements[v * ne + e];
+        double J[9];
+        const float *P[3] = {px, py, pz};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double p0 = P[r][ev[0]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[r * 3 + c] = (double)P[r][ev[c + 1]] - p0;
+        }
+        double A[9], det;
+        adjugate3(J, A, det);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) adjugate[e * 9 + k] = (float)A[k];
+        determinant[e] = (float)det;
+    }
+}
+
 struct GeomInputs {
     DeviceArray<int32_t> elements;
     DeviceArray<float> points;  // [3][nn]
@@ -159,16 +183,20 @@ int b200fem_fff_fill(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t
 
 int b200fem_adjugate_and_det_fill(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                                   const float *const *points, float *adjugate, float *determinant) {
-    if (element_type != B200FEM_HEX8 && element_type != B200FEM_SSHEX8) B2_FAIL("adjugate_and_det_fill: hex8/sshex8 only");
+    if (element_type != B200FEM_HEX8 && element_type != B200FEM_SSHEX8 && element_type != B200FEM_TET4)
+        B2_FAIL("adjugate_and_det_fill: tet4 / hex8 / sshex8 only");
     if (ne == 0) return B200FEM_SUCCESS;
     if (!elements || !points || !adjugate || !determinant) B2_FAIL("adjugate_and_det_fill: NULL argument");
     GeomInputs in;
-    if (in.upload(8, ne, nn, elements, points)) return B200FEM_FAILURE;
+    if (in.upload(element_type == B200FEM_TET4 ? 4 : 8, ne, nn, elements, points)) return B200FEM_FAILURE;
     DeviceArray<float> adj, det;
     if (adj.alloc((size_t)ne * 9) || det.alloc((size_t)ne)) return B200FEM_FAILURE;
     const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
     const float *px = in.points.ptr, *py = px + nn, *pz = py + nn;
-    hex8_adjugate_kernel<<<grid, 256>>>(ne, in.elements.ptr, px, py, pz, adj.ptr, det.ptr);
+    if (element_type == B200FEM_TET4)
+        tet4_adjugate_kernel<<<grid, 256>>>(ne, in.elements.ptr, px, py, pz, adj.ptr, det.ptr);
+    else
+        hex8_adjugate_kernel<<<grid, 256>>>(ne, in.elements.ptr, px, py, pz, adj.ptr, det.ptr);
     B2_CHECK_LAUNCH();
     B2_CUDA(cudaMemcpy(adjugate, adj.ptr, adj.bytes(), cudaMemcpyDeviceToHost));
     B2_CUDA(cudaMemcpy(determinant, det.ptr, det.bytes(), cudaMemcpyDeviceToHost));

@@ -221,6 +221,7 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
     if (ne > 0 && (!adjugate || !determinant)) B2_FAIL("adjugate/determinant is NULL");
     OpBase *impl = nullptr;
     switch (element_type) {
+        case B200FEM_TET4: impl = make_tet4_linear_elasticity(ne, nn, elements, adjugate, determinant, mu, lambda, real_type); break;
         case B200FEM_HEX8: impl = make_hex8_linear_elasticity(ne, nn, elements, adjugate, determinant, mu, lambda, real_type); break;
         case B200FEM_SSHEX8:
             if (level < 2) B2_FAIL("sshex8 level must be >= 2");
@@ -254,8 +255,10 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
     (void)level;
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
     if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
-    if (element_type != B200FEM_HEX8) B2_FAIL("linear elasticity from points: hex8 (hex8_linear_elasticity_apply, isoparametric) only");
-    OpBase *impl = make_hex8_le_isoparametric(ne, nn, elements, points, mu, lambda, real_type);
+    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4)
+        B2_FAIL("linear elasticity from points: tet4 (tet4_linear_elasticity_apply) and hex8 (hex8_linear_elasticity_apply, isoparametric) only");
+    OpBase *impl = element_type == B200FEM_TET4 ? make_tet4_le_from_points(ne, nn, elements, points, mu, lambda, real_type)
+                                                : make_hex8_le_isoparametric(ne, nn, elements, points, mu, lambda, real_type);
     if (!impl) return B200FEM_FAILURE;
     *op = new b200fem_op_s{impl};
     return B200FEM_SUCCESS;

@@ -183,3 +183,39 @@ def test_sshex8_em_linear_elasticity(oracles, real, level):
     # == the matrix-free macro-adjugate operator
     assert _rel(y.cpu().numpy(), orc.sshex8_linear_elasticity_apply(level, m["elements"], adj, det, mu, lam, u, nn)) < (
         1e-11 if real == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_tet4_linear_elasticity(oracles, real):
+    """tet4 linear elasticity: from the points like the reference's tet4_linear_elasticity_apply /
+    _diag (operators/tet4/tet4_linear_elasticity.cpp:86-230), and from a cached fp32 adjugate (b200fem_adjugate_and_det_fill +
+    b200fem_linear_elasticity_create with TET4; exact on dyadic geometry)."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    mu, lam = 1.3, 0.7
+    el, pts = mesh.box_tet4(7, 6, 8)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    op = lib.linear_elasticity_from_points(lib.TET4, el, pts, mu, lam, nn, _dt(real))
+    u = np.random.default_rng(11).uniform(-1, 1, nn * 3)
+    x, y = _apply(op, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.tet4_linear_elasticity_apply_points(el, pts, mu, lam, u, nn)) < TOL[real]
+    d = torch.zeros(nn * 3, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    assert _rel(d.cpu().numpy(), orc.tet4_linear_elasticity_diag_points(el, pts, mu, lam, nn)) < TOL[real]
+    x, y = _apply(op, np.tile(np.array([0.3, -1.2, 0.5]), nn), _dt(real))  # rigid translation
+    assert float(y.abs().max()) < (1e-12 if real == "f64" else 1e-4)
+    # cached adjugate, dyadic geometry: identical to the from-points operator
+    el, pts = mesh.box_tet4(5, 6, 4, 4.0, 5.0, 3.0)
+    pts = mesh.shear_points(pts, 0.25, 0.5, 0.125)
+    nn = pts.shape[1]
+    adj, det = lib.adjugate_and_det_fill(lib.TET4, el, pts)
+    opc = lib.linear_elasticity(lib.TET4, el, adj, det, mu, lam, nn, _dt(real))
+    u = np.random.default_rng(12).uniform(-1, 1, nn * 3)
+    x, y = _apply(opc, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.tet4_linear_elasticity_apply_points(el, pts, mu, lam, u, nn)) < TOL[real]
+    d = torch.zeros(nn * 3, dtype=_dt(real), device="cuda")
+    opc.diag(d)
+    assert _rel(d.cpu().numpy(), orc.tet4_linear_elasticity_diag_points(el, pts, mu, lam, nn)) < TOL[real]

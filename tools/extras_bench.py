@@ -48,7 +48,7 @@ def _entry(name, rows, alg_bytes, ms, extra=None):
     return d
 
 
-def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "transfer", "blas")):
+def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "em", "transfer", "blas")):
     from sfem_b200 import lib, mesh
 
     out = []
@@ -142,6 +142,36 @@ def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "transfer",
                                   nn * vs * 8.0 + m["elements"].size * 4.0, ms))
                 del f, c
             del tr
+        del m
+    if "em" in which:
+        # stored-element-matrix semi-structured operators (ss:em:Laplacian / ss:em:LinearElasticity): the reference's fastest
+        # published GPU formulation (24.6 - 38 GDOF/s on its hardware, notebook/SEMISTRUCTURED.md). B_alg counts the stored
+        # matrix as the geometry stream: (8 bs)^2 reals per macro element.
+        m = mesh.sshex8_box(8, 64, 64, 64, with_points=False)
+        nn = m["n_nodes"]
+        fff = lib.fff_fill(lib.HEX8, m["m_elements"], m["m_points"])
+        for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            M = lib.sshex8_laplacian_element_matrix(8, fff, dt)
+            op = lib.sshex8_em(8, m["elements"], M, 1, nn, dt)
+            x = torch.rand(nn, dtype=dt, device="cuda")
+            y = torch.zeros_like(x)
+            ms = _time(lambda: op.apply_overwrite(x, y), torch, steps=10)
+            out.append(_entry(f"ss:em:Laplacian L8 {rt} 64^3 macro (stored 8x8 per macro element, y = A x)", nn, op.algorithmic_bytes, ms))
+            del op, x, y
+        del m
+        mm = 44
+        m = mesh.sshex8_box(8, mm, mm, mm, with_points=False)
+        nn = m["n_nodes"]
+        adj, det = lib.adjugate_and_det_fill(lib.HEX8, m["m_elements"], m["m_points"])
+        for rt, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            K = lib.sshex8_linear_elasticity_element_matrix(8, adj, det, 1.0, 1.0, dt)
+            op = lib.sshex8_em(8, m["elements"], K, 3, nn, dt)
+            x = torch.rand(nn * 3, dtype=dt, device="cuda")
+            y = torch.zeros_like(x)
+            ms = _time(lambda: op.apply_overwrite(x, y), torch, steps=5)
+            out.append(_entry(f"ss:em:LinearElasticity L8 {rt} {mm}^3 macro (stored 24x24 per macro element, y = A x)", nn * 3,
+                              op.algorithmic_bytes, ms, {"fp_ops_TFLOPs": 2.0 * 576 * 512 * m["elements"].shape[1] / ms / 1e9}))
+            del op, x, y
         del m
     if "blas" in which:
         from sfem_b200.lib import blas
