@@ -199,10 +199,17 @@ template <typename T>
 struct Hex8LaplacianLocal {
     const float *fff;  // SoA [6][ne]
     ptrdiff_t ne;
-    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[8], T (&out)[8]) const {
+    struct Geo {
+        float f[6];
+    };
+    __device__ __forceinline__ void load(const ptrdiff_t e, Geo &g) const {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g.f[k] = ldg_stream(&fff[k * ne + e]);
+    }
+    __device__ __forceinline__ void compute(const Geo &g, const T (&uin)[8], T (&out)[8]) const {
         T f[6], ul[8], ol[8];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+        for (int k = 0; k < 6; ++k) f[k] = (T)g.f[k];
 #pragma unroll
         for (int v = 0; v < 8; ++v) ul[kVtkToLex[v]] = uin[v];
         hex8_laplacian_local(f, ul, ol);
@@ -217,11 +224,19 @@ struct Hex8LinearElasticityLocal {
     const float *determinant;  // [ne]
     ptrdiff_t ne;
     T mu, lambda;
-    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[24], T (&out)[24]) const {
+    struct Geo {
+        float a[9], det;
+    };
+    __device__ __forceinline__ void load(const ptrdiff_t e, Geo &g) const {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g.a[k] = ldg_stream(&adjugate[k * ne + e]);
+        g.det = ldg_stream(&determinant[e]);
+    }
+    __device__ __forceinline__ void compute(const Geo &g, const T (&uin)[24], T (&out)[24]) const {
         T A[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
-        const T det = (T)ldg_stream(&determinant[e]);
+        for (int k = 0; k < 9; ++k) A[k] = (T)g.a[k];
+        const T det = (T)g.det;
         T c[3][8], O[3][8];
 #pragma unroll
         for (int v = 0; v < 8; ++v)

@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(BT)
 #pragma unroll
                 for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[jj[v] * BS + a];
             }
-            local(e0 + e, uin, out);
+            typename Local::Geo geo;
+            local.load(e0 + e, geo);
+            local.compute(geo, uin, out);
 #pragma unroll
             for (int v = 0; v < NXE; ++v)
 #pragma unroll
@@ -199,67 +201,6 @@ __global__ void __launch_bounds__(BT)
     }
 }
 
-// The direct form: index lists read from global memory inside the phases, 36 KB (tet4) of shared memory per CTA. Lower
-// latency tolerance per CTA, but 5 CTAs per SM: for the light operators (tet4 / hex8 Laplacian, ~45 - 90 flop per element,
-// the FFF stream is 60 % of the bytes and is read by the element phase itself) the extra CTAs keep more bytes in flight
-// than the staged kernel below does with its 2 CTAs, and it measures faster there (tet4 260^3: 1.56 against 2.07 ms).
-template <typename T, int NXE, int BS, int E, int BT, class Local>
-__global__ void __launch_bounds__(BT)
-    patch_apply_direct_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
-    extern __shared__ __align__(16) unsigned char patch_smem[];
-    T *xs = reinterpret_cast<T *>(patch_smem);   // [max_u][BS]
-    T *contrib = xs + (size_t)max_u * BS;         // [BS][NXE][E]
-    const int tid = threadIdx.x;
-    for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
-        const int64_t u0 = p.chunk_uoff[c];
-        const int U = p.chunk_u[c];
-        const ptrdiff_t e0 = c * E;
-        const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
-        // 1. stage the unique nodes' values
-        for (int j = tid; j < U; j += BT) {
-            const ptrdiff_t node = p.unodes[u0 + j];
-#pragma unroll
-            for (int a = 0; a < BS; ++a) xs[j * BS + a] = u[node * BS + a];
-        }
-        __syncthreads();
-        // 2. element operator from shared memory into per-element slots
-        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
-        for (int e = tid; e < nel; e += BT) {
-            T uin[NXE * BS], out[NXE * BS];
-#pragma unroll
-            for (int v = 0; v < NXE; ++v) {
-                const int j = ldg_stream(&li[v * E + e]);
-#pragma unroll
-                for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[j * BS + a];
-            }
-            local(e0 + e, uin, out);
-#pragma unroll
-            for (int v = 0; v < NXE; ++v)
-#pragma unroll
-                for (int a = 0; a < BS; ++a) contrib[(a * NXE + v) * E + e] = out[v * BS + a];
-        }
-        __syncthreads();
-        // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
-        const uint16_t *ns = p.nslot + (size_t)c * NXE * E;
-        const uint16_t *no = p.noff + u0;
-        for (int j = tid; j < U; j += BT) {
-            const int b = no[j], eend = no[j + 1];
-            T acc[BS];
-#pragma unroll
-            for (int a = 0; a < BS; ++a) acc[a] = T(0);
-            for (int s = b; s < eend; ++s) {
-                const int slot = ldg_stream(&ns[s]);
-#pragma unroll
-                for (int a = 0; a < BS; ++a) acc[a] += contrib[a * NXE * E + slot];
-            }
-            const ptrdiff_t node = p.unodes[u0 + j];
-#pragma unroll
-            for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], acc[a]);
-        }
-        __syncthreads();
-    }
-}
-
 __device__ __forceinline__ void patch_cp16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -269,6 +210,97 @@ __device__ __forceinline__ void patch_cp_value(T *smem, const T *gmem) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+// The direct form: index lists read from global memory inside the phases, 36 KB (tet4) of shared memory per CTA. Lower
+// latency tolerance per CTA, but 5 CTAs per SM: for the light operators (tet4 / hex8 Laplacian, ~45 - 90 flop per element,
+// the FFF stream is 60 % of the bytes and is read by the element phase itself) the extra CTAs keep more bytes in flight
+// than the staged kernel below does with its 2 CTAs, and it measures faster there (tet4 260^3: 1.56 against 2.07 ms).
+// STAGE_LISTS: the incidence lists of phase 3 (slots + CSR offsets) are copied into shared memory by cp.async at the start
+// of the patch and land behind phases 1 and 2, so the per-node walk of phase 3 reads shared memory instead of a chain of
+// dependent global loads (24 per node for tet4).
+template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false>
+__global__ void __launch_bounds__(BT)
+    patch_apply_direct_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
+    extern __shared__ __align__(16) unsigned char patch_smem[];
+    constexpr int NC = NXE * E;
+    uint16_t *s_ns = reinterpret_cast<uint16_t *>(patch_smem);  // [NC] + [up] when STAGE_LISTS
+    const int up = (max_u + 1 + 7) / 8 * 8;
+    uint16_t *s_no = s_ns + NC;
+    T *xs = reinterpret_cast<T *>(patch_smem + (STAGE_LISTS ? ((size_t)NC + up) * 2 : 0));   // [max_u][BS]
+    T *contrib = xs + (size_t)max_u * BS;         // [BS][NXE][E]
+    const int tid = threadIdx.x;
+    for (ptrdiff_t c = blockIdx.x; c < p.nchunks; c += gridDim.x) {
+        const int64_t u0 = p.chunk_uoff[c];
+        const int U = p.chunk_u[c];
+        const ptrdiff_t e0 = c * E;
+        const int nel = (int)((p.ne - e0) < (ptrdiff_t)E ? (p.ne - e0) : (ptrdiff_t)E);
+        if (STAGE_LISTS) {
+            const int4 *g_ns = reinterpret_cast<const int4 *>(p.nslot + (size_t)c * NC);
+            const int4 *g_no = reinterpret_cast<const int4 *>(p.noff + u0);
+            for (int i = tid; i < NC * 2 / 16; i += BT) patch_cp16(reinterpret_cast<int4 *>(s_ns) + i, g_ns + i);
+            for (int i = tid; i < ((U + 1) * 2 + 15) / 16; i += BT) patch_cp16(reinterpret_cast<int4 *>(s_no) + i, g_no + i);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        // 1. stage the unique nodes' values
+        for (int j = tid; j < U; j += BT) {
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) xs[j * BS + a] = u[node * BS + a];
+        }
+        __syncthreads();
+        // 2. element operator from shared memory into per-element slots
+        // (fully unrolled over the E / BT elements of a thread, indices clamped instead of predicated: the index and
+        // geometry loads of all of them are issued together instead of one global round trip per element; a clamped
+        // duplicate recomputes the last element and rewrites its slots with the same values)
+        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
+        static_assert(E % BT == 0, "a patch is a whole number of elements per thread");
+        constexpr int EPT = E / BT;
+        typename Local::Geo geo[EPT];
+        int jj[EPT][NXE];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int e = min(tid + k * BT, nel - 1);
+            local.load(e0 + e, geo[k]);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) jj[k][v] = ldg_stream(&li[v * E + e]);
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int e = min(tid + k * BT, nel - 1);
+            T uin[NXE * BS], out[NXE * BS];
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) {
+#pragma unroll
+                for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[jj[k][v] * BS + a];
+            }
+            local.compute(geo[k], uin, out);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v)
+#pragma unroll
+                for (int a = 0; a < BS; ++a) contrib[(a * NXE + v) * E + e] = out[v * BS + a];
+        }
+        if (STAGE_LISTS) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
+        const uint16_t *ns = STAGE_LISTS ? s_ns : p.nslot + (size_t)c * NXE * E;
+        const uint16_t *no = STAGE_LISTS ? s_no : p.noff + u0;
+        for (int j = tid; j < U; j += BT) {
+            const int b = no[j], eend = no[j + 1];
+            T acc[BS];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) acc[a] = T(0);
+            for (int s = b; s < eend; ++s) {
+                const int slot = STAGE_LISTS ? (int)ns[s] : (int)ldg_stream(&ns[s]);
+#pragma unroll
+                for (int a = 0; a < BS; ++a) acc[a] += contrib[a * NXE * E + slot];
+            }
+            const ptrdiff_t node = p.unodes[u0 + j];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) red_add(&y[node * BS + a], acc[a]);
+        }
+        __syncthreads();
+    }
 }
 
 // Software-pipelined patch kernel. The first version of this kernel read its index lists (local corner indices, incidence
@@ -353,6 +385,8 @@ __global__ void __launch_bounds__(BT)
         // 2. element operator from shared memory into per-element slots
         const uint16_t *li = st_lidx(si);
         for (int e = tid; e < nel; e += BT) {
+            typename Local::Geo geo;
+            local.load(e0 + e, geo);
             T uin[NXE * BS], out[NXE * BS];
 #pragma unroll
             for (int v = 0; v < NXE; ++v) {
@@ -360,7 +394,7 @@ __global__ void __launch_bounds__(BT)
 #pragma unroll
                 for (int a = 0; a < BS; ++a) uin[v * BS + a] = xs[j * BS + a];
             }
-            local(e0 + e, uin, out);
+            local.compute(geo, uin, out);
 #pragma unroll
             for (int v = 0; v < NXE; ++v)
 #pragma unroll
@@ -404,10 +438,11 @@ int launch_patch_apply_smem_atomic(const PatchPlan &plan, const Local &local, co
     return B200FEM_SUCCESS;
 }
 
-template <typename T, int NXE, int BS, int E, int BT, class Local>
+template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false>
 int launch_patch_apply_direct(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
-    auto kern = patch_apply_direct_kernel<T, NXE, BS, E, BT, Local>;
-    const size_t smem = ((size_t)plan.max_u * BS + (size_t)NXE * BS * E) * sizeof(T);
+    auto kern = patch_apply_direct_kernel<T, NXE, BS, E, BT, Local, STAGE_LISTS>;
+    const size_t smem = ((size_t)plan.max_u * BS + (size_t)NXE * BS * E) * sizeof(T) +
+                        (STAGE_LISTS ? ((size_t)NXE * E + (size_t)plan.max_u_pad()) * 2 : 0);
     static SmemOptIn opt;
     if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
     if (plan.nchunks == 0) return B200FEM_SUCCESS;

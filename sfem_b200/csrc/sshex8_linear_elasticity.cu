@@ -33,13 +33,17 @@ namespace b200fem {
 static constexpr int kLEExplicit = 0;
 static constexpr int kLEBoxes = 1;
 
-template <int L>
+template <int L, int EPB_ = 0>
 struct Sshex8LECfg {
     static constexpr int N = L + 1;
     static constexpr int NXE = N * N * N;
     static constexpr int H = L / 2;            // micro elements per direction and colour
     static constexpr int TPE = H * H * H;      // threads per macro element
-    static constexpr int EPB = (L == 8) ? 6 : (L == 4 ? 16 : 64);  // macro elements per CTA batch
+    // macro elements per CTA batch. L = 8: a 6-element tile fills the SM with ONE CTA whose 12 warps pass through gather,
+    // compute and scatter together (memory idle while the FP64 pipe works and vice versa); 2- or 3-element tiles give 3 / 2
+    // independent CTAs per SM that drift apart and overlap their phases (EPB_ = 0: the default of the level)
+    static constexpr int EPB = EPB_ ? EPB_ : ((L == 8) ? 6 : (L == 4 ? 16 : 64));
+    static constexpr int MIN_CTAS = (L == 8) ? 6 / EPB : 1;
     static constexpr int BT = TPE * EPB;
     // Shared-memory tile layout: index = z * PZ + y * N + xi(x) with the even x of a row first and the odd x behind
     // them (xi(x) = (x & 1) * XE + x / 2) and PZ = N^2 padded to 2 (mod 8). The threads of a half-warp are the (i, k)
@@ -55,12 +59,12 @@ struct Sshex8LECfg {
     static_assert(L % 2 == 0, "parity colouring needs an even level");
 };
 
-template <typename T, int L, int MODE, bool PLAIN_INTERIOR>
-__global__ void __launch_bounds__(Sshex8LECfg<L>::BT, 1)
+template <typename T, int L, int MODE, bool PLAIN_INTERIOR, int EPB_ = 0>
+__global__ void __launch_bounds__(Sshex8LECfg<L, EPB_>::BT, Sshex8LECfg<L, EPB_>::MIN_CTAS)
     sshex8_le_apply_kernel(const ptrdiff_t ne, const int32_t *__restrict__ idx_aos, const BoxDesc *__restrict__ boxes,
                            const float *__restrict__ adjugate, const float *__restrict__ determinant, const T mu,
                            const T lambda, const T *__restrict__ u, T *__restrict__ y) {
-    using Cfg = Sshex8LECfg<L>;
+    using Cfg = Sshex8LECfg<L, EPB_>;
     constexpr int N = Cfg::N, NXE = Cfg::NXE, H = Cfg::H, TPE = Cfg::TPE, EPB = Cfg::EPB, BT = Cfg::BT;
     constexpr int PZ = Cfg::PZ, CS = Cfg::CS;
     constexpr int ES = 3 * CS;  // values per element tile
@@ -217,11 +221,27 @@ struct Sshex8LinearElasticity final : OpBase {
     DeviceArray<float> adj, det;
     double mu = 1, lambda = 1;
 
+    int epb = 0;  // L = 8 only: macro elements per CTA tile (1, 2, 3, 6); 0 = the measured best for the precision
+
     template <typename T, int L, int MODE, bool PLAIN>
     int launch(const T *x, T *y, cudaStream_t s) {
-        using Cfg = Sshex8LECfg<L>;
+        if constexpr (L == 8) {
+            // default: 1-element tiles in fp64 (2.53 ms at the C5 shard against 2.59 / 2.74 / 3.21 for 2 / 3 / 6), 3 in fp32
+            // (2.25 ms against 2.51 / 2.41 / 2.44 for 1 / 2 / 6): profiles/r02n_le_sweep.jsonl
+            const int e = epb ? epb : (sizeof(T) == 8 ? 1 : 3);
+            if (e == 1) return launch_epb<T, L, MODE, PLAIN, 1>(x, y, s);
+            if (e == 2) return launch_epb<T, L, MODE, PLAIN, 2>(x, y, s);
+            if (e == 3) return launch_epb<T, L, MODE, PLAIN, 3>(x, y, s);
+            return launch_epb<T, L, MODE, PLAIN, 6>(x, y, s);
+        }
+        return launch_epb<T, L, MODE, PLAIN, 0>(x, y, s);
+    }
+
+    template <typename T, int L, int MODE, bool PLAIN, int EPB_>
+    int launch_epb(const T *x, T *y, cudaStream_t s) {
+        using Cfg = Sshex8LECfg<L, EPB_>;
         const size_t smem = (size_t)Cfg::EPB * 2 * 3 * Cfg::CS * sizeof(T) + (MODE == kLEBoxes ? (size_t)Cfg::EPB * 27 * sizeof(BoxDesc) : 0);
-        auto kern = sshex8_le_apply_kernel<T, L, MODE, PLAIN>;
+        auto kern = sshex8_le_apply_kernel<T, L, MODE, PLAIN, EPB_>;
         static SmemOptIn opt;
         if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
         const ptrdiff_t nbatches = (ne + Cfg::EPB - 1) / Cfg::EPB;
@@ -286,6 +306,11 @@ struct Sshex8LinearElasticity final : OpBase {
         return 1 + (overwrite ? (int)std::max<size_t>(zero_ranges.size(), 1) : 0);
     }
     int set_option(const char *key, int value) override {
+        if (!strcmp(key, "epb")) {
+            if (value != 0 && value != 1 && value != 2 && value != 3 && value != 6) B2_FAIL("epb must be 0 (default), 1, 2, 3 or 6");
+            epb = value;
+            return B200FEM_SUCCESS;
+        }
         if (!strcmp(key, "explicit_index")) {
             if (value)
                 mode = kLEExplicit;

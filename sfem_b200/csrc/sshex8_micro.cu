@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -36,7 +37,10 @@ struct MicroCfg {
     static constexpr int H = L / 2;
     static constexpr int TPE = H * H * H;  // threads per macro element = micro elements per colour
     // macro elements per CTA batch: >= 2 warps of work, tile of BS components within ~100 KB
-    static constexpr int EPB = (L == 8) ? (BS == 1 ? 6 : 3) : (L == 4 ? 16 : (BS == 1 ? 64 : 32));
+    // small tiles, several independent CTAs per SM whose gather / compute / scatter phases overlap (the same finding as
+    // for sshex8_le_apply_kernel): bs = 1: 2 elements, 128 threads, 3 CTAs (168 registers); bs = 3: 1 element, 64 threads, 4 CTAs
+    static constexpr int EPB = (L == 8) ? (BS == 1 ? 2 : 1) : (L == 4 ? 16 : (BS == 1 ? 64 : 32));
+    static constexpr int MIN_CTAS = (L == 8) ? (BS == 1 ? 3 : 4) : 1;
     static constexpr int BT = TPE * EPB;
     static constexpr int XE = (N + 1) / 2;
     static constexpr int PZ = (N * N + 5) / 8 * 8 + 2;  // plane stride = 2 (mod 8): see Sshex8LECfg
@@ -47,32 +51,65 @@ struct MicroCfg {
 // ---------------------------------------------------------------------------------------------------------------
 // local operators
 // ---------------------------------------------------------------------------------------------------------------
-// stored matrix, VTK order; ul / ol come in lexicographic corner order (x + 2y + 4z)
+// stored matrix, VTK order; ul / ol come in lexicographic corner order (x + 2y + 4z).
+// bs = 1: the 64 entries of the element's matrix are loaded ONCE into registers (a thread applies it to its 8 micro
+// elements, one per colour): 8 + 16 shared-memory accesses per micro element instead of 64 + 24.
+// bs = 3: 576 entries stay in shared memory and are read as 16-byte warp-wide broadcasts.
 template <typename T, int BS>
 struct MicroMatrixLocal {
     static constexpr int NB = 8 * BS;
     static constexpr int kSlotValues = NB * NB;
+    struct Regs {
+        T m[BS == 1 ? 64 : 1];
+    };
     const T *matrices;  // [ne][NB * NB]
     __device__ __forceinline__ void stage(const ptrdiff_t e, T *slot, const int t, const int nt) const {
         const T *src = matrices + (size_t)e * kSlotValues;
         for (int i = t; i < kSlotValues; i += nt) slot[i] = ldg_stream(&src[i]);
     }
-    __device__ __forceinline__ void apply(const T *slot, int, int, int, const T (&ul)[BS][8], T (&ol)[BS][8]) const {
+    __device__ __forceinline__ void load_regs(const T *slot, Regs &r) const {
+        if constexpr (BS == 1) {
+            // lexicographic on both sides: r.m[li * 8 + lj] = M[vtk(li)][vtk(lj)]
 #pragma unroll
-        for (int c = 0; c < BS; ++c)
+            for (int vi = 0; vi < 8; ++vi)
 #pragma unroll
-            for (int v = 0; v < 8; ++v) ol[c][v] = T(0);
-        // out_j += u_i M[i][j]; i, j = component * 8 + VTK corner
+                for (int vj = 0; vj < 8; ++vj) r.m[kVtkToLex[vi] * 8 + kVtkToLex[vj]] = slot[vi * 8 + vj];
+        }
+    }
+    __device__ __forceinline__ void apply(const Regs &r, const T *slot, int, int, int, const T (&ul)[BS][8], T (&ol)[BS][8]) const {
+        if constexpr (BS == 1) {
 #pragma unroll
-        for (int ci = 0; ci < BS; ++ci) {
+            for (int j = 0; j < 8; ++j) {
+                T acc = ul[0][0] * r.m[j];
 #pragma unroll
-            for (int vi = 0; vi < 8; ++vi) {
-                const T ui = ul[ci][kVtkToLex[vi]];
-                const T *row = slot + (ci * 8 + vi) * NB;
+                for (int i = 1; i < 8; ++i) acc = le_fma(ul[0][i], r.m[i * 8 + j], acc);
+                ol[0][j] = acc;
+            }
+        } else {
+            using V = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
+            constexpr int VW = 16 / (int)sizeof(T);
 #pragma unroll
-                for (int cj = 0; cj < BS; ++cj)
+            for (int c = 0; c < BS; ++c)
 #pragma unroll
-                    for (int vj = 0; vj < 8; ++vj) ol[cj][kVtkToLex[vj]] = le_fma(ui, row[cj * 8 + vj], ol[cj][kVtkToLex[vj]]);
+                for (int v = 0; v < 8; ++v) ol[c][v] = T(0);
+            // out_j += u_i M[i][j]; i, j = component * 8 + VTK corner; a row is NB contiguous values
+#pragma unroll
+            for (int ci = 0; ci < BS; ++ci) {
+#pragma unroll
+                for (int vi = 0; vi < 8; ++vi) {
+                    const T ui = ul[ci][kVtkToLex[vi]];
+                    const V *row = reinterpret_cast<const V *>(slot + (ci * 8 + vi) * NB);
+#pragma unroll
+                    for (int q = 0; q < NB / VW; ++q) {
+                        const V w = row[q];
+                        const T *wv = reinterpret_cast<const T *>(&w);
+#pragma unroll
+                        for (int k = 0; k < VW; ++k) {
+                            const int j = q * VW + k, cj = j / 8, vj = j % 8;
+                            ol[cj][kVtkToLex[vj]] = le_fma(ui, wv[k], ol[cj][kVtkToLex[vj]]);
+                        }
+                    }
+                }
             }
         }
     }
@@ -82,6 +119,8 @@ struct MicroMatrixLocal {
 template <typename T>
 struct NonAffineLaplacianLocal {
     static constexpr int kSlotValues = 24;  // corner coordinates x[8] | y[8] | z[8], VTK order
+    struct Regs {};
+    __device__ __forceinline__ void load_regs(const T *, Regs &) const {}
     const int32_t *idx_aos;                 // [ne][NXE]
     const float *points;                    // [3][nn]
     ptrdiff_t nn;
@@ -131,7 +170,8 @@ struct NonAffineLaplacianLocal {
 #pragma unroll
             for (int j = i; j < 3; ++j) fff[k++] = (A[i * 3] * A[j * 3] + A[i * 3 + 1] * A[j * 3 + 1] + A[i * 3 + 2] * A[j * 3 + 2]) * idet;
     }
-    __device__ __forceinline__ void apply(const T *slot, const int xi, const int yi, const int zi, const T (&ul)[1][8], T (&ol)[1][8]) const {
+    __device__ __forceinline__ void apply(const Regs &, const T *slot, const int xi, const int yi, const int zi, const T (&ul)[1][8],
+                                          T (&ol)[1][8]) const {
         const T h = T(1) / T(level);
         const T q6[6][3] = {{0, .5, .5}, {.5, 0, .5}, {.5, .5, 0}, {.5, .5, 1}, {.5, 1, .5}, {1, .5, .5}};
 #pragma unroll
@@ -170,7 +210,7 @@ struct NonAffineLaplacianLocal {
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int L, int BS, class Local>
-__global__ void __launch_bounds__(MicroCfg<L, BS>::BT, 1)
+__global__ void __launch_bounds__(MicroCfg<L, BS>::BT, MicroCfg<L, BS>::MIN_CTAS)
     sshex8_micro_apply_kernel(const ptrdiff_t ne, const int32_t *__restrict__ idx_aos, const Local local,
                               const T *__restrict__ u, T *__restrict__ y) {
     using Cfg = MicroCfg<L, BS>;
@@ -212,6 +252,8 @@ __global__ void __launch_bounds__(MicroCfg<L, BS>::BT, 1)
             const T *tu = tile_u + slot * ES;
             T *to = tile_o + slot * ES;
             const T *sl = slots + (size_t)slot * Local::kSlotValues;
+            typename Local::Regs regs;
+            if (active) local.load_regs(sl, regs);
 #pragma unroll 1
             for (int colour = 0; colour < 8; ++colour) {
                 if (active) {
@@ -223,7 +265,7 @@ __global__ void __launch_bounds__(MicroCfg<L, BS>::BT, 1)
                     for (int c = 0; c < BS; ++c)
 #pragma unroll
                         for (int v = 0; v < 8; ++v) ul[c][v] = tu[c * CS + base + ((v >> 2) & 1) * PZ + ((v >> 1) & 1) * N + xo[v & 1]];
-                    local.apply(sl, x0, y0, z0, ul, ol);
+                    local.apply(regs, sl, x0, y0, z0, ul, ol);
 #pragma unroll
                     for (int c = 0; c < BS; ++c)
 #pragma unroll

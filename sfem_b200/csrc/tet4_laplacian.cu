@@ -65,10 +65,17 @@ template <typename T>
 struct Tet4LaplacianLocal {
     const float *fff;  // SoA [6][ne]
     ptrdiff_t ne;
-    __device__ __forceinline__ void operator()(const ptrdiff_t e, const T (&uin)[4], T (&out)[4]) const {
+    struct Geo {
+        float f[6];
+    };
+    __device__ __forceinline__ void load(const ptrdiff_t e, Geo &g) const {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g.f[k] = ldg_stream(&fff[k * ne + e]);
+    }
+    __device__ __forceinline__ void compute(const Geo &g, const T (&uin)[4], T (&out)[4]) const {
         T f[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+        for (int k = 0; k < 6; ++k) f[k] = (T)g.f[k];
         const T d1 = uin[1] - uin[0], d2 = uin[2] - uin[0], d3 = uin[3] - uin[0];
         const T w0 = f[0] * d1 + f[1] * d2 + f[2] * d3;
         const T w1 = f[1] * d1 + f[3] * d2 + f[4] * d3;
@@ -101,7 +108,8 @@ struct Tet4Laplacian final : OpBase {
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
     PatchPlan patch;
-    int patch_pipelined = 0;    // 1 = the staged / software-pipelined patch kernel (slower for this light operator)
+    int patch_pipelined = 2;    // 0 = direct, 2 = direct with the incidence lists staged by cp.async (default: 1.47 vs 1.55 ms at
+                                // 260^3), 1 = fully software-pipelined kernel (2 CTAs per SM: slower for this light operator)
     int patch_smem_atomic = 0;  // 1 = shared-memory atomics instead of the incidence lists (order not fixed)
     static constexpr int kPatchE = 1024;
 
@@ -111,7 +119,9 @@ struct Tet4Laplacian final : OpBase {
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) <= 200 * 1024) {
             if (patch_smem_atomic)
                 return launch_patch_apply_smem_atomic<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
-            if (patch_pipelined) return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            if (patch_pipelined == 1) return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            if (patch_pipelined == 2)
+                return launch_patch_apply_direct<T, 4, 1, kPatchE, 256, Tet4LaplacianLocal<T>, true>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             return launch_patch_apply_direct<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         }
         if (scatter == B200FEM_SCATTER_COLORED) {
