@@ -211,7 +211,7 @@ struct Sshex8Laplacian final : OpBase {
     // kernel wins, 0.66 against 0.79 ms), 2 = whenever it applies, 0 = never. The plane-streaming kernel stays the path
     // for everything else (and for the ne % 3 left-over elements).
     int use_ws = 1;
-    int ws_cfg = 0;
+    int ws_cfg = 11;  // 11 = the two-barrier kernel with static accumulator phases, ring depth 3 (0 - 4: the first ws kernel)
     ptrdiff_t range_e0 = 0, range_e1 = -1;  // element range of the stream launch in flight (-1: the whole mesh)
 
     template <typename T, int L, int TW, int NTEAM, int D, bool PLAIN>

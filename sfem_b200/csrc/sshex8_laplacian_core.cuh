@@ -67,6 +67,16 @@ struct Sshex8LaplacianRow {
 
     // fff: the macro element's 6 FFF entries already widened to T (00 01 02 11 12 22)
     B2_HD void init(const T fff[6], const int y_) {
+        set(fff, y_);
+        clear();
+    }
+    B2_HD void clear() {
+#pragma unroll
+        for (int x = 0; x < N; ++x) acc[0][x] = acc[1][x] = acc[2][x] = T(0);
+    }
+    // coefficients only: the accumulators keep their values (callers that carry the last output plane of one element
+    // into the first step of the next)
+    B2_HD void set(const T fff[6], const int y_) {
         y = y_;
         const T h = T(1) / T(L);
         const T Sxx = fff[0] * h, Sxy = fff[1] * h, Sxz = fff[2] * h, Syy = fff[3] * h, Syz = fff[4] * h,
@@ -107,8 +117,6 @@ struct Sshex8LaplacianRow {
             gy[d] = T(0.5) * Sxz * Mt[d] * fy[d];  // times sigma_x sigma_z at use
         }
         gx = T(0.5) * Syz * sy;  // times sigma_z at use
-#pragma unroll
-        for (int x = 0; x < N; ++x) acc[0][x] = acc[1][x] = acc[2][x] = T(0);
     }
 
     // acc[x] += sum_dx cc[dx+1] * r[x+dx] with the x-boundary rule (h0 = r[0]/2, hL = r[L]/2)
@@ -170,6 +178,21 @@ struct Sshex8LaplacianRow {
 #pragma unroll
             for (int x = 0; x < N; ++x) accC[x] *= T(0.5);
         }
+    }
+
+    // The edge terms of a boundary plane (z = 0: sgn2 = -2, z = L: sgn2 = +2) applied in one piece, for callers that run the
+    // plane through the interior-class code (accC pre-doubled for z = L, halved afterwards for both): r0 / rL = the end values
+    // of the three rows, rmid = the dy = 0 row. gx is zero on lanes whose row is not on a y-boundary, so the x-edge taps run
+    // unconditionally.
+    B2_HD void z_boundary_terms(T (&accC)[N], const T sgn2, const T (&r0)[3], const T (&rL)[3], const T (&rmid)[N]) const {
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            accC[0] = b2_fma(-sgn2 * gy[iy], r0[iy], accC[0]);
+            accC[L] = b2_fma(sgn2 * gy[iy], rL[iy], accC[L]);
+        }
+        const T g = gx * sgn2;
+        const T m[3] = {g * T(1.0 / 6.0), g * T(2.0 / 3.0), g * T(1.0 / 6.0)};
+        row_taps(m, rmid, T(0.5) * rmid[0], T(0.5) * rmid[L], accC);
     }
 
     // dense-plane form: `plane` points at this element's plane zp; row yy starts at plane[yy * ystride]

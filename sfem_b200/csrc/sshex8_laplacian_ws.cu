@@ -48,6 +48,23 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     return B200FEM_SUCCESS;
 }
 
+template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, bool BULK = false, int DBG = 0>
+static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg) {
+    constexpr int L = 8;
+    using Cfg = Sshex8WsCfg<T, L, NC, D, D>;
+    auto kern = sshex8_laplacian_ws2_kernel<T, L, NC, D, PLAIN, PHASED, BULK, DBG>;
+    static SmemOptIn opt;
+    if (opt.ensure(kern, Cfg::smem_bytes)) return B200FEM_FAILURE;
+    const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;
+    if (ngroups == 0) return B200FEM_SUCCESS;
+    alignas(64) CUtensorMap map;
+    if (encode_vector_map(x, nn, &map)) return B200FEM_FAILURE;
+    const int grid = (int)std::min<ptrdiff_t>((ngroups + NC - 1) / NC, (ptrdiff_t)max_ctas);
+    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers, map, x, y, dbg);
+    B2_CHECK_LAUNCH();
+    return B200FEM_SUCCESS;
+}
+
 template <typename T, bool PLAIN>
 static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s) {
     const int dbg = cfg >> 8;  // A/B switch (ws_cfg + 256): interior runs per node instead of TMA
@@ -58,6 +75,20 @@ static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *hea
         case 2: return launch_cfg<T, 8, 4, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 3: return launch_cfg<T, 8, 6, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 4: return launch_cfg<T, 8, 4, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // phase-unrolled z loop
+        case 8: return launch_ws2<T, 8, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);  // two-barrier protocol
+        case 9: return launch_ws2<T, 8, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 10: return launch_ws2<T, 8, 5, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + static accumulator phases
+        case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 13: return launch_ws2<T, 8, 3, PLAIN, true, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + bulk interior stores
+        case 14: return launch_ws2<T, 8, 4, PLAIN, true, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 15: return launch_ws2<T, 8, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        // bracketing runs of the D = 3 phased kernel (profiles/r02*_ws2_brackets): parts switched off at compile time
+        case 20: return launch_ws2<T, 8, 3, PLAIN, true, false, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);        // no arithmetic
+        case 21: return launch_ws2<T, 8, 3, PLAIN, true, false, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // arithmetic only
+        case 22: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);  // protocol only
+        case 23: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 4>(ne, nn, headers, x, y, max_ctas, s, dbg);    // loads only
+        case 24: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // stores only
     }
 }
 

@@ -243,7 +243,9 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 __syncwarp();
                 plane_set(hb, ldI, ldS, ldB);
             }
-            if (zp == 0 || zp == L) {
+            if (dbg & 8) {  // experiment: no loads at all (the barrier protocol stays)
+                if (tl == 0) mbar_arrive(bar);
+            } else if (zp == 0 || zp == L) {
                 if (tl == 0) mbar_arrive(bar);
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
@@ -285,7 +287,8 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         auto scatter_plane = [&](const int ss, const uint32_t sp, const unsigned char *hb, const int z, const int nv) {
             const T *src = stage + (size_t)ss * PLANE;
             mbar_wait(sfull + ss, sp);
-            if (z == 0 || z == L) {
+            if (dbg & 4) {  // experiment: no stores (the barrier protocol stays)
+            } else if (z == 0 || z == L) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     if (i >= nv) break;
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 }
                 const int kin = (Bs + NI * zp) & (AL - 1);
                 const T *pk = plane + kin, *ps = plane + dk * kin;  // interior rows / skeleton positions
-                row.step_with(zp, [&](const int iy, T(&r)[N]) {
+                if (!(dbg & 2)) row.step_with(zp, [&](const int iy, T(&r)[N]) {
                     const T *pm = (rint[iy] ? pk : ps) + am[iy];
                     r[0] = ps[a0[iy]];
 #pragma unroll
@@ -487,5 +490,436 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// "ws2": the same roles, layout and arithmetic with HALF the hand-offs. Bracketing the first kernel with its parts switched
+// off (profiles/r02p_ws_brackets.jsonl, C3 fp64): everything 0.86 ms; arithmetic alone (movers only run the barrier protocol)
+// 0.73 ms; loads + stores alone 0.68 ms; the barrier protocol ALONE 0.29 ms. A DFMA stream needs 2 cycles per instruction and
+// scheduler (tools/dev/dfma_probe.cu: one warp with >= 4 independent chains saturates the pipe), i.e. 0.30 ms for this kernel:
+// the four waits / arrivals a warp pair exchanges per plane cost as much as the arithmetic. Here
+//   * the compute warp emits output plane t-1 after EVERY step t (the last plane of a group rides into the first step of the
+//     next group: ZC = 0 steps do not touch that accumulator), so `sfull` of step t also says "ring slot t % D has been
+//     read": no `empty` barrier;
+//   * the mover issues the loads of plane t + D, scatters plane t - 1, and only then adds the last arrival to full[t % D]:
+//     with as many staging slots as ring slots, `full` of plane t says "staging slot t % D has been scattered": no `sempty`
+//     barrier either (a phantom plane T covers the final emit);
+//   * all 32 lanes arrive on `sfull` (no __syncwarp + elected arrive).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, bool BULK, int DBG = 0>
+__global__ void __launch_bounds__(2 * NC * 32, 1)
+    sshex8_laplacian_ws2_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers, const __grid_constant__ CUtensorMap tmap_u,
+                                const T *__restrict__ u, T *__restrict__ y, const int) {
+    constexpr int dbg = DBG;  // experiment switches (bracketing runs): 2 = no arithmetic, 4 = no stores, 8 = no loads, 16 = no REDs, 32 = no plain stores
+    using Cfg = Sshex8WsCfg<T, L, NC, D, D>;
+    using Lay = WsLayout<T>;
+    constexpr int N = Cfg::N, NI = Cfg::NI, EPT = Cfg::EPT, PS = Cfg::PS, PLANE = Cfg::PLANE;
+    constexpr int HSZ = (int)sizeof(Sshex8Header);
+    constexpr int HBUF = EPT * HSZ;
+    constexpr uint32_t TX_BYTES = (uint32_t)(EPT * Lay::BOX * sizeof(T));
+    constexpr int AL = 16 / (int)sizeof(T);
+    constexpr int REG_MOVER = 80;
+    constexpr int REG_COMPUTE = (65536 / 32 - NC * REG_MOVER) / NC / 8 * 8;
+    static_assert(D < N, "ring deeper than a group");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // (the shuffle tells the compiler that the warp index, and everything derived from it, is warp-uniform)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), tl = threadIdx.x & 31;
+    const bool is_mover = warp >= NC;
+    const int cw = is_mover ? warp - NC : warp;
+    unsigned char *wbase = smem_raw + (size_t)cw * Cfg::warp_bytes;
+    T *ring = reinterpret_cast<T *>(wbase);                                 // [D][EPT][PS]
+    T *stage = ring + (size_t)D * PLANE;                                    // [D][EPT][PS]
+    unsigned char *hdr_bytes = wbase + Cfg::ring_bytes + Cfg::stage_bytes;  // [3][EPT] headers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hdr_bytes + Cfg::hdr_bytes);
+    uint64_t *full = bars, *sfull = bars + D;
+
+    const int ngroups = (int)((ne + EPT - 1) / EPT);
+    const int nteams = (int)gridDim.x * NC;
+    const int gteam = (int)blockIdx.x * NC + cw;
+    const int my_groups = gteam < ngroups ? (ngroups - gteam + nteams - 1) / nteams : 0;
+    const int T_steps = my_groups * N;
+
+    if (!is_mover && tl == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            mbar_init(full + i, 33);   // 32 cp.async-triggered arrivals + the mover's closing arrival
+            mbar_init(sfull + i, 32);  // every lane of the compute warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    auto group_of = [&](int g_local) -> int { return gteam + g_local * nteams; };
+
+    if (is_mover) {
+        // =========================================================================================== mover warp
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_MOVER));
+        if (my_groups == 0) return;
+
+        int sk_x, sk_y;
+        plane_pos_to_xy<L>(NI + tl, sk_x, sk_y);
+        const int sk_cxy = ((sk_x == 0) ? 0 : (sk_x == L ? 2 : 1)) + 3 * ((sk_y == 0) ? 0 : (sk_y == L ? 2 : 1));
+        const int sk_off0 = ws_offset<T, L>(0, sk_x, sk_y);
+        const bool in_second = tl < NI - 32;
+        const int q1 = in_second ? 32 + tl : 0;
+        const int x0 = 1 + tl % (L - 1), y0 = 1 + tl / (L - 1), x1 = 1 + q1 % (L - 1), y1 = 1 + q1 / (L - 1);
+
+        auto issue_headers = [&](int g_local) {
+            if (g_local >= my_groups) return;
+            const int4 *src = reinterpret_cast<const int4 *>(headers + (size_t)group_of(g_local) * EPT);
+            int4 *dst = reinterpret_cast<int4 *>(hdr_bytes + (g_local % 3) * HBUF);
+            for (int i = tl; i < EPT * 29; i += 32) cp_async_16(dst + i, src + i);
+        };
+        // per group and slot: G = id of the first interior node of plane 0 (the interior run of plane z starts at G + NI z: kept
+        // as a running value), I / Sz = id and z stride of this lane's skeleton position on the z-interior planes
+        auto plane_set = [&](const unsigned char *hb, int (&I)[EPT], int (&Sz)[EPT], int (&G)[EPT]) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int4 d = *reinterpret_cast<const int4 *>(hb + i * HSZ + (9 + sk_cxy) * 16);
+                I[i] = d.x + d.y * sk_x + d.z * sk_y;
+                Sz[i] = d.w;
+                const int4 c = *reinterpret_cast<const int4 *>(hb + i * HSZ + 13 * 16);
+                G[i] = c.x + c.y + c.z;  // id(1, 1, z) = G + NI z with the canonical strides (1, L-1, (L-1)^2)
+            }
+        };
+        auto boundary_id = [&](const unsigned char *hb, int slot, int x, int yy, int cxy, int z) -> int {
+            const int4 d = *reinterpret_cast<const int4 *>(hb + slot * HSZ + ((z == 0 ? 0 : 18) + cxy) * 16);
+            return d.x + d.y * x + d.z * yy + d.w * z;
+        };
+        // predicated forms (no branch, no reconvergence point around a store / copy)
+        auto put_if = [&](const bool ok, T *p, const T v, auto plain_tag) {
+            if (dbg & (decltype(plain_tag)::value ? 32 : 16)) return;  // experiment: no plain stores / no REDs
+            if constexpr (decltype(plain_tag)::value) {
+                if constexpr (sizeof(T) == 8)
+                    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p st.global.cs.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((int)ok));
+                else
+                    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p st.global.cs.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"((int)ok));
+            } else {
+                if constexpr (sizeof(T) == 8)
+                    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p red.global.add.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((int)ok));
+                else
+                    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p red.global.add.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"((int)ok));
+            }
+        };
+        auto copy_if = [&](const bool ok, T *smem, const T *gmem) {
+            if constexpr (sizeof(T) == 8)
+                asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 8;\n}\n" ::"r"(smem_u32(smem)), "l"(gmem),
+                             "r"((int)ok)
+                             : "memory");
+            else
+                asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"(smem_u32(smem)), "l"(gmem),
+                             "r"((int)ok)
+                             : "memory");
+        };
+        using PlainT = std::integral_constant<bool, PLAIN_INTERIOR>;
+        using RedT = std::integral_constant<bool, false>;
+        constexpr bool kBulk = BULK && sizeof(T) == 8;  // interior output runs by cp.async.bulk (fp64: 48 of the 49 values are 16-byte aligned)
+
+        int ldI[EPT], ldS[EPT], ldG[EPT];  // planes being gathered
+        int scI[EPT], scS[EPT], scG[EPT];  // planes being scattered
+
+        // gather plane zp into ring slot `rs` (free). The lanes' copies arrive on full[rs] by themselves; the 33rd arrival is
+        // the caller's.
+        auto issue_plane = [&](const int rs, const unsigned char *hb, const int zp) {
+            uint64_t *bar = full + rs;
+            T *dst = ring + (size_t)rs * PLANE;
+            if (zp == 0) {
+                cp_async_wait<N - 2>();  // headers of this group were issued N commit groups ago
+                __syncwarp();
+                plane_set(hb, ldI, ldS, ldG);
+            }
+            if (dbg & 8) {  // experiment: no loads (the barrier protocol stays)
+            } else if (zp == 0 || zp == L) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = ldG[i] & (AL - 1);
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k), u + boundary_id(hb, i, sk_x, sk_y, sk_cxy, zp));
+                    cp_async_value(dst + (i * PS + k + tl), u + boundary_id(hb, i, x0, y0, 4, zp));
+                    copy_if(in_second, dst + (i * PS + k + q1), u + boundary_id(hb, i, x1, y1, 4, zp));
+                    asm volatile("" ::: "memory");  // one slot at a time: small register budget
+                }
+            } else {
+                if (tl == 0) {
+                    mbar_expect_tx(bar, TX_BYTES);
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) tma_load_1d(dst + i * PS, &tmap_u, ldG[i] & ~(AL - 1), bar);
+                }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = ldG[i] & (AL - 1);
+                    cp_async_value(dst + (sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k), u + ldI[i]);
+                }
+            }
+            cp_async_mbar_arrive_noinc(bar);
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                ldG[i] += NI;
+                ldI[i] += ldS[i];
+            }
+        };
+
+        // output plane z of the group with header buffer hb, staged in slot ss
+        auto scatter_plane = [&](const int ss, const unsigned char *hb, const int z, const int nv) {
+            const T *src = stage + (size_t)ss * PLANE;
+            if (z == 0 || z == L) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const bool ok = i < nv;
+                    const int k = scG[i] & (AL - 1);
+                    put_if(ok, y + boundary_id(hb, i, sk_x, sk_y, sk_cxy, z), src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
+                    put_if(ok, y + boundary_id(hb, i, x0, y0, 4, z), src[i * PS + k + tl], RedT{});
+                    put_if(ok && in_second, y + boundary_id(hb, i, x1, y1, 4, z), src[i * PS + k + q1], RedT{});
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = scG[i] & (AL - 1);
+                    put_if(i < nv, y + scI[i], src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
+                }
+                if constexpr (kBulk) {
+                    // values [k, k + 48) of the run (k = its alignment offset) in one bulk copy, the 49th by lane 1 + slot
+                    if (tl == 0 && !(dbg & 32)) {
+                        fence_proxy_async_smem();  // the compute warp's stores (acquired through sfull) before the bulk engine reads
+#pragma unroll
+                        for (int i = 0; i < EPT; ++i) {
+                            if (i < nv) {
+                                const int k = scG[i] & 1;
+                                if constexpr (PLAIN_INTERIOR)
+                                    bulk_s2g(y + (scG[i] + k), src + (i * PS + 2 * k), (NI - 1) * (int)sizeof(T));
+                                else
+                                    bulk_red_add(y + (scG[i] + k), src + (i * PS + 2 * k), (NI - 1) * (int)sizeof(T));
+                            }
+                        }
+                        bulk_commit();
+                    }
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const int k = scG[i] & 1, j0 = k ? 0 : NI - 1;
+                        put_if(i < nv && tl == 1 + i, y + (scG[i] + j0), src[i * PS + k + j0], PlainT{});
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const int k = scG[i] & (AL - 1);
+                        put_if(i < nv, y + (scG[i] + tl), src[i * PS + k + tl], PlainT{});
+                        put_if(i < nv && in_second, y + (scG[i] + q1), src[i * PS + k + q1], PlainT{});
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                scG[i] += NI;
+                scI[i] += scS[i];
+            }
+        };
+
+        // ---- prologue: headers of groups 0 and 1, planes 0 .. D-1
+        issue_headers(0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        issue_headers(1);
+#pragma unroll 1
+        for (int s = 0; s < D; ++s) {
+            issue_plane(s, hdr_bytes, s);  // D < N <= T_steps: all in group 0
+            cp_async_commit();
+            if (tl == 0) mbar_arrive(full + s);
+        }
+        // ---- stream: iteration t follows the compute warp's step t (t = T_steps: the final emit).
+        // (gn, zn, hn) = group, plane, header buffer of plane t + D; rs = t % D = its ring slot = the staging slot of output
+        // plane t - 1; ph = parity of sfull[rs]; (zs, hs, gs) = plane, header buffer, group of output plane t - 1.
+        int gn = 0, zn = D, hn = 0, rs = 0;
+        uint32_t ph = 0;
+        int zs = 0, hs = 0, gs = 0, nv = EPT;
+#pragma unroll 1
+        for (int t = 0; t <= T_steps; ++t) {
+            mbar_wait(sfull + rs, ph);
+            const bool more = t + D < T_steps;
+            const bool closing = more || (t + D == T_steps);  // plane T_steps is a phantom: it only carries "staging slot free"
+            if (more) {
+                if (zn == 0) issue_headers(gn + 1);  // headers of group g+2 travel with the first plane of g+1
+                issue_plane(rs, hdr_bytes + hn * HBUF, zn);
+            } else if (closing) {
+                cp_async_mbar_arrive_noinc(full + rs);
+            }
+            cp_async_commit();
+            if (++zn == N) { zn = 0; ++gn; hn = (hn == 2) ? 0 : hn + 1; }
+            if (t > 0) {
+                const unsigned char *hb = hdr_bytes + hs * HBUF;
+                if (zs == 0) {
+                    plane_set(hb, scI, scS, scG);
+                    const int left = (int)ne - group_of(gs) * EPT;
+                    nv = left < EPT ? left : EPT;
+                }
+                if (!(dbg & 4)) scatter_plane(rs, hb, zs, nv);
+                if (++zs == N) { zs = 0; ++gs; hs = (hs == 2) ? 0 : hs + 1; }
+            }
+            if (tl == 0) {
+                if constexpr (kBulk) bulk_wait_read_all();  // the staging slot has been read: full[rs] may say so
+                if (closing) mbar_arrive(full + rs);
+            }
+            if (++rs == D) { rs = 0; ph ^= 1u; }
+        }
+        cp_async_wait<0>();
+        if constexpr (kBulk) {
+            if (tl == 0) bulk_wait_all();
+        }
+    } else {
+        // ========================================================================================= compute warp
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_COMPUTE));
+        if (my_groups == 0) return;
+        const int cl = tl < EPT * N ? tl : EPT * N - 1;
+        const int slot = cl / N;
+        const int yrow = cl - slot * N;
+        int a0[3], am[3];
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const int yy = yrow + iy - 1;  // unclamped, see ws_offset
+            a0[iy] = ws_offset<T, L>(slot, 0, yy);
+            am[iy] = ws_offset<T, L>(slot, 1, yy);
+        }
+        bool rint[3];
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const int yy = yrow + iy - 1;
+            rint[iy] = (yy >= 1 && yy <= L - 1);
+        }
+        const int dk = (slot == 0) ? Lay::DK(0) : (slot == 1 ? Lay::DK(1) : Lay::DK(2));
+        int Bs = 0, Bs_prev = 0;  // id of lattice node (1, 1, 0) of this lane's element, and of the previous group's
+        Sshex8LaplacianRow<T, L> row;
+        row.clear();
+
+        // this lane's row of output plane z of the element whose interior starts at B, into staging slot ss
+        auto stage_row = [&](const int ss, const int z, const int B, const T(&vals)[N]) {
+            T *dst = stage + (size_t)ss * PLANE;
+            const int k = (B + NI * z) & (AL - 1);
+            T *ds = dst + dk * k;
+            T *dm = (rint[1] ? dst + k : ds) + am[1];
+            ds[a0[1]] = vals[0];
+#pragma unroll
+            for (int x = 1; x < L; ++x) dm[x - 1] = vals[x];
+            ds[a0[1] + (rint[1] ? L - 1 : L)] = vals[L];
+        };
+
+        if constexpr (PHASED) {
+            // Static accumulator phases (plane z accumulates in acc[z % 3]: no register rotation), four step bodies: z = 0,
+            // and the interior class in phases 0 / 1 / 2; z = L runs through the phase-2 body with its accumulator pre-doubled,
+            // the edge terms applied in one piece afterwards, and the (meaningless) contribution to plane L + 1 zeroed.
+            int rs = 0;
+            uint32_t ph = 0;
+            bool first = true;
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            auto z_step = [&](auto zc_tag, auto p_tag, const int g_local, const int zp) {
+                constexpr int ZC = decltype(zc_tag)::value, P = decltype(p_tag)::value;
+                const T *plane = ring + (size_t)rs * PLANE;
+                mbar_wait(full + rs, ph);
+                if constexpr (ZC == 0) {
+                    const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
+                    T f[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                    row.set(f, yrow);
+                    Bs_prev = Bs;
+                    Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
+                }
+                const int kin = (Bs + NI * zp) & (AL - 1);
+                const T *pk = plane + kin, *ps = plane + dk * kin;
+                auto loader = [&](const int iy, T(&r)[N]) {
+                    const T *pm = (rint[iy] ? pk : ps) + am[iy];
+                    r[0] = ps[a0[iy]];
+#pragma unroll
+                    for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
+                    r[L] = ps[a0[iy] + (rint[iy] ? L - 1 : L)];
+                };
+                const bool zhi = (P == 2) && zp == L;  // warp-uniform
+                if (P == 2 && zhi) {
+#pragma unroll
+                    for (int x = 0; x < N; ++x) row.acc[2][x] *= T(2);
+                }
+                if (!(dbg & 2)) row.template step_class_with<ZC, P>(loader);
+                if (P == 2 && zhi) {
+                    T r0[3], rL[3], rmid[N];
+#pragma unroll
+                    for (int iy = 0; iy < 3; ++iy) {
+                        r0[iy] = ps[a0[iy]];
+                        rL[iy] = ps[a0[iy] + (rint[iy] ? L - 1 : L)];
+                    }
+                    loader(1, rmid);
+                    row.z_boundary_terms(row.acc[2], T(2), r0, rL, rmid);
+#pragma unroll
+                    for (int x = 0; x < N; ++x) {
+                        row.acc[2][x] *= T(0.5);
+                        row.acc[0][x] = T(0);  // what the interior-class code sent towards plane L + 1
+                    }
+                }
+                // output plane zp - 1 (z = 0: the previous group's plane L) is final: stage it, hand the slot over, recycle
+                if (!first) stage_row(rs, ZC == 0 ? L : zp - 1, ZC == 0 ? Bs_prev : Bs, row.acc[(P + 2) % 3]);
+                first = false;
+                mbar_arrive(sfull + rs);
+#pragma unroll
+                for (int x = 0; x < N; ++x) row.acc[(P + 2) % 3][x] = T(0);
+                if (++rs == D) { rs = 0; ph ^= 1u; }
+            };
+            static_assert(N % 3 == 0 && L % 3 == 2, "phase pattern: N a multiple of 3, plane L in phase 2");
+#pragma unroll 1
+            for (int g_local = 0; g_local < my_groups; ++g_local) {
+#pragma unroll 1
+                for (int zz = 0; zz < N; zz += 3) {
+                    if (zz == 0)
+                        z_step(I0{}, I0{}, g_local, 0);
+                    else
+                        z_step(I1{}, I0{}, g_local, zz);
+                    z_step(I1{}, I1{}, g_local, zz + 1);
+                    z_step(I1{}, I2{}, g_local, zz + 2);
+                }
+            }
+            mbar_wait(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
+            stage_row(rs, L, Bs, row.acc[2]);
+            mbar_arrive(sfull + rs);
+            return;
+        }
+        int g_local = 0, zp = 0, rs = 0;
+        uint32_t ph = 0;
+#pragma unroll 1
+        for (int t = 0; t < T_steps; ++t) {
+            const T *plane = ring + (size_t)rs * PLANE;
+            mbar_wait(full + rs, ph);
+            if (zp == 0) {
+                const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
+                T f[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) f[k] = (T)h->fff[k];
+                row.set(f, yrow);  // acc[0] still holds the last output plane of the previous group (ZC = 0 leaves it alone)
+                Bs_prev = Bs;
+                Bs = h->box[13][0] + h->box[13][1] + h->box[13][2];
+            }
+            const int kin = (Bs + NI * zp) & (AL - 1);
+            const T *pk = plane + kin, *ps = plane + dk * kin;
+            if (!(dbg & 2)) row.step_with(zp, [&](const int iy, T(&r)[N]) {
+                const T *pm = (rint[iy] ? pk : ps) + am[iy];
+                r[0] = ps[a0[iy]];
+#pragma unroll
+                for (int x = 1; x < L; ++x) r[x] = pm[x - 1];
+                r[L] = ps[a0[iy] + (rint[iy] ? L - 1 : L)];
+            });
+            if (t > 0) stage_row(rs, zp == 0 ? L : zp - 1, zp == 0 ? Bs_prev : Bs, row.acc[0]);
+            mbar_arrive(sfull + rs);
+            row.rotate();
+            if (++zp == N) { zp = 0; ++g_local; }
+            if (++rs == D) { rs = 0; ph ^= 1u; }
+        }
+        mbar_wait(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
+        stage_row(rs, L, Bs, row.acc[0]);
+        mbar_arrive(sfull + rs);
+    }
+}
+
 
 }  // namespace b200fem
