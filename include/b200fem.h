@@ -153,6 +153,13 @@ int b200fem_op_apply_overwrite(b200fem_op_t op, const void *x, void *y, void *st
  * ranges return B200FEM_FAILURE (the caller then uses the whole-mesh entry points). */
 int b200fem_op_apply_range(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_begin, ptrdiff_t e_end, int mode,
                            void *stream);
+/* y = A x in ONE launch whose elements >= e_dependent wait, inside the kernel, until *ready_flag >= ready_value (acquire,
+ * GPU scope) before they read x: the ghost-dependent elements of a distributed apply, ordered last, start when the
+ * receiver half of the halo gather (b200fem_halo_gather_end_deferred, on another stream) has filled the ghost block, while
+ * everything else runs at once. The launch leaves one SM free for that other stream. Operators without the in-kernel wait
+ * return B200FEM_FAILURE and enqueue nothing (b200fem_op_get_option "ghost_wait" tells beforehand). */
+int b200fem_op_apply_overwrite_after(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_dependent,
+                                     const unsigned long long *ready_flag, unsigned long long ready_value, void *stream);
 /* diag += diag(A)  (Op::hessian_diag, frontend/ops/sfem_Op.hpp:194; laplacian_diag,
  * operators/laplacian.cpp:156-195; affine_hex8_linear_elasticity_diag,
  * operators/hex8/hex8_linear_elasticity.cpp:1043) */
@@ -162,6 +169,7 @@ int b200fem_op_diag(b200fem_op_t op, void *diag, void *stream);
 int b200fem_op_block_diag_sym(b200fem_op_t op, void *bdiag, void *stream);
 
 ptrdiff_t b200fem_op_rows(b200fem_op_t op); /* nnodes * block_size */
+ptrdiff_t b200fem_op_nelements(b200fem_op_t op); /* what b200fem_op_apply_range's element ranges count over */
 int b200fem_op_block_size(b200fem_op_t op);
 int b200fem_op_real_type(b200fem_op_t op);
 /* Canonical algorithmic bytes per apply: ne*(nxe*4 + geometry bytes) + rows*2*sizeof(real)
@@ -285,6 +293,20 @@ int b200fem_halo_create(b200fem_halo_t *halo, b200fem_comm_t comm, int real_type
                         const ptrdiff_t *recv_count, int transport);
 int b200fem_halo_destroy(b200fem_halo_t halo);
 int b200fem_halo_gather(b200fem_halo_t halo, void *x_local, void *stream);
+/* The gather in two halves, for a distributed apply that runs its ghost-independent elements in between
+ * (b200fem_op_apply_range): begin = the owner side (push over NVLink / pack + grouped NCCL calls),
+ * end = the receiver side (wait for the peers' arrival flags, copy into the ghost block; nothing to do for NCCL).
+ * begin + end on one stream is b200fem_halo_gather. */
+int b200fem_halo_gather_begin(b200fem_halo_t halo, void *x_local, void *stream);
+int b200fem_halo_gather_end(b200fem_halo_t halo, void *x_local, void *stream);
+/* The whole gather on the halo's OWN stream (ordered behind what `stream` holds so far), for an apply kernel that waits
+ * for the ghost block itself: *ready_flag is a device word that reaches *ready_value (release, GPU scope) once the ghost
+ * block of x is complete; hand both to b200fem_op_apply_overwrite_after, which leaves one SM to this stream. Neither the
+ * push over NVLink nor the wait for the peers then sits in front of the apply. *ready_flag == NULL: the gather has been
+ * enqueued on `stream` in the ordinary way (one rank, NCCL transport, nothing to receive). The next operation that WRITES
+ * x on `stream` must come after the apply that consumed the flag (any use of the apply's result does). */
+int b200fem_halo_gather_deferred(b200fem_halo_t halo, void *x_local, void *stream, const unsigned long long **ready_flag,
+                                 unsigned long long *ready_value);
 int b200fem_halo_transport(b200fem_halo_t halo); /* the transport in use */
 ptrdiff_t b200fem_halo_values_sent(b200fem_halo_t halo);
 int b200fem_halo_launches_per_gather(b200fem_halo_t halo);

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kHaloThreads)
 template <typename T>
 __global__ void __launch_bounds__(kHaloThreads)
     halo_wait_copy_kernel(const RecvArgs a, T *__restrict__ x, const unsigned long long epoch,
-                          const unsigned long long timeout_ns, int *err) {
+                          const unsigned long long timeout_ns, int *err, unsigned long long *ready, unsigned int *ready_ticket) {
     const RecvPeer &p = a.p[blockIdx.y];
     const int par = (int)(epoch & 1ull);
     block_wait_epoch(p.arrive[par], epoch, timeout_ns, err);
@@ -225,6 +225,16 @@ __global__ void __launch_bounds__(kHaloThreads)
     for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_values; i += (ptrdiff_t)gridDim.x * blockDim.x)
         dst[i] = __ldcg(&src[i]);  // L2 only: the lines were written by the peer, never trust this SM's L1
     block_release_epoch(p.ticket, p.remote_credit[par], epoch);
+    // deferred form: the last block of the whole grid tells the apply kernel that spins on `ready` (same GPU) that the ghost
+    // block of x is complete (every block's stores were fenced in block_release_epoch)
+    if (ready && threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ready_ticket, 1u);
+        if (t == gridDim.x * gridDim.y - 1) {
+            *ready_ticket = 0u;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(ready), "l"(epoch) : "memory");
+        }
+    }
 }
 
 template <typename T>
@@ -275,6 +285,10 @@ struct b200fem_halo_s {
     RecvArgs recv{};
     unsigned long long epoch = 0;
     long n_gathers = 0;
+    // deferred receiver half (b200fem_halo_gather_end_deferred): its own stream, a ready flag + ticket in device memory
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_event = nullptr;
+    unsigned long long *ready = nullptr;  // [0] = epoch of the last complete ghost block, [1] = ticket
 };
 
 namespace b200fem {
@@ -287,6 +301,12 @@ static void halo_release(b200fem_halo_s *h) {
         if (h->peer_block[q]) cudaIpcCloseMemHandle(h->peer_block[q]);
     if (h->tickets) cudaFree(h->tickets);
     if (h->block) cudaFree(h->block);
+    if (h->side) {
+        cudaStreamSynchronize(h->side);
+        cudaStreamDestroy(h->side);
+    }
+    if (h->side_event) cudaEventDestroy(h->side_event);
+    if (h->ready) cudaFree(h->ready);
     delete h;
 }
 
@@ -392,34 +412,50 @@ static int halo_setup_push(b200fem_halo_s *h) {
     return B200FEM_SUCCESS;
 }
 
+// phase: 0 = the whole gather, 1 = begin (the owner side: push / pack + send), 2 = end (the receiver side: wait + copy).
+// The NCCL transport is one grouped call and runs entirely in `begin`.
 template <typename T>
-static int halo_gather_t(b200fem_halo_s *h, T *x, cudaStream_t s) {
+static int halo_gather_t(b200fem_halo_s *h, T *x, cudaStream_t s, int phase = 0) {
     b200fem_comm_s *c = h->comm;
-    h->n_gathers++;
+    const bool deferred = phase == 3;  // the whole gather on the halo's own stream (ordered behind `s`), announcing through h->ready
+    if (deferred) phase = 0;
+    if (phase != 2) h->n_gathers++;
     if (c->world == 1 || (h->send_peers.empty() && h->recv_peers.empty())) return B200FEM_SUCCESS;
     if (h->transport == B200FEM_HALO_PUSH) {
-        const unsigned long long epoch = ++h->epoch;
+        const unsigned long long epoch = phase == 2 ? h->epoch : ++h->epoch;
         ptrdiff_t max_send = 0, max_recv = 0;
         for (auto n : h->send_count) max_send = std::max(max_send, n * h->bs);
         for (size_t j = 0; j < h->recv_count.size(); ++j) max_recv = std::max(max_recv, h->recv_count[j] * (ptrdiff_t)h->bs);
         const ptrdiff_t cap = (ptrdiff_t)sm_count() * 4;
-        if (!h->send_peers.empty()) {
+        if (deferred) {
+            // the push reads x, the copy writes its ghost block: behind everything `s` has been given so far (the producers
+            // of x, the previous apply that read the block), concurrent with what follows on `s`
+            B2_CUDA(cudaEventRecord(h->side_event, s));
+            B2_CUDA(cudaStreamWaitEvent(h->side, h->side_event, 0));
+        }
+        if (phase != 2 && !h->send_peers.empty()) {
             const int gx = (int)std::max<ptrdiff_t>(1, std::min<ptrdiff_t>((max_send + kHaloThreads * 4 - 1) / (kHaloThreads * 4),
                                                                           cap / (ptrdiff_t)h->send_peers.size()));
-            halo_push_kernel<T><<<dim3(gx, (unsigned)h->send_peers.size()), kHaloThreads, 0, s>>>(h->push, h->bs, x, epoch,
-                                                                                                 c->timeout_ns, c->err_dev);
+            halo_push_kernel<T><<<dim3(gx, (unsigned)h->send_peers.size()), kHaloThreads, 0, deferred ? h->side : s>>>(
+                    h->push, h->bs, x, epoch, c->timeout_ns, c->err_dev);
             B2_CHECK_LAUNCH();
         }
-        if (!h->recv_peers.empty()) {
+        if (phase != 1 && !h->recv_peers.empty()) {
             const int gx = (int)std::max<ptrdiff_t>(1, std::min<ptrdiff_t>((max_recv + kHaloThreads * 4 - 1) / (kHaloThreads * 4),
                                                                           cap / (ptrdiff_t)h->recv_peers.size()));
-            halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, s>>>(h->recv, x, epoch,
-                                                                                                      c->timeout_ns, c->err_dev);
+            if (deferred) {
+                halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, h->side>>>(
+                        h->recv, x, epoch, c->timeout_ns, c->err_dev, h->ready, reinterpret_cast<unsigned int *>(h->ready + 1));
+            } else {
+                halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, s>>>(h->recv, x, epoch, c->timeout_ns,
+                                                                                                          c->err_dev, nullptr, nullptr);
+            }
             B2_CHECK_LAUNCH();
         }
         return B200FEM_SUCCESS;
     }
     // NCCL transport
+    if (phase == 2) return B200FEM_SUCCESS;
     const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
     for (size_t j = 0; j < h->send_peers.size(); ++j) {
         const ptrdiff_t total = h->send_count[j] * h->bs;
@@ -654,6 +690,40 @@ int b200fem_halo_gather(b200fem_halo_t h, void *x_local, void *stream) {
     if (!h || !x_local) B2_FAIL("halo_gather: NULL argument");
     if (h->real_type == B200FEM_F64) return halo_gather_t<double>(h, (double *)x_local, as_stream(stream));
     return halo_gather_t<float>(h, (float *)x_local, as_stream(stream));
+}
+int b200fem_halo_gather_begin(b200fem_halo_t h, void *x_local, void *stream) {
+    if (!h || !x_local) B2_FAIL("halo_gather_begin: NULL argument");
+    if (h->real_type == B200FEM_F64) return halo_gather_t<double>(h, (double *)x_local, as_stream(stream), 1);
+    return halo_gather_t<float>(h, (float *)x_local, as_stream(stream), 1);
+}
+int b200fem_halo_gather_deferred(b200fem_halo_t h, void *x_local, void *stream, const unsigned long long **ready_flag,
+                                 unsigned long long *ready_value) {
+    if (!h || !x_local || !ready_flag || !ready_value) B2_FAIL("halo_gather_deferred: NULL argument");
+    *ready_flag = nullptr;
+    *ready_value = 0;
+    if (h->comm->world == 1 || h->transport != B200FEM_HALO_PUSH || h->recv_peers.empty()) {
+        // nothing to wait for in a kernel: the ordinary gather on `stream`
+        return b200fem_halo_gather(h, x_local, stream);
+    }
+    if (!h->side) {
+        int lo = 0, hi = 0;
+        B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B2_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+        B2_CUDA(cudaEventCreateWithFlags(&h->side_event, cudaEventDisableTiming));
+        B2_CUDA(cudaMalloc((void **)&h->ready, 2 * sizeof(unsigned long long)));
+        B2_CUDA(cudaMemset(h->ready, 0, 2 * sizeof(unsigned long long)));
+    }
+    const int rc = h->real_type == B200FEM_F64 ? halo_gather_t<double>(h, (double *)x_local, as_stream(stream), 3)
+                                               : halo_gather_t<float>(h, (float *)x_local, as_stream(stream), 3);
+    if (rc) return rc;
+    *ready_flag = h->ready;
+    *ready_value = h->epoch;
+    return B200FEM_SUCCESS;
+}
+int b200fem_halo_gather_end(b200fem_halo_t h, void *x_local, void *stream) {
+    if (!h || !x_local) B2_FAIL("halo_gather_end: NULL argument");
+    if (h->real_type == B200FEM_F64) return halo_gather_t<double>(h, (double *)x_local, as_stream(stream), 2);
+    return halo_gather_t<float>(h, (float *)x_local, as_stream(stream), 2);
 }
 
 }  // extern "C"

@@ -114,6 +114,12 @@ struct OpBase {
         set_error("apply_range not implemented for this operator");
         return B200FEM_FAILURE;
     }
+    virtual int apply_overwrite_after(const void *x, void *y, ptrdiff_t e_dep, const unsigned long long *flag, unsigned long long want,
+                                      cudaStream_t s) {
+        (void)x; (void)y; (void)e_dep; (void)flag; (void)want; (void)s;
+        set_error("apply_overwrite_after (in-kernel ghost wait) not implemented for this operator");
+        return B200FEM_FAILURE;
+    }
     virtual int diag(void *d, cudaStream_t s) {
         (void)d; (void)s;
         set_error("diag not implemented for this operator");

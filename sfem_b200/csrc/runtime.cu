@@ -341,6 +341,15 @@ int b200fem_op_block_diag_sym(b200fem_op_t op, void *bdiag, void *stream) {
 }
 
 ptrdiff_t b200fem_op_rows(b200fem_op_t op) { return (op && op->impl) ? op->impl->nn * op->impl->block_size : -1; }
+int b200fem_op_apply_overwrite_after(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_dependent, const unsigned long long *ready_flag,
+                                     unsigned long long ready_value, void *stream) {
+    B2_OP_CHECK(op);
+    if (!x || !y) B2_FAIL("apply_overwrite_after: NULL vector");
+    if (e_dependent < 0 || e_dependent > op->impl->ne) B2_FAIL("apply_overwrite_after: first dependent element out of bounds");
+    if (!ready_flag) return op->impl->apply(x, y, true, as_stream(stream));
+    return op->impl->apply_overwrite_after(x, y, e_dependent, ready_flag, ready_value, as_stream(stream));
+}
+ptrdiff_t b200fem_op_nelements(b200fem_op_t op) { return (op && op->impl) ? op->impl->ne : -1; }
 int b200fem_op_block_size(b200fem_op_t op) { return (op && op->impl) ? op->impl->block_size : -1; }
 int b200fem_op_real_type(b200fem_op_t op) { return (op && op->impl) ? op->impl->real_type : -1; }
 double b200fem_op_algorithmic_bytes(b200fem_op_t op) { return (op && op->impl) ? op->impl->algorithmic_bytes() : -1.0; }

@@ -367,11 +367,42 @@ struct Sshex8Laplacian final : OpBase {
             }
         }
         if (e1 == e0) return B200FEM_SUCCESS;
+        if (L == 8 && ws_applies(x)) {
+            // the warp-specialised kernel on the sub-range: a partial last group reads the headers that follow the range (or
+            // the padding at the end of the array) for its missing slots and does not scatter them
+            const int max_ctas = std::max(1, sm_count() - reserve_sms);
+            return sshex8_laplacian_ws_launch(sizeof(T) == 8 ? B200FEM_F64 : B200FEM_F32, mode != 0 && interior_exclusive, ws_cfg, e1 - e0, nn,
+                                              headers.ptr + e0, x, y, max_ctas, s);
+        }
         range_e0 = e0;
         range_e1 = e1;
         const int rc = (mode != 0 && interior_exclusive) ? launch_stream<T, L, true>(x, y, s) : launch_stream<T, L, false>(x, y, s);
         range_e1 = -1;
         return rc;
+    }
+
+    // one launch of the warp-specialised kernel whose groups from e_dep / 3 on wait for the ghost block inside the kernel; one
+    // SM stays free for the receiver half of the halo gather, which runs on another stream while this kernel holds the rest
+    template <typename T>
+    bool ghost_wait_applies(const T *x) const {
+        return level == 8 && mode == kModeBoxes && use_stream && ws_cfg == 11 && ws_applies(x) && !tma_applies_flag();
+    }
+    bool tma_applies_flag() const { return use_tma != 0; }
+    template <typename T>
+    int apply_after_t(const T *x, T *y, ptrdiff_t e_dep, const unsigned long long *flag, unsigned long long want, cudaStream_t s) {
+        if (!ghost_wait_applies(x)) B2_FAIL("apply_overwrite_after: needs the level-8 warp-specialised kernel (ws_cfg 11, compact numbering)");
+        if (zero_skeleton(y, s)) return B200FEM_FAILURE;
+        WsDependency dep;
+        dep.flag = flag;
+        dep.want = want;
+        dep.first_group = (int)(e_dep / 3);
+        const int max_ctas = std::max(1, sm_count() - std::max(1, reserve_sms));
+        return sshex8_laplacian_ws_launch(sizeof(T) == 8 ? B200FEM_F64 : B200FEM_F32, true, ws_cfg, ne, nn, headers.ptr, x, y, max_ctas, s, &dep);
+    }
+    int apply_overwrite_after(const void *x, void *y, ptrdiff_t e_dep, const unsigned long long *flag, unsigned long long want,
+                              cudaStream_t s) override {
+        return real_type == B200FEM_F64 ? apply_after_t<double>((const double *)x, (double *)y, e_dep, flag, want, s)
+                                        : apply_after_t<float>((const float *)x, (float *)y, e_dep, flag, want, s);
     }
 
     int apply_range(const void *x, void *y, ptrdiff_t e0, ptrdiff_t e1, int mode, cudaStream_t s) override {
@@ -460,6 +491,13 @@ struct Sshex8Laplacian final : OpBase {
         if (!strcmp(key, "use_stream")) { *value = use_stream; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_tma")) { *value = use_tma; return B200FEM_SUCCESS; }
         if (!strcmp(key, "use_ws")) { *value = use_ws; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "ghost_wait")) {  // b200fem_op_apply_overwrite_after available (vector alignment is checked per call)
+            *value = (level == 8 && mode == kModeBoxes && use_stream && ws_cfg == 11 && use_tma == 0 && interior_exclusive &&
+                      (use_ws == 2 || (use_ws == 1 && real_type == B200FEM_F64)) && nn >= 64)
+                             ? 1
+                             : 0;
+            return B200FEM_SUCCESS;
+        }
         if (!strcmp(key, "tma_ok")) { *value = tma_ok ? 1 : 0; return B200FEM_SUCCESS; }
         return OpBase::get_option(key, value);
     }

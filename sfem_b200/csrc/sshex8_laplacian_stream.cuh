@@ -40,8 +40,14 @@ static_assert(sizeof(Sshex8Header) == 29 * 16, "header must be 29 x 16 B");
 // of 3 elements (padding = copies of the last element; only valid slots are scattered); compact numbering
 // (interior block of an element = one contiguous id run, x fastest) and 16-byte aligned x required. real_type is
 // B200FEM_F64 / B200FEM_F32; `plain` = interior nodes are stored, not added (overwriting apply).
+// elements of groups >= first_group wait in the kernel until *flag >= want (acquire, GPU scope): see b200fem_op_apply_overwrite_after
+struct WsDependency {
+    const unsigned long long *flag = nullptr;
+    unsigned long long want = 0;
+    int first_group = 0;
+};
 int sshex8_laplacian_ws_launch(int real_type, bool plain, int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const void *x,
-                               void *y, int max_ctas, cudaStream_t s);
+                               void *y, int max_ctas, cudaStream_t s, const WsDependency *dep = nullptr);
 
 // The 4/8-byte copies and the scatter stores below carry NO "memory" clobber on purpose: their ordering
 // against ordinary shared-memory traffic is established by the team barrier and cp.async.wait_group (which

@@ -48,11 +48,12 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     return B200FEM_SUCCESS;
 }
 
-template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, bool BULK = false, int DBG = 0>
-static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg) {
+template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, int DBG = 0, bool FACEOUT = false>
+static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg,
+                      const WsDependency *dep = nullptr) {
     constexpr int L = 8;
-    using Cfg = Sshex8WsCfg<T, L, NC, D, D>;
-    auto kern = sshex8_laplacian_ws2_kernel<T, L, NC, D, PLAIN, PHASED, BULK, DBG>;
+    using Cfg = Sshex8WsCfg<T, L, NC, D, D, FACEOUT>;
+    auto kern = sshex8_laplacian_ws2_kernel<T, L, NC, D, PLAIN, PHASED, DBG, FACEOUT>;
     static SmemOptIn opt;
     if (opt.ensure(kern, Cfg::smem_bytes)) return B200FEM_FAILURE;
     const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;
@@ -60,13 +61,15 @@ static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     alignas(64) CUtensorMap map;
     if (encode_vector_map(x, nn, &map)) return B200FEM_FAILURE;
     const int grid = (int)std::min<ptrdiff_t>((ngroups + NC - 1) / NC, (ptrdiff_t)max_ctas);
-    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers, map, x, y, dbg);
+    kern<<<grid, Cfg::threads, Cfg::smem_bytes, s>>>(ne, headers, map, x, y, dep ? *dep : WsDependency{});
     B2_CHECK_LAUNCH();
     return B200FEM_SUCCESS;
 }
 
 template <typename T, bool PLAIN>
-static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s) {
+static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s,
+                    const WsDependency *dep) {
+    if (dep && (cfg & 255) != 11) B2_FAIL("the in-kernel ghost wait is built into ws_cfg 11 only");
     const int dbg = cfg >> 8;  // A/B switch (ws_cfg + 256): interior runs per node instead of TMA
     switch (cfg & 255) {
         default:
@@ -78,27 +81,29 @@ static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *hea
         case 8: return launch_ws2<T, 8, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);  // two-barrier protocol
         case 9: return launch_ws2<T, 8, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 10: return launch_ws2<T, 8, 5, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + static accumulator phases
+        case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg, dep);  // + static accumulator phases
         case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 13: return launch_ws2<T, 8, 3, PLAIN, true, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + bulk interior stores
-        case 14: return launch_ws2<T, 8, 4, PLAIN, true, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 15: return launch_ws2<T, 8, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral-face output buffer
+        case 17: return launch_ws2<T, 8, 4, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 25: return launch_ws2<T, 8, 3, PLAIN, true, 2, true>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
+        case 26: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
         // bracketing runs of the D = 3 phased kernel (profiles/r02*_ws2_brackets): parts switched off at compile time
-        case 20: return launch_ws2<T, 8, 3, PLAIN, true, false, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);        // no arithmetic
-        case 21: return launch_ws2<T, 8, 3, PLAIN, true, false, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // arithmetic only
-        case 22: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);  // protocol only
-        case 23: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 4>(ne, nn, headers, x, y, max_ctas, s, dbg);    // loads only
-        case 24: return launch_ws2<T, 8, 3, PLAIN, true, false, 2 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // stores only
+        case 20: return launch_ws2<T, 8, 3, PLAIN, true, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);        // no arithmetic
+        case 21: return launch_ws2<T, 8, 3, PLAIN, true, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // arithmetic only
+        case 22: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);  // protocol only
+        case 23: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 4>(ne, nn, headers, x, y, max_ctas, s, dbg);    // loads only
+        case 24: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // stores only
     }
 }
 
 int sshex8_laplacian_ws_launch(int real_type, bool plain, int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const void *x,
-                               void *y, int max_ctas, cudaStream_t s) {
+                               void *y, int max_ctas, cudaStream_t s, const WsDependency *dep) {
     if (real_type == B200FEM_F64)
-        return plain ? launch_t<double, true>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s)
-                     : launch_t<double, false>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s);
-    return plain ? launch_t<float, true>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s)
-                 : launch_t<float, false>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s);
+        return plain ? launch_t<double, true>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s, dep)
+                     : launch_t<double, false>(cfg, ne, nn, headers, (const double *)x, (double *)y, max_ctas, s, dep);
+    return plain ? launch_t<float, true>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s, dep)
+                 : launch_t<float, false>(cfg, ne, nn, headers, (const float *)x, (float *)y, max_ctas, s, dep);
 }
 
 }  // namespace b200fem

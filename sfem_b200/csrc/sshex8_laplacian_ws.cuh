@@ -59,7 +59,7 @@ struct WsLayout<float> {
     __host__ __device__ static constexpr int DK(int) { return 0; }
 };
 
-template <typename T, int L, int NC, int D, int S>
+template <typename T, int L, int NC, int D, int S, bool FACEOUT = false>
 struct Sshex8WsCfg {
     static constexpr int N = L + 1;
     static constexpr int NI = (L - 1) * (L - 1);  // interior positions of a plane
@@ -71,7 +71,9 @@ struct Sshex8WsCfg {
     static constexpr size_t stage_bytes = (size_t)S * PLANE * sizeof(T);
     static constexpr size_t hdr_bytes = (size_t)3 * EPT * sizeof(Sshex8Header);
     static constexpr size_t bar_bytes = (size_t)(2 * D + 2 * S) * sizeof(uint64_t);
-    static constexpr size_t warp_bytes = ((ring_bytes + stage_bytes + hdr_bytes + bar_bytes + 127) / 128) * 128;
+    static constexpr int FOS = 228;  // elements per slot of the lateral-face output buffer (32 x (L-1) = 224 used; 228: 3 wavefronts per store, bank model)
+    static constexpr size_t fo_bytes = FACEOUT ? (size_t)EPT * FOS * sizeof(T) : 0;
+    static constexpr size_t warp_bytes = ((ring_bytes + stage_bytes + hdr_bytes + bar_bytes + fo_bytes + 127) / 128) * 128;
     static constexpr size_t smem_bytes = warp_bytes * NC;
     static constexpr int threads = 2 * NC * 32;
     static_assert(L == 8, "the ws kernel is built for level 8 (EPT = 3, 32 skeleton positions per plane)");
@@ -504,17 +506,21 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 //     with as many staging slots as ring slots, `full` of plane t says "staging slot t % D has been scattered": no `sempty`
 //     barrier either (a phantom plane T covers the final emit);
 //   * all 32 lanes arrive on `sfull` (no __syncwarp + elected arrive).
+// Tried and dropped: the interior output runs by cp.async.bulk (48 of the 49 values of a run are 16-byte aligned) instead of two
+// coalesced stores per slot -- 0.99 against 0.85 ms: the mover has to wait for the bulk engine to have read the staging slot
+// before it may hand the slot back (profiles/r02q_ws2.jsonl and the runs around it).
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, bool BULK, int DBG = 0>
+template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, int DBG = 0, bool FACEOUT = false>
 __global__ void __launch_bounds__(2 * NC * 32, 1)
     sshex8_laplacian_ws2_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers, const __grid_constant__ CUtensorMap tmap_u,
-                                const T *__restrict__ u, T *__restrict__ y, const int) {
+                                const T *__restrict__ u, T *__restrict__ y, const WsDependency dep) {
     constexpr int dbg = DBG;  // experiment switches (bracketing runs): 2 = no arithmetic, 4 = no stores, 8 = no loads, 16 = no REDs, 32 = no plain stores
-    using Cfg = Sshex8WsCfg<T, L, NC, D, D>;
+    using Cfg = Sshex8WsCfg<T, L, NC, D, D, FACEOUT>;
     using Lay = WsLayout<T>;
+    constexpr int FOS = Cfg::FOS;
     constexpr int N = Cfg::N, NI = Cfg::NI, EPT = Cfg::EPT, PS = Cfg::PS, PLANE = Cfg::PLANE;
     constexpr int HSZ = (int)sizeof(Sshex8Header);
     constexpr int HBUF = EPT * HSZ;
@@ -535,6 +541,12 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
     unsigned char *hdr_bytes = wbase + Cfg::ring_bytes + Cfg::stage_bytes;  // [3][EPT] headers
     uint64_t *bars = reinterpret_cast<uint64_t *>(hdr_bytes + Cfg::hdr_bytes);
     uint64_t *full = bars, *sfull = bars + D;
+    // FACEOUT: the skeleton values of the z-interior output planes of the current group, [slot][32 positions][L-1 planes]:
+    // written by the compute warp plane after plane, reduced into y by the mover in two sweeps per group with z fastest --
+    // the lateral faces of the reference numbering are contiguous along z, so a sweep instruction touches 8 - 11 sectors where
+    // the 32 positions of one plane are 32 sectors (profiles/r02*_ws2_brackets: the store path, 101 M single-sector REDs, is
+    // what bounds the kernel once the hand-offs are cheap)
+    T *fo = reinterpret_cast<T *>(wbase + Cfg::ring_bytes + Cfg::stage_bytes + Cfg::hdr_bytes + Cfg::bar_bytes);
 
     const int ngroups = (int)((ne + EPT - 1) / EPT);
     const int nteams = (int)gridDim.x * NC;
@@ -617,7 +629,31 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         };
         using PlainT = std::integral_constant<bool, PLAIN_INTERIOR>;
         using RedT = std::integral_constant<bool, false>;
-        constexpr bool kBulk = BULK && sizeof(T) == 8;  // interior output runs by cp.async.bulk (fp64: 48 of the 49 values are 16-byte aligned)
+
+        // sweep items of this lane: half A = planes 1 .. 4 (4 items: position (tl >> 2) + 8 q, plane 1 + (tl & 3)), half B = planes
+        // 5 .. L-1 (3 items: position j / 3, plane 5 + j % 3, j = tl + 32 q), packed as box byte offset | x << 9 | y << 13 |
+        // buffer offset << 17 | plane << 25
+        int sweepA[4], sweepB[3];
+        if constexpr (FACEOUT) {
+            auto pack = [&](int pos, int zpl) {
+                int x, yy;
+                plane_pos_to_xy<L>(NI + pos, x, yy);
+                const int cxy = ((x == 0) ? 0 : (x == L ? 2 : 1)) + 3 * ((yy == 0) ? 0 : (yy == L ? 2 : 1));
+                return ((9 + cxy) * 16) | (x << 9) | (yy << 13) | ((pos * (L - 1) + zpl - 1) << 17) | (zpl << 25);
+            };
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sweepA[q] = pack((tl >> 2) + 8 * q, 1 + (tl & 3));
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sweepB[q] = pack((tl + 32 * q) / 3, 5 + (tl + 32 * q) % 3);
+        }
+        auto sweep = [&](const unsigned char *hb, const int item, const int nv) {
+            const int boxoff = item & 0x1ff, x = (item >> 9) & 15, yy = (item >> 13) & 15, off = (item >> 17) & 255, zpl = item >> 25;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int4 d = *reinterpret_cast<const int4 *>(hb + i * HSZ + boxoff);
+                put_if(i < nv, y + (d.x + d.y * x + d.z * yy + d.w * zpl), fo[i * FOS + off], RedT{});
+            }
+        };
 
         int ldI[EPT], ldS[EPT], ldG[EPT];  // planes being gathered
         int scI[EPT], scS[EPT], scG[EPT];  // planes being scattered
@@ -676,39 +712,18 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     asm volatile("" ::: "memory");
                 }
             } else {
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) {
-                    const int k = scG[i] & (AL - 1);
-                    put_if(i < nv, y + scI[i], src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
-                }
-                if constexpr (kBulk) {
-                    // values [k, k + 48) of the run (k = its alignment offset) in one bulk copy, the 49th by lane 1 + slot
-                    if (tl == 0 && !(dbg & 32)) {
-                        fence_proxy_async_smem();  // the compute warp's stores (acquired through sfull) before the bulk engine reads
-#pragma unroll
-                        for (int i = 0; i < EPT; ++i) {
-                            if (i < nv) {
-                                const int k = scG[i] & 1;
-                                if constexpr (PLAIN_INTERIOR)
-                                    bulk_s2g(y + (scG[i] + k), src + (i * PS + 2 * k), (NI - 1) * (int)sizeof(T));
-                                else
-                                    bulk_red_add(y + (scG[i] + k), src + (i * PS + 2 * k), (NI - 1) * (int)sizeof(T));
-                            }
-                        }
-                        bulk_commit();
-                    }
-#pragma unroll
-                    for (int i = 0; i < EPT; ++i) {
-                        const int k = scG[i] & 1, j0 = k ? 0 : NI - 1;
-                        put_if(i < nv && tl == 1 + i, y + (scG[i] + j0), src[i * PS + k + j0], PlainT{});
-                    }
-                } else {
+                if constexpr (!FACEOUT) {
 #pragma unroll
                     for (int i = 0; i < EPT; ++i) {
                         const int k = scG[i] & (AL - 1);
-                        put_if(i < nv, y + (scG[i] + tl), src[i * PS + k + tl], PlainT{});
-                        put_if(i < nv && in_second, y + (scG[i] + q1), src[i * PS + k + q1], PlainT{});
+                        put_if(i < nv, y + scI[i], src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
                     }
+                }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int k = scG[i] & (AL - 1);
+                    put_if(i < nv, y + (scG[i] + tl), src[i * PS + k + tl], PlainT{});
+                    put_if(i < nv && in_second, y + (scG[i] + q1), src[i * PS + k + q1], PlainT{});
                 }
             }
 #pragma unroll
@@ -718,12 +733,33 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             }
         };
 
+        // distributed apply: the groups from dep.first_group on read ghost values; before the first plane of such a group is
+        // gathered, wait until the receiver half of the halo gather (another stream, another SM) has announced the ghost block
+        // of x. Bounded (2 s): a flag that never comes must not hang the GPU -- the apply then runs on stale ghosts and the
+        // communicator's own time-out reports the failed exchange.
+        auto wait_ghosts = [&](const int g_local) {
+            if (dep.flag == nullptr || group_of(g_local) < dep.first_group) return;
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(dep.flag) : "memory");
+            if (v < dep.want) {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+                do {
+                    __nanosleep(200);
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(dep.flag) : "memory");
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                } while (v < dep.want && t1 - t0 < 2000000000ull);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA reads of the ghost block come after the acquire
+            __syncwarp();
+        };
         // ---- prologue: headers of groups 0 and 1, planes 0 .. D-1
         issue_headers(0);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
         issue_headers(1);
+        wait_ghosts(0);
 #pragma unroll 1
         for (int s = 0; s < D; ++s) {
             issue_plane(s, hdr_bytes, s);  // D < N <= T_steps: all in group 0
@@ -742,7 +778,10 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             const bool more = t + D < T_steps;
             const bool closing = more || (t + D == T_steps);  // plane T_steps is a phantom: it only carries "staging slot free"
             if (more) {
-                if (zn == 0) issue_headers(gn + 1);  // headers of group g+2 travel with the first plane of g+1
+                if (zn == 0) {
+                    issue_headers(gn + 1);  // headers of group g+2 travel with the first plane of g+1
+                    wait_ghosts(gn);
+                }
                 issue_plane(rs, hdr_bytes + hn * HBUF, zn);
             } else if (closing) {
                 cp_async_mbar_arrive_noinc(full + rs);
@@ -757,18 +796,30 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     nv = left < EPT ? left : EPT;
                 }
                 if (!(dbg & 4)) scatter_plane(rs, hb, zs, nv);
-                if (++zs == N) { zs = 0; ++gs; hs = (hs == 2) ? 0 : hs + 1; }
             }
             if (tl == 0) {
-                if constexpr (kBulk) bulk_wait_read_all();  // the staging slot has been read: full[rs] may say so
                 if (closing) mbar_arrive(full + rs);
+            }
+            if (t > 0) {
+                if constexpr (FACEOUT) {
+                    // after the closing arrival (the sweeps read the lateral buffer, not the staging slot; the half they read is
+                    // rewritten 6 steps later at the earliest, behind the closing arrivals of the iterations in between)
+                    if (!(dbg & 4)) {
+                        const unsigned char *hb = hdr_bytes + hs * HBUF;
+                        if (zs == 4) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) sweep(hb, sweepA[q], nv);
+                        } else if (zs == L - 1) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) sweep(hb, sweepB[q], nv);
+                        }
+                    }
+                }
+                if (++zs == N) { zs = 0; ++gs; hs = (hs == 2) ? 0 : hs + 1; }
             }
             if (++rs == D) { rs = 0; ph ^= 1u; }
         }
         cp_async_wait<0>();
-        if constexpr (kBulk) {
-            if (tl == 0) bulk_wait_all();
-        }
     } else {
         // ========================================================================================= compute warp
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_COMPUTE));
@@ -794,10 +845,27 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         Sshex8LaplacianRow<T, L> row;
         row.clear();
 
+        // FACEOUT: positions of this lane's x = 0 / x = L nodes among the 32 skeleton positions of a plane (the rows y = 0 / L
+        // are positions 0 .. L and N .. N + L, the columns follow); x = 1 .. L-1 of a lateral row go to positions posA + x
+        const int posA = yrow == 0 ? 0 : (yrow == L ? N : 2 * N + yrow - 1);
+        const int posB = yrow == 0 ? L : (yrow == L ? N + L : 2 * N + (L - 1) + yrow - 1);
+        T *fo_lane = fo + slot * FOS;
+        const int mid_stride = rint[1] ? 1 : (L - 1);
         // this lane's row of output plane z of the element whose interior starts at B, into staging slot ss
         auto stage_row = [&](const int ss, const int z, const int B, const T(&vals)[N]) {
             T *dst = stage + (size_t)ss * PLANE;
             const int k = (B + NI * z) & (AL - 1);
+            if constexpr (FACEOUT) {
+                if (z != 0 && z != L) {  // warp-uniform
+                    T *f = fo_lane + (z - 1);
+                    f[posA * (L - 1)] = vals[0];
+                    f[posB * (L - 1)] = vals[L];
+                    T *dmid = rint[1] ? (dst + k + am[1]) : (f + (posA + 1) * (L - 1));
+#pragma unroll
+                    for (int x = 1; x < L; ++x) dmid[(x - 1) * mid_stride] = vals[x];
+                    return;
+                }
+            }
             T *ds = dst + dk * k;
             T *dm = (rint[1] ? dst + k : ds) + am[1];
             ds[a0[1]] = vals[0];

@@ -69,6 +69,7 @@ _SIG = {
     "b200host_halo_values_sent": (ssz, [vp]),
     "b200host_halo_launches_per_gather": (i32, [vp]),
     "b200host_parallel_op": (vp, [vp, vp, ssz, ssz]),
+    "b200host_parallel_op_set_independent_range": (i32, [vp, ssz, ssz]),
     "b200host_blas_set_comm": (i32, [vp, vp]),
     "b200host_blas_reserve_allocation": (i32, [vp, ssz, ssz]),
     "b200host_blas_reductions": (C.c_long, [vp]),
@@ -228,9 +229,15 @@ class Halo(Handle):
         return _h.b200host_halo_launches_per_gather(self.ptr)
 
 
-def parallel_op(local_op: Handle, in_halo: Halo, owned_rows: int, owned_cols: int) -> Handle:
-    """ParallelMatrixFreeOperator: gather the ghost block of x (input space), then the local operator."""
-    return Handle(_h.b200host_parallel_op(local_op.ptr, in_halo.ptr, owned_rows, owned_cols), keep=[local_op, in_halo])
+def parallel_op(local_op: Handle, in_halo: Halo, owned_rows: int, owned_cols: int, independent_range=None) -> Handle:
+    """ParallelMatrixFreeOperator: gather the ghost block of x (input space), then the local operator. With
+    independent_range = (e0, e1) (elements that read no ghost value) the overwriting apply runs them between the two
+    halves of the gather; .overlapped tells whether the local operator supports it."""
+    h = Handle(_h.b200host_parallel_op(local_op.ptr, in_halo.ptr, owned_rows, owned_cols), keep=[local_op, in_halo])
+    h.overlapped = False
+    if independent_range is not None and independent_range[1] > independent_range[0]:
+        h.overlapped = _h.b200host_parallel_op_set_independent_range(h.ptr, int(independent_range[0]), int(independent_range[1])) == 0
+    return h
 
 
 class Function(Handle):

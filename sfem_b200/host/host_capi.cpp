@@ -290,6 +290,21 @@ void *b200host_parallel_op(void *local_op, void *in_halo, ptrdiff_t owned_rows, 
         return box<double>(std::make_shared<ParallelMatrixFreeOperator<double>>(op_of<double>(o), h, owned_rows, owned_cols), K_OP, nullptr);
     return box<float>(std::make_shared<ParallelMatrixFreeOperator<float>>(op_of<float>(o), h, owned_rows, owned_cols), K_OP, nullptr);
 }
+/* elements [e0, e1) of the local operator read no ghost value: run them between the two halves of the gather */
+int b200host_parallel_op_set_independent_range(void *pop, ptrdiff_t e0, ptrdiff_t e1) {
+    Box *o = (Box *)pop;
+    if (!o || e0 < 0 || e1 < e0) return 1;
+    if (o->real_type == B200FEM_F64) {
+        auto p = std::dynamic_pointer_cast<ParallelMatrixFreeOperator<double>>(op_of<double>(o));
+        if (!p) return 1;
+        p->set_independent_range(e0, e1);
+        return p->overlapped() ? 0 : 2;
+    }
+    auto p = std::dynamic_pointer_cast<ParallelMatrixFreeOperator<float>>(op_of<float>(o));
+    if (!p) return 1;
+    p->set_independent_range(e0, e1);
+    return p->overlapped() ? 0 : 2;
+}
 /* reductions of this BLAS run over the communicator (device-side sum + ncclAllReduce + one host read) */
 int b200host_blas_set_comm(void *blas, void *comm) {
     Box *b = (Box *)blas;

@@ -107,6 +107,8 @@ _SIG = {
     "b200fem_halo_create": [C.POINTER(vp), vp, i32, i32, ssz, ssz, i32, vp, vp, vp, i32, vp, vp, vp, i32],
     "b200fem_halo_destroy": [vp],
     "b200fem_halo_gather": [vp, vp, vp],
+    "b200fem_halo_gather_begin": [vp, vp, vp],
+    "b200fem_halo_gather_end": [vp, vp, vp],
     "b200fem_halo_transport": [vp],
     "b200fem_halo_launches_per_gather": [vp],
     "b200fem_transfer_prolongate": [vp, i32, i32, vp, vp, vp],
@@ -124,7 +126,7 @@ _lib.b200fem_op_rows.argtypes = [vp]
 _lib.b200fem_op_rows.restype = ssz
 _lib.b200fem_op_algorithmic_bytes.argtypes = [vp]
 _lib.b200fem_op_algorithmic_bytes.restype = f64
-for _name in ("b200fem_transfer_fine_nodes", "b200fem_transfer_coarse_nodes", "b200fem_halo_values_sent"):
+for _name in ("b200fem_transfer_fine_nodes", "b200fem_transfer_coarse_nodes", "b200fem_halo_values_sent", "b200fem_op_nelements"):
     getattr(_lib, _name).argtypes = [vp]
     getattr(_lib, _name).restype = ssz
 _lib.b200fem_op_streamed_bytes.argtypes = [vp, i32]

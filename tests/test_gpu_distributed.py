@@ -51,6 +51,14 @@ def test_distributed_mg_elasticity_matches_serial():
     assert out["residual_history"][-1] < 1e-9
 
 
+def test_overlapped_apply_matches_plain_distributed_apply():
+    """the ghost-independent elements between the two halves of the halo gather (one stream, sub-range launches of the
+    warp-specialised kernel) give the rows the gather-then-apply form gives"""
+    out = _run(2, ["apply", "--macro", "8", "--layers", "4", "--level", "8"])
+    assert out["rc"] == 0 and out["overlapped"] is True, out
+    assert out["max_rel_diff"] < 1e-13, out
+
+
 def test_single_rank_goes_through_the_same_layer():
     """world 1: Communicator / Halo / ParallelMatrixFreeOperator degenerate to the plain solve (no NCCL call)."""
     out = _run(1, ["c4", "--side", "25", "--check"])

@@ -74,6 +74,41 @@ def _timed(torch, comm, fn):
     return out, comm.max(e0.elapsed_time(e1))
 
 
+def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
+    """ParallelMatrixFreeOperator::apply_overwrite with the ghost-independent elements between the two halves of the halo
+    gather against the plain gather-then-apply form: same x, every rank compares its owned rows (RED order only)."""
+    from sfem_b200 import host, lib, parallel
+
+    torch, dt = d.torch, d.torch.float64
+    lm = parallel.sshex8_slab(level, macro, macro, layers, d.rank, d.world)
+    fff = lib.fff_fill(lib.HEX8, lm.extra["m_elements"], lm.extra["m_points"])
+    op = lib.laplacian(lib.SSHEX8, lm.elements, fff, lm.n_local, dt, level=level)
+    f = host.Function(dt, lm.n_local, 1)
+    f.add_operator(op)
+    halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object))
+    ind = parallel.independent_range(lm)
+    plain = host.parallel_op(f, halo, lm.n_owned, lm.n_owned)
+    over = host.parallel_op(f, halo, lm.n_owned, lm.n_owned, independent_range=ind)
+    x = torch.from_numpy(np.random.default_rng(7 + d.rank).uniform(-1, 1, lm.n_local)).to(d.dev)
+    y0, y1 = torch.zeros_like(x), torch.full_like(x, 3.0)
+    assert host.apply_overwrite(plain, x, y0) == 0
+    assert host.apply_overwrite(over, x, y1) == 0
+    torch.cuda.synchronize()
+    n = lm.n_owned
+    diff = float((y0[:n] - y1[:n]).abs().max() / y0[:n].abs().max())
+    ms = {}
+    for name, A in (("plain", plain), ("overlapped", over)):
+        for _ in range(3):
+            host.apply_overwrite(A, x, y1)
+        _, t = _timed(torch, d.comm, lambda: [host.apply_overwrite(A, x, y1) for _ in range(steps)])
+        ms[name] = t / steps
+    ne = int(lm.elements.shape[1])
+    return dict(name=f"overlapped distributed apply, sshex8 L{level} {macro}x{macro}x{layers} macro per GPU x {d.world}", rc=0,
+                overlapped=bool(over.overlapped), independent_range=list(ind) if ind else None, elements=ne,
+                max_rel_diff=d.comm.max(diff), ms_plain=ms["plain"], ms_overlapped=ms["overlapped"], n_gpus=d.world)
+
+
+
 def cg_poisson_tet4(d: Dist, n=465, rtol=1e-6, max_it=20000, peak_gbs=6470.5, check=False):
     from sfem_b200 import host, lib, mesh, parallel
 
@@ -280,7 +315,7 @@ def main():
     import torch
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("case", choices=["c4", "c5"])
+    ap.add_argument("case", choices=["c4", "c5", "apply"])
     ap.add_argument("--side", type=int, default=465)
     ap.add_argument("--rtol", type=float, default=1e-6)
     ap.add_argument("--max-it", type=int, default=20000)
@@ -293,6 +328,8 @@ def main():
     d = Dist(torch)
     if a.case == "c4":
         out = cg_poisson_tet4(d, a.side, a.rtol, a.max_it, check=a.check)
+    elif a.case == "apply":
+        out = overlapped_apply_check(d, a.macro, a.layers, a.level)
     else:
         out = mg_elasticity(d, a.macro, a.layers, a.level, a.sweeps, check=a.check)
     if d.rank == 0:
