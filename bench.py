@@ -504,7 +504,7 @@ def run_b200(a):
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": alg, "streamed_bytes": streamed,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
-            "kernel": ("sshex8_laplacian_ws_kernel" if (a.real == "f64" and a.level == 8) else "sshex8_laplacian_stream_kernel")
+            "kernel": ("sshex8_laplacian_ws2_kernel" if (a.real == "f64" and a.level == 8) else "sshex8_laplacian_stream_kernel")
             + " (+ the memsets of the skeleton ranges that belong to the call)",
             "kernel_ms": ms_kernel, "frac_of_8TBs_nominal": achieved / 8000.0,
         },

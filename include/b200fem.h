@@ -299,14 +299,18 @@ int b200fem_halo_gather(b200fem_halo_t halo, void *x_local, void *stream);
  * begin + end on one stream is b200fem_halo_gather. */
 int b200fem_halo_gather_begin(b200fem_halo_t halo, void *x_local, void *stream);
 int b200fem_halo_gather_end(b200fem_halo_t halo, void *x_local, void *stream);
-/* The whole gather on the halo's OWN stream (ordered behind what `stream` holds so far), for an apply kernel that waits
- * for the ghost block itself: *ready_flag is a device word that reaches *ready_value (release, GPU scope) once the ghost
- * block of x is complete; hand both to b200fem_op_apply_overwrite_after, which leaves one SM to this stream. Neither the
- * push over NVLink nor the wait for the peers then sits in front of the apply. *ready_flag == NULL: the gather has been
- * enqueued on `stream` in the ordinary way (one rank, NCCL transport, nothing to receive). The next operation that WRITES
- * x on `stream` must come after the apply that consumed the flag (any use of the apply's result does). */
-int b200fem_halo_gather_deferred(b200fem_halo_t halo, void *x_local, void *stream, const unsigned long long **ready_flag,
-                                 unsigned long long *ready_value);
+/* The whole gather on the halo's OWN low-priority stream, for an apply kernel that waits for the ghost block itself:
+ *   deferred_begin  : orders that stream behind what `stream` holds so far and returns a device word *ready_flag that will
+ *                     reach *ready_value (release, GPU scope) once the ghost block of x is complete; launches nothing.
+ *   b200fem_op_apply_overwrite_after(op, x, y, e_dependent, flag, value, stream) : the apply, one SM left free.
+ *   deferred_launch : push over NVLink + wait for the peers + copy into the ghost block, on the halo's stream -- AFTER the
+ *                     apply has been launched, so that the apply's CTAs take their SMs first and the gather fills the rest.
+ * Neither the push nor the wait for the peers then sits in front of the apply. *ready_flag == NULL after deferred_begin: the
+ * gather has been enqueued on `stream` in the ordinary way (one rank, NCCL transport, nothing to receive); do not call
+ * deferred_launch. The next operation that WRITES x on `stream` must come after the apply (any use of its result does). */
+int b200fem_halo_gather_deferred_begin(b200fem_halo_t halo, void *x_local, void *stream, const unsigned long long **ready_flag,
+                                       unsigned long long *ready_value);
+int b200fem_halo_gather_deferred_launch(b200fem_halo_t halo, void *x_local);
 int b200fem_halo_transport(b200fem_halo_t halo); /* the transport in use */
 ptrdiff_t b200fem_halo_values_sent(b200fem_halo_t halo);
 int b200fem_halo_launches_per_gather(b200fem_halo_t halo);

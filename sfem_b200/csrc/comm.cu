@@ -417,22 +417,16 @@ static int halo_setup_push(b200fem_halo_s *h) {
 template <typename T>
 static int halo_gather_t(b200fem_halo_s *h, T *x, cudaStream_t s, int phase = 0) {
     b200fem_comm_s *c = h->comm;
-    const bool deferred = phase == 3;  // the whole gather on the halo's own stream (ordered behind `s`), announcing through h->ready
+    const bool deferred = phase == 3;  // the whole gather on the halo's own stream, announcing through h->ready (epoch set by _begin)
     if (deferred) phase = 0;
     if (phase != 2) h->n_gathers++;
     if (c->world == 1 || (h->send_peers.empty() && h->recv_peers.empty())) return B200FEM_SUCCESS;
     if (h->transport == B200FEM_HALO_PUSH) {
-        const unsigned long long epoch = phase == 2 ? h->epoch : ++h->epoch;
+        const unsigned long long epoch = (phase == 2 || deferred) ? h->epoch : ++h->epoch;
         ptrdiff_t max_send = 0, max_recv = 0;
         for (auto n : h->send_count) max_send = std::max(max_send, n * h->bs);
         for (size_t j = 0; j < h->recv_count.size(); ++j) max_recv = std::max(max_recv, h->recv_count[j] * (ptrdiff_t)h->bs);
         const ptrdiff_t cap = (ptrdiff_t)sm_count() * 4;
-        if (deferred) {
-            // the push reads x, the copy writes its ghost block: behind everything `s` has been given so far (the producers
-            // of x, the previous apply that read the block), concurrent with what follows on `s`
-            B2_CUDA(cudaEventRecord(h->side_event, s));
-            B2_CUDA(cudaStreamWaitEvent(h->side, h->side_event, 0));
-        }
         if (phase != 2 && !h->send_peers.empty()) {
             const int gx = (int)std::max<ptrdiff_t>(1, std::min<ptrdiff_t>((max_send + kHaloThreads * 4 - 1) / (kHaloThreads * 4),
                                                                           cap / (ptrdiff_t)h->send_peers.size()));
@@ -696,9 +690,9 @@ int b200fem_halo_gather_begin(b200fem_halo_t h, void *x_local, void *stream) {
     if (h->real_type == B200FEM_F64) return halo_gather_t<double>(h, (double *)x_local, as_stream(stream), 1);
     return halo_gather_t<float>(h, (float *)x_local, as_stream(stream), 1);
 }
-int b200fem_halo_gather_deferred(b200fem_halo_t h, void *x_local, void *stream, const unsigned long long **ready_flag,
-                                 unsigned long long *ready_value) {
-    if (!h || !x_local || !ready_flag || !ready_value) B2_FAIL("halo_gather_deferred: NULL argument");
+int b200fem_halo_gather_deferred_begin(b200fem_halo_t h, void *x_local, void *stream, const unsigned long long **ready_flag,
+                                       unsigned long long *ready_value) {
+    if (!h || !x_local || !ready_flag || !ready_value) B2_FAIL("halo_gather_deferred_begin: NULL argument");
     *ready_flag = nullptr;
     *ready_value = 0;
     if (h->comm->world == 1 || h->transport != B200FEM_HALO_PUSH || h->recv_peers.empty()) {
@@ -706,19 +700,26 @@ int b200fem_halo_gather_deferred(b200fem_halo_t h, void *x_local, void *stream, 
         return b200fem_halo_gather(h, x_local, stream);
     }
     if (!h->side) {
+        // LOWEST priority: the apply kernel that follows on `stream` takes its SMs first, the gather's blocks fill what it leaves
         int lo = 0, hi = 0;
         B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        B2_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+        B2_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
         B2_CUDA(cudaEventCreateWithFlags(&h->side_event, cudaEventDisableTiming));
         B2_CUDA(cudaMalloc((void **)&h->ready, 2 * sizeof(unsigned long long)));
         B2_CUDA(cudaMemset(h->ready, 0, 2 * sizeof(unsigned long long)));
     }
-    const int rc = h->real_type == B200FEM_F64 ? halo_gather_t<double>(h, (double *)x_local, as_stream(stream), 3)
-                                               : halo_gather_t<float>(h, (float *)x_local, as_stream(stream), 3);
-    if (rc) return rc;
+    // the push reads x, the copy writes its ghost block: behind everything `stream` has been given so far (the producers of
+    // x, the previous apply that read the block), concurrent with what follows on `stream`
+    B2_CUDA(cudaEventRecord(h->side_event, as_stream(stream)));
+    B2_CUDA(cudaStreamWaitEvent(h->side, h->side_event, 0));
     *ready_flag = h->ready;
-    *ready_value = h->epoch;
+    *ready_value = ++h->epoch;
     return B200FEM_SUCCESS;
+}
+int b200fem_halo_gather_deferred_launch(b200fem_halo_t h, void *x_local) {
+    if (!h || !x_local) B2_FAIL("halo_gather_deferred_launch: NULL argument");
+    if (!h->side) B2_FAIL("halo_gather_deferred_launch: no deferred gather has been begun");
+    return h->real_type == B200FEM_F64 ? halo_gather_t<double>(h, (double *)x_local, nullptr, 3) : halo_gather_t<float>(h, (float *)x_local, nullptr, 3);
 }
 int b200fem_halo_gather_end(b200fem_halo_t h, void *x_local, void *stream) {
     if (!h || !x_local) B2_FAIL("halo_gather_end: NULL argument");

@@ -1109,9 +1109,10 @@ namespace b200fem {
         int  gather(void *x_local, void *stream = nullptr) const { return b200fem_halo_gather(h_, x_local, stream); }
         int  gather_begin(void *x_local, void *stream = nullptr) const { return b200fem_halo_gather_begin(h_, x_local, stream); }
         int  gather_end(void *x_local, void *stream = nullptr) const { return b200fem_halo_gather_end(h_, x_local, stream); }
-        int  gather_deferred(void *x_local, void *stream, const unsigned long long **flag, unsigned long long *want) const {
-            return b200fem_halo_gather_deferred(h_, x_local, stream, flag, want);
+        int  gather_deferred_begin(void *x_local, void *stream, const unsigned long long **flag, unsigned long long *want) const {
+            return b200fem_halo_gather_deferred_begin(h_, x_local, stream, flag, want);
         }
+        int  gather_deferred_launch(void *x_local) const { return b200fem_halo_gather_deferred_launch(h_, x_local); }
         b200fem_halo_t                get() const { return h_; }
         std::shared_ptr<Communicator> comm() const { return comm_; }
 
@@ -1161,9 +1162,12 @@ namespace b200fem {
                  * for the ghost block inside the kernel */
                 const unsigned long long *flag = nullptr;
                 unsigned long long        want = 0;
-                B200FEM_TRY(halo_->gather_deferred(const_cast<T *>(x), stream_, &flag, &want));
+                B200FEM_TRY(halo_->gather_deferred_begin(const_cast<T *>(x), stream_, &flag, &want));
                 if (!flag) return local_->apply_overwrite(x, y); /* the gather went onto this stream in the ordinary way */
-                return local_->apply_overwrite_after(x, y, ind1_, flag, want);
+                const int rc = local_->apply_overwrite_after(x, y, ind1_, flag, want);
+                /* launched even if the apply failed to enqueue: the peers wait for this rank's push */
+                B200FEM_TRY(halo_->gather_deferred_launch(const_cast<T *>(x)));
+                return rc;
             }
             if (overlapped()) {
                 const std::ptrdiff_t ne = local_->range_elements();
