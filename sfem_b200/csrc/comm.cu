@@ -700,10 +700,10 @@ int b200fem_halo_gather_deferred_begin(b200fem_halo_t h, void *x_local, void *st
         return b200fem_halo_gather(h, x_local, stream);
     }
     if (!h->side) {
-        // LOWEST priority: the apply kernel that follows on `stream` takes its SMs first, the gather's blocks fill what it leaves
+        // highest priority: the gather's (few, short) blocks must not queue behind the apply's persistent CTAs
         int lo = 0, hi = 0;
         B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        B2_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+        B2_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
         B2_CUDA(cudaEventCreateWithFlags(&h->side_event, cudaEventDisableTiming));
         B2_CUDA(cudaMalloc((void **)&h->ready, 2 * sizeof(unsigned long long)));
         B2_CUDA(cudaMemset(h->ready, 0, 2 * sizeof(unsigned long long)));

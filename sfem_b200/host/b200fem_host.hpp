@@ -1164,10 +1164,8 @@ namespace b200fem {
                 unsigned long long        want = 0;
                 B200FEM_TRY(halo_->gather_deferred_begin(const_cast<T *>(x), stream_, &flag, &want));
                 if (!flag) return local_->apply_overwrite(x, y); /* the gather went onto this stream in the ordinary way */
-                const int rc = local_->apply_overwrite_after(x, y, ind1_, flag, want);
-                /* launched even if the apply failed to enqueue: the peers wait for this rank's push */
                 B200FEM_TRY(halo_->gather_deferred_launch(const_cast<T *>(x)));
-                return rc;
+                return local_->apply_overwrite_after(x, y, ind1_, flag, want);
             }
             if (overlapped()) {
                 const std::ptrdiff_t ne = local_->range_elements();
