@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: halo gather in front of the apply instead of overlapped with the ghost-independent elements")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: the halo gather on its own stream, ghost-dependent element groups wait inside the apply kernel (faster on 2 GPUs, "
+                         "slower on 4: which of the two streams gets the SMs first is a race; default = gather in front of the apply)")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: grouped ncclSend/ncclRecv instead of the owner-push transport")
     ap.add_argument("--c4-side", type=int, default=465, help="nodes per side of the config-4 tet4 cube (strong scaling)")
     ap.add_argument("--c5-macro", type=int, default=87, help="config 5: macro elements per x / y side")
@@ -328,7 +330,7 @@ def run_b200(a):
         halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object),
                          transport=lib.HALO_NCCL if a.nccl_halo else lib.HALO_AUTO)
         # the elements that read no ghost value run between the two halves of the gather (--no-overlap: gather, then apply)
-        ind = None if a.no_overlap else parallel.independent_range(lm)
+        ind = parallel.independent_range(lm) if a.overlap else None
         A = host.parallel_op(f, halo, n_owned, n_owned, independent_range=ind)
         halo_kind = {"push": "owner-push: the owner's pack kernel stores into the peer's receive block over NVLink (cudaIpc-mapped), "
                              "acquire / release epoch flags, a second kernel waits and copies into the ghost block",

@@ -204,7 +204,9 @@ int b200fem_laplacian_create(b200fem_op_t *op, int element_type, int level, ptrd
         case B200FEM_TET4: impl = make_tet4_laplacian(ne, nn, elements, fff, real_type); break;
         case B200FEM_HEX8: impl = make_hex8_laplacian(ne, nn, elements, fff, real_type); break;
         case B200FEM_SSHEX8:
-            if (level < 2) B2_FAIL("sshex8 level must be >= 2");
+            // apply is built for levels 2, 4 and 8 (the levels of the reference's multigrid hierarchies): refuse the others at
+            // creation instead of at the first apply, like the linear-elasticity factory does
+            if (level != 2 && level != 4 && level != 8) B2_FAIL("sshex8 laplacian: level must be 2, 4 or 8");
             impl = make_sshex8_laplacian(level, ne, nn, elements, fff, real_type);
             break;
         default: B2_FAIL("laplacian: unsupported element type");

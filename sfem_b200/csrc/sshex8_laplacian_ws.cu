@@ -48,12 +48,12 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     return B200FEM_SUCCESS;
 }
 
-template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, int DBG = 0, bool FACEOUT = false>
+template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, int DBG = 0, bool FACEOUT = false, int HINT = 0>
 static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg,
                       const WsDependency *dep = nullptr) {
     constexpr int L = 8;
     using Cfg = Sshex8WsCfg<T, L, NC, D, D, FACEOUT>;
-    auto kern = sshex8_laplacian_ws2_kernel<T, L, NC, D, PLAIN, PHASED, DBG, FACEOUT>;
+    auto kern = sshex8_laplacian_ws2_kernel<T, L, NC, D, PLAIN, PHASED, DBG, FACEOUT, HINT>;
     static SmemOptIn opt;
     if (opt.ensure(kern, Cfg::smem_bytes)) return B200FEM_FAILURE;
     const ptrdiff_t ngroups = (ne + Cfg::EPT - 1) / Cfg::EPT;
@@ -84,6 +84,9 @@ static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *hea
         case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg, dep);  // + static accumulator phases
         case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 15: return launch_ws2<T, 8, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 30: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 200>(ne, nn, headers, x, y, max_ctas, s, dbg);   // try_wait suspend hints
+        case 31: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 1000>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 32: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 5000>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral-face output buffer
         case 17: return launch_ws2<T, 8, 4, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 25: return launch_ws2<T, 8, 3, PLAIN, true, 2, true>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic

@@ -509,11 +509,25 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 // Tried and dropped: the interior output runs by cp.async.bulk (48 of the 49 values of a run are 16-byte aligned) instead of two
 // coalesced stores per slot -- 0.99 against 0.85 ms: the mover has to wait for the bulk engine to have read the staging slot
 // before it may hand the slot back (profiles/r02q_ws2.jsonl and the runs around it).
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint runs out) instead of
+// re-issuing the poll -- the polls of a waiting role take issue slots from the role it waits for
+template <int HINT_NS>
+__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t parity) {
+    if constexpr (HINT_NS == 0) {
+        mbar_wait(bar, parity);
+    } else {
+        asm volatile(
+            "{\n .reg .pred p;\n WAITH_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONEH_%=;\n bra WAITH_%=;\n DONEH_%=:\n}\n" ::"r"(
+                smem_u32(bar)),
+            "r"(parity), "r"(HINT_NS)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, int DBG = 0, bool FACEOUT = false>
+template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, int DBG = 0, bool FACEOUT = false, int HINT = 0>
 __global__ void __launch_bounds__(2 * NC * 32, 1)
     sshex8_laplacian_ws2_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers, const __grid_constant__ CUtensorMap tmap_u,
                                 const T *__restrict__ u, T *__restrict__ y, const WsDependency dep) {
@@ -774,7 +788,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         int zs = 0, hs = 0, gs = 0, nv = EPT;
 #pragma unroll 1
         for (int t = 0; t <= T_steps; ++t) {
-            mbar_wait(sfull + rs, ph);
+            mbar_wait_hint<HINT>(sfull + rs, ph);
             const bool more = t + D < T_steps;
             const bool closing = more || (t + D == T_steps);  // plane T_steps is a phantom: it only carries "staging slot free"
             if (more) {
@@ -887,7 +901,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             auto z_step = [&](auto zc_tag, auto p_tag, const int g_local, const int zp) {
                 constexpr int ZC = decltype(zc_tag)::value, P = decltype(p_tag)::value;
                 const T *plane = ring + (size_t)rs * PLANE;
-                mbar_wait(full + rs, ph);
+                mbar_wait_hint<HINT>(full + rs, ph);
                 if constexpr (ZC == 0) {
                     const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
                     T f[6];
@@ -948,7 +962,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     z_step(I1{}, I2{}, g_local, zz + 2);
                 }
             }
-            mbar_wait(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
+            mbar_wait_hint<HINT>(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
             stage_row(rs, L, Bs, row.acc[2]);
             mbar_arrive(sfull + rs);
             return;
@@ -958,7 +972,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 #pragma unroll 1
         for (int t = 0; t < T_steps; ++t) {
             const T *plane = ring + (size_t)rs * PLANE;
-            mbar_wait(full + rs, ph);
+            mbar_wait_hint<HINT>(full + rs, ph);
             if (zp == 0) {
                 const Sshex8Header *h = reinterpret_cast<const Sshex8Header *>(hdr_bytes + (g_local % 3) * HBUF) + slot;
                 T f[6];
@@ -983,7 +997,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
             if (++zp == N) { zp = 0; ++g_local; }
             if (++rs == D) { rs = 0; ph ^= 1u; }
         }
-        mbar_wait(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
+        mbar_wait_hint<HINT>(full + rs, ph);  // the phantom plane: staging slot rs has been scattered
         stage_row(rs, L, Bs, row.acc[0]);
         mbar_arrive(sfull + rs);
     }
