@@ -50,9 +50,10 @@ def parse_args():
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: the halo gather on its own stream, ghost-dependent element groups wait inside the apply kernel (faster on 2 GPUs, "
-                         "slower on 4: which of the two streams gets the SMs first is a race; default = gather in front of the apply)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: halo gather in front of the apply (default: the gather on the halo's own stream while the apply kernel runs, its "
+                         "ghost-dependent element groups wait for the ghost block inside the kernel)")
+    ap.add_argument("--full-halo", action="store_true", help="N > 1: exchange every ghost node of the aura elements, not only those that can reach an owned row")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: grouped ncclSend/ncclRecv instead of the owner-push transport")
     ap.add_argument("--c4-side", type=int, default=465, help="nodes per side of the config-4 tet4 cube (strong scaling)")
     ap.add_argument("--c5-macro", type=int, default=87, help="config 5: macro elements per x / y side")
@@ -327,11 +328,16 @@ def run_b200(a):
         # ParallelMatrixFreeOperator of the C++ host layer: halo gather of x (in place, into its ghost block) + local apply
         f = host.Function(dt, n_local, 1)
         f.add_operator(op)
-        halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object),
+        # only the ghosts that share a micro element with an owned node travel (one lattice plane of the aura layer instead of
+        # all `level` of them: the others cannot reach an owned row); --full-halo: every node of the aura elements, like the
+        # reference's Exchange
+        needed = None if a.full_halo else parallel.sshex8_reachable_ghosts(lm)
+        halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object, needed=needed),
                          transport=lib.HALO_NCCL if a.nccl_halo else lib.HALO_AUTO)
         # the elements that read no ghost value run between the two halves of the gather (--no-overlap: gather, then apply)
-        ind = parallel.independent_range(lm) if a.overlap else None
+        ind = None if a.no_overlap else parallel.independent_range(lm)
         A = host.parallel_op(f, halo, n_owned, n_owned, independent_range=ind)
+        halo_values = halo.values_sent
         halo_kind = {"push": "owner-push: the owner's pack kernel stores into the peer's receive block over NVLink (cudaIpc-mapped), "
                              "acquire / release epoch flags, a second kernel waits and copies into the ghost block",
                      "nccl": "pack kernel + grouped ncclSend / ncclRecv into the ghost block"}[halo.transport]
@@ -496,7 +502,9 @@ def run_b200(a):
             "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
             "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
             "parallelism": (f"z-slab x{world}, owned/ghost/aura; every step = ParallelMatrixFreeOperator::apply of the C++ host "
-                            f"layer: halo gather of x ({halo_kind}), "
+                            f"layer: halo gather of x ({halo_kind}; "
+                            + ("every ghost node of the aura elements" if a.full_halo else "the ghost nodes that share a micro element with an owned "
+                               "node only, the others cannot reach an owned row") + f": {halo_values} values sent by rank 0), "
                             + ("on the halo's own stream while the apply kernel runs; its ghost-dependent element groups, ordered last, "
                                "wait for the ghost block inside the kernel" if overlapped else "then the local kernel")
                             + (f"; rank 0 bound to NUMA node {numa_node}" if numa_node is not None else ""))

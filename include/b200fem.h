@@ -155,7 +155,7 @@ int b200fem_op_apply_range(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_
                            void *stream);
 /* y = A x in ONE launch whose elements >= e_dependent wait, inside the kernel, until *ready_flag >= ready_value (acquire,
  * GPU scope) before they read x: the ghost-dependent elements of a distributed apply, ordered last, start when the
- * receiver half of the halo gather (b200fem_halo_gather_end_deferred, on another stream) has filled the ghost block, while
+ * halo gather (b200fem_halo_gather_deferred_begin / _launch, on another stream) has filled the ghost block, while
  * everything else runs at once. The launch leaves one SM free for that other stream. Operators without the in-kernel wait
  * return B200FEM_FAILURE and enqueue nothing (b200fem_op_get_option "ghost_wait" tells beforehand). */
 int b200fem_op_apply_overwrite_after(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_dependent,
@@ -291,6 +291,12 @@ int b200fem_halo_create(b200fem_halo_t *halo, b200fem_comm_t comm, int real_type
                         ptrdiff_t n_local, int n_send_peers, const int *send_peers, const ptrdiff_t *send_offsets,
                         const int32_t *send_idx, int n_recv_peers, const int *recv_peers, const ptrdiff_t *recv_begin,
                         const ptrdiff_t *recv_count, int transport);
+/* Indexed receive: the values received from recv_peers[j] are those of the local ghost nodes recv_idx[recv_offsets[j] ..
+ * recv_offsets[j+1]) (counts as given to b200fem_halo_create) instead of a contiguous range. For exchanging only the ghosts
+ * that can reach an owned row: a matrix-free apply reads a ghost value only through an element that also holds an owned
+ * node, and on a semi-structured mesh that is one lattice plane of the aura layer, not all L of them (the reference's
+ * Exchange gathers every node of the aura elements). Call on every rank or on none, before the first gather. */
+int b200fem_halo_set_recv_index(b200fem_halo_t halo, const ptrdiff_t *recv_offsets, const int32_t *recv_idx);
 int b200fem_halo_destroy(b200fem_halo_t halo);
 int b200fem_halo_gather(b200fem_halo_t halo, void *x_local, void *stream);
 /* The gather in two halves, for a distributed apply that runs its ghost-independent elements in between

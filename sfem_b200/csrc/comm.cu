@@ -134,6 +134,7 @@ struct RecvPeer {
     const unsigned long long *arrive[2];      // my arrive[parity][peer]
     unsigned long long *remote_credit[2];     // peer's credit[parity][me]
     unsigned int *ticket;
+    const int32_t *idx;                 // indexed receive: local node id of every received node (NULL: the contiguous range)
 };
 struct PushArgs {
     PushPeer p[kMaxPeers];
@@ -215,13 +216,19 @@ __global__ void __launch_bounds__(kHaloThreads)
 
 template <typename T>
 __global__ void __launch_bounds__(kHaloThreads)
-    halo_wait_copy_kernel(const RecvArgs a, T *__restrict__ x, const unsigned long long epoch,
+    halo_wait_copy_kernel(const RecvArgs a, const int bs, T *__restrict__ x, const unsigned long long epoch,
                           const unsigned long long timeout_ns, int *err, unsigned long long *ready, unsigned int *ready_ticket) {
     const RecvPeer &p = a.p[blockIdx.y];
     const int par = (int)(epoch & 1ull);
     block_wait_epoch(p.arrive[par], epoch, timeout_ns, err);
     const T *src = reinterpret_cast<const T *>(p.data[par]);
     T *dst = x + p.dst_offset;
+    if (p.idx) {  // indexed receive: the values of the requested nodes only, scattered to their places
+        for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_values; i += (ptrdiff_t)gridDim.x * blockDim.x) {
+            const ptrdiff_t node = i / bs;
+            x[(ptrdiff_t)p.idx[node] * bs + (int)(i - node * bs)] = __ldcg(&src[i]);
+        }
+    } else
     for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_values; i += (ptrdiff_t)gridDim.x * blockDim.x)
         dst[i] = __ldcg(&src[i]);  // L2 only: the lines were written by the peer, never trust this SM's L1
     block_release_epoch(p.ticket, p.remote_credit[par], epoch);
@@ -244,6 +251,16 @@ __global__ void __launch_bounds__(kHaloThreads)
     for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ptrdiff_t)gridDim.x * blockDim.x) {
         const ptrdiff_t node = i / bs;
         dst[i] = src[(ptrdiff_t)idx[node] * bs + (int)(i - node * bs)];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kHaloThreads)
+    halo_unpack_kernel(ptrdiff_t n, const int32_t *__restrict__ idx, int bs, const T *__restrict__ src, T *__restrict__ dst) {
+    const ptrdiff_t total = n * bs;
+    for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ptrdiff_t)gridDim.x * blockDim.x) {
+        const ptrdiff_t node = i / bs;
+        dst[(ptrdiff_t)idx[node] * bs + (int)(i - node * bs)] = src[i];
     }
 }
 
@@ -274,8 +291,9 @@ struct b200fem_halo_s {
     std::vector<int> send_peers, recv_peers;
     std::vector<ptrdiff_t> send_count, recv_begin, recv_count;
     std::vector<DeviceArray<int32_t>> send_idx;
+    std::vector<DeviceArray<int32_t>> recv_idx;  // indexed receive (b200fem_halo_set_recv_index), empty otherwise
     // NCCL transport
-    std::vector<void *> send_buf;
+    std::vector<void *> send_buf, recv_stage;  // recv_stage: indexed receive only
     // PUSH transport
     unsigned char *block = nullptr;  // [flags | parity 0 | parity 1]
     size_t parity_stride = 0;
@@ -296,6 +314,8 @@ namespace b200fem {
 static void halo_release(b200fem_halo_s *h) {
     if (!h) return;
     for (void *p : h->send_buf)
+        if (p) cudaFree(p);
+    for (void *p : h->recv_stage)
         if (p) cudaFree(p);
     for (size_t q = 0; q < h->peer_block.size(); ++q)
         if (h->peer_block[q]) cudaIpcCloseMemHandle(h->peer_block[q]);
@@ -439,9 +459,9 @@ static int halo_gather_t(b200fem_halo_s *h, T *x, cudaStream_t s, int phase = 0)
                                                                           cap / (ptrdiff_t)h->recv_peers.size()));
             if (deferred) {
                 halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, h->side>>>(
-                        h->recv, x, epoch, c->timeout_ns, c->err_dev, h->ready, reinterpret_cast<unsigned int *>(h->ready + 1));
+                        h->recv, h->bs, x, epoch, c->timeout_ns, c->err_dev, h->ready, reinterpret_cast<unsigned int *>(h->ready + 1));
             } else {
-                halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, s>>>(h->recv, x, epoch, c->timeout_ns,
+                halo_wait_copy_kernel<T><<<dim3(gx, (unsigned)h->recv_peers.size()), kHaloThreads, 0, s>>>(h->recv, h->bs, x, epoch, c->timeout_ns,
                                                                                                           c->err_dev, nullptr, nullptr);
             }
             B2_CHECK_LAUNCH();
@@ -462,10 +482,21 @@ static int halo_gather_t(b200fem_halo_s *h, T *x, cudaStream_t s, int phase = 0)
     B2_NCCL(api->GroupStart());
     for (size_t j = 0; j < h->send_peers.size(); ++j)
         if (h->send_count[j]) B2_NCCL(api->Send(h->send_buf[j], (size_t)(h->send_count[j] * h->bs), dt, h->send_peers[j], c->nccl, s));
+    const bool indexed = !h->recv_idx.empty();
     for (size_t j = 0; j < h->recv_peers.size(); ++j)
         if (h->recv_count[j])
-            B2_NCCL(api->Recv(x + h->recv_begin[j] * h->bs, (size_t)(h->recv_count[j] * h->bs), dt, h->recv_peers[j], c->nccl, s));
+            B2_NCCL(api->Recv(indexed ? h->recv_stage[j] : (void *)(x + h->recv_begin[j] * h->bs), (size_t)(h->recv_count[j] * h->bs), dt,
+                              h->recv_peers[j], c->nccl, s));
     B2_NCCL(api->GroupEnd());
+    if (indexed) {
+        for (size_t j = 0; j < h->recv_peers.size(); ++j) {
+            const ptrdiff_t total = h->recv_count[j] * h->bs;
+            if (total == 0) continue;
+            const int grid = (int)std::min<ptrdiff_t>((total + kHaloThreads - 1) / kHaloThreads, (ptrdiff_t)sm_count() * 8);
+            halo_unpack_kernel<T><<<grid, kHaloThreads, 0, s>>>(h->recv_count[j], h->recv_idx[j].ptr, h->bs, (const T *)h->recv_stage[j], x);
+            B2_CHECK_LAUNCH();
+        }
+    }
     return B200FEM_SUCCESS;
 }
 
@@ -667,6 +698,27 @@ int b200fem_halo_destroy(b200fem_halo_t h) {
     return B200FEM_SUCCESS;
 }
 
+int b200fem_halo_set_recv_index(b200fem_halo_t h, const ptrdiff_t *recv_offsets, const int32_t *recv_idx) {
+    if (!h || !recv_offsets) B2_FAIL("halo_set_recv_index: NULL argument");
+    const size_t np = h->recv_peers.size();
+    std::vector<DeviceArray<int32_t>> idx(np);
+    for (size_t j = 0; j < np; ++j) {
+        const ptrdiff_t n = recv_offsets[j + 1] - recv_offsets[j];
+        if (n != h->recv_count[j]) B2_FAIL("halo_set_recv_index: count differs from the plan's receive count");
+        for (ptrdiff_t i = recv_offsets[j]; i < recv_offsets[j + 1]; ++i)
+            if (recv_idx[i] < h->n_owned || recv_idx[i] >= h->n_local) B2_FAIL("halo_set_recv_index: an index is not a ghost node");
+        if (idx[j].upload(recv_idx + recv_offsets[j], (size_t)n)) return B200FEM_FAILURE;
+    }
+    h->recv_idx = std::move(idx);
+    if (h->transport == B200FEM_HALO_PUSH) {
+        for (size_t j = 0; j < np; ++j) h->recv.p[j].idx = h->recv_idx[j].ptr;
+    } else if (h->comm->world > 1) {
+        h->recv_stage.assign(np, nullptr);
+        for (size_t j = 0; j < np; ++j)
+            if (h->recv_count[j]) B2_CUDA(cudaMalloc(&h->recv_stage[j], (size_t)h->recv_count[j] * (size_t)h->bs * (size_t)h->real_type));
+    }
+    return B200FEM_SUCCESS;
+}
 int b200fem_halo_transport(b200fem_halo_t h) { return h ? h->transport : -1; }
 ptrdiff_t b200fem_halo_values_sent(b200fem_halo_t h) {
     ptrdiff_t n = 0;

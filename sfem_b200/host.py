@@ -65,6 +65,7 @@ _SIG = {
     "b200host_comm_barrier": (None, [vp]),
     "b200host_halo": (vp, [vp, i32, i32, ssz, ssz, i32, vp, vp, vp, i32, vp, vp, vp, i32]),
     "b200host_halo_gather": (i32, [vp, vp]),
+    "b200host_halo_set_recv_index": (i32, [vp, vp, vp]),
     "b200host_halo_transport": (i32, [vp]),
     "b200host_halo_values_sent": (ssz, [vp]),
     "b200host_halo_launches_per_gather": (i32, [vp]),
@@ -212,6 +213,9 @@ class Halo(Handle):
                                so.ctypes.data, si.ctypes.data if si.size else None, rp.size, rp.ctypes.data, rb.ctypes.data,
                                rc.ctypes.data, transport)
         super().__init__(ptr, keep=[comm])
+        if "recv_idx" in plan:  # indexed receive: only the ghosts that can reach an owned row travel
+            ro, ri = cp(plan["recv_offsets"]), ci(plan["recv_idx"])
+            _l.check(_h.b200host_halo_set_recv_index(self.ptr, ro.ctypes.data, ri.ctypes.data if ri.size else None), "halo_set_recv_index")
 
     def gather(self, x_local):
         _l.check(_h.b200host_halo_gather(self.ptr, _p(x_local)), "halo_gather")

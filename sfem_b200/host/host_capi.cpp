@@ -275,6 +275,9 @@ void *b200host_halo(void *comm, int real_type, int block_size, ptrdiff_t n_owned
     b->kind      = K_HALO;
     return b;
 }
+int b200host_halo_set_recv_index(void *halo, const ptrdiff_t *recv_offsets, const int32_t *recv_idx) {
+    return b200fem_halo_set_recv_index(halo_of(halo)->get(), recv_offsets, recv_idx);
+}
 int b200host_halo_gather(void *halo, void *x_local) { return halo_of(halo)->gather(x_local); }
 int b200host_halo_transport(void *halo) { return b200fem_halo_transport(halo_of(halo)->get()); }
 ptrdiff_t b200host_halo_values_sent(void *halo) { return b200fem_halo_values_sent(halo_of(halo)->get()); }

@@ -107,6 +107,7 @@ _SIG = {
     "b200fem_halo_create": [C.POINTER(vp), vp, i32, i32, ssz, ssz, i32, vp, vp, vp, i32, vp, vp, vp, i32],
     "b200fem_halo_destroy": [vp],
     "b200fem_halo_gather": [vp, vp, vp],
+    "b200fem_halo_set_recv_index": [vp, vp, vp],
     "b200fem_halo_gather_begin": [vp, vp, vp],
     "b200fem_halo_gather_end": [vp, vp, vp],
     "b200fem_halo_transport": [vp],

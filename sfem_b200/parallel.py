@@ -219,10 +219,37 @@ def independent_range(lm: LocalMesh):
     return int(ind[starts[k]]), int(ind[ends[k] - 1]) + 1
 
 
-def halo_plan(lm: LocalMesh, all_gather_object=None) -> dict:
+def sshex8_reachable_ghosts(lm: LocalMesh) -> np.ndarray:
+    """bool [n_local - n_owned]: the ghost nodes that share a MICRO element with an owned node, i.e. the only ghost values a
+    matrix-free apply can carry into an owned row (one lattice plane of the aura layer instead of all `level` of them)."""
+    L = lm.extra["level"]
+    N = L + 1
+    el = lm.elements
+    dep = np.flatnonzero((el >= lm.n_owned).any(axis=0))
+    need = np.zeros(lm.n_local, dtype=bool)
+    for c0 in range(0, dep.size, 4096):  # chunks: 729 x 4096 lattice ids at a time
+        e = el[:, dep[c0:c0 + 4096]].reshape(N, N, N, -1)  # sshex8_lidx: z slowest, x fastest
+        owned = e < lm.n_owned
+        touch = np.zeros((L, L, L, e.shape[-1]), dtype=bool)  # micro elements with an owned corner
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    touch |= owned[dz:dz + L, dy:dy + L, dx:dx + L]
+        reach = np.zeros_like(owned)
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    reach[dz:dz + L, dy:dy + L, dx:dx + L] |= touch
+        need[e[reach]] = True
+    return need[lm.n_owned:]
+
+
+def halo_plan(lm: LocalMesh, all_gather_object=None, needed=None) -> dict:
     """The exchange plan of one space in the form b200fem_halo_create takes it (include/b200fem.h): per peer the
     contiguous ghost range I receive and the owned local ids I send, in the order of the peer's range.
-    `all_gather_object(obj) -> [obj of every rank]` is the launcher's collective (setup only)."""
+    `all_gather_object(obj) -> [obj of every rank]` is the launcher's collective (setup only).
+    needed (bool per ghost, e.g. sshex8_reachable_ghosts): exchange those ghosts only -- the plan then carries
+    recv_offsets / recv_idx for b200fem_halo_set_recv_index (pass it on every rank or on none)."""
     plan = dict(n_owned=lm.n_owned, n_local=lm.n_local, send_peers=[], send_offsets=[0], send_idx=np.zeros(0, np.int32),
                 recv_peers=[], recv_begin=[], recv_count=[])
     if lm.world == 1:
@@ -230,11 +257,17 @@ def halo_plan(lm: LocalMesh, all_gather_object=None) -> dict:
     ghost_owner = lm.owner[lm.n_owned:]
     ghost_gid = lm.global_ids[lm.n_owned:]
     need = {}
+    if needed is not None:
+        plan["recv_offsets"], ridx = [0], []
     for p in np.unique(ghost_owner):
         sel = np.flatnonzero(ghost_owner == p)
         assert sel.size == sel[-1] - sel[0] + 1, "ghosts must be sorted by owner"
         plan["recv_peers"].append(int(p))
         plan["recv_begin"].append(lm.n_owned + int(sel[0]))
+        if needed is not None:
+            sel = sel[needed[sel]]
+            ridx.append((lm.n_owned + sel).astype(np.int32))
+            plan["recv_offsets"].append(plan["recv_offsets"][-1] + int(sel.size))
         plan["recv_count"].append(int(sel.size))
         need[int(p)] = ghost_gid[sel]
     all_need = all_gather_object(need)
@@ -252,6 +285,8 @@ def halo_plan(lm: LocalMesh, all_gather_object=None) -> dict:
         plan["send_offsets"].append(plan["send_offsets"][-1] + int(loc.size))
         chunks.append(loc.astype(np.int32))
     plan["send_idx"] = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
+    if needed is not None:
+        plan["recv_idx"] = np.concatenate(ridx) if ridx else np.zeros(0, np.int32)
     return plan
 
 
@@ -270,7 +305,7 @@ def torch_all_gather_object(group=None):
 class HaloExchange:
     """`gather(x_local)`: fill the ghost block of a local vector from the owners (Exchange::gather)."""
 
-    def __init__(self, lm: LocalMesh, block_size: int = 1, group=None, device=None):
+    def __init__(self, lm: LocalMesh, block_size: int = 1, group=None, device=None, needed=None):
         import torch
         import torch.distributed as dist
 
@@ -278,13 +313,15 @@ class HaloExchange:
         self.rank, self.world, self.bs = lm.rank, lm.world, block_size
         self.n_owned, self.n_local = lm.n_owned, lm.n_local
         self.device = device
-        self.peers, self.recv_ranges, self.send_idx = [], {}, {}
+        self.peers, self.recv_ranges, self.send_idx, self.recv_idx = [], {}, {}, {}
         if self.world == 1:
             return
-        # the same plan the C++ layer takes (b200fem_halo_create through host.Halo)
-        self.plan = plan = halo_plan(lm, torch_all_gather_object(group))
-        for p, b, c in zip(plan["recv_peers"], plan["recv_begin"], plan["recv_count"]):
+        # the same plan the C++ layer takes (b200fem_halo_create [+ b200fem_halo_set_recv_index] through host.Halo)
+        self.plan = plan = halo_plan(lm, torch_all_gather_object(group), needed=needed)
+        for j, (p, b, c) in enumerate(zip(plan["recv_peers"], plan["recv_begin"], plan["recv_count"])):
             self.recv_ranges[p] = (b, b + c)
+            if "recv_idx" in plan:  # indexed receive: c values that go to the listed ghost nodes
+                self.recv_idx[p] = torch.from_numpy(plan["recv_idx"][plan["recv_offsets"][j]:plan["recv_offsets"][j + 1]].astype(np.int64))
         for j, q in enumerate(plan["send_peers"]):
             loc = torch.from_numpy(plan["send_idx"][plan["send_offsets"][j]:plan["send_offsets"][j + 1]].copy())
             self.send_idx[q] = loc.to(device) if device is not None else loc
@@ -309,7 +346,7 @@ class HaloExchange:
         if self.world == 1 or not self.peers:
             return x_local
         torch, dist = self.torch, self.dist
-        ops = []
+        ops, staged = [], []
         for q in self.peers:
             if q in self.send_idx:
                 buf = self._send_buffer(q, x_local)
@@ -323,9 +360,15 @@ class HaloExchange:
                 ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
             if q in self.recv_ranges:
                 a, b = self.recv_ranges[q]
-                ops.append(dist.P2POp(dist.irecv, x_local[a * self.bs:b * self.bs], q, group=self.group))
+                if q in self.recv_idx:
+                    staged.append((q, torch.empty((b - a) * self.bs, dtype=x_local.dtype, device=x_local.device)))
+                    ops.append(dist.P2POp(dist.irecv, staged[-1][1], q, group=self.group))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, x_local[a * self.bs:b * self.bs], q, group=self.group))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+        for q, buf in staged:
+            x_local.view(-1, self.bs)[self.recv_idx[q].to(x_local.device)] = buf.view(-1, self.bs)
         return x_local
 
 

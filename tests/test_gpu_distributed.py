@@ -57,6 +57,9 @@ def test_overlapped_apply_matches_plain_distributed_apply():
     out = _run(2, ["apply", "--macro", "8", "--layers", "4", "--level", "8"])
     assert out["rc"] == 0 and out["overlapped"] is True, out
     assert out["max_rel_diff"] < 1e-13, out
+    # the exchange restricted to the ghosts that can reach an owned row, the other ghost entries poisoned
+    assert out["max_rel_diff_reduced_halo"] < 1e-13, out
+    assert out["values_sent_rank0_reduced"] <= out["values_sent_rank0"]
 
 
 def test_single_rank_goes_through_the_same_layer():

@@ -104,6 +104,22 @@ def _worker(rank, world, port, case):
         y_local = apply(x_local.numpy())
         err = np.abs(y_local[: lm.n_owned] - ref_of_gid(lm.global_ids[: lm.n_owned])).max()
         assert err < 1e-10, err
+        if case == "sshex8" and world > 1:
+            # exchanging only the ghosts that share a micro element with an owned node (b200fem_halo_set_recv_index): the
+            # other ghost values cannot reach an owned row -- poison them and compare the owned rows again
+            needed = parallel.sshex8_reachable_ghosts(lm)
+            assert needed.sum() > 0
+            if rank < world - 1:  # ranks with an aura layer: only its first lattice plane can reach an owned row
+                assert needed.sum() < needed.size, "the reduced ghost set must be a proper subset of the aura nodes"
+            ex2 = parallel.HaloExchange(lm, needed=needed)
+            x2 = torch.full((lm.n_local,), 1e30, dtype=torch.float64)
+            x2[: lm.n_owned] = x_local[: lm.n_owned]
+            ex2.gather(x2)
+            got = x2.numpy()[lm.n_owned:]
+            assert np.array_equal(got[needed], u_of_gid(lm.global_ids[lm.n_owned:])[needed])
+            assert np.all(got[~needed] == 1e30)
+            y2 = apply(x2.numpy())
+            assert np.abs(y2[: lm.n_owned] - ref_of_gid(lm.global_ids[: lm.n_owned])).max() < 1e-10
         # owned dot product summed over ranks == serial dot product
         d = torch.tensor([float(x_local[: lm.n_owned].numpy() @ y_local[: lm.n_owned])], dtype=torch.float64)
         dist.all_reduce(d)
@@ -130,7 +146,7 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2), ("tet4_slab", 2), ("tet4_slab", 3)])
+@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2), ("sshex8", 3), ("tet4_slab", 2), ("tet4_slab", 3)])
 def test_distributed_apply_matches_serial(case, world, oracles):
     import torch.multiprocessing as mp
 

@@ -86,9 +86,13 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
     f = host.Function(dt, lm.n_local, 1)
     f.add_operator(op)
     halo = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object))
+    # the same exchange restricted to the ghosts that can reach an owned row (b200fem_halo_set_recv_index)
+    needed = parallel.sshex8_reachable_ghosts(lm)
+    halo_r = host.Halo(d.comm, dt, 1, parallel.halo_plan(lm, d.all_gather_object, needed=needed))
     ind = parallel.independent_range(lm)
     plain = host.parallel_op(f, halo, lm.n_owned, lm.n_owned)
     over = host.parallel_op(f, halo, lm.n_owned, lm.n_owned, independent_range=ind)
+    reduced = host.parallel_op(f, halo_r, lm.n_owned, lm.n_owned)
     x = torch.from_numpy(np.random.default_rng(7 + d.rank).uniform(-1, 1, lm.n_local)).to(d.dev)
     y0, y1 = torch.zeros_like(x), torch.full_like(x, 3.0)
     assert host.apply_overwrite(plain, x, y0) == 0
@@ -96,8 +100,14 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
     torch.cuda.synchronize()
     n = lm.n_owned
     diff = float((y0[:n] - y1[:n]).abs().max() / y0[:n].abs().max())
+    x2 = x.clone()
+    x2[n:] = 1e30  # ghosts the reduced exchange does not refresh must not matter
+    y2 = torch.zeros_like(x)
+    assert host.apply_overwrite(reduced, x2, y2) == 0
+    torch.cuda.synchronize()
+    diff_r = float((y0[:n] - y2[:n]).abs().max() / y0[:n].abs().max())
     ms = {}
-    for name, A in (("plain", plain), ("overlapped", over)):
+    for name, A in (("plain", plain), ("overlapped", over), ("reduced", reduced)):
         for _ in range(3):
             host.apply_overwrite(A, x, y1)
         _, t = _timed(torch, d.comm, lambda: [host.apply_overwrite(A, x, y1) for _ in range(steps)])
@@ -105,7 +115,9 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
     ne = int(lm.elements.shape[1])
     return dict(name=f"overlapped distributed apply, sshex8 L{level} {macro}x{macro}x{layers} macro per GPU x {d.world}", rc=0,
                 overlapped=bool(over.overlapped), independent_range=list(ind) if ind else None, elements=ne,
-                max_rel_diff=d.comm.max(diff), ms_plain=ms["plain"], ms_overlapped=ms["overlapped"], n_gpus=d.world)
+                max_rel_diff=d.comm.max(diff), max_rel_diff_reduced_halo=d.comm.max(diff_r), values_sent_rank0=halo.values_sent,
+                values_sent_rank0_reduced=halo_r.values_sent, ms_plain=ms["plain"], ms_overlapped=ms["overlapped"],
+                ms_reduced_halo=ms["reduced"], n_gpus=d.world)
 
 
 
