@@ -48,7 +48,7 @@ static int launch_cfg(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, c
     return B200FEM_SUCCESS;
 }
 
-template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, int DBG = 0, bool FACEOUT = false, int HINT = 0>
+template <typename T, int NC, int D, bool PLAIN, bool PHASED = false, int DBG = 0, int FACEOUT = 0, int HINT = 0>
 static int launch_ws2(ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *headers, const T *x, T *y, int max_ctas, cudaStream_t s, int dbg,
                       const WsDependency *dep = nullptr) {
     constexpr int L = 8;
@@ -84,13 +84,16 @@ static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *hea
         case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg, dep);  // + static accumulator phases
         case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
         case 15: return launch_ws2<T, 8, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 30: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 200>(ne, nn, headers, x, y, max_ctas, s, dbg);   // try_wait suspend hints
-        case 31: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 1000>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 32: return launch_ws2<T, 8, 3, PLAIN, true, 0, false, 5000>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral-face output buffer
-        case 17: return launch_ws2<T, 8, 4, PLAIN, true, 0, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 25: return launch_ws2<T, 8, 3, PLAIN, true, 2, true>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
-        case 26: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
+        case 18: return launch_ws2<T, 8, 3, PLAIN, true, 0, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);  // lateral buffer for the x = 0 / L positions only
+        case 27: return launch_ws2<T, 8, 3, PLAIN, true, 2, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
+        case 28: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
+        case 30: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 200>(ne, nn, headers, x, y, max_ctas, s, dbg);   // try_wait suspend hints
+        case 31: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 1000>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 32: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 5000>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral-face output buffer
+        case 17: return launch_ws2<T, 8, 4, PLAIN, true, 0, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 25: return launch_ws2<T, 8, 3, PLAIN, true, 2, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
+        case 26: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
         // bracketing runs of the D = 3 phased kernel (profiles/r02*_ws2_brackets): parts switched off at compile time
         case 20: return launch_ws2<T, 8, 3, PLAIN, true, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);        // no arithmetic
         case 21: return launch_ws2<T, 8, 3, PLAIN, true, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // arithmetic only

@@ -59,7 +59,7 @@ struct WsLayout<float> {
     __host__ __device__ static constexpr int DK(int) { return 0; }
 };
 
-template <typename T, int L, int NC, int D, int S, bool FACEOUT = false>
+template <typename T, int L, int NC, int D, int S, int FACEOUT = 0>
 struct Sshex8WsCfg {
     static constexpr int N = L + 1;
     static constexpr int NI = (L - 1) * (L - 1);  // interior positions of a plane
@@ -71,7 +71,9 @@ struct Sshex8WsCfg {
     static constexpr size_t stage_bytes = (size_t)S * PLANE * sizeof(T);
     static constexpr size_t hdr_bytes = (size_t)3 * EPT * sizeof(Sshex8Header);
     static constexpr size_t bar_bytes = (size_t)(2 * D + 2 * S) * sizeof(uint64_t);
-    static constexpr int FOS = 228;  // elements per slot of the lateral-face output buffer (32 x (L-1) = 224 used; 228: 3 wavefronts per store, bank model)
+    // elements per slot of the lateral output buffer. FACEOUT 1: all 32 skeleton positions x (L-1) planes = 224 used (228: 3
+    // wavefronts per store, bank model); FACEOUT 2: the 18 positions with x = 0 or x = L only = 126 used (129)
+    static constexpr int FOS = FACEOUT == 2 ? 129 : 228;
     static constexpr size_t fo_bytes = FACEOUT ? (size_t)EPT * FOS * sizeof(T) : 0;
     static constexpr size_t warp_bytes = ((ring_bytes + stage_bytes + hdr_bytes + bar_bytes + fo_bytes + 127) / 128) * 128;
     static constexpr size_t smem_bytes = warp_bytes * NC;
@@ -527,7 +529,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, int DBG = 0, bool FACEOUT = false, int HINT = 0>
+template <typename T, int L, int NC, int D, bool PLAIN_INTERIOR, bool PHASED, int DBG = 0, int FACEOUT = 0, int HINT = 0>
 __global__ void __launch_bounds__(2 * NC * 32, 1)
     sshex8_laplacian_ws2_kernel(const ptrdiff_t ne, const Sshex8Header *__restrict__ headers, const __grid_constant__ CUtensorMap tmap_u,
                                 const T *__restrict__ u, T *__restrict__ y, const WsDependency dep) {
@@ -648,24 +650,42 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         // 5 .. L-1 (3 items: position j / 3, plane 5 + j % 3, j = tl + 32 q), packed as box byte offset | x << 9 | y << 13 |
         // buffer offset << 17 | plane << 25
         int sweepA[4], sweepB[3];
-        if constexpr (FACEOUT) {
+        constexpr int NSA = FACEOUT == 2 ? 3 : 4, NSB = FACEOUT == 2 ? 2 : 3;  // RED instructions per slot and half
+        if constexpr (FACEOUT == 1) {
             auto pack = [&](int pos, int zpl) {
                 int x, yy;
                 plane_pos_to_xy<L>(NI + pos, x, yy);
                 const int cxy = ((x == 0) ? 0 : (x == L ? 2 : 1)) + 3 * ((yy == 0) ? 0 : (yy == L ? 2 : 1));
-                return ((9 + cxy) * 16) | (x << 9) | (yy << 13) | ((pos * (L - 1) + zpl - 1) << 17) | (zpl << 25);
+                return ((9 + cxy) * 16) | (x << 9) | (yy << 13) | ((pos * (L - 1) + zpl - 1) << 17) | (zpl << 25) | (1 << 28);
             };
 #pragma unroll
             for (int q = 0; q < 4; ++q) sweepA[q] = pack((tl >> 2) + 8 * q, 1 + (tl & 3));
 #pragma unroll
             for (int q = 0; q < 3; ++q) sweepB[q] = pack((tl + 32 * q) / 3, 5 + (tl + 32 * q) % 3);
         }
+        if constexpr (FACEOUT == 2) {
+            // FACEOUT 2: only the 18 positions with x = 0 or x = L (the columns of the lateral x-faces + the four z-edges) go
+            // through the buffer -- a compute lane writes them as two scalars, at no cost in its staging code; the rows y = 0 / L
+            // keep the per-plane path. Buffer position c: 0..3 = (0,0) (L,0) (0,L) (L,L), 4..10 = (0, 1..L-1), 11..17 = (L, 1..L-1)
+            auto pack2 = [&](int j, int nval, int c, int zpl) {
+                c = c < 18 ? c : 17;
+                const int x = (c < 4) ? ((c & 1) ? L : 0) : (c < 11 ? 0 : L);
+                const int yy = (c < 4) ? ((c & 2) ? L : 0) : (c < 11 ? c - 3 : c - 10);
+                const int cxy = ((x == 0) ? 0 : 2) + 3 * ((yy == 0) ? 0 : (yy == L ? 2 : 1));
+                return ((9 + cxy) * 16) | (x << 9) | (yy << 13) | ((c * (L - 1) + zpl - 1) << 17) | (zpl << 25) | ((j < nval ? 1 : 0) << 28);
+            };
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sweepA[q] = pack2(tl + 32 * q, 18 * 4, (tl + 32 * q) >> 2, 1 + ((tl + 32 * q) & 3));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) sweepB[q] = pack2(tl + 32 * q, 18 * 3, (tl + 32 * q) / 3, 5 + (tl + 32 * q) % 3);
+        }
         auto sweep = [&](const unsigned char *hb, const int item, const int nv) {
-            const int boxoff = item & 0x1ff, x = (item >> 9) & 15, yy = (item >> 13) & 15, off = (item >> 17) & 255, zpl = item >> 25;
+            const int boxoff = item & 0x1ff, x = (item >> 9) & 15, yy = (item >> 13) & 15, off = (item >> 17) & 255, zpl = (item >> 25) & 7;
+            const bool valid = (item >> 28) & 1;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int4 d = *reinterpret_cast<const int4 *>(hb + i * HSZ + boxoff);
-                put_if(i < nv, y + (d.x + d.y * x + d.z * yy + d.w * zpl), fo[i * FOS + off], RedT{});
+                put_if(i < nv && valid, y + (d.x + d.y * x + d.z * yy + d.w * zpl), fo[i * FOS + off], RedT{});
             }
         };
 
@@ -726,11 +746,13 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     asm volatile("" ::: "memory");
                 }
             } else {
-                if constexpr (!FACEOUT) {
+                if constexpr (FACEOUT != 1) {
+                    // FACEOUT 2: the lanes of the rows y = 0 / L with 0 < x < L only (the x = 0 / x = L positions are swept)
+                    const bool mine = FACEOUT == 0 || (sk_x > 0 && sk_x < L);
 #pragma unroll
                     for (int i = 0; i < EPT; ++i) {
                         const int k = scG[i] & (AL - 1);
-                        put_if(i < nv, y + scI[i], src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
+                        put_if(i < nv && mine, y + scI[i], src[sk_off0 + ws_slot_shift<T>(i) + Lay::DK(i) * k], RedT{});
                     }
                 }
 #pragma unroll
@@ -822,10 +844,10 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                         const unsigned char *hb = hdr_bytes + hs * HBUF;
                         if (zs == 4) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) sweep(hb, sweepA[q], nv);
+                            for (int q = 0; q < NSA; ++q) sweep(hb, sweepA[q], nv);
                         } else if (zs == L - 1) {
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) sweep(hb, sweepB[q], nv);
+                            for (int q = 0; q < NSB; ++q) sweep(hb, sweepB[q], nv);
                         }
                     }
                 }
@@ -861,15 +883,16 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
 
         // FACEOUT: positions of this lane's x = 0 / x = L nodes among the 32 skeleton positions of a plane (the rows y = 0 / L
         // are positions 0 .. L and N .. N + L, the columns follow); x = 1 .. L-1 of a lateral row go to positions posA + x
-        const int posA = yrow == 0 ? 0 : (yrow == L ? N : 2 * N + yrow - 1);
-        const int posB = yrow == 0 ? L : (yrow == L ? N + L : 2 * N + (L - 1) + yrow - 1);
+        const int posA = FACEOUT == 2 ? (yrow == 0 ? 0 : (yrow == L ? 2 : 3 + yrow)) : (yrow == 0 ? 0 : (yrow == L ? N : 2 * N + yrow - 1));
+        const int posB = FACEOUT == 2 ? (yrow == 0 ? 1 : (yrow == L ? 3 : 10 + yrow))
+                                      : (yrow == 0 ? L : (yrow == L ? N + L : 2 * N + (L - 1) + yrow - 1));
         T *fo_lane = fo + slot * FOS;
         const int mid_stride = rint[1] ? 1 : (L - 1);
         // this lane's row of output plane z of the element whose interior starts at B, into staging slot ss
         auto stage_row = [&](const int ss, const int z, const int B, const T(&vals)[N]) {
             T *dst = stage + (size_t)ss * PLANE;
             const int k = (B + NI * z) & (AL - 1);
-            if constexpr (FACEOUT) {
+            if constexpr (FACEOUT == 1) {
                 if (z != 0 && z != L) {  // warp-uniform
                     T *f = fo_lane + (z - 1);
                     f[posA * (L - 1)] = vals[0];
@@ -877,6 +900,17 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     T *dmid = rint[1] ? (dst + k + am[1]) : (f + (posA + 1) * (L - 1));
 #pragma unroll
                     for (int x = 1; x < L; ++x) dmid[(x - 1) * mid_stride] = vals[x];
+                    return;
+                }
+            }
+            if constexpr (FACEOUT == 2) {
+                if (z != 0 && z != L) {  // warp-uniform: x = 0 / x = L into the lateral buffer, the rest staged as always
+                    T *f = fo_lane + (z - 1);
+                    f[posA * (L - 1)] = vals[0];
+                    f[posB * (L - 1)] = vals[L];
+                    T *dm2 = (rint[1] ? dst + k : dst + dk * k) + am[1];
+#pragma unroll
+                    for (int x = 1; x < L; ++x) dm2[x - 1] = vals[x];
                     return;
                 }
             }
