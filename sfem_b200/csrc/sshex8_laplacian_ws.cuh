@@ -842,7 +842,11 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                     // rewritten 6 steps later at the earliest, behind the closing arrivals of the iterations in between)
                     if (!(dbg & 4)) {
                         const unsigned char *hb = hdr_bytes + hs * HBUF;
-                        if (zs == 4) {
+                        if constexpr (FACEOUT == 2) {
+                            // one sweep instruction set per iteration (planes 1 .. 4 are complete from zs = 4 on, planes 5 .. L-1
+                            // from zs = L-1 on): an iteration that did a whole half at once fell behind its compute warp
+                            if (zs >= 4) sweep(hb, zs == 4 ? sweepA[0] : (zs == 5 ? sweepA[1] : (zs == 6 ? sweepA[2] : (zs == 7 ? sweepB[0] : sweepB[1]))), nv);
+                        } else if (zs == 4) {
 #pragma unroll
                             for (int q = 0; q < NSA; ++q) sweep(hb, sweepA[q], nv);
                         } else if (zs == L - 1) {

@@ -93,6 +93,7 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
     plain = host.parallel_op(f, halo, lm.n_owned, lm.n_owned)
     over = host.parallel_op(f, halo, lm.n_owned, lm.n_owned, independent_range=ind)
     reduced = host.parallel_op(f, halo_r, lm.n_owned, lm.n_owned)
+    both = host.parallel_op(f, halo_r, lm.n_owned, lm.n_owned, independent_range=ind)  # what bench.py runs
     x = torch.from_numpy(np.random.default_rng(7 + d.rank).uniform(-1, 1, lm.n_local)).to(d.dev)
     y0, y1 = torch.zeros_like(x), torch.full_like(x, 3.0)
     assert host.apply_overwrite(plain, x, y0) == 0
@@ -107,7 +108,7 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
     torch.cuda.synchronize()
     diff_r = float((y0[:n] - y2[:n]).abs().max() / y0[:n].abs().max())
     ms = {}
-    for name, A in (("plain", plain), ("overlapped", over), ("reduced", reduced)):
+    for name, A in (("plain", plain), ("overlapped", over), ("reduced", reduced), ("both", both)):
         for _ in range(3):
             host.apply_overwrite(A, x, y1)
         _, t = _timed(torch, d.comm, lambda: [host.apply_overwrite(A, x, y1) for _ in range(steps)])
@@ -117,7 +118,8 @@ def overlapped_apply_check(d: Dist, macro=8, layers=4, level=8, steps=10):
                 overlapped=bool(over.overlapped), independent_range=list(ind) if ind else None, elements=ne,
                 max_rel_diff=d.comm.max(diff), max_rel_diff_reduced_halo=d.comm.max(diff_r), values_sent_rank0=halo.values_sent,
                 values_sent_rank0_reduced=halo_r.values_sent, ms_plain=ms["plain"], ms_overlapped=ms["overlapped"],
-                ms_reduced_halo=ms["reduced"], n_gpus=d.world)
+                ms_reduced_halo=ms["reduced"], ms_reduced_halo_overlapped=ms["both"], owned_dofs_total=d.comm.sum(float(lm.n_owned)),
+                n_gpus=d.world)
 
 
 
