@@ -242,11 +242,14 @@ def _mg_problem(d, lm, level, dt, side_x, distributed=True):
     blas.set_comm(d.comm)
     blas.reserve_allocation(lm.n_owned * 3, lm.n_local * 3)
     blas.reserve_allocation(cm.n_owned * 3, cm.n_local * 3)
-    A = host.parallel_op(f, halo_f, lm.n_owned * 3, lm.n_owned * 3)
+    # the fine-level operator (62 applies per cycle) exchanges only the ghosts that can reach an owned row -- one lattice plane of
+    # the aura layer; the transfers reach across whole macro elements and keep the full plan
+    halo_op = host.Halo(d.comm, dt, 3, parallel.halo_plan(lm, d.all_gather_object, needed=parallel.sshex8_reachable_ghosts(lm)))
+    A = host.parallel_op(f, halo_op, lm.n_owned * 3, lm.n_owned * 3)
     Ac = host.parallel_op(fc, halo_c, cm.n_owned * 3, cm.n_owned * 3)
     Rp = host.parallel_op(R, halo_f, cm.n_owned * 3, lm.n_owned * 3)
     Pp = host.parallel_op(P, halo_c, lm.n_owned * 3, cm.n_owned * 3)
-    return dict(f=f, fc=fc, A=A, Ac=Ac, R=Rp, P=Pp, blas=blas, lm=lm, cm=cm, keep=keep + [R, P], halo=halo_f)
+    return dict(f=f, fc=fc, A=A, Ac=Ac, R=Rp, P=Pp, blas=blas, lm=lm, cm=cm, keep=keep + [R, P, halo_f], halo=halo_op)
 
 
 def _mg_solve(d, pr, dt, sweeps, max_cycles, tol, seed):
