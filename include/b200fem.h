@@ -156,7 +156,9 @@ int b200fem_op_apply_range(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_
 /* y = A x in ONE launch whose elements >= e_dependent wait, inside the kernel, until *ready_flag >= ready_value (acquire,
  * GPU scope) before they read x: the ghost-dependent elements of a distributed apply, ordered last, start when the
  * halo gather (b200fem_halo_gather_deferred_begin / _launch, on another stream) has filled the ghost block, while
- * everything else runs at once. The launch leaves one SM free for that other stream. Operators without the in-kernel wait
+ * everything else runs at once. The launch leaves one SM free for that other stream. Whatever sets the flag must not need a
+ * FIRST launch of its kernel while this one waits (lazy module loading may synchronise with running kernels: the wait would
+ * run into its 2 s bound; b200fem_halo_gather_deferred_launch goes first for that reason). Operators without the in-kernel wait
  * return B200FEM_FAILURE and enqueue nothing (b200fem_op_get_option "ghost_wait" tells beforehand). */
 int b200fem_op_apply_overwrite_after(b200fem_op_t op, const void *x, void *y, ptrdiff_t e_dependent,
                                      const unsigned long long *ready_flag, unsigned long long ready_value, void *stream);

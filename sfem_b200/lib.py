@@ -62,6 +62,7 @@ _SIG = {
     "b200fem_op_apply": [vp, vp, vp, vp],
     "b200fem_op_apply_overwrite": [vp, vp, vp, vp],
     "b200fem_op_apply_range": [vp, vp, vp, ssz, ssz, i32, vp],
+    "b200fem_op_apply_overwrite_after": [vp, vp, vp, ssz, vp, C.c_uint64, vp],
     "b200fem_op_diag": [vp, vp, vp],
     "b200fem_op_block_diag_sym": [vp, vp, vp],
     "b200fem_op_block_size": [vp],
@@ -274,6 +275,14 @@ class Op:
         """Elements [e_begin, e_end) only. mode 0: accumulate; 1 / 2: first part / continuation of an overwriting apply."""
         _vec(x, self.rows), _vec(y, self.rows)
         check(_lib.b200fem_op_apply_range(self._h, _p(x), _p(y), e_begin, e_end, mode, _stream()), "op_apply_range")
+        return y
+
+    def apply_overwrite_after(self, x, y, e_dependent: int, ready_flag, ready_value: int):
+        """y = A x in one launch whose elements >= e_dependent wait inside the kernel until the device word `ready_flag`
+        (a uint64 / int64 CUDA tensor of one element, or None) has reached ready_value."""
+        _vec(x, self.rows), _vec(y, self.rows)
+        check(_lib.b200fem_op_apply_overwrite_after(self._h, _p(x), _p(y), e_dependent, _p(ready_flag) if ready_flag is not None else None,
+                                                    ready_value, _stream()), "op_apply_overwrite_after")
         return y
 
     def diag(self, d):

@@ -212,6 +212,53 @@ def test_sshex8_laplacian_element_ranges(oracles, real):
         tet.apply_range(x[: tet_pts.shape[1]], y[: tet_pts.shape[1]], 0, 1, 0)
 
 
+def test_sshex8_laplacian_in_kernel_ghost_wait(oracles):
+    """b200fem_op_apply_overwrite_after: the element groups from e_dependent on wait inside the kernel for a device flag (the
+    distributed apply hands it the halo's ready flag). With the flag already at its value, and with the flag set by a second
+    stream while the kernel is running, the result is the plain y = A x."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, "f64")
+    L = 8
+    m = mesh.sshex8_box(L, 5, 4, 3)
+    fff = orc.hex8_fff_fill(m["m_elements"], mesh.shear_points(m["m_points"]))
+    nn, ne = m["n_nodes"], m["elements"].shape[1]
+    op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, torch.float64, level=L)
+    assert op.get_option("ghost_wait") == 1
+    u = np.random.default_rng(5).uniform(-1, 1, nn)
+    ref = orc.sshex8_laplacian_apply(L, m["elements"], fff, u)
+    x = torch.from_numpy(u).cuda()
+    flag = torch.full((1,), 7, dtype=torch.int64, device="cuda")
+    y = torch.full((nn,), 3.0, dtype=torch.float64, device="cuda")
+    op.apply_overwrite_after(x, y, ne // 2, flag, 7)          # already there
+    assert _rel(y.cpu().numpy(), ref) < TOL["f64"]
+    op.apply_overwrite_after(x, y, 0, None, 0)               # no flag: the plain apply
+    assert _rel(y.cpu().numpy(), ref) < TOL["f64"]
+    # the flag arrives from another stream after the kernel has been launched
+    y.fill_(3.0)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):  # load the two kernels now: a first launch (lazy module loading) may wait for running kernels
+        torch.cuda._sleep(1000)
+        flag.fill_(7)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    op.apply_overwrite_after(x, y, 3, flag, 8)
+    e1.record()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(2_000_000)  # ~1 ms on the SM the apply leaves free
+        flag.fill_(8)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu().numpy(), ref) < TOL["f64"]
+    ms = e0.elapsed_time(e1)
+    assert 0.3 < ms < 1000.0, f"{ms} ms: the kernel neither waited for the flag nor ran into its 2 s time-out"
+    tet_el, tet_pts = mesh.box_tet4(3, 3, 3)
+    tet = lib.laplacian(lib.TET4, tet_el, orc.tet4_fff_fill(tet_el, tet_pts), tet_pts.shape[1], torch.float64)
+    with pytest.raises(lib.B200FemError):
+        tet.apply_overwrite_after(x[: tet_pts.shape[1]], y[: tet_pts.shape[1]], 0, flag, 9)
+
+
 def test_sshex8_laplacian_hierarchical_numbering(oracles):
     """Non-affine numbering (coarse lattices first) must take the explicit-index path and still match."""
     torch = _torch()
