@@ -212,6 +212,13 @@ def cpu_flags():
     return set()
 
 
+def workload_config(a):
+    """`config` of the JSON line: the same dict in both arms (what differs between them is said in `config_details`)"""
+    return {"workload": workload_name(a),
+            "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair (one call, b200fem_op_apply_overwrite, in the b200 arm)",
+            "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush"}
+
+
 def run_reference(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -227,8 +234,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.real, "data": "synthetic",
-        "config": {"workload": workload_name(a),
-                   "arm": "the reference's OpenMP kernel (oracle/_ref) on the host cores of rank 0, one rank's block"},
+        # `config` is the same dict in both arms (the driver compares them); what differs is said beside it
+        "config": workload_config(a),
+        "config_details": {"arm": "the reference's OpenMP kernel (oracle/_ref) on the host cores of rank 0, one rank's block"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "isa", "host_GB_s")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -495,11 +503,10 @@ def run_b200(a):
         "metric": METRIC, "value": total_owned / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.real, "data": "synthetic",
-        "config": {
-            "workload": workload_name(a), "dofs_owned_total": total_owned, "dofs_local_rank0": n_local,
+        "config": workload_config(a),
+        "config_details": {
+            "dofs_owned_total": total_owned, "dofs_local_rank0": n_local,
             "macro_elements_rank0": n_elements,
-            "semantics": "y = A x: the reference's zeros(y) + Op::apply(x, y) pair as one call (b200fem_op_apply_overwrite)",
-            "l2_policy": "x + y + connectivity = 2.2 GB per apply, larger than the 126 MB L2; no flush",
             "connectivity": "27 affine boxes per macro element (432 B instead of 2916 B of int32 indices)",
             "parallelism": (f"z-slab x{world}, owned/ghost/aura; every step = ParallelMatrixFreeOperator::apply of the C++ host "
                             f"layer: halo gather of x ({halo_kind}; "
