@@ -371,12 +371,25 @@ __global__ void __launch_bounds__(BT)
     wait_all();
     __syncthreads();
 
+    // E == BT (one element per thread and patch): the geometry of the NEXT patch's element is loaded into registers while the
+    // current one computes -- it is the one global load of the element phase that the staging above does not cover (ncu of the
+    // hex8 elasticity instance: 2.4 long-scoreboard stall cycles per issue with 4 warps per scheduler)
+    constexpr bool kPrefetchGeo = (E == BT);
+    typename Local::Geo geo_cur, geo_next;
+    if (kPrefetchGeo && c0 < p.nchunks) {
+        const ptrdiff_t last = p.ne - 1, e = c0 * E + tid;
+        local.load(e < last ? e : last, geo_cur);
+    }
     int k = 0;
     for (ptrdiff_t c = c0; c < p.nchunks; c += stride, ++k) {
         const int si = k % 3, sx = k & 1;
         issue_idx(c + 2 * stride, (k + 2) % 3);
         issue_x(c + stride, (k + 1) % 3, (k + 1) & 1);
         commit();
+        if (kPrefetchGeo && c + stride < p.nchunks) {
+            const ptrdiff_t last = p.ne - 1, e = (c + stride) * E + tid;
+            local.load(e < last ? e : last, geo_next);
+        }
 
         const int U = p.chunk_u[c];
         const ptrdiff_t e0 = c * E;
@@ -386,7 +399,10 @@ __global__ void __launch_bounds__(BT)
         const uint16_t *li = st_lidx(si);
         for (int e = tid; e < nel; e += BT) {
             typename Local::Geo geo;
-            local.load(e0 + e, geo);
+            if (kPrefetchGeo)
+                geo = geo_cur;
+            else
+                local.load(e0 + e, geo);
             T uin[NXE * BS], out[NXE * BS];
 #pragma unroll
             for (int v = 0; v < NXE; ++v) {
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(BT)
 #pragma unroll
                 for (int a = 0; a < BS; ++a) contrib[(a * NXE + v) * E + e] = out[v * BS + a];
         }
+        if (kPrefetchGeo) geo_cur = geo_next;
         __syncthreads();
         // 3. per unique node: fixed-order sum of its incidence slots, one RED per (node, component)
         const uint16_t *ns = st_nslot(si);
