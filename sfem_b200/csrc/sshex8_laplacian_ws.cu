@@ -72,34 +72,22 @@ static int launch_t(int cfg, ptrdiff_t ne, ptrdiff_t nn, const Sshex8Header *hea
     if (dep && (cfg & 255) != 11) B2_FAIL("the in-kernel ghost wait is built into ws_cfg 11 only");
     const int dbg = cfg >> 8;  // A/B switch (ws_cfg + 256): interior runs per node instead of TMA
     switch (cfg & 255) {
+        // the round-1 kernel (four hand-offs per plane), kept for A/B
+        case 0: return launch_cfg<T, 8, 4, 2, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
+        case 4: return launch_cfg<T, 8, 4, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // phase-unrolled z loop, five bodies
+        // the two-barrier kernel
+        case 9: return launch_ws2<T, 8, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);              // rolled z loop
         default:
-        case 0: return launch_cfg<T, 8, 4, 2, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);  // measured best at C3
-        case 1: return launch_cfg<T, 8, 4, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 2: return launch_cfg<T, 8, 4, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 3: return launch_cfg<T, 8, 6, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 4: return launch_cfg<T, 8, 4, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);  // phase-unrolled z loop
-        case 8: return launch_ws2<T, 8, 4, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);  // two-barrier protocol
-        case 9: return launch_ws2<T, 8, 3, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 10: return launch_ws2<T, 8, 5, PLAIN>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg, dep);  // + static accumulator phases
-        case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 15: return launch_ws2<T, 8, 2, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 18: return launch_ws2<T, 8, 3, PLAIN, true, 0, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);  // lateral buffer for the x = 0 / L positions only
-        case 27: return launch_ws2<T, 8, 3, PLAIN, true, 2, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
-        case 28: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
-        case 30: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 200>(ne, nn, headers, x, y, max_ctas, s, dbg);   // try_wait suspend hints
-        case 31: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 1000>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 32: return launch_ws2<T, 8, 3, PLAIN, true, 0, 0, 5000>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral-face output buffer
-        case 17: return launch_ws2<T, 8, 4, PLAIN, true, 0, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);
-        case 25: return launch_ws2<T, 8, 3, PLAIN, true, 2, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);      // no arithmetic
-        case 26: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);  // stores only
-        // bracketing runs of the D = 3 phased kernel (profiles/r02*_ws2_brackets): parts switched off at compile time
-        case 20: return launch_ws2<T, 8, 3, PLAIN, true, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);        // no arithmetic
-        case 21: return launch_ws2<T, 8, 3, PLAIN, true, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // arithmetic only
+        case 11: return launch_ws2<T, 8, 3, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg, dep);  // + static accumulator phases: the default
+        case 12: return launch_ws2<T, 8, 4, PLAIN, true>(ne, nn, headers, x, y, max_ctas, s, dbg);       // ring depth 4
+        case 16: return launch_ws2<T, 8, 3, PLAIN, true, 0, 1>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral output buffer, all 32 positions
+        case 18: return launch_ws2<T, 8, 3, PLAIN, true, 0, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);  // + lateral output buffer, x = 0 / L only
+        // bracketing runs of the default kernel (profiles/r02*_brackets*): parts switched off at compile time
+        case 20: return launch_ws2<T, 8, 3, PLAIN, true, 2>(ne, nn, headers, x, y, max_ctas, s, dbg);          // no arithmetic
+        case 21: return launch_ws2<T, 8, 3, PLAIN, true, 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);      // arithmetic only
         case 22: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 4 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);  // protocol only
-        case 23: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 4>(ne, nn, headers, x, y, max_ctas, s, dbg);    // loads only
-        case 24: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);    // stores only
+        case 23: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 4>(ne, nn, headers, x, y, max_ctas, s, dbg);      // loads only
+        case 24: return launch_ws2<T, 8, 3, PLAIN, true, 2 + 8>(ne, nn, headers, x, y, max_ctas, s, dbg);      // stores only
     }
 }
 

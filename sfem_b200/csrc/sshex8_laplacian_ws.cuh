@@ -1,5 +1,8 @@
-// sshex8 Laplacian, warp-specialised plane-streaming kernel ("ws"): compute warps only read shared memory and
-// issue FMAs, mover warps own every global access. Same arithmetic (sshex8_laplacian_core.cuh), same element
+// sshex8 Laplacian, warp-specialised plane-streaming kernels: compute warps only read shared memory and
+// issue FMAs, mover warps own every global access. Two kernels live here: sshex8_laplacian_ws_kernel (round 1: four hand-offs
+// per plane; kept for A/B) and sshex8_laplacian_ws2_kernel further down (round 2, the default: two hand-offs per plane,
+// static accumulator phases, optional in-kernel wait for the ghost block of a distributed apply). What follows describes what
+// they share. Same arithmetic (sshex8_laplacian_core.cuh), same element
 // headers and same plane ring as sshex8_laplacian_stream.cuh; what changes is who does what, and how the interior
 // of a plane travels.
 //
@@ -247,9 +250,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 __syncwarp();
                 plane_set(hb, ldI, ldS, ldB);
             }
-            if (dbg & 8) {  // experiment: no loads at all (the barrier protocol stays)
-                if (tl == 0) mbar_arrive(bar);
-            } else if (zp == 0 || zp == L) {
+            if (zp == 0 || zp == L) {
                 if (tl == 0) mbar_arrive(bar);
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
@@ -291,8 +292,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
         auto scatter_plane = [&](const int ss, const uint32_t sp, const unsigned char *hb, const int z, const int nv) {
             const T *src = stage + (size_t)ss * PLANE;
             mbar_wait(sfull + ss, sp);
-            if (dbg & 4) {  // experiment: no stores (the barrier protocol stays)
-            } else if (z == 0 || z == L) {
+            if (z == 0 || z == L) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     if (i >= nv) break;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
                 }
                 const int kin = (Bs + NI * zp) & (AL - 1);
                 const T *pk = plane + kin, *ps = plane + dk * kin;  // interior rows / skeleton positions
-                if (!(dbg & 2)) row.step_with(zp, [&](const int iy, T(&r)[N]) {
+                row.step_with(zp, [&](const int iy, T(&r)[N]) {
                     const T *pm = (rint[iy] ? pk : ps) + am[iy];
                     r[0] = ps[a0[iy]];
 #pragma unroll

@@ -133,7 +133,7 @@ def test_hex8_linear_elasticity(oracles, real, scatter):
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
 @pytest.mark.parametrize("level", [2, 4, 8])
-@pytest.mark.parametrize("path", ["ws", "tma", "stream", "explicit"])
+@pytest.mark.parametrize("path", ["ws", "ws_r1", "ws_rolled", "ws_fo1", "ws_fo2", "tma", "stream", "explicit"])
 def test_sshex8_laplacian(oracles, real, level, path):
     torch = _torch()
     from sfem_b200 import lib, mesh
@@ -141,17 +141,22 @@ def test_sshex8_laplacian(oracles, real, level, path):
     orc = _orc(oracles, real)
     # 23 macro elements: not a multiple of any batch size -> ragged last batch
     m = mesh.sshex8_box(level, 23, 1, 1) if level == 2 else mesh.sshex8_box(level, 3, 2, 3)
-    if path == "ws":
+    # the warp-specialised kernels: the default (two barriers, static phases), the round-1 kernel, the two-barrier kernel with
+    # the rolled z loop, and the two lateral output buffers (sfem_b200/csrc/sshex8_laplacian_ws.cu: ws_cfg)
+    ws_cfg = {"ws": 11, "ws_r1": 0, "ws_rolled": 9, "ws_fo1": 16, "ws_fo2": 18}.get(path)
+    if ws_cfg is not None:
         if level != 8:
-            pytest.skip("the warp-specialised kernel serves level 8")
-        m = mesh.sshex8_box(level, 5, 2, 2)  # 20 elements: 6 groups of 3 + 2 for the clean-up launch
+            pytest.skip("the warp-specialised kernels serve level 8")
+        m = mesh.sshex8_box(level, 5, 2, 2)  # 20 elements: 6 groups of 3 + a partial group of 2
     mpts = mesh.shear_points(m["m_points"])
     fff = orc.hex8_fff_fill(m["m_elements"], mpts)
     nn = m["n_nodes"]
     op = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=level)
     assert op.get_option("mode") == 1 and op.get_option("interior_exclusive") == 1
     assert op.get_option("tma_ok") == 1  # every entity box of the generator's numbering is a contiguous id run
-    op.set_option("use_ws", 2 if path == "ws" else 0)  # 2 = wherever it applies (fp32 too)
+    op.set_option("use_ws", 2 if ws_cfg is not None else 0)  # 2 = wherever it applies (fp32 too)
+    if ws_cfg is not None:
+        op.set_option("ws_cfg", ws_cfg)
     op.set_option("explicit_index", int(path == "explicit"))
     op.set_option("use_tma", int(path == "tma"))  # the TMA kernel serves level >= 4; level 2 streams either way
     u = np.random.default_rng(level).uniform(-1, 1, nn)
