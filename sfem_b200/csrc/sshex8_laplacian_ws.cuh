@@ -544,6 +544,9 @@ __global__ void __launch_bounds__(2 * NC * 32, 1)
     constexpr int AL = 16 / (int)sizeof(T);
     constexpr int REG_MOVER = 80;
     constexpr int REG_COMPUTE = (65536 / 32 - NC * REG_MOVER) / NC / 8 * 8;
+    // the register pool of the CTA is threads x the launch allocation, which is 65536 only for NC = 8 (128 registers at launch):
+    // with more warp pairs setmaxnreg.inc would wait for registers that never come
+    static_assert(NC == 8, "register budgets are derived for 8 warp pairs (512 threads x 128 registers)");
     static_assert(D < N, "ring deeper than a group");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
