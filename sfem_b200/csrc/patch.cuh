@@ -219,7 +219,7 @@ __device__ __forceinline__ void patch_cp_value(T *smem, const T *gmem) {
 // STAGE_LISTS: the incidence lists of phase 3 (slots + CSR offsets) are copied into shared memory by cp.async at the start
 // of the patch and land behind phases 1 and 2, so the per-node walk of phase 3 reads shared memory instead of a chain of
 // dependent global loads (24 per node for tet4).
-template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false>
+template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false, bool HOIST_LOADS = false>
 __global__ void __launch_bounds__(BT)
     patch_apply_direct_kernel(const PatchArrays p, const Local local, const int max_u, const T *__restrict__ u, T *__restrict__ y) {
     extern __shared__ __align__(16) unsigned char patch_smem[];
@@ -242,6 +242,25 @@ __global__ void __launch_bounds__(BT)
             for (int i = tid; i < ((U + 1) * 2 + 15) / 16; i += BT) patch_cp16(reinterpret_cast<int4 *>(s_no) + i, g_no + i);
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
+        // 0. the element phase's own global loads (geometry + local corner indices of the E / BT elements of this thread, indices
+        // clamped instead of predicated: a clamped duplicate recomputes the last element and rewrites its slots with the same
+        // values). HOIST_LOADS: issued before the node gather instead of behind its barrier, so the two latencies overlap
+        // (ncu of the tet4 instance: 12 long-scoreboard stall cycles per issue) at the price of holding them in registers.
+        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
+        static_assert(E % BT == 0, "a patch is a whole number of elements per thread");
+        constexpr int EPT = E / BT;
+        typename Local::Geo geo[EPT];
+        int jj[EPT][NXE];
+        auto load_elements = [&]() {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int e = min(tid + k * BT, nel - 1);
+                local.load(e0 + e, geo[k]);
+#pragma unroll
+                for (int v = 0; v < NXE; ++v) jj[k][v] = ldg_stream(&li[v * E + e]);
+            }
+        };
+        if (HOIST_LOADS) load_elements();
         // 1. stage the unique nodes' values
         for (int j = tid; j < U; j += BT) {
             const ptrdiff_t node = p.unodes[u0 + j];
@@ -250,21 +269,7 @@ __global__ void __launch_bounds__(BT)
         }
         __syncthreads();
         // 2. element operator from shared memory into per-element slots
-        // (fully unrolled over the E / BT elements of a thread, indices clamped instead of predicated: the index and
-        // geometry loads of all of them are issued together instead of one global round trip per element; a clamped
-        // duplicate recomputes the last element and rewrites its slots with the same values)
-        const uint16_t *li = p.lidx + (size_t)c * NXE * E;
-        static_assert(E % BT == 0, "a patch is a whole number of elements per thread");
-        constexpr int EPT = E / BT;
-        typename Local::Geo geo[EPT];
-        int jj[EPT][NXE];
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int e = min(tid + k * BT, nel - 1);
-            local.load(e0 + e, geo[k]);
-#pragma unroll
-            for (int v = 0; v < NXE; ++v) jj[k][v] = ldg_stream(&li[v * E + e]);
-        }
+        if (!HOIST_LOADS) load_elements();
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
             const int e = min(tid + k * BT, nel - 1);
@@ -455,9 +460,9 @@ int launch_patch_apply_smem_atomic(const PatchPlan &plan, const Local &local, co
     return B200FEM_SUCCESS;
 }
 
-template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false>
+template <typename T, int NXE, int BS, int E, int BT, class Local, bool STAGE_LISTS = false, bool HOIST_LOADS = false>
 int launch_patch_apply_direct(const PatchPlan &plan, const Local &local, const T *x, T *y, cudaStream_t s) {
-    auto kern = patch_apply_direct_kernel<T, NXE, BS, E, BT, Local, STAGE_LISTS>;
+    auto kern = patch_apply_direct_kernel<T, NXE, BS, E, BT, Local, STAGE_LISTS, HOIST_LOADS>;
     const size_t smem = ((size_t)plan.max_u * BS + (size_t)NXE * BS * E) * sizeof(T) +
                         (STAGE_LISTS ? ((size_t)NXE * E + (size_t)plan.max_u_pad()) * 2 : 0);
     static SmemOptIn opt;

@@ -108,8 +108,9 @@ struct Tet4Laplacian final : OpBase {
     DeviceArray<float> fff;         // [6][ne]
     ColorPlan colors;
     PatchPlan patch;
-    int patch_pipelined = 2;    // 0 = direct, 2 = direct with the incidence lists staged by cp.async (default: 1.47 vs 1.55 ms at
-                                // 260^3), 1 = fully software-pipelined kernel (2 CTAs per SM: slower for this light operator)
+    int patch_pipelined = 3;    // 0 = direct, 2 = direct with the incidence lists staged by cp.async (1.45 vs 1.53 ms at 260^3),
+                                // 3 = 2 + the element loads issued before the node gather (default: 1.37 ms), 1 = fully
+                                // software-pipelined kernel (2 CTAs per SM: slower for this light operator)
     int patch_smem_atomic = 0;  // 1 = shared-memory atomics instead of the incidence lists (order not fixed)
     static constexpr int kPatchE = 1024;
 
@@ -122,6 +123,8 @@ struct Tet4Laplacian final : OpBase {
             if (patch_pipelined == 1) return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             if (patch_pipelined == 2)
                 return launch_patch_apply_direct<T, 4, 1, kPatchE, 256, Tet4LaplacianLocal<T>, true>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            if (patch_pipelined == 3)  // + the element loads issued before the node gather
+                return launch_patch_apply_direct<T, 4, 1, kPatchE, 256, Tet4LaplacianLocal<T>, true, true>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             return launch_patch_apply_direct<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         }
         if (scatter == B200FEM_SCATTER_COLORED) {

@@ -23,7 +23,7 @@ ref = torch.zeros_like(x)
 op.apply_overwrite(x, ref)
 print(json.dumps(_entry(f"tet4 {n}^3 atomic", nn, op.algorithmic_bytes, _time(lambda: op.apply_overwrite(x, y), torch))), flush=True)
 op.set_option("scatter", lib.SCATTER_PATCH)
-for v, name in ((0, "direct"), (2, "direct + staged incidence lists"), (1, "pipelined")):
+for v, name in ((2, "direct + staged incidence lists"), (3, "direct + staged lists + element loads before the node gather")):
     op.set_option("patch_pipelined", v)
     op.apply_overwrite(x, y)
     err = float((y - ref).norm() / ref.norm())
