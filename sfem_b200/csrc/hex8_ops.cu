@@ -263,7 +263,7 @@ struct Hex8Laplacian final : OpBase {
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) <= 200 * 1024)
-            return launch_patch_apply_direct<T, 8, 1, kPatchE, 256>(patch, Hex8LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
+            return launch_patch_apply_direct<T, 8, 1, kPatchE, 256, Hex8LaplacianLocal<T>, true, true>(patch, Hex8LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
         if (scatter == B200FEM_SCATTER_COLORED) {
             if (colors.build(ne, nn)) return B200FEM_FAILURE;
             for (int c = 0; c < colors.ncolors(); ++c) {
