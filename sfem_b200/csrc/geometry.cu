@@ -6,7 +6,7 @@
 // Restated from the definitions: J[r][c] = d x_r / d xi_c, adj = det(J) J^-1 (row j = det * grad xi_j),
 //   tet4: FFF = adj adj^T / (6 det)     hex8: FFF = adj adj^T / det .
 // Arithmetic is fp64 from the fp32 coordinates, results stored fp32 (jacobian_t). The reference's
-// tet4 path evaluates in fp32; the two agree to fp32 rounding (tests/test_geometry.py), and operator
+// tet4 path evaluates in fp32; the two agree to fp32 rounding (tests/test_gpu_operators.py::test_geometry_fill), and operator
 // parity tests always hand both sides the same fp32 arrays.
 #include <vector>
 

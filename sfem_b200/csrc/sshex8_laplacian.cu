@@ -450,8 +450,12 @@ struct Sshex8Laplacian final : OpBase {
         return double(ne) * (idx + 24.0) + vec;
     }
     int launches(bool overwrite) const override {
-        // kernels + memset nodes; the clean-up launch of the streaming kernel exists when ne % EPT != 0 (EPT = 3 at L = 8)
-        return 1 + (overwrite ? (int)std::max<size_t>(zero_ranges.size(), 1) : 0);
+        // kernels + memset nodes. The warp-specialised kernel handles a partial last group itself; the plane-streaming kernel
+        // (fp32, levels 2 / 4, unaligned vectors) adds a one-CTA clean-up launch when ne is not a multiple of its team size
+        const bool ws = (use_ws == 2 || (use_ws == 1 && real_type == B200FEM_F64)) && level == 8 && interior_exclusive && nn >= 64;
+        const int team = 32 / (level + 1);  // one-warp teams (the default stream configuration): 3 / 6 / 10 elements at level 8 / 4 / 2
+        const int tail = (!ws && mode == kModeBoxes && use_stream && !use_tma && ne % team != 0) ? 1 : 0;
+        return 1 + tail + (overwrite ? (int)std::max<size_t>(zero_ranges.size(), 1) : 0);
     }
 
     int set_option(const char *key, int value) override {
