@@ -121,6 +121,15 @@ int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int
 int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements,
                                                  ptrdiff_t nnodes, const int32_t *const *elements, const float *const *points,
                                                  double mu, double lambda, int real_type);
+/* Mass and LumpedMass, the neighbouring operators on the same gather -> local -> scatter skeleton:
+ *   apply / apply_overwrite <- Mass::apply -> apply_mass (frontend/ops/sfem_Mass.cpp:107-125, operators/mass.cpp:158-207) ->
+ *                        hex8_apply_mass (operators/hex8/hex8_mass.cpp:8-60): isoparametric Q1, 27-point Gauss. TET4 fails,
+ *                        as in the reference (its dispatcher has no tet4 case);
+ *   diag               <- LumpedMass::hessian_diag -> assemble_lumped_mass (frontend/ops/sfem_LumpedMass.cpp, operators/mass.cpp:
+ *                        65-114) -> hex8_assemble_lumped_mass (hex8_mass.cpp:62-103) / tet4_assemble_lumped_mass
+ *                        (operators/tet4/tet4_mass.cpp:231-282): diag += row sums. Scalar fields (block_size 1). */
+int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
+                        const float *const *points, int real_type);
 /* Stored-element-matrix ("EM") semi-structured operators: ss:em:Laplacian / ss:em:LinearElasticity
  * (frontend/ops/sfem_SemiStructuredEMLaplacian.cpp, sfem_SemiStructuredEMLinearElasticity.cpp; kernels
  * operators/stencil/sshex8_stencil_element_matrix_apply.cpp:10-160, GPU twins GPUEMOp / GPUEMWarpOp over

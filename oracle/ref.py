@@ -210,6 +210,37 @@ class Oracle:
                    _soa_ptrs(pts, C.c_float), pu, out.ctypes.data_as(C.POINTER(self.crt)))
         return out
 
+    # ---- mass (reference build only: hex8_mass.cpp / tet4_mass.cpp compiled where they lie)
+    def hex8_apply_mass(self, elements, points, u, nnodes):
+        """hex8_apply_mass (operators/hex8/hex8_mass.cpp:8-60): out += M u, 27-point Gauss, isoparametric."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        self._call("hex8_apply_mass", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), C.c_ssize_t(1), pu, C.c_ssize_t(1), out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def hex8_lumped_mass(self, elements, points, nnodes):
+        """hex8_assemble_lumped_mass (operators/hex8/hex8_mass.cpp:62-103)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        self._call("hex8_assemble_lumped_mass", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), C.c_ssize_t(1), out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def tet4_lumped_mass(self, elements, points, nnodes):
+        """tet4_assemble_lumped_mass (operators/tet4/tet4_mass.cpp:231-282; C++ linkage, void)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        fn = self._symbol("tet4_assemble_lumped_mass")
+        fn.restype = None
+        fn(C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+           out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
     def hex8_linear_elasticity_apply_isoparametric(self, elements, points, mu, lam, u, nnodes):
         el = np.ascontiguousarray(elements, dtype=np.int32)
         pts = np.ascontiguousarray(points, dtype=np.float32)

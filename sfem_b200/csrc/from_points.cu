@@ -352,16 +352,103 @@ OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     return op;
 }
 
+// Mass (consistent: y += M x) and lumped mass of the isoparametric Q1 hex, 27-point Gauss on [0,1]^3: hex8_apply_mass /
+// hex8_assemble_lumped_mass (operators/hex8/hex8_mass.cpp:8-103; point kernels hex8_mass_apply_points / hex8_lumped_mass_points,
+// hex8_mass_inline_cpu.hpp:135-286; points and weights q27_*, hex8_quadrature.hpp:46-84 -- the reference's 15-digit literals).
+// Per point: out_i += w det J(q) phi_i(q) sum_j phi_j(q) u_j (lumped: the row sum, sum_j phi_j = 1).
+template <typename T, bool LUMPED>
+__global__ void __launch_bounds__(128)
+    hex8_mass_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                     const T *__restrict__ u, T *__restrict__ y) {
+    const T qp[3] = {T(0.112701665379258), T(0.5), T(0.887298334620742)};
+    // weight by the number of centre coordinates among (qx, qy, qz)
+    const T qw[4] = {T(0.021433470507545), T(0.034293552812071), T(0.054869684499314), T(0.087791495198903)};
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[8];  // lexicographic corners
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ev[kVtkToLex[v]] = ldg_stream(&elements[v * ne + e]);
+        T X[3][8], U[8], O[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) X[d][i] = (T)points[(size_t)d * nn + ev[i]];
+            U[i] = LUMPED ? T(1) : u[ev[i]];
+            O[i] = T(0);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 27; ++q) {
+            const int ix = q % 3, iy = (q / 3) % 3, iz = q / 9;
+            const T x = qp[ix], yq = qp[iy], z = qp[iz];
+            const T w = qw[(ix == 1) + (iy == 1) + (iz == 1)];
+            T phi[8], J[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) J[k] = T(0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int bx = i & 1, by = (i >> 1) & 1, bz = (i >> 2) & 1;
+                const T sx = bx ? x : T(1) - x, sy = by ? yq : T(1) - yq, sz = bz ? z : T(1) - z;
+                phi[i] = sx * sy * sz;
+                const T gx = (bx ? T(1) : T(-1)) * sy * sz, gy = sx * (by ? T(1) : T(-1)) * sz, gz = sx * sy * (bz ? T(1) : T(-1));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    J[r * 3 + 0] = le_fma(X[r][i], gx, J[r * 3 + 0]);
+                    J[r * 3 + 1] = le_fma(X[r][i], gy, J[r * 3 + 1]);
+                    J[r * 3 + 2] = le_fma(X[r][i], gz, J[r * 3 + 2]);
+                }
+            }
+            const T det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+            T uq = T(0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) uq = le_fma(phi[i], U[i], uq);
+            const T val = w * det * uq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) O[i] = le_fma(phi[i], val, O[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red_add(&y[ev[i]], O[i]);
+    }
+}
+
+// lumped mass of the P1 tet: det / 24 on each of its nodes (tet4_assemble_lumped_mass, operators/tet4/tet4_mass.cpp:66-92,
+// 231-282; the reference expands the determinant into its 24 monomials, here it is the triple product of the edge vectors)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    tet4_lumped_mass_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                            T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        T p[3][4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) p[d][v] = (T)points[(size_t)d * nn + ev[v]];
+        const T ax = p[0][1] - p[0][0], ay = p[1][1] - p[1][0], az = p[2][1] - p[2][0];
+        const T bx = p[0][2] - p[0][0], by = p[1][2] - p[1][0], bz = p[2][2] - p[2][0];
+        const T cx = p[0][3] - p[0][0], cy = p[1][3] - p[1][0], cz = p[2][3] - p[2][0];
+        const T det = ax * (by * cz - bz * cy) - ay * (bx * cz - bz * cx) + az * (bx * cy - by * cx);
+        const T m = det * T(1.0 / 24.0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) red_add(&y[ev[v]], m);
+    }
+}
+
 struct PointsOp final : OpBase {
     DeviceArray<int32_t> elements;  // SoA [nxe][ne]
     DeviceArray<float> points;      // [3][nn]
     double mu = 1, lambda = 1;
     bool elasticity = false;
+    bool mass = false;  // Mass / LumpedMass: apply = hex8_apply_mass (tet4: none, like the reference's dispatcher), diag = lumped mass
 
     template <typename T>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         if (ne == 0) return B200FEM_SUCCESS;
-        if (elasticity && nxe == 4) {
+        if (mass) {
+            if (nxe != 8) B2_FAIL("mass apply: hex8 only (apply_mass, operators/mass.cpp:158-207, has no tet4 case)");
+            const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+            hex8_mass_kernel<T, false><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, x, y);
+        } else if (elasticity && nxe == 4) {
             const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
             tet4_le_points_kernel<T, false><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (T)mu, (T)lambda, x, y);
         } else if (elasticity) {
@@ -379,6 +466,25 @@ struct PointsOp final : OpBase {
         return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, s) : apply_t<float>((const float *)x, (float *)y, s);
     }
     int diag(void *d, cudaStream_t s) override {
+        if (mass) {  // LumpedMass::hessian_diag: diag += row sums of the mass matrix
+            if (ne == 0) return B200FEM_SUCCESS;
+            const bool f64 = real_type == B200FEM_F64;
+            if (nxe == 8) {
+                const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+                if (f64)
+                    hex8_mass_kernel<double, true><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, nullptr, (double *)d);
+                else
+                    hex8_mass_kernel<float, true><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, nullptr, (float *)d);
+            } else {
+                const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+                if (f64)
+                    tet4_lumped_mass_kernel<double><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (double *)d);
+                else
+                    tet4_lumped_mass_kernel<float><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float *)d);
+            }
+            B2_CHECK_LAUNCH();
+            return B200FEM_SUCCESS;
+        }
         if (!(elasticity && nxe == 4)) return OpBase::diag(d, s);
         if (ne == 0) return B200FEM_SUCCESS;
         const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
@@ -420,6 +526,16 @@ OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_
                                         int real_type) {
     OpBase *op = make_points_op(4, ne, nn, elements, points, real_type, "tet4 laplacian (from points)");
     if (op) op->elem_type = B200FEM_TET4;
+    return op;
+}
+
+OpBase *make_mass_from_points(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
+                              int real_type) {
+    OpBase *op = make_points_op(element_type == B200FEM_HEX8 ? 8 : 4, ne, nn, elements, points, real_type, "mass");
+    if (op) {
+        op->elem_type = element_type;
+        static_cast<PointsOp *>(op)->mass = true;
+    }
     return op;
 }
 

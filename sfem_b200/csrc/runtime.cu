@@ -251,6 +251,17 @@ int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int
     return B200FEM_SUCCESS;
 }
 
+int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                        const float *const *points, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
+    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4) B2_FAIL("mass: hex8 (apply + lumped) and tet4 (lumped) only");
+    OpBase *impl = make_mass_from_points(element_type, ne, nn, elements, points, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
 int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t ne, ptrdiff_t nn,
                                                  const int32_t *const *elements, const float *const *points, double mu,
                                                  double lambda, int real_type) {

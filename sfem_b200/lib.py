@@ -54,6 +54,7 @@ _SIG = {
     "b200fem_linear_elasticity_create": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float),
                                          C.POINTER(C.c_float), f64, f64, i32],
     "b200fem_laplacian_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
+    "b200fem_mass_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_linear_elasticity_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, f64, f64, i32],
     "b200fem_sshex8_em_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, i32, vp, i32],
     "b200fem_sshex8_laplacian_element_matrix": [i32, ssz, C.POINTER(C.c_float), i32, vp],
@@ -329,6 +330,16 @@ def laplacian_from_points(element_type: int, elements: np.ndarray, points: np.nd
     h = vp()
     check(_lib.b200fem_laplacian_create_from_points(C.byref(h), element_type, level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
                                                     _soa_ptrs(pts, C.c_float), _rt(dtype)), "laplacian_create_from_points")
+    return Op(h, nnodes)
+
+
+def mass(element_type: int, elements: np.ndarray, points: np.ndarray, nnodes: int, dtype) -> Op:
+    """Mass / LumpedMass: apply = hex8_apply_mass (HEX8 only, like the reference), diag = the lumped mass (HEX8, TET4)."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_mass_create(C.byref(h), element_type, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+                                   _rt(dtype)), "mass_create")
     return Op(h, nnodes)
 
 

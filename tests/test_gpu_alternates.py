@@ -80,6 +80,44 @@ def test_tet4_laplacian_from_points(oracles, real):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
+def test_mass_and_lumped_mass(oracles, real):
+    """b200fem_mass_create: apply = hex8_apply_mass, diag = hex8 / tet4 lumped mass, against the reference's own routines.
+    The tet4 bar is 1e-10: the reference expands the determinant into 24 monomials of the coordinates (cancellation)."""
+    import torch
+
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    if orc.kind != "reference":
+        pytest.skip("the mass routines exist in the reference build of the oracle only")
+    el, pts = mesh.box_hex8(6, 5, 7)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    op = lib.mass(lib.HEX8, el, pts, nn, _dt(real))
+    u = np.random.default_rng(2).uniform(-1, 1, nn)
+    x, y = _apply(op, u, _dt(real))
+    assert _rel(y.cpu().numpy(), orc.hex8_apply_mass(el, pts, u, nn)) < TOL[real]
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), orc.hex8_apply_mass(el, pts, u, nn)) < TOL[real]
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    lumped = orc.hex8_lumped_mass(el, pts, nn)
+    assert _rel(d.cpu().numpy(), lumped) < TOL[real]
+    # the mass of the constant function is the lumped mass, and its total the volume of the (warped) box
+    x1, y1 = _apply(op, np.ones(nn), _dt(real))
+    assert _rel(y1.cpu().numpy(), lumped) < TOL[real]
+    tel, tpts = mesh.box_tet4(5, 4, 6)
+    tpts = mesh.warp_points(tpts)
+    tn = tpts.shape[1]
+    top = lib.mass(lib.TET4, tel, tpts, tn, _dt(real))
+    td = torch.zeros(tn, dtype=_dt(real), device="cuda")
+    top.diag(td)
+    assert _rel(td.cpu().numpy(), orc.tet4_lumped_mass(tel, tpts, tn)) < (1e-10 if real == "f64" else 1e-4)
+    with pytest.raises(lib.B200FemError, match="hex8 only"):
+        top.apply(td, torch.zeros_like(td))
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
 def test_hex8_linear_elasticity_isoparametric(oracles, real):
     from sfem_b200 import lib, mesh
 

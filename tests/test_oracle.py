@@ -38,6 +38,37 @@ def test_unit_tet_matrix_known_answer(oracles):
         assert np.allclose(orc.tet4_laplacian_diag_opt(el, fff, 4), np.diag(A), atol=1e-7)
 
 
+def test_mass_known_answers(oracles):
+    """Mass oracles (reference build only): the unit tet's lumped mass is |T| / 4 = 1 / 24 per node, the consistent hex8 mass
+    of the unit cube is the tensor product of the 1-D P1 mass matrix [[1/3, 1/6], [1/6, 1/3]], the mass of the constant is the
+    lumped mass and sums to the volume."""
+    if ("reference", "f64") not in oracles:
+        pytest.skip("the mass routines are compiled from the reference only")
+    orc = oracles[("reference", "f64")]
+    el = np.array([[0], [1], [2], [3]], dtype=np.int32)
+    pts = np.array([[0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+    assert np.allclose(orc.tet4_lumped_mass(el, pts, 4), 1.0 / 24.0, atol=1e-15)
+    hel = np.arange(8, dtype=np.int32).reshape(8, 1)  # VTK corner order
+    hpts = np.array([[0, 1, 1, 0, 0, 1, 1, 0], [0, 0, 1, 1, 0, 0, 1, 1], [0, 0, 0, 0, 1, 1, 1, 1]], dtype=np.float32)
+    m1 = np.array([[1 / 3, 1 / 6], [1 / 6, 1 / 3]])
+    M = np.zeros((8, 8))
+    for i in range(8):
+        for j in range(8):
+            M[i, j] = np.prod([m1[int(hpts[d, i]), int(hpts[d, j])] for d in range(3)])
+    for j in range(8):
+        e = np.zeros(8)
+        e[j] = 1
+        assert np.allclose(orc.hex8_apply_mass(hel, hpts, e, 8), M[:, j], atol=1e-13)  # the 15-digit quadrature literals
+    assert np.allclose(orc.hex8_lumped_mass(hel, hpts, 8), 1.0 / 8.0, atol=1e-13)
+    from sfem_b200 import mesh
+
+    bel, bpts = mesh.box_hex8(5, 4, 6)
+    nn = bpts.shape[1]
+    lumped = orc.hex8_lumped_mass(bel, bpts, nn)
+    assert np.allclose(orc.hex8_apply_mass(bel, bpts, np.ones(nn), nn), lumped, atol=1e-14)
+    assert abs(lumped.sum() - 1.0) < 1e-12
+
+
 def test_stencil_known_answer(oracles):
     """Known answer in the spirit of operators/stencil/tests/sfem_StencilTest.cpp:143-218 (a quadratic field
     gives a constant at every interior stencil row): for u = x^2 + y^2 + z^2 on a unit-cube macro element the
