@@ -172,7 +172,33 @@ namespace sfem {
         return ret;
     }
 
+    /* ------------------------------------------------------------------------------------------ B200Mass */
+    std::unique_ptr<Op> B200Mass::create(const std::shared_ptr<FunctionSpace> &space) {
+        assert(1 == space->block_size());
+        return std::make_unique<B200Mass>(space);
+    }
+
+    b200fem_op_t B200Mass::create_plan(const OpDomain &domain) {
+        DomainGeometry g = geometry_of(space, domain);
+        if (g.type != B200FEM_HEX8 && g.type != B200FEM_TET4) {
+            fprintf(stderr, "[b200fem] mass: hex8 (apply + lumped) and tet4 (lumped) blocks only\n");
+            return nullptr;
+        }
+        b200fem_op_t plan = nullptr; /* apply_mass / assemble_lumped_mass read the mesh points, no cached geometry */
+        if (b200fem_mass_create(&plan, g.type, g.ne, g.nn, g.elements, space->mesh_ptr()->points()->data(), kRealType)) return nullptr;
+        return plan;
+    }
+
+    std::shared_ptr<Op> B200Mass::clone() const {
+        auto ret     = std::make_shared<B200Mass>(space);
+        ret->domains = domains;
+        ret->stream  = stream;
+        return ret;
+    }
+
     void register_b200_ops() {
+        Factory::register_op("gpu:Mass", &B200Mass::create);
+        Factory::register_op("gpu:LumpedMass", &B200Mass::create);
         Factory::register_op("gpu:Laplacian", &B200Laplacian::create);
         Factory::register_op("ss:gpu:Laplacian", &B200Laplacian::create);
         Factory::register_op("gpu:LinearElasticity", &B200LinearElasticity::create);

@@ -97,6 +97,20 @@ namespace sfem {
         b200fem_op_t create_plan(const OpDomain &domain) override;
     };
 
+    /* Mass / LumpedMass (frontend/ops/sfem_Mass.cpp, sfem_LumpedMass.cpp): apply = Mass::apply (hex8 blocks: apply_mass has no
+     * other 3-D case), hessian_diag = LumpedMass::hessian_diag (hex8, tet4). One class under both keys. */
+    class B200Mass final : public B200Op {
+    public:
+        using B200Op::B200Op;
+        static std::unique_ptr<Op> create(const std::shared_ptr<FunctionSpace> &space);
+        const char *name() const override { return "gpu:Mass"; }
+        int         initialize(const std::vector<std::string> &block_names = {}) override { return initialize_domains(block_names); }
+        std::shared_ptr<Op> clone() const override;
+
+    protected:
+        b200fem_op_t create_plan(const OpDomain &domain) override;
+    };
+
     /* sfem::BLAS<T> over b200fem_blas_*; injected like CUDA_BLAS (algebra/cuda/sfem_cuda_solver.hpp:15-49):
      *     cg->blas = std::make_shared<B200BLAS<real_t>>(); cg->execution_space_ = EXECUTION_SPACE_DEVICE; */
     template <typename T>

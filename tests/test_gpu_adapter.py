@@ -121,6 +121,46 @@ def test_factory_creates_our_laplacian(oracles, case):
 
 
 @pytest.mark.gpu
+def test_factory_creates_our_mass(oracles):
+    """sfem::create_op(space, "Mass" | "LumpedMass", DEVICE): Mass::apply on a hex8 block, LumpedMass::hessian_diag on hex8 and
+    tet4 blocks, against the reference's own hex8_mass.cpp / tet4_mass.cpp."""
+    import torch
+
+    from sfem_b200 import mesh
+
+    h = _lib()
+    if ("reference", "f64") not in oracles:
+        pytest.skip("the mass routines exist in the reference build of the oracle only")
+    orc = oracles[("reference", "f64")]
+    el, pts = mesh.box_hex8(6, 7, 5)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    u = np.random.default_rng(4).uniform(-1, 1, nn)
+    sp = _space(h, 8, 0, el, pts, 1)
+    op = h.adapter_create_op(sp, b"Mass")
+    assert op and h.adapter_op_name(op) == b"gpu:Mass" and h.adapter_op_execution_space(op) == 1
+    x = torch.from_numpy(u).cuda()
+    y = torch.zeros_like(x)
+    assert h.adapter_op_apply(op, x.data_ptr(), y.data_ptr()) == 0
+    assert _rel(y.cpu().numpy(), orc.hex8_apply_mass(el, pts, u, nn)) < 1e-12
+    lm = h.adapter_create_op(sp, b"LumpedMass")
+    d = torch.zeros_like(x)
+    assert lm and h.adapter_op_hessian_diag(lm, d.data_ptr()) == 0
+    assert _rel(d.cpu().numpy(), orc.hex8_lumped_mass(el, pts, nn)) < 1e-12
+    tel, tpts = mesh.box_tet4(5, 6, 4)
+    tn = tpts.shape[1]
+    tsp = _space(h, 4, 0, tel, tpts, 1)
+    tlm = h.adapter_create_op(tsp, b"LumpedMass")
+    td = torch.zeros(tn, dtype=torch.float64, device="cuda")
+    assert tlm and h.adapter_op_hessian_diag(tlm, td.data_ptr()) == 0
+    assert _rel(td.cpu().numpy(), orc.tet4_lumped_mass(tel, tpts, tn)) < 1e-10
+    for o in (op, lm, tlm):
+        h.adapter_op_destroy(o)
+    h.adapter_space_destroy(sp)
+    h.adapter_space_destroy(tsp)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", ["hex8", "sshex8"])
 def test_factory_creates_our_linear_elasticity(oracles, case):
     import torch
