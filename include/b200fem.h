@@ -128,6 +128,12 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
  *   diag               <- LumpedMass::hessian_diag -> assemble_lumped_mass (frontend/ops/sfem_LumpedMass.cpp, operators/mass.cpp:
  *                        65-114) -> hex8_assemble_lumped_mass (hex8_mass.cpp:62-103) / tet4_assemble_lumped_mass
  *                        (operators/tet4/tet4_mass.cpp:231-282): diag += row sums. Scalar fields (block_size 1). */
+/* VectorLaplacian on hex8: the scalar Laplacian on every component of an AoS field [nnodes * vector_size]
+ * (VectorLaplacian::apply -> vector_laplacian_apply_opt -> affine_hex8_vector_laplacian_apply_fff, frontend/ops/
+ * sfem_VectorLaplacian.cpp:191-206, operators/vector_laplacian.cpp:41-66, operators/hex8/hex8_vector_laplacian.cpp:78-138);
+ * fff as for b200fem_laplacian_create. The semi-structured twin is not built. */
+int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t nelements, ptrdiff_t nnodes,
+                                    const int32_t *const *elements, const float *fff, int vector_size, int real_type);
 int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
                         const float *const *points, int real_type);
 /* Stored-element-matrix ("EM") semi-structured operators: ss:em:Laplacian / ss:em:LinearElasticity

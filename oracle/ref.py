@@ -210,6 +210,20 @@ class Oracle:
                    _soa_ptrs(pts, C.c_float), pu, out.ctypes.data_as(C.POINTER(self.crt)))
         return out
 
+    def hex8_vector_laplacian_apply(self, elements, fff, vector_size, u, nnodes):
+        """affine_hex8_vector_laplacian_apply_fff (operators/hex8/hex8_vector_laplacian.cpp:78-138); u / out AoS [nn * vs]."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        f, pf = self._f32(fff)
+        u, _ = self._r(u)
+        out = np.zeros_like(u)
+        sz = u.itemsize
+        pp = C.POINTER(self.crt) * vector_size
+        up = pp(*[C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(vector_size)])
+        op = pp(*[C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(vector_size)])
+        self._call("affine_hex8_vector_laplacian_apply_fff", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf,
+                   C.c_int(vector_size), C.c_ssize_t(vector_size), up, op)
+        return out
+
     # ---- mass (reference build only: hex8_mass.cpp / tet4_mass.cpp compiled where they lie)
     def hex8_apply_mass(self, elements, points, u, nnodes):
         """hex8_apply_mass (operators/hex8/hex8_mass.cpp:8-60): out += M u, 27-point Gauss, isoparametric."""

@@ -156,6 +156,8 @@ OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_
                                         int real_type);
 OpBase *make_tet4_le_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,
                                  double lambda, int real_type);
+OpBase *make_hex8_vector_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int vector_size,
+                                   int real_type);
 OpBase *make_mass_from_points(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
                               int real_type);
 OpBase *make_hex8_le_isoparametric(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,

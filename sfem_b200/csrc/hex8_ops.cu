@@ -72,6 +72,36 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// VectorLaplacian on hex8: the scalar operator on every component of an AoS field [nn * bs]
+// (affine_hex8_vector_laplacian_apply_fff, operators/hex8/hex8_vector_laplacian.cpp:78-138: one element matrix, applied per component)
+template <typename T, bool DIAG>
+__global__ void __launch_bounds__(256)
+    hex8_vector_laplacian_kernel(const ptrdiff_t ne, const int bs, const int32_t *__restrict__ elements, const float *__restrict__ fff,
+                                 const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[8];
+        T f[6];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+#pragma unroll 1
+        for (int d = 0; d < bs; ++d) {
+            if (DIAG) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) red_add(&y[(ptrdiff_t)ev[v] * bs + d], hex8_laplacian_diag_entry(f, kVtkToLex[v]));
+            } else {
+                T ul[8], ol[8];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) ul[kVtkToLex[v]] = u[(ptrdiff_t)ev[v] * bs + d];
+                hex8_laplacian_local(f, ul, ol);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) red_add(&y[(ptrdiff_t)ev[v] * bs + d], ol[kVtkToLex[v]]);
+            }
+        }
+    }
+}
+
 // T^{ab} (3x3 in j,l) for one (a,b) pair
 template <typename T>
 __device__ __forceinline__ void le_coeff(const T A[9], const T AAt_mu[6], const T lam_idet, const T mu_idet, int a,
@@ -416,6 +446,54 @@ OpBase *make_hex8_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *el
     op->colors.keep(8, ne, elements);
     if (op->patch.build(8, Hex8Laplacian::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
         op->fff.upload(f.data(), f.size())) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+namespace {
+struct Hex8VectorLaplacian final : OpBase {
+    DeviceArray<int32_t> elements;  // [8][ne]
+    DeviceArray<float> fff;         // [6][ne]
+    template <typename T, bool DIAG>
+    int run(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        hex8_vector_laplacian_kernel<T, DIAG><<<grid, 256, 0, s>>>(ne, block_size, elements.ptr, fff.ptr, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * block_size * real_type, s));
+        return real_type == B200FEM_F64 ? run<double, false>((const double *)x, (double *)y, s) : run<float, false>((const float *)x, (float *)y, s);
+    }
+    int diag(void *d, cudaStream_t s) override {
+        return real_type == B200FEM_F64 ? run<double, true>(nullptr, (double *)d, s) : run<float, true>(nullptr, (float *)d, s);
+    }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+};
+}  // namespace
+
+OpBase *make_hex8_vector_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int vector_size,
+                                   int real_type) {
+    if (!check_indices(8, ne, nn, elements)) {
+        set_error("hex8 vector laplacian: node index out of range");
+        return nullptr;
+    }
+    auto *op = new Hex8VectorLaplacian();
+    op->elem_type = B200FEM_HEX8;
+    op->real_type = real_type;
+    op->block_size = vector_size;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = 8;
+    op->geom_bytes_per_elem = 24;
+    std::vector<int32_t> el;
+    std::vector<float> f;
+    soa_copy(8, ne, elements, el);
+    aos_to_soa(6, ne, fff, f);
+    if (op->elements.upload(el.data(), el.size()) || op->fff.upload(f.data(), f.size())) {
         delete op;
         return nullptr;
     }

@@ -251,6 +251,18 @@ int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int
     return B200FEM_SUCCESS;
 }
 
+int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                                    const float *fff, int vector_size, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (ne > 0 && !fff) B2_FAIL("fff is NULL");
+    if (vector_size < 1 || vector_size > 16) B2_FAIL("vector laplacian: vector_size out of range");
+    if (element_type != B200FEM_HEX8) B2_FAIL("vector laplacian: hex8 only (affine_hex8_vector_laplacian_apply_fff)");
+    OpBase *impl = make_hex8_vector_laplacian(ne, nn, elements, fff, vector_size, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
 int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                         const float *const *points, int real_type) {
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;

@@ -55,6 +55,7 @@ _SIG = {
                                          C.POINTER(C.c_float), f64, f64, i32],
     "b200fem_laplacian_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_mass_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
+    "b200fem_vector_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32, i32],
     "b200fem_linear_elasticity_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, f64, f64, i32],
     "b200fem_sshex8_em_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, i32, vp, i32],
     "b200fem_sshex8_laplacian_element_matrix": [i32, ssz, C.POINTER(C.c_float), i32, vp],
@@ -330,6 +331,16 @@ def laplacian_from_points(element_type: int, elements: np.ndarray, points: np.nd
     h = vp()
     check(_lib.b200fem_laplacian_create_from_points(C.byref(h), element_type, level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
                                                     _soa_ptrs(pts, C.c_float), _rt(dtype)), "laplacian_create_from_points")
+    return Op(h, nnodes)
+
+
+def vector_laplacian(element_type: int, elements: np.ndarray, fff: np.ndarray, nnodes: int, vector_size: int, dtype) -> Op:
+    """HEX8: affine_hex8_vector_laplacian_apply_fff, the scalar Laplacian on every component of an AoS field."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    f = np.ascontiguousarray(fff, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_vector_laplacian_create(C.byref(h), element_type, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
+                                               f.ctypes.data_as(C.POINTER(C.c_float)), vector_size, _rt(dtype)), "vector_laplacian_create")
     return Op(h, nnodes)
 
 

@@ -80,6 +80,37 @@ def test_tet4_laplacian_from_points(oracles, real):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("vs", [1, 3])
+def test_hex8_vector_laplacian(oracles, real, vs):
+    """b200fem_vector_laplacian_create against affine_hex8_vector_laplacian_apply_fff (AoS fields of vs components)"""
+    import torch
+
+    from sfem_b200 import lib, mesh
+
+    orc = _orc(oracles, real)
+    if orc.kind != "reference":
+        pytest.skip("hex8_vector_laplacian.cpp is compiled into the reference build of the oracle only")
+    el, pts = mesh.box_hex8(7, 5, 6)
+    pts = mesh.shear_points(pts)
+    nn = pts.shape[1]
+    fff = orc.hex8_fff_fill(el, pts)
+    op = lib.vector_laplacian(lib.HEX8, el, fff, nn, vs, _dt(real))
+    u = np.random.default_rng(vs).uniform(-1, 1, nn * vs)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    ref = orc.hex8_vector_laplacian_apply(el, fff, vs, u, nn)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    d = torch.zeros_like(x)
+    op.diag(d)
+    # the reference's diagonal recomputes the FFF from the points in its own precision: 1e-6 (as in test_hex8_diagonals)
+    assert _rel(d.cpu().numpy().reshape(nn, vs)[:, 0], orc.hex8_laplacian_diag(el, pts, nn)) < 1e-5
+    assert float((d.reshape(nn, vs) - d.reshape(nn, vs)[:, :1]).abs().max()) == 0.0  # every component gets the scalar diagonal
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
 def test_mass_and_lumped_mass(oracles, real):
     """b200fem_mass_create: apply = hex8_apply_mass, diag = hex8 / tet4 lumped mass, against the reference's own routines.
     The tet4 bar is 1e-10: the reference expands the determinant into 24 monomials of the coordinates (cancellation)."""
