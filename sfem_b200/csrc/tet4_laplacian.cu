@@ -118,6 +118,8 @@ struct Tet4Laplacian final : OpBase {
     int apply_t(const T *x, T *y, cudaStream_t s) {
         const int maxgrid = sm_count() * 16;
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) <= 200 * 1024) {
+            if (patch.E == 256)  // small meshes: 256-tet patches, 8 CTAs per SM (see make_tet4_laplacian)
+                return launch_patch_apply_direct<T, 4, 1, 256, 256, Tet4LaplacianLocal<T>, true, true>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             if (patch_smem_atomic)
                 return launch_patch_apply_smem_atomic<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
             if (patch_pipelined == 1) return launch_patch_apply<T, 4, 1, kPatchE, 256>(patch, Tet4LaplacianLocal<T>{fff.ptr, ne}, x, y, s);
@@ -198,7 +200,12 @@ OpBase *make_tet4_laplacian(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *el
     std::vector<float> f((size_t)6 * ne);
     for (ptrdiff_t e = 0; e < ne; ++e)
         for (int k = 0; k < 6; ++k) f[(size_t)k * ne + e] = fff[e * 6 + k];
-    if (op->patch.build(4, Tet4Laplacian::kPatchE, ne, elements) || op->elements.upload(el.data(), el.size()) ||
+    // patch size: 1024 tets amortise a patch's unique nodes best (0.45 nodes per tet) and win on large meshes; a mesh of a few
+    // million tets is only a handful of such patches per SM and the apply is bound by the latency chain of ONE patch (C1, 1e6
+    // tets: 22 - 26 us for 5 us of bytes), so small meshes take 256-tet patches, 8 CTAs per SM
+    int patch_e = ne <= (ptrdiff_t)4000000 ? 256 : Tet4Laplacian::kPatchE;
+    if (const char *env = getenv("B200FEM_TET4_PATCH_E")) patch_e = atoi(env) == 256 ? 256 : Tet4Laplacian::kPatchE;
+    if (op->patch.build(4, patch_e, ne, elements) || op->elements.upload(el.data(), el.size()) ||
         op->fff.upload(f.data(), f.size())) {
         delete op;
         return nullptr;

@@ -42,11 +42,17 @@ def _orc(oracles, real):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
-@pytest.mark.parametrize("scatter", ["patch", "atomic", "colored"])
-def test_tet4_laplacian(oracles, real, scatter):
+@pytest.mark.parametrize("scatter", ["patch", "patch1024", "atomic", "colored"])
+def test_tet4_laplacian(oracles, real, scatter, monkeypatch):
     torch = _torch()
     from sfem_b200 import lib, mesh
 
+    # meshes up to 4e6 tets take 256-tet patches, larger ones 1024-tet patches: force the large-mesh plan here as well
+    if scatter == "patch1024":
+        monkeypatch.setenv("B200FEM_TET4_PATCH_E", "1024")
+        scatter = "patch"
+    else:
+        monkeypatch.delenv("B200FEM_TET4_PATCH_E", raising=False)
     orc = _orc(oracles, real)
     el, pts = mesh.box_tet4(9, 7, 8)
     pts = mesh.warp_points(pts)
