@@ -38,6 +38,10 @@ extern "C" {
 #define B200FEM_TET4 4
 #define B200FEM_HEX8 8
 #define B200FEM_SSHEX8 800 /* semi-structured hex8; the refinement level is a separate argument */
+#define B200FEM_TET10 10        /* quadratic tetrahedron; nodes 0-3 corners, 4 = edge(0,1), 5 = (1,2), 6 = (0,2), 7 = (0,3),
+                                   8 = (1,3), 9 = (2,3) (operators/tet10/tet10_laplacian_inline_cpu.hpp:6-28)               */
+#define B200FEM_MACRO_TET4 1004 /* P1-iso-P2: the same 10 nodes as 8 linear sub-tets
+                                   (operators/macro_tet4/macro_tet4_laplacian.cpp:12-125)                                     */
 
 /* scatter strategies of b200fem_op_set_option("scatter", ...) */
 #define B200FEM_SCATTER_AUTO 0
@@ -88,13 +92,24 @@ int b200fem_adjugate_and_det_fill(int element_type, ptrdiff_t nelements, ptrdiff
  *                                 (operators/tet4/tet4_laplacian.cpp:237), HEX8 -> hex8_laplacian_apply_opt
  *                                 (operators/hex8/hex8_laplacian.cpp:309), SSHEX8 ->
  *                                 affine_sshex8_laplacian_stencil_apply_fff
- *                                 (operators/sshex8/sshex8_laplacian.cpp:698); GPU twin being superseded:
+ *                                 (operators/sshex8/sshex8_laplacian.cpp:698), TET10 -> tet10_laplacian_apply_opt /
+ *                                 _diag_opt (operators/tet10/tet10_laplacian.cpp:232-302), MACRO_TET4 ->
+ *                                 macro_tet4_laplacian_apply_opt / _diag_opt
+ *                                 (operators/macro_tet4/macro_tet4_laplacian.cpp:401-490); the 10-node families take the
+ *                                 tet4 FFF of their 4 corners. tet10 `diag` reproduces the reference's value, which is
+ *                                 1/6 of the diagonal of its own apply (option "reference_diag" = 0 gives the consistent
+ *                                 one). GPU twin being superseded:
  *                                 cu_laplacian_apply (frontend/cuda/sfem_Function_incore_cuda.cpp:683-697).
  *   b200fem_linear_elasticity_create <- TET4: tet4_linear_elasticity_apply_opt (operators/tet4/tet4_linear_elasticity.cpp:237-300),
  *                                 HEX8: affine_hex8_linear_elasticity_apply_adjugate_soa
  *                                 (operators/hex8/hex8_linear_elasticity.cpp:625), SSHEX8:
  *                                 affine_sshex8_linear_elasticity_apply_macro_adjugate
- *                                 (operators/sshex8/sshex8_linear_elasticity.cpp:275).
+ *                                 (operators/sshex8/sshex8_linear_elasticity.cpp:275), TET10:
+ *                                 tet10_linear_elasticity_apply_opt / _diag_opt
+ *                                 (operators/tet10/tet10_linear_elasticity.cpp:209-355), MACRO_TET4:
+ *                                 macro_tet4_linear_elasticity_apply_opt / _diag_opt
+ *                                 (operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277, 397-437); both with the
+ *                                 tet4 adjugate / determinant of the 4 corners.
  * `level` is ignored unless element_type == B200FEM_SSHEX8 (then nxe = (level+1)^3 rows of
  * `elements`, local lattice index z*(L+1)^2 + y*(L+1) + x, operators/sshex8/sshex8.hpp:18).
  * The plan copies and re-lays-out connectivity and geometry on the current device; the host

@@ -339,6 +339,55 @@ class Oracle:
                    _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
+    # ---- 10-node tetrahedra (reference build only): P2 (tet10) and P1-iso-P2 (macro_tet4), geometry of the 4 corners
+    def p2tet_laplacian_apply_opt(self, family, elements, fff, u):
+        """tet10_laplacian_apply_opt (operators/tet10/tet10_laplacian.cpp:232-266; C++ linkage) /
+        macro_tet4_laplacian_apply_opt (operators/macro_tet4/macro_tet4_laplacian.cpp:401-440)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        self._call(f"{family}_laplacian_apply_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf, pu,
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def p2tet_laplacian_diag_opt(self, family, elements, fff, nnodes):
+        """tet10_laplacian_diag_opt (tet10_laplacian.cpp:268-302) / macro_tet4_laplacian_diag_opt (macro_tet4_laplacian.cpp:442-490)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        fff, pf = self._f32(fff)
+        out = np.zeros(nnodes, dtype=self.rt)
+        self._call(f"{family}_laplacian_diag_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf,
+                   out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
+    def p2tet_linear_elasticity_apply_opt(self, family, elements, adjugate_aos, det, mu, lam, u):
+        """tet10_linear_elasticity_apply_opt (operators/tet10/tet10_linear_elasticity.cpp:209-283) /
+        macro_tet4_linear_elasticity_apply_opt (operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277)."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        adj, pa = self._f32(adjugate_aos)
+        det, pd = self._f32(det)
+        u, _ = self._r(u)
+        out = np.zeros_like(u)
+        sz = u.itemsize
+        up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call(f"{family}_linear_elasticity_apply_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pa, pd,
+                   self.crt(mu), self.crt(lam), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
+    def p2tet_linear_elasticity_diag_opt(self, family, elements, adjugate_aos, det, mu, lam, nnodes):
+        """tet10_linear_elasticity_diag_opt (tet10_linear_elasticity.cpp:285-355) / macro_tet4_linear_elasticity_diag_opt
+        (macro_tet4_linear_elasticity.cpp:397-437)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        adj, pa = self._f32(adjugate_aos)
+        det, pd = self._f32(det)
+        out = np.zeros(nnodes * 3, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        self._call(f"{family}_linear_elasticity_diag_opt", C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pa, pd,
+                   self.crt(mu), self.crt(lam), C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
     def hex8_laplacian_diag(self, elements, points, nnodes):
         """hex8_laplacian_diag (operators/hex8/hex8_laplacian.hpp:36; geometry from the fp32 points, in scalar_t)."""
         el = np.ascontiguousarray(elements, dtype=np.int32)

@@ -152,6 +152,9 @@ OpBase *make_sshex8_linear_elasticity(int level, ptrdiff_t ne, ptrdiff_t nn, con
 
 OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
                                     const float *determinant, double mu, double lambda, int real_type);
+OpBase *make_p2tet_laplacian(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type);
+OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
+                                     const float *determinant, double mu, double lambda, int real_type);
 OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
                                         int real_type);
 OpBase *make_tet4_le_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,

@@ -151,7 +151,10 @@ using namespace b200fem;
 // the 8 macro corners inside an sshex8 connectivity are not known here: callers pass them as `elements`
 static int corner_count(int element_type) {
     switch (element_type) {
-        case B200FEM_TET4: return 4;
+        case B200FEM_TET4:
+        case B200FEM_TET10:       // 10-node tetrahedra: the affine map of the 4 corners (first 4 rows of `elements`), as
+        case B200FEM_MACRO_TET4:  // tet10_laplacian_apply / macro_tet4_laplacian_apply do (tet4_fff_s on ev[0..3])
+            return 4;
         case B200FEM_HEX8:
         case B200FEM_SSHEX8: return 8;
         default: return 0;
@@ -183,17 +186,17 @@ int b200fem_fff_fill(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t
 
 int b200fem_adjugate_and_det_fill(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                                   const float *const *points, float *adjugate, float *determinant) {
-    if (element_type != B200FEM_HEX8 && element_type != B200FEM_SSHEX8 && element_type != B200FEM_TET4)
-        B2_FAIL("adjugate_and_det_fill: tet4 / hex8 / sshex8 only");
+    const int nxe = corner_count(element_type);
+    if (!nxe) B2_FAIL("adjugate_and_det_fill: tet4 / tet10 / macro_tet4 / hex8 / sshex8 only");
     if (ne == 0) return B200FEM_SUCCESS;
     if (!elements || !points || !adjugate || !determinant) B2_FAIL("adjugate_and_det_fill: NULL argument");
     GeomInputs in;
-    if (in.upload(element_type == B200FEM_TET4 ? 4 : 8, ne, nn, elements, points)) return B200FEM_FAILURE;
+    if (in.upload(nxe, ne, nn, elements, points)) return B200FEM_FAILURE;
     DeviceArray<float> adj, det;
     if (adj.alloc((size_t)ne * 9) || det.alloc((size_t)ne)) return B200FEM_FAILURE;
     const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
     const float *px = in.points.ptr, *py = px + nn, *pz = py + nn;
-    if (element_type == B200FEM_TET4)
+    if (nxe == 4)
         tet4_adjugate_kernel<<<grid, 256>>>(ne, in.elements.ptr, px, py, pz, adj.ptr, det.ptr);
     else
         hex8_adjugate_kernel<<<grid, 256>>>(ne, in.elements.ptr, px, py, pz, adj.ptr, det.ptr);

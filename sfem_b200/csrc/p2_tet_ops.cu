@@ -1,0 +1,336 @@
+// 10-node tetrahedra: tet10 (P2) and macro_tet4 (P1-iso-P2) Laplacian and linear elasticity from the
+// cached tet4 geometry of the 4 corners, matrix-free:  y[ev] += K_e u[ev].
+//
+// Replaces
+//   tet10_laplacian_apply_opt / _diag_opt                 operators/tet10/tet10_laplacian.cpp:232-302
+//   macro_tet4_laplacian_apply_opt / _diag_opt            operators/macro_tet4/macro_tet4_laplacian.cpp:401-490
+//   tet10_linear_elasticity_apply_opt / _diag_opt         operators/tet10/tet10_linear_elasticity.cpp:209-355
+//   macro_tet4_linear_elasticity_apply_opt / _diag_opt    operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277, 397-437
+// Local operators: p2_tet_local.cuh (corner-gradient form of P2, table-driven sub-tets).
+//
+// Data layout in HBM (plan): connectivity SoA int32 [10][ne]; FFF SoA fp32 [6][ne] or adjugate SoA fp32 [9][ne] +
+// determinant [ne], streamed once per apply. A 10-node tet shares each corner with ~24 and each edge node with ~5
+// elements, so the default scatter is the patch kernel of patch.cuh (256 consecutive elements staged in shared memory,
+// one RED per unique node of the patch); B200FEM_SCATTER_ATOMIC is the thread-per-element form with one RED per
+// (element, node, component).
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "coloring.cuh"
+#include "common.cuh"
+#include "p2_tet_local.cuh"
+#include "patch.cuh"
+
+namespace b200fem {
+
+template <typename T, bool MACRO>
+struct P2TetLaplacianLocal {
+    const float *fff;  // SoA [6][ne]
+    ptrdiff_t ne;
+    struct Geo {
+        float f[6];
+    };
+    __device__ __forceinline__ void load(const ptrdiff_t e, Geo &g) const {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g.f[k] = ldg_stream(&fff[k * ne + e]);
+    }
+    __device__ __forceinline__ void compute(const Geo &g, const T (&uin)[10], T (&out)[10]) const {
+        T f[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)g.f[k];
+        if (MACRO)
+            macro_tet4_laplacian_local(f, uin, out);
+        else
+            tet10_laplacian_local(f, uin, out);
+    }
+};
+
+template <typename T, bool MACRO>
+struct P2TetLELocal {
+    const float *adjugate;     // SoA [9][ne]
+    const float *determinant;  // [ne]
+    ptrdiff_t ne;
+    T mu, lambda;
+    struct Geo {
+        float a[9], det;
+    };
+    __device__ __forceinline__ void load(const ptrdiff_t e, Geo &g) const {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g.a[k] = ldg_stream(&adjugate[k * ne + e]);
+        g.det = ldg_stream(&determinant[e]);
+    }
+    __device__ __forceinline__ void compute(const Geo &g, const T (&uin)[30], T (&out)[30]) const {
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)g.a[k];
+        T ul[10][3], ol[10][3];
+#pragma unroll
+        for (int v = 0; v < 10; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) ul[v][b] = uin[v * 3 + b];
+        p2tet_le_local<T, MACRO>(A, (T)g.det, mu, lambda, ul, ol);
+#pragma unroll
+        for (int v = 0; v < 10; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) out[v * 3 + b] = ol[v][b];
+    }
+};
+
+// thread-per-element forms (B200FEM_SCATTER_ATOMIC, and the fallback when a patch does not fit shared memory)
+template <typename T, bool MACRO>
+__global__ void __launch_bounds__(128)
+    p2tet_laplacian_apply_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ fff,
+                                 const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[10];
+#pragma unroll
+        for (int v = 0; v < 10; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        T f[6], ul[10], ol[10];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)ldg_stream(&fff[k * ne + e]);
+#pragma unroll
+        for (int v = 0; v < 10; ++v) ul[v] = u[ev[v]];
+        if (MACRO)
+            macro_tet4_laplacian_local(f, ul, ol);
+        else
+            tet10_laplacian_local(f, ul, ol);
+#pragma unroll
+        for (int v = 0; v < 10; ++v) red_add(&y[ev[v]], ol[v]);
+    }
+}
+
+template <typename T, bool MACRO>
+__global__ void __launch_bounds__(128)
+    p2tet_laplacian_diag_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ fff,
+                                const bool reference_scale, T *__restrict__ diag) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        T f[6], ol[10];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[k] = (T)fff[k * ne + e];
+        if (MACRO)
+            macro_tet4_laplacian_local_diag(f, ol);
+        else
+            tet10_laplacian_local_diag(f, reference_scale, ol);
+#pragma unroll
+        for (int v = 0; v < 10; ++v) red_add(&diag[elements[v * ne + e]], ol[v]);
+    }
+}
+
+template <typename T, bool MACRO>
+__global__ void __launch_bounds__(128)
+    p2tet_le_apply_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ adjugate,
+                          const float *__restrict__ determinant, const T mu, const T lambda, const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[10];
+#pragma unroll
+        for (int v = 0; v < 10; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)ldg_stream(&adjugate[k * ne + e]);
+        const T det = (T)ldg_stream(&determinant[e]);
+        T ul[10][3], ol[10][3];
+#pragma unroll
+        for (int v = 0; v < 10; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) ul[v][b] = u[(ptrdiff_t)ev[v] * 3 + b];
+        p2tet_le_local<T, MACRO>(A, det, mu, lambda, ul, ol);
+#pragma unroll
+        for (int v = 0; v < 10; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) red_add(&y[(ptrdiff_t)ev[v] * 3 + b], ol[v][b]);
+    }
+}
+
+// diagonal: one thread per (element, local dof): row (v, b) of the 30 x 30 element matrix applied to its own unit vector
+template <typename T, bool MACRO>
+__global__ void __launch_bounds__(128)
+    p2tet_le_diag_kernel(const ptrdiff_t ne, const int32_t *__restrict__ elements, const float *__restrict__ adjugate,
+                         const float *__restrict__ determinant, const T mu, const T lambda, T *__restrict__ diag) {
+    const ptrdiff_t total = ne * 30;
+    for (ptrdiff_t i = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ptrdiff_t)gridDim.x * blockDim.x) {
+        const ptrdiff_t e = i % ne;  // consecutive threads: consecutive elements of the same local dof
+        const int dof = (int)(i / ne), v = dof / 3, b = dof % 3;
+        T A[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[k] = (T)adjugate[k * ne + e];
+        const T det = (T)determinant[e];
+        T ul[10][3], ol[10][3];
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ul[j][c] = (j == v && c == b) ? T(1) : T(0);
+        p2tet_le_local<T, MACRO>(A, det, mu, lambda, ul, ol);
+        T r = T(0);
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (j == v && c == b) r = ol[j][c];
+        red_add(&diag[(ptrdiff_t)elements[v * ne + e] * 3 + b], r);
+    }
+}
+
+static constexpr int kP2PatchE = 256;
+
+struct P2TetLaplacian final : OpBase {
+    bool macro = false;
+    DeviceArray<int32_t> elements;  // [10][ne]
+    DeviceArray<float> fff;         // [6][ne]
+    PatchPlan patch;
+    int reference_diag = 1;  // tet10: reproduce the reference's diagonal (1/6 of the apply's, see p2_tet_local.cuh)
+
+    template <typename T, bool MACRO>
+    int apply_t(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) + (size_t)20 * kP2PatchE + 2 * patch.max_u_pad() <= 200 * 1024)
+            return launch_patch_apply_direct<T, 10, 1, kP2PatchE, 256, P2TetLaplacianLocal<T, MACRO>, true, true>(
+                patch, P2TetLaplacianLocal<T, MACRO>{fff.ptr, ne}, x, y, s);
+        const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+        p2tet_laplacian_apply_kernel<T, MACRO><<<grid, 128, 0, s>>>(ne, elements.ptr, fff.ptr, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * real_type, s));
+        if (real_type == B200FEM_F64)
+            return macro ? apply_t<double, true>((const double *)x, (double *)y, s) : apply_t<double, false>((const double *)x, (double *)y, s);
+        return macro ? apply_t<float, true>((const float *)x, (float *)y, s) : apply_t<float, false>((const float *)x, (float *)y, s);
+    }
+    template <typename T>
+    int diag_t(T *d, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+        if (macro)
+            p2tet_laplacian_diag_kernel<T, true><<<grid, 128, 0, s>>>(ne, elements.ptr, fff.ptr, false, d);
+        else
+            p2tet_laplacian_diag_kernel<T, false><<<grid, 128, 0, s>>>(ne, elements.ptr, fff.ptr, reference_diag != 0, d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int diag(void *d, cudaStream_t s) override { return real_type == B200FEM_F64 ? diag_t((double *)d, s) : diag_t((float *)d, s); }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+    double streamed_bytes(bool overwrite) const override {
+        const double idx = (scatter == B200FEM_SCATTER_PATCH && patch.ready) ? patch.index_bytes() : 40.0 * ne;
+        return idx + 24.0 * ne + double(nn) * real_type * (overwrite ? 2.0 : 3.0);
+    }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "reference_diag")) { reference_diag = value; return B200FEM_SUCCESS; }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "reference_diag")) { *value = reference_diag; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "patch_avg_unique_nodes")) { *value = patch.ready ? (int)patch.avg_u : 0; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
+};
+
+struct P2TetLinearElasticity final : OpBase {
+    bool macro = false;
+    DeviceArray<int32_t> elements;  // [10][ne]
+    DeviceArray<float> adjugate;    // SoA [9][ne]
+    DeviceArray<float> determinant;
+    PatchPlan patch;
+    double mu = 1, lambda = 1;
+
+    template <typename T, bool MACRO>
+    int apply_t(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(3, sizeof(T)) + (size_t)20 * kP2PatchE + 2 * patch.max_u_pad() <= 200 * 1024)
+            return launch_patch_apply_direct<T, 10, 3, kP2PatchE, 256, P2TetLELocal<T, MACRO>, true, false>(
+                patch, P2TetLELocal<T, MACRO>{adjugate.ptr, determinant.ptr, ne, (T)mu, (T)lambda}, x, y, s);
+        const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+        p2tet_le_apply_kernel<T, MACRO><<<grid, 128, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (T)mu, (T)lambda, x, y);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * 3 * real_type, s));
+        if (real_type == B200FEM_F64)
+            return macro ? apply_t<double, true>((const double *)x, (double *)y, s) : apply_t<double, false>((const double *)x, (double *)y, s);
+        return macro ? apply_t<float, true>((const float *)x, (float *)y, s) : apply_t<float, false>((const float *)x, (float *)y, s);
+    }
+    template <typename T>
+    int diag_t(T *d, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne * 30 + 127) / 128, (ptrdiff_t)sm_count() * 16);
+        if (macro)
+            p2tet_le_diag_kernel<T, true><<<grid, 128, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (T)mu, (T)lambda, d);
+        else
+            p2tet_le_diag_kernel<T, false><<<grid, 128, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (T)mu, (T)lambda, d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int diag(void *d, cudaStream_t s) override { return real_type == B200FEM_F64 ? diag_t((double *)d, s) : diag_t((float *)d, s); }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+    double streamed_bytes(bool overwrite) const override {
+        const double idx = (scatter == B200FEM_SCATTER_PATCH && patch.ready) ? patch.index_bytes() : 40.0 * ne;
+        return idx + 40.0 * ne + double(nn) * 3 * real_type * (overwrite ? 2.0 : 3.0);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "patch_avg_unique_nodes")) { *value = patch.ready ? (int)patch.avg_u : 0; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
+};
+
+static bool upload_connectivity(ptrdiff_t ne, const int32_t *const *elements, DeviceArray<int32_t> &dst) {
+    std::vector<int32_t> el((size_t)10 * ne);
+    for (int v = 0; v < 10; ++v) std::copy(elements[v], elements[v] + ne, el.begin() + (size_t)v * ne);
+    return dst.upload(el.data(), el.size()) != 0;
+}
+
+OpBase *make_p2tet_laplacian(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type) {
+    if (!check_indices(10, ne, nn, elements)) {
+        set_error("tet10 / macro_tet4 laplacian: node index out of range");
+        return nullptr;
+    }
+    auto *op = new P2TetLaplacian();
+    op->macro = element_type == B200FEM_MACRO_TET4;
+    op->elem_type = element_type;
+    op->real_type = real_type;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = 10;
+    op->geom_bytes_per_elem = 24;
+    op->scatter = B200FEM_SCATTER_PATCH;
+    std::vector<float> f((size_t)6 * ne);
+    for (ptrdiff_t e = 0; e < ne; ++e)
+        for (int k = 0; k < 6; ++k) f[(size_t)k * ne + e] = fff[e * 6 + k];
+    if (op->patch.build(10, kP2PatchE, ne, elements) || upload_connectivity(ne, elements, op->elements) || op->fff.upload(f.data(), f.size())) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
+                                     const float *determinant, double mu, double lambda, int real_type) {
+    if (!check_indices(10, ne, nn, elements)) {
+        set_error("tet10 / macro_tet4 linear elasticity: node index out of range");
+        return nullptr;
+    }
+    auto *op = new P2TetLinearElasticity();
+    op->macro = element_type == B200FEM_MACRO_TET4;
+    op->elem_type = element_type;
+    op->real_type = real_type;
+    op->block_size = 3;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = 10;
+    op->geom_bytes_per_elem = 40;
+    op->mu = mu;
+    op->lambda = lambda;
+    op->scatter = B200FEM_SCATTER_PATCH;
+    std::vector<float> a((size_t)9 * ne);
+    for (ptrdiff_t e = 0; e < ne; ++e)
+        for (int k = 0; k < 9; ++k) a[(size_t)k * ne + e] = adjugate[e * 9 + k];
+    if (op->patch.build(10, kP2PatchE, ne, elements) || upload_connectivity(ne, elements, op->elements) ||
+        op->adjugate.upload(a.data(), a.size()) || op->determinant.upload(determinant, (size_t)ne)) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+}  // namespace b200fem

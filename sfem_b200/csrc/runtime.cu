@@ -203,6 +203,8 @@ int b200fem_laplacian_create(b200fem_op_t *op, int element_type, int level, ptrd
     switch (element_type) {
         case B200FEM_TET4: impl = make_tet4_laplacian(ne, nn, elements, fff, real_type); break;
         case B200FEM_HEX8: impl = make_hex8_laplacian(ne, nn, elements, fff, real_type); break;
+        case B200FEM_TET10:
+        case B200FEM_MACRO_TET4: impl = make_p2tet_laplacian(element_type, ne, nn, elements, fff, real_type); break;
         case B200FEM_SSHEX8:
             // apply is built for levels 2, 4 and 8 (the levels of the reference's multigrid hierarchies): refuse the others at
             // creation instead of at the first apply, like the linear-elasticity factory does
@@ -225,6 +227,10 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
     switch (element_type) {
         case B200FEM_TET4: impl = make_tet4_linear_elasticity(ne, nn, elements, adjugate, determinant, mu, lambda, real_type); break;
         case B200FEM_HEX8: impl = make_hex8_linear_elasticity(ne, nn, elements, adjugate, determinant, mu, lambda, real_type); break;
+        case B200FEM_TET10:
+        case B200FEM_MACRO_TET4:
+            impl = make_p2tet_linear_elasticity(element_type, ne, nn, elements, adjugate, determinant, mu, lambda, real_type);
+            break;
         case B200FEM_SSHEX8:
             if (level < 2) B2_FAIL("sshex8 level must be >= 2");
             impl = make_sshex8_linear_elasticity(level, ne, nn, elements, adjugate, determinant, mu, lambda, real_type);

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libb200fem.so")
 
 F32, F64 = 4, 8
 TET4, HEX8, SSHEX8 = 4, 8, 800
+TET10, MACRO_TET4 = 10, 1004
 SCATTER_AUTO, SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_PATCH = 0, 1, 2, 3
 UNIQUE_ID_BYTES = 128
 HALO_AUTO, HALO_PUSH, HALO_NCCL = 0, 1, 2

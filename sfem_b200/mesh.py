@@ -83,6 +83,32 @@ def box_tet4(nx: int, ny: int, nz: int, w=1.0, h=1.0, t=1.0):
     return el, box_points(nx, ny, nz, w, h, t)
 
 
+# edge (a, b) carrying local node 4 + k of a 10-node tetrahedron (reference order: tet10 shape functions,
+# operators/tet10/tet10_laplacian_inline_cpu.hpp:6-28; macro_tet4 sub-tets, operators/macro_tet4/macro_tet4_laplacian.cpp:22-66)
+TET10_EDGES = ((0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3))
+
+
+def tet4_to_tet10(elements: np.ndarray, points: np.ndarray):
+    """Promote a tet4 mesh to 10-node tetrahedra (P2 / macro_tet4): one new node per unique edge at its midpoint, numbered
+    after the corner nodes in order of first appearance of the sorted (lo, hi) edge key.
+    Returns (elements[10][ne] int32, points[3][nn2] fp32)."""
+    el = np.asarray(elements, dtype=np.int64)
+    nn = points.shape[1]
+    ne = el.shape[1]
+    keys = np.empty((6, ne), dtype=np.int64)
+    for k, (a, b) in enumerate(TET10_EDGES):
+        lo, hi = np.minimum(el[a], el[b]), np.maximum(el[a], el[b])
+        keys[k] = lo * nn + hi
+    uniq, inv = np.unique(keys.ravel(), return_inverse=True)
+    out = np.empty((10, ne), dtype=idx_t)
+    out[:4] = el
+    out[4:] = (nn + inv.reshape(6, ne)).astype(idx_t)
+    lo, hi = uniq // nn, uniq % nn
+    p64 = points.astype(np.float64)
+    mid = 0.5 * (p64[:, lo] + p64[:, hi])
+    return out, np.concatenate([points, mid.astype(geom_t)], axis=1)
+
+
 def warp_points(points: np.ndarray) -> np.ndarray:
     """Smooth warp used by the reference's distributed apply test
     (frontend/tests/mpi/sfem_ParallelLaplacianApplyTest.cpp:22-35): keeps the mesh valid while

@@ -288,3 +288,94 @@ def test_tet4_linear_elasticity(oracles, real):
     d = torch.zeros(nn * 3, dtype=_dt(real), device="cuda")
     opc.diag(d)
     assert _rel(d.cpu().numpy(), orc.tet4_linear_elasticity_diag_points(el, pts, mu, lam, nn)) < TOL[real]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet10", "macro_tet4"])
+@pytest.mark.parametrize("scatter", ["patch", "atomic"])
+def test_p2_tet_laplacian(oracles, real, family, scatter):
+    """10-node tetrahedra: tet10_laplacian_apply_opt / _diag_opt (operators/tet10/tet10_laplacian.cpp:232-302)
+    and macro_tet4_laplacian_apply_opt / _diag_opt (operators/macro_tet4/macro_tet4_laplacian.cpp:401-490), the reference's own
+    routines compiled into the oracle, FFF of the 4 corners from b200fem_fff_fill."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    el, pts = mesh.box_tet4(9, 7, 8)
+    pts = mesh.warp_points(pts)
+    el10, pts10 = mesh.tet4_to_tet10(el, pts)
+    nn = pts10.shape[1]
+    et = lib.TET10 if family == "tet10" else lib.MACRO_TET4
+    fff = lib.fff_fill(et, el10, pts10)
+    assert _rel(fff, orc.tet4_fff_fill(el, pts)) < 1e-5
+    fff = orc.tet4_fff_fill(el, pts)
+    op = lib.laplacian(et, el10, fff, nn, _dt(real))
+    assert op.get_option("scatter") == lib.SCATTER_PATCH
+    op.set_option("scatter", lib.SCATTER_PATCH if scatter == "patch" else lib.SCATTER_ATOMIC)
+    for seed in (0, 1):
+        u = np.random.default_rng(seed).uniform(-1, 1, nn)
+        ref = orc.p2tet_laplacian_apply_opt(family, el10, fff, u)
+        x = torch.from_numpy(u).to(_dt(real)).cuda()
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    op.apply(x, y)  # accumulate semantics
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    y.fill_(7.0)
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    ones = torch.ones(nn, dtype=_dt(real), device="cuda")
+    op.apply_overwrite(ones, y)
+    assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    ref_d = orc.p2tet_laplacian_diag_opt(family, el10, fff, nn)
+    assert _rel(d.cpu().numpy(), ref_d) < TOL[real]
+    if family == "tet10":
+        # the reference's tet10 diagonal is 1/6 of the diagonal of its own apply (tests/test_p2_tet_core.py pins that);
+        # reference_diag = 0 gives the consistent one
+        assert op.get_option("reference_diag") == 1
+        op.set_option("reference_diag", 0)
+        d.zero_()
+        op.diag(d)
+        assert _rel(d.cpu().numpy(), 6 * ref_d) < TOL[real]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet10", "macro_tet4"])
+@pytest.mark.parametrize("scatter", ["patch", "atomic"])
+def test_p2_tet_linear_elasticity(oracles, real, family, scatter):
+    """tet10_linear_elasticity_apply_opt / _diag_opt (operators/tet10/tet10_linear_elasticity.cpp:209-355) and
+    macro_tet4_linear_elasticity_apply_opt / _diag_opt (operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277, 397-437)
+    with the adjugate / determinant of the 4 corners from b200fem_adjugate_and_det_fill. tet10 fp64 bar 1e-11: the reference
+    writes its face-centroid quadrature points as 0.333333333333 and sits 1.5e-12 from the exact integral this kernel computes."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    el, pts = mesh.box_tet4(7, 6, 8)
+    pts = mesh.warp_points(pts)
+    el10, pts10 = mesh.tet4_to_tet10(el, pts)
+    nn = pts10.shape[1]
+    et = lib.TET10 if family == "tet10" else lib.MACRO_TET4
+    adj, det = lib.adjugate_and_det_fill(et, el10, pts10)
+    mu, lam = 1.3, 0.7
+    tol = (1e-11 if family == "tet10" else 1e-12) if real == "f64" else 1e-5
+    op = lib.linear_elasticity(et, el10, adj, det, mu, lam, nn, _dt(real))
+    op.set_option("scatter", lib.SCATTER_PATCH if scatter == "patch" else lib.SCATTER_ATOMIC)
+    u = np.random.default_rng(11).uniform(-1, 1, nn * 3)
+    ref = orc.p2tet_linear_elasticity_apply_opt(family, el10, adj, det, mu, lam, u)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < tol
+    y.fill_(3.0)
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < tol
+    d = torch.zeros(nn * 3, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    assert _rel(d.cpu().numpy(), orc.p2tet_linear_elasticity_diag_opt(family, el10, adj, det, mu, lam, nn)) < tol
