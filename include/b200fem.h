@@ -143,6 +143,32 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
  *   diag               <- LumpedMass::hessian_diag -> assemble_lumped_mass (frontend/ops/sfem_LumpedMass.cpp, operators/mass.cpp:
  *                        65-114) -> hex8_assemble_lumped_mass (hex8_mass.cpp:62-103) / tet4_assemble_lumped_mass
  *                        (operators/tet4/tet4_mass.cpp:231-282): diag += row sums. Scalar fields (block_size 1). */
+/* Packed meshes: the Laplacian on smesh::PackedMesh<uint16_t> connectivity, the data PackedLaplacian::apply hands to
+ * packed_laplacian_apply<uint16_t> (frontend/ops/sfem_PackedLaplacian.cpp:111-176, 551-612, 875-930; FunctionSpace::PackedIdxType,
+ * frontend/sfem_FunctionSpace.hpp:19). Elements are cut into packs of n_elements_per_pack consecutive elements; pack p owns the
+ * contiguous node range [owned_nodes_ptr[p], owned_nodes_ptr[p+1]), the last n_shared[p] of which other packs touch too; its
+ * other nodes are ghost_idx[ghost_ptr[p] .. ghost_ptr[p+1]); `elements[v][e]` is LOCAL to the pack of e: l < n_owned is node
+ * owned_nodes_ptr[p] + l, else ghost l - n_owned. TET4, HEX8, TET10 (the reference's three micro kernels) and MACRO_TET4;
+ * fff [nelements * 6] as for b200fem_laplacian_create. All arrays HOST, copied by the plan. Only apply / apply_overwrite exist
+ * (the reference's PackedLaplacian implements nothing else). Option "packed_kernel" = 1 forces the direct kernel.
+ *
+ * b200fem_packed_mesh_create builds such a packing from plain connectivity (what smesh::PackedMesh<T>::create(mesh, {}, true)
+ * does inside FunctionSpace::initialize_packed_mesh, frontend/sfem_FunctionSpace.cpp:236-239; smesh is absent from the reference
+ * checkout, so the node order inside a pack is ours): nodes are RENUMBERED, `new_to_old[i]` = input id of packed node i -- vectors
+ * and points have to be permuted with it. n_elements_per_pack <= 0 picks 1024. Arrays returned by _arrays live until _destroy. */
+typedef struct b200fem_packed_mesh_s *b200fem_packed_mesh_t;
+int b200fem_packed_mesh_create(b200fem_packed_mesh_t *pm, int nodes_per_element, ptrdiff_t nelements, ptrdiff_t nnodes,
+                               const int32_t *const *elements, ptrdiff_t n_elements_per_pack);
+int b200fem_packed_mesh_destroy(b200fem_packed_mesh_t pm);
+int b200fem_packed_mesh_sizes(b200fem_packed_mesh_t pm, ptrdiff_t *n_packs, ptrdiff_t *n_elements_per_pack,
+                              ptrdiff_t *max_nodes_per_pack, ptrdiff_t *n_ghost_entries);
+int b200fem_packed_mesh_arrays(b200fem_packed_mesh_t pm, const uint16_t *const **elements, const ptrdiff_t **owned_nodes_ptr,
+                               const ptrdiff_t **n_shared, const ptrdiff_t **ghost_ptr, const int32_t **ghost_idx,
+                               const int32_t **new_to_old);
+int b200fem_packed_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t n_packs, ptrdiff_t n_elements_per_pack,
+                                    ptrdiff_t nelements, ptrdiff_t nnodes, ptrdiff_t max_nodes_per_pack,
+                                    const uint16_t *const *elements, const float *fff, const ptrdiff_t *owned_nodes_ptr,
+                                    const ptrdiff_t *n_shared, const ptrdiff_t *ghost_ptr, const int32_t *ghost_idx, int real_type);
 /* VectorLaplacian on hex8: the scalar Laplacian on every component of an AoS field [nnodes * vector_size]
  * (VectorLaplacian::apply -> vector_laplacian_apply_opt -> affine_hex8_vector_laplacian_apply_fff, frontend/ops/
  * sfem_VectorLaplacian.cpp:191-206, operators/vector_laplacian.cpp:41-66, operators/hex8/hex8_vector_laplacian.cpp:78-138);

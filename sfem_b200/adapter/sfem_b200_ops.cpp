@@ -38,8 +38,10 @@ namespace sfem {
             } else if (d.element_type == smesh::HEX8) {
                 g.type = B200FEM_HEX8;
                 for (int v = 0; v < 8; v++) g.corners.push_back(g.elements[v]);
-            } else if (d.element_type == smesh::TET4) {
-                g.type = B200FEM_TET4;
+            } else if (d.element_type == smesh::TET4 || d.element_type == smesh::TET10 || d.element_type == smesh::MACRO_TET4) {
+                /* 10-node tetrahedra take the affine geometry of their 4 corners (rows 0-3), like
+                 * laplacian_apply_opt / linear_elasticity_apply_opt do (operators/laplacian.cpp:221-226) */
+                g.type = d.element_type == smesh::TET4 ? B200FEM_TET4 : d.element_type == smesh::TET10 ? B200FEM_TET10 : B200FEM_MACRO_TET4;
                 for (int v = 0; v < 4; v++) g.corners.push_back(g.elements[v]);
             }
             return g;
@@ -90,7 +92,7 @@ namespace sfem {
         /* the FFF cache of Laplacian::initialize (smesh::FFF::create_AoS, frontend/ops/sfem_Laplacian.cpp:88): fp32,
          * [ne * 6]; for sshex8 one set per macro element from its 8 corners */
         std::vector<float> fff((size_t)g.ne * 6);
-        const int          geo_type = g.type == B200FEM_TET4 ? B200FEM_TET4 : B200FEM_HEX8;
+        const int          geo_type = g.corners.size() == 4 ? B200FEM_TET4 : B200FEM_HEX8;
         if (b200fem_fff_fill(geo_type, g.ne, g.nn, g.corners.data(), space->mesh_ptr()->points()->data(), fff.data())) return nullptr;
         b200fem_op_t plan = nullptr;
         if (b200fem_laplacian_create(&plan, g.type, g.level, g.ne, g.nn, g.elements, fff.data(), kRealType)) return nullptr;
@@ -131,14 +133,14 @@ namespace sfem {
 
     b200fem_op_t B200LinearElasticity::create_plan(const OpDomain &domain) {
         DomainGeometry g = geometry_of(space, domain);
-        if (g.type != B200FEM_HEX8 && g.type != B200FEM_SSHEX8) {
-            fprintf(stderr, "[b200fem] linear elasticity: hex8 and sshex8 blocks only\n");
+        if (!g.type) {
+            fprintf(stderr, "[b200fem] linear elasticity: tet4 / tet10 / macro_tet4 / hex8 / sshex8 blocks only\n");
             return nullptr;
         }
         /* JacobianAdjugateAndDeterminant cache (sfem_LinearElasticity.cpp:275-279): adjugate [ne * 9] and determinant [ne],
          * fp32, at the reference point (1/2, 1/2, 1/2) of the (macro) element */
         std::vector<float> adj((size_t)g.ne * 9), det((size_t)g.ne);
-        if (b200fem_adjugate_and_det_fill(B200FEM_HEX8, g.ne, g.nn, g.corners.data(), space->mesh_ptr()->points()->data(), adj.data(),
+        if (b200fem_adjugate_and_det_fill(g.corners.size() == 4 ? B200FEM_TET4 : B200FEM_HEX8, g.ne, g.nn, g.corners.data(), space->mesh_ptr()->points()->data(), adj.data(),
                                           det.data()))
             return nullptr;
         const real_t m = domain.parameters ? domain.parameters->get_real_value("mu", mu) : mu;

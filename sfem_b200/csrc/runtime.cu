@@ -257,6 +257,26 @@ int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int
     return B200FEM_SUCCESS;
 }
 
+int b200fem_packed_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t n_packs, ptrdiff_t n_elements_per_pack, ptrdiff_t ne,
+                                    ptrdiff_t nn, ptrdiff_t max_nodes_per_pack, const uint16_t *const *elements, const float *fff,
+                                    const ptrdiff_t *owned_nodes_ptr, const ptrdiff_t *n_shared, const ptrdiff_t *ghost_ptr,
+                                    const int32_t *ghost_idx, int real_type) {
+    if (!op) B2_FAIL("op output pointer is NULL");
+    *op = nullptr;
+    if (ne < 0 || nn < 0 || n_packs < 0) B2_FAIL("negative sizes");
+    if (real_type != B200FEM_F32 && real_type != B200FEM_F64) B2_FAIL("real_type must be B200FEM_F32 or B200FEM_F64");
+    if (!owned_nodes_ptr || !ghost_ptr || (n_packs > 0 && !n_shared)) B2_FAIL("packed laplacian: NULL pack arrays");
+    if (ne > 0 && (!elements || !fff)) B2_FAIL("packed laplacian: elements / fff is NULL");
+    if (n_packs > 0 && ghost_ptr[n_packs] > 0 && !ghost_idx) B2_FAIL("packed laplacian: ghost_idx is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B2_FAIL("no CUDA device: b200fem has no CPU fallback");
+    OpBase *impl = make_packed_laplacian(element_type, n_packs, n_elements_per_pack, ne, nn, max_nodes_per_pack, elements, fff,
+                                         owned_nodes_ptr, n_shared, ghost_ptr, ghost_idx, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
 int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                                     const float *fff, int vector_size, int real_type) {
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;

@@ -57,6 +57,13 @@ _SIG = {
     "b200fem_laplacian_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_mass_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_vector_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32, i32],
+    "b200fem_packed_mesh_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, ssz],
+    "b200fem_packed_mesh_destroy": [vp],
+    "b200fem_packed_mesh_sizes": [vp, C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz)],
+    "b200fem_packed_mesh_arrays": [vp, C.POINTER(C.POINTER(C.POINTER(C.c_uint16))), C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(ssz)),
+                                   C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))],
+    "b200fem_packed_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, ssz, ssz, ssz, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_float),
+                                        C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz), C.POINTER(C.c_int32), i32],
     "b200fem_linear_elasticity_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, f64, f64, i32],
     "b200fem_sshex8_em_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, i32, vp, i32],
     "b200fem_sshex8_laplacian_element_matrix": [i32, ssz, C.POINTER(C.c_float), i32, vp],
@@ -333,6 +340,68 @@ def laplacian_from_points(element_type: int, elements: np.ndarray, points: np.nd
     check(_lib.b200fem_laplacian_create_from_points(C.byref(h), element_type, level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
                                                     _soa_ptrs(pts, C.c_float), _rt(dtype)), "laplacian_create_from_points")
     return Op(h, nnodes)
+
+
+class PackedMesh:
+    """smesh::PackedMesh<uint16_t> as PackedLaplacian::apply reads it (frontend/ops/sfem_PackedLaplacian.cpp:875-930), built by
+    b200fem_packed_mesh_create. numpy copies of the arrays; nodes are renumbered: packed node i is input node new_to_old[i]."""
+
+    def __init__(self, elements: np.ndarray, nnodes: int, n_elements_per_pack: int = 0):
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        nxe, ne = el.shape
+        h = vp()
+        check(_lib.b200fem_packed_mesh_create(C.byref(h), nxe, ne, nnodes, _soa_ptrs(el, C.c_int32), n_elements_per_pack), "packed_mesh_create")
+        try:
+            a, b, c, d = ssz(), ssz(), ssz(), ssz()
+            check(_lib.b200fem_packed_mesh_sizes(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "packed_mesh_sizes")
+            self.n_packs, self.n_elements_per_pack, self.max_nodes_per_pack, self.n_ghost_entries = a.value, b.value, c.value, d.value
+            rows = C.POINTER(C.POINTER(C.c_uint16))()
+            onp, nsh, gp = C.POINTER(ssz)(), C.POINTER(ssz)(), C.POINTER(ssz)()
+            gi, n2o = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+            check(_lib.b200fem_packed_mesh_arrays(h, C.byref(rows), C.byref(onp), C.byref(nsh), C.byref(gp), C.byref(gi), C.byref(n2o)),
+                  "packed_mesh_arrays")
+            cp = lambda ptr, n, dt: np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dtype=dt)
+            self.elements = np.stack([cp(rows[v], ne, np.uint16) for v in range(nxe)]) if ne else np.zeros((nxe, 0), dtype=np.uint16)
+            self.owned_nodes_ptr = cp(onp, self.n_packs + 1, np.int64)
+            self.n_shared = cp(nsh, self.n_packs, np.int64)
+            self.ghost_ptr = cp(gp, self.n_packs + 1, np.int64)
+            self.ghost_idx = cp(gi, self.n_ghost_entries, np.int32)
+            self.new_to_old = cp(n2o, nnodes, np.int32)
+        finally:
+            _lib.b200fem_packed_mesh_destroy(h)
+        self.n_nodes, self.n_elements = nnodes, ne
+
+    def global_elements(self) -> np.ndarray:
+        """The packed connectivity expanded to (packed) global node ids [nxe][ne] -- what the local indices stand for."""
+        ne = self.n_elements
+        pack = np.arange(ne) // max(self.n_elements_per_pack, 1)
+        base = self.owned_nodes_ptr[pack]
+        n_owned = self.owned_nodes_ptr[pack + 1] - base
+        out = np.empty(self.elements.shape, dtype=np.int32)
+        for v in range(self.elements.shape[0]):
+            l = self.elements[v].astype(np.int64)
+            own = l < n_owned
+            g = np.where(own, base + l, 0)
+            gh = ~own
+            g[gh] = self.ghost_idx[self.ghost_ptr[pack[gh]] + l[gh] - n_owned[gh]]
+            out[v] = g
+        return out
+
+
+def packed_laplacian(element_type: int, pm: "PackedMesh", fff: np.ndarray, dtype) -> Op:
+    """PackedLaplacian on a PackedMesh (TET4 / HEX8 / TET10 / MACRO_TET4); vectors in the packed node numbering."""
+    el = np.ascontiguousarray(pm.elements, dtype=np.uint16)
+    f = np.ascontiguousarray(fff, dtype=np.float32)
+    onp = np.ascontiguousarray(pm.owned_nodes_ptr, dtype=np.int64)
+    nsh = np.ascontiguousarray(pm.n_shared, dtype=np.int64)
+    gp = np.ascontiguousarray(pm.ghost_ptr, dtype=np.int64)
+    gi = np.ascontiguousarray(pm.ghost_idx, dtype=np.int32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    h = vp()
+    check(_lib.b200fem_packed_laplacian_create(C.byref(h), element_type, pm.n_packs, pm.n_elements_per_pack, pm.n_elements, pm.n_nodes,
+                                               pm.max_nodes_per_pack, _soa_ptrs(el, C.c_uint16), P(f, C.c_float), P(onp, ssz), P(nsh, ssz),
+                                               P(gp, ssz), P(gi, C.c_int32), _rt(dtype)), "packed_laplacian_create")
+    return Op(h, pm.n_nodes)
 
 
 def vector_laplacian(element_type: int, elements: np.ndarray, fff: np.ndarray, nnodes: int, vector_size: int, dtype) -> Op:

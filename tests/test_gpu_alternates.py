@@ -379,3 +379,79 @@ def test_p2_tet_linear_elasticity(oracles, real, family, scatter):
     d = torch.zeros(nn * 3, dtype=_dt(real), device="cuda")
     op.diag(d)
     assert _rel(d.cpu().numpy(), orc.p2tet_linear_elasticity_diag_opt(family, el10, adj, det, mu, lam, nn)) < tol
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet4", "hex8", "tet10", "macro_tet4"])
+def test_packed_laplacian(oracles, real, family):
+    """PackedLaplacian: b200fem_packed_laplacian_create on the arrays of a PackedMesh<uint16_t>
+    (b200fem_packed_mesh_create), staged and direct kernels, against the reference's own *_laplacian_apply_opt on the packed
+    connectivity expanded to global ids -- the sum PackedLaplacianApply::apply (frontend/ops/sfem_PackedLaplacian.cpp:111-176)
+    forms pack by pack with the same element operators."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    if family == "hex8":
+        el, pts = mesh.box_hex8(11, 9, 10)
+        pts = mesh.shear_points(pts)
+        et, epp = lib.HEX8, 128
+    else:
+        el, pts = mesh.box_tet4(9, 7, 8)
+        pts = mesh.warp_points(pts)
+        et, epp = lib.TET4, 256
+        if family != "tet4":
+            el, pts = mesh.tet4_to_tet10(el, pts)
+            et = lib.TET10 if family == "tet10" else lib.MACRO_TET4
+    nn = pts.shape[1]
+    pm = lib.PackedMesh(el, nn, epp)
+    assert pm.n_packs > 3
+    g = pm.global_elements()
+    ppts = np.ascontiguousarray(pts[:, pm.new_to_old])  # points in the packed numbering
+    if family == "hex8":
+        fff = orc.hex8_fff_fill(g, ppts)
+        ref_apply = lambda u: orc.hex8_laplacian_apply_opt(g, fff, u)
+    elif family == "tet4":
+        fff = orc.tet4_fff_fill(g, ppts)
+        ref_apply = lambda u: orc.tet4_laplacian_apply_opt(g, fff, u)
+    else:
+        fff = orc.tet4_fff_fill(g[:4], ppts)
+        ref_apply = lambda u: orc.p2tet_laplacian_apply_opt(family, g, fff, u)
+    op = lib.packed_laplacian(et, pm, fff, _dt(real))
+    assert op.get_option("packed_staged") == 1
+    u = np.random.default_rng(21).uniform(-1, 1, nn)
+    ref = ref_apply(u)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    for direct in (0, 1):
+        op.set_option("packed_kernel", direct)
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        assert _rel(y.cpu().numpy(), ref) < TOL[real], direct
+        op.apply(x, y)  # accumulate semantics (the exclusively owned nodes take a plain read-modify-write)
+        assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real], direct
+        y.fill_(5.0)
+        op.apply_overwrite(x, y)
+        assert _rel(y.cpu().numpy(), ref) < TOL[real], direct
+    # the same operator as the unpacked one on the input numbering
+    ones = torch.ones(nn, dtype=_dt(real), device="cuda")
+    op.apply_overwrite(ones, y)
+    assert np.abs(y.cpu().numpy()).max() < (1e-12 if real == "f64" else 1e-4)
+    # one pack holding every element of a 30^3-node box: more nodes than shared memory takes -> the direct kernel is chosen
+    if family in ("tet4", "hex8"):
+        elb, ptb = (mesh.box_hex8 if family == "hex8" else mesh.box_tet4)(30, 30, 30)
+        nb = ptb.shape[1]
+        big = lib.PackedMesh(elb, nb, elb.shape[1])
+        assert big.n_packs == 1 and 2 * big.max_nodes_per_pack * 4 > 200 * 1024
+        gb = big.global_elements()
+        bp = np.ascontiguousarray(ptb[:, big.new_to_old])
+        fb = orc.hex8_fff_fill(gb, bp) if family == "hex8" else orc.tet4_fff_fill(gb, bp)
+        opb = lib.packed_laplacian(et, big, fb, _dt(real))
+        assert opb.get_option("packed_staged") == 0
+        ub = np.random.default_rng(22).uniform(-1, 1, nb)
+        refb = orc.hex8_laplacian_apply_opt(gb, fb, ub) if family == "hex8" else orc.tet4_laplacian_apply_opt(gb, fb, ub)
+        xb = torch.from_numpy(ub).to(_dt(real)).cuda()
+        yb = torch.zeros_like(xb)
+        opb.apply(xb, yb)
+        assert _rel(yb.cpu().numpy(), refb) < TOL[real]
