@@ -172,9 +172,19 @@ int b200fem_packed_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_
 /* VectorLaplacian on hex8: the scalar Laplacian on every component of an AoS field [nnodes * vector_size]
  * (VectorLaplacian::apply -> vector_laplacian_apply_opt -> affine_hex8_vector_laplacian_apply_fff, frontend/ops/
  * sfem_VectorLaplacian.cpp:191-206, operators/vector_laplacian.cpp:41-66, operators/hex8/hex8_vector_laplacian.cpp:78-138);
- * fff as for b200fem_laplacian_create. The semi-structured twin is not built. */
+ * fff as for b200fem_laplacian_create.
+ * The semi-structured twin, b200fem_sshex8_vector_laplacian_create <- affine_sshex8_vector_laplacian_apply_fff
+ * (operators/sshex8/sshex8_vector_laplacian.cpp:16-97): `elements` / `fff` / `level` as for b200fem_laplacian_create(SSHEX8);
+ * the scalar stencil kernel runs component by component on plan-owned work vectors (2 x nnodes scalars). */
 int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t nelements, ptrdiff_t nnodes,
                                     const int32_t *const *elements, const float *fff, int vector_size, int real_type);
+int b200fem_sshex8_vector_laplacian_create(b200fem_op_t *op, int level, ptrdiff_t nelements, ptrdiff_t nnodes,
+                                           const int32_t *const *elements, const float *fff, int vector_size, int real_type);
+/* LumpedMass on sshex8 <- affine_sshex8_mass_lumped (operators/sshex8/sshex8_mass.cpp:11-115; assemble_lumped_mass,
+ * operators/mass.cpp:74-77): `diag` only (apply fails: apply_mass has no semi-structured case). `elements` = the (level+1)^3
+ * lattice rows, `points[3][nnodes]` read at the 8 macro corners. */
+int b200fem_sshex8_lumped_mass_create(b200fem_op_t *op, int level, ptrdiff_t nelements, ptrdiff_t nnodes,
+                                      const int32_t *const *elements, const float *const *points, int real_type);
 int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t nelements, ptrdiff_t nnodes, const int32_t *const *elements,
                         const float *const *points, int real_type);
 /* Stored-element-matrix ("EM") semi-structured operators: ss:em:Laplacian / ss:em:LinearElasticity

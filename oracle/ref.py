@@ -224,6 +224,29 @@ class Oracle:
                    C.c_int(vector_size), C.c_ssize_t(vector_size), up, op)
         return out
 
+    def sshex8_vector_laplacian_apply(self, level, elements, fff, vector_size, u):
+        """affine_sshex8_vector_laplacian_apply_fff (operators/sshex8/sshex8_vector_laplacian.cpp:16-97); u / out AoS [nn * vs]."""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        f, pf = self._f32(fff)
+        u, _ = self._r(u)
+        out = np.zeros_like(u)
+        sz = u.itemsize
+        pp = C.POINTER(self.crt) * vector_size
+        up = pp(*[C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(vector_size)])
+        op = pp(*[C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(vector_size)])
+        self._call("affine_sshex8_vector_laplacian_apply_fff", C.c_int(level), C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf,
+                   C.c_int(vector_size), C.c_ssize_t(vector_size), up, op)
+        return out
+
+    def sshex8_lumped_mass(self, level, elements, points, nnodes):
+        """affine_sshex8_mass_lumped (operators/sshex8/sshex8_mass.cpp:11-115; C++ linkage): points read at the macro corners"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        self._call("affine_sshex8_mass_lumped", C.c_int(level), C.c_ssize_t(el.shape[1]), C.c_ssize_t(0), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
     # ---- mass (reference build only: hex8_mass.cpp / tet4_mass.cpp compiled where they lie)
     def hex8_apply_mass(self, elements, points, u, nnodes):
         """hex8_apply_mass (operators/hex8/hex8_mass.cpp:8-60): out += M u, 27-point Gauss, isoparametric."""

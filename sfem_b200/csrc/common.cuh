@@ -158,6 +158,10 @@ OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t n
 OpBase *make_packed_laplacian(int element_type, ptrdiff_t n_packs, ptrdiff_t epp, ptrdiff_t ne, ptrdiff_t nn, ptrdiff_t max_nodes,
                               const uint16_t *const *elements, const float *fff, const ptrdiff_t *owned_nodes_ptr, const ptrdiff_t *n_shared,
                               const ptrdiff_t *ghost_ptr, const int32_t *ghost_idx, int real_type);
+OpBase *make_sshex8_vector_laplacian(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int vector_size,
+                                     int real_type);
+OpBase *make_sshex8_lumped_mass(int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
+                                int real_type);
 OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
                                         int real_type);
 OpBase *make_tet4_le_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points, double mu,

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "hex8_le_core.cuh"
 #include "hex8_local.cuh"
+#include "hex8_mass_local.cuh"
 
 namespace b200fem {
 
@@ -352,17 +353,12 @@ OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
     return op;
 }
 
-// Mass (consistent: y += M x) and lumped mass of the isoparametric Q1 hex, 27-point Gauss on [0,1]^3: hex8_apply_mass /
-// hex8_assemble_lumped_mass (operators/hex8/hex8_mass.cpp:8-103; point kernels hex8_mass_apply_points / hex8_lumped_mass_points,
-// hex8_mass_inline_cpu.hpp:135-286; points and weights q27_*, hex8_quadrature.hpp:46-84 -- the reference's 15-digit literals).
-// Per point: out_i += w det J(q) phi_i(q) sum_j phi_j(q) u_j (lumped: the row sum, sum_j phi_j = 1).
+// Mass (consistent: y += M x) and lumped mass of the isoparametric Q1 hex: hex8_apply_mass / hex8_assemble_lumped_mass
+// (operators/hex8/hex8_mass.cpp:8-103); the 27-point element operator is hex8_mass_local (hex8_mass_local.cuh)
 template <typename T, bool LUMPED>
 __global__ void __launch_bounds__(128)
     hex8_mass_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
                      const T *__restrict__ u, T *__restrict__ y) {
-    const T qp[3] = {T(0.112701665379258), T(0.5), T(0.887298334620742)};
-    // weight by the number of centre coordinates among (qx, qy, qz)
-    const T qw[4] = {T(0.021433470507545), T(0.034293552812071), T(0.054869684499314), T(0.087791495198903)};
     for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
         int32_t ev[8];  // lexicographic corners
 #pragma unroll
@@ -373,37 +369,8 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
             for (int d = 0; d < 3; ++d) X[d][i] = (T)points[(size_t)d * nn + ev[i]];
             U[i] = LUMPED ? T(1) : u[ev[i]];
-            O[i] = T(0);
         }
-#pragma unroll 1
-        for (int q = 0; q < 27; ++q) {
-            const int ix = q % 3, iy = (q / 3) % 3, iz = q / 9;
-            const T x = qp[ix], yq = qp[iy], z = qp[iz];
-            const T w = qw[(ix == 1) + (iy == 1) + (iz == 1)];
-            T phi[8], J[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) J[k] = T(0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int bx = i & 1, by = (i >> 1) & 1, bz = (i >> 2) & 1;
-                const T sx = bx ? x : T(1) - x, sy = by ? yq : T(1) - yq, sz = bz ? z : T(1) - z;
-                phi[i] = sx * sy * sz;
-                const T gx = (bx ? T(1) : T(-1)) * sy * sz, gy = sx * (by ? T(1) : T(-1)) * sz, gz = sx * sy * (bz ? T(1) : T(-1));
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    J[r * 3 + 0] = le_fma(X[r][i], gx, J[r * 3 + 0]);
-                    J[r * 3 + 1] = le_fma(X[r][i], gy, J[r * 3 + 1]);
-                    J[r * 3 + 2] = le_fma(X[r][i], gz, J[r * 3 + 2]);
-                }
-            }
-            const T det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
-            T uq = T(0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) uq = le_fma(phi[i], U[i], uq);
-            const T val = w * det * uq;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) O[i] = le_fma(phi[i], val, O[i]);
-        }
+        hex8_mass_local(X, U, O);
 #pragma unroll
         for (int i = 0; i < 8; ++i) red_add(&y[ev[i]], O[i]);
     }

@@ -289,6 +289,29 @@ int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_
     return B200FEM_SUCCESS;
 }
 
+int b200fem_sshex8_vector_laplacian_create(b200fem_op_t *op, int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                                           const float *fff, int vector_size, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (ne > 0 && !fff) B2_FAIL("fff is NULL");
+    if (vector_size < 1 || vector_size > 16) B2_FAIL("vector laplacian: vector_size out of range");
+    if (level != 2 && level != 4 && level != 8) B2_FAIL("sshex8 vector laplacian: level must be 2, 4 or 8");
+    OpBase *impl = make_sshex8_vector_laplacian(level, ne, nn, elements, fff, vector_size, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_sshex8_lumped_mass_create(b200fem_op_t *op, int level, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                                      const float *const *points, int real_type) {
+    if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
+    if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
+    if (level < 1) B2_FAIL("sshex8 lumped mass: level must be >= 1");
+    OpBase *impl = make_sshex8_lumped_mass(level, ne, nn, elements, points, real_type);
+    if (!impl) return B200FEM_FAILURE;
+    *op = new b200fem_op_s{impl};
+    return B200FEM_SUCCESS;
+}
+
 int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                         const float *const *points, int real_type) {
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;

@@ -57,6 +57,8 @@ _SIG = {
     "b200fem_laplacian_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_mass_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_vector_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32, i32],
+    "b200fem_sshex8_vector_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, C.POINTER(C.c_float), i32, i32],
+    "b200fem_sshex8_lumped_mass_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, c_f32_pp, i32],
     "b200fem_packed_mesh_create": [C.POINTER(vp), i32, ssz, ssz, c_idx_pp, ssz],
     "b200fem_packed_mesh_destroy": [vp],
     "b200fem_packed_mesh_sizes": [vp, C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz)],
@@ -411,6 +413,27 @@ def vector_laplacian(element_type: int, elements: np.ndarray, fff: np.ndarray, n
     h = vp()
     check(_lib.b200fem_vector_laplacian_create(C.byref(h), element_type, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
                                                f.ctypes.data_as(C.POINTER(C.c_float)), vector_size, _rt(dtype)), "vector_laplacian_create")
+    return Op(h, nnodes)
+
+
+def sshex8_vector_laplacian(level: int, elements: np.ndarray, fff: np.ndarray, nnodes: int, vector_size: int, dtype) -> Op:
+    """affine_sshex8_vector_laplacian_apply_fff: the scalar sshex8 Laplacian on every component of an AoS field."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    f = np.ascontiguousarray(fff, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_sshex8_vector_laplacian_create(C.byref(h), level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
+                                                      f.ctypes.data_as(C.POINTER(C.c_float)), vector_size, _rt(dtype)),
+          "sshex8_vector_laplacian_create")
+    return Op(h, nnodes)
+
+
+def sshex8_lumped_mass(level: int, elements: np.ndarray, points: np.ndarray, nnodes: int, dtype) -> Op:
+    """affine_sshex8_mass_lumped: diag only."""
+    el = np.ascontiguousarray(elements, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    h = vp()
+    check(_lib.b200fem_sshex8_lumped_mass_create(C.byref(h), level, el.shape[1], nnodes, _soa_ptrs(el, C.c_int32),
+                                                 _soa_ptrs(pts, C.c_float), _rt(dtype)), "sshex8_lumped_mass_create")
     return Op(h, nnodes)
 
 

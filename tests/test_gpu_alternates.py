@@ -455,3 +455,69 @@ def test_packed_laplacian(oracles, real, family):
         yb = torch.zeros_like(xb)
         opb.apply(xb, yb)
         assert _rel(yb.cpu().numpy(), refb) < TOL[real]
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level,vs", [(2, 3), (4, 2), (8, 3)])
+def test_sshex8_vector_laplacian(oracles, real, level, vs):
+    """b200fem_sshex8_vector_laplacian_create against affine_sshex8_vector_laplacian_apply_fff
+    (operators/sshex8/sshex8_vector_laplacian.cpp:16-97): AoS fields of vs components on the semi-structured lattice."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    m = mesh.sshex8_box(level, 3, 2, 2)
+    mpts = mesh.shear_points(m["m_points"])
+    nn = m["n_nodes"]
+    fff = orc.hex8_fff_fill(m["m_elements"], mpts)
+    op = lib.sshex8_vector_laplacian(level, m["elements"], fff, nn, vs, _dt(real))
+    u = np.random.default_rng(level + vs).uniform(-1, 1, nn * vs)
+    ref = orc.sshex8_vector_laplacian_apply(level, m["elements"], fff, vs, u)
+    x = torch.from_numpy(u).to(_dt(real)).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    op.apply(x, y)  # accumulate semantics
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    y.fill_(9.0)
+    op.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    # every component takes the scalar operator's diagonal
+    sop = lib.laplacian(lib.SSHEX8, m["elements"], fff, nn, _dt(real), level=level)
+    ds = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    sop.diag(ds)
+    d = torch.zeros_like(x)
+    op.diag(d)
+    # (the scalar diagonal is accumulated with REDs: two runs agree to rounding, not bit for bit)
+    assert float(((d.reshape(nn, vs) - ds[:, None]).abs() / ds[:, None]).max()) < (1e-14 if real == "f64" else 1e-6)
+    assert float((d.reshape(nn, vs) - d.reshape(nn, vs)[:, :1]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("level", [1, 2, 4, 8])
+def test_sshex8_lumped_mass(oracles, real, level):
+    """b200fem_sshex8_lumped_mass_create against affine_sshex8_mass_lumped (operators/sshex8/sshex8_mass.cpp:11-115) on a warped
+    (non-affine) macro mesh; the total is the volume of the mesh."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    m = mesh.sshex8_box(level, 3, 2, 4)
+    mpts = mesh.warp_points(m["m_points"])
+    nn = m["n_nodes"]
+    pts = np.zeros((3, nn), dtype=np.float32)  # coordinates by sshex8 node id: only the macro corners are read
+    corners = [mesh.sshex8_lidx(level, cx * level, cy * level, cz * level) for cx, cy, cz in mesh.HEX8_CORNERS]
+    for k, c in enumerate(corners):
+        pts[:, m["elements"][c]] = mpts[:, m["m_elements"][k]]
+    op = lib.sshex8_lumped_mass(level, m["elements"], pts, nn, _dt(real))
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    ref = orc.sshex8_lumped_mass(level, m["elements"], pts, nn)
+    assert _rel(d.cpu().numpy(), ref) < TOL[real]
+    assert float(d.min()) > 0
+    with pytest.raises(RuntimeError):
+        op.apply(d, d)
