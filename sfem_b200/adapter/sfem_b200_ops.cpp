@@ -174,6 +174,40 @@ namespace sfem {
         return ret;
     }
 
+    /* ------------------------------------------------------------------------------ B200VectorLaplacian */
+    std::unique_ptr<Op> B200VectorLaplacian::create(const std::shared_ptr<FunctionSpace> &space) {
+        return std::make_unique<B200VectorLaplacian>(space);
+    }
+
+    b200fem_op_t B200VectorLaplacian::create_plan(const OpDomain &domain) {
+        DomainGeometry g = geometry_of(space, domain);
+        if (g.type != B200FEM_HEX8 && g.type != B200FEM_SSHEX8) {
+            fprintf(stderr, "[b200fem] vector laplacian: hex8 and sshex8 blocks only\n");
+            return nullptr;
+        }
+        std::vector<float> fff((size_t)g.ne * 6);
+        if (b200fem_fff_fill(B200FEM_HEX8, g.ne, g.nn, g.corners.data(), space->mesh_ptr()->points()->data(), fff.data())) return nullptr;
+        b200fem_op_t plan = nullptr;
+        const int    vs   = space->block_size();
+        const int    rc   = g.type == B200FEM_SSHEX8
+                                    ? b200fem_sshex8_vector_laplacian_create(&plan, g.level, g.ne, g.nn, g.elements, fff.data(), vs, kRealType)
+                                    : b200fem_vector_laplacian_create(&plan, g.type, g.ne, g.nn, g.elements, fff.data(), vs, kRealType);
+        return rc ? nullptr : plan;
+    }
+
+    std::shared_ptr<Op> B200VectorLaplacian::derefine_op(const std::shared_ptr<FunctionSpace> &derefined_space) {
+        auto ret = std::make_shared<B200VectorLaplacian>(derefined_space);
+        if (ret->initialize(selected_block_names()) != SFEM_SUCCESS) return nullptr;
+        return ret;
+    }
+
+    std::shared_ptr<Op> B200VectorLaplacian::clone() const {
+        auto ret     = std::make_shared<B200VectorLaplacian>(space);
+        ret->domains = domains;
+        ret->stream  = stream;
+        return ret;
+    }
+
     /* ------------------------------------------------------------------------------------------ B200Mass */
     std::unique_ptr<Op> B200Mass::create(const std::shared_ptr<FunctionSpace> &space) {
         assert(1 == space->block_size());
@@ -182,11 +216,16 @@ namespace sfem {
 
     b200fem_op_t B200Mass::create_plan(const OpDomain &domain) {
         DomainGeometry g = geometry_of(space, domain);
-        if (g.type != B200FEM_HEX8 && g.type != B200FEM_TET4) {
-            fprintf(stderr, "[b200fem] mass: hex8 (apply + lumped) and tet4 (lumped) blocks only\n");
+        if (g.type != B200FEM_HEX8 && g.type != B200FEM_TET4 && g.type != B200FEM_SSHEX8) {
+            fprintf(stderr, "[b200fem] mass: hex8 (apply + lumped), tet4 and sshex8 (lumped) blocks only\n");
             return nullptr;
         }
         b200fem_op_t plan = nullptr; /* apply_mass / assemble_lumped_mass read the mesh points, no cached geometry */
+        if (g.type == B200FEM_SSHEX8) { /* assemble_lumped_mass -> affine_sshex8_mass_lumped (operators/mass.cpp:74-77) */
+            if (b200fem_sshex8_lumped_mass_create(&plan, g.level, g.ne, g.nn, g.elements, space->mesh_ptr()->points()->data(), kRealType))
+                return nullptr;
+            return plan;
+        }
         if (b200fem_mass_create(&plan, g.type, g.ne, g.nn, g.elements, space->mesh_ptr()->points()->data(), kRealType)) return nullptr;
         return plan;
     }
@@ -201,6 +240,9 @@ namespace sfem {
     void register_b200_ops() {
         Factory::register_op("gpu:Mass", &B200Mass::create);
         Factory::register_op("gpu:LumpedMass", &B200Mass::create);
+        Factory::register_op("ss:gpu:LumpedMass", &B200Mass::create);
+        Factory::register_op("gpu:VectorLaplacian", &B200VectorLaplacian::create);
+        Factory::register_op("ss:gpu:VectorLaplacian", &B200VectorLaplacian::create);
         Factory::register_op("gpu:Laplacian", &B200Laplacian::create);
         Factory::register_op("ss:gpu:Laplacian", &B200Laplacian::create);
         Factory::register_op("gpu:LinearElasticity", &B200LinearElasticity::create);

@@ -97,13 +97,28 @@ namespace sfem {
         b200fem_op_t create_plan(const OpDomain &domain) override;
     };
 
+    /* VectorLaplacian (frontend/ops/sfem_VectorLaplacian.cpp): the scalar Laplacian on every component of an AoS field with
+     * block_size components; hex8 and sshex8 blocks (vector_laplacian_apply_opt, operators/vector_laplacian.cpp:41-66) */
+    class B200VectorLaplacian final : public B200Op {
+    public:
+        using B200Op::B200Op;
+        static std::unique_ptr<Op> create(const std::shared_ptr<FunctionSpace> &space);
+        const char *name() const override { return is_semistructured_type(element_type) ? "ss:gpu:VectorLaplacian" : "gpu:VectorLaplacian"; }
+        int         initialize(const std::vector<std::string> &block_names = {}) override { return initialize_domains(block_names); }
+        std::shared_ptr<Op> derefine_op(const std::shared_ptr<FunctionSpace> &derefined_space) override;
+        std::shared_ptr<Op> clone() const override;
+
+    protected:
+        b200fem_op_t create_plan(const OpDomain &domain) override;
+    };
+
     /* Mass / LumpedMass (frontend/ops/sfem_Mass.cpp, sfem_LumpedMass.cpp): apply = Mass::apply (hex8 blocks: apply_mass has no
-     * other 3-D case), hessian_diag = LumpedMass::hessian_diag (hex8, tet4). One class under both keys. */
+     * other 3-D case), hessian_diag = LumpedMass::hessian_diag (hex8, tet4, sshex8: "ss:gpu:LumpedMass"). One class under all keys. */
     class B200Mass final : public B200Op {
     public:
         using B200Op::B200Op;
         static std::unique_ptr<Op> create(const std::shared_ptr<FunctionSpace> &space);
-        const char *name() const override { return "gpu:Mass"; }
+        const char *name() const override { return is_semistructured_type(element_type) ? "ss:gpu:LumpedMass" : "gpu:Mass"; }
         int         initialize(const std::vector<std::string> &block_names = {}) override { return initialize_domains(block_names); }
         std::shared_ptr<Op> clone() const override;
 

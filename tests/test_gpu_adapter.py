@@ -274,3 +274,60 @@ def test_derefine_op_gives_the_coarse_operator(oracles):
         h.adapter_op_destroy(o)
     for s in (coarse, fine):
         h.adapter_space_destroy(s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["hex8", "sshex8"])
+def test_factory_creates_our_vector_laplacian_and_ss_lumped_mass(oracles, case):
+    """sfem::create_op(space, "VectorLaplacian", DEVICE) on hex8 and sshex8 spaces with block_size 3 ("gpu:" / "ss:gpu:" keys), and
+    "LumpedMass" on the sshex8 space ("ss:gpu:LumpedMass"), against the reference's own routines."""
+    import torch
+
+    from sfem_b200 import mesh
+
+    h = _lib()
+    orc = oracles.get(("reference", "f64"))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    vs = 3
+    if case == "hex8":
+        el, pts = mesh.box_hex8(6, 5, 7)
+        pts = mesh.shear_points(pts, 0.25, 0.5, 0.125)
+        nn = pts.shape[1]
+        u = np.random.default_rng(8).uniform(-1, 1, nn * vs)
+        ref = orc.hex8_vector_laplacian_apply(el, orc.hex8_fff_fill(el, pts), vs, u, nn)
+        sp = _space(h, 8, 0, el, pts, vs)
+        key = b"gpu:VectorLaplacian"
+    else:
+        level = 4
+        m = mesh.sshex8_box(level, 2, 3, 2)
+        mpts = mesh.shear_points(m["m_points"], 0.25, 0.5, 0.125)
+        nn = m["n_nodes"]
+        u = np.random.default_rng(9).uniform(-1, 1, nn * vs)
+        ref = orc.sshex8_vector_laplacian_apply(level, m["elements"], orc.hex8_fff_fill(m["m_elements"], mpts), vs, u)
+        pts = np.zeros((3, nn), dtype=np.float32)
+        corners = [mesh.sshex8_lidx(level, cx * level, cy * level, cz * level) for cx, cy, cz in mesh.HEX8_CORNERS]
+        for k, c in enumerate(corners):
+            pts[:, m["elements"][c]] = mpts[:, m["m_elements"][k]]
+        el = m["elements"]
+        sp = _space(h, 800, level, el, pts, vs)
+        key = b"ss:gpu:VectorLaplacian"
+    op = h.adapter_create_op(sp, b"VectorLaplacian")
+    assert op and h.adapter_op_name(op) == key and h.adapter_op_n_dofs(op) == nn * vs
+    x = torch.from_numpy(u).cuda()
+    y = torch.zeros_like(x)
+    assert h.adapter_op_apply(op, x.data_ptr(), y.data_ptr()) == 0
+    assert _rel(y.cpu().numpy(), ref) < 1e-6  # fp32 FFF from b200fem_fff_fill against the reference's fill
+    assert h.adapter_op_apply(op, x.data_ptr(), y.data_ptr()) == 0
+    assert _rel(y.cpu().numpy(), 2 * ref) < 1e-6
+    h.adapter_op_destroy(op)
+    h.adapter_space_destroy(sp)
+    if case == "sshex8":
+        sp1 = _space(h, 800, level, el, pts, 1)
+        lm = h.adapter_create_op(sp1, b"LumpedMass")
+        assert lm and h.adapter_op_name(lm) == b"ss:gpu:LumpedMass"
+        d = torch.zeros(nn, dtype=torch.float64, device="cuda")
+        assert h.adapter_op_hessian_diag(lm, d.data_ptr()) == 0
+        assert _rel(d.cpu().numpy(), orc.sshex8_lumped_mass(level, el, pts, nn)) < 1e-12
+        h.adapter_op_destroy(lm)
+        h.adapter_space_destroy(sp1)
