@@ -150,7 +150,8 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
  * other nodes are ghost_idx[ghost_ptr[p] .. ghost_ptr[p+1]); `elements[v][e]` is LOCAL to the pack of e: l < n_owned is node
  * owned_nodes_ptr[p] + l, else ghost l - n_owned. TET4, HEX8, TET10 (the reference's three micro kernels) and MACRO_TET4;
  * fff [nelements * 6] as for b200fem_laplacian_create. All arrays HOST, copied by the plan. Only apply / apply_overwrite exist
- * (the reference's PackedLaplacian implements nothing else). Option "packed_kernel" = 1 forces the direct kernel.
+ * (the reference's PackedLaplacian implements nothing else). Option "packed_kernel": 1 = direct kernel (default), 0 = the
+ * kernel that stages a pack in shared memory (when it fits).
  *
  * b200fem_packed_mesh_create builds such a packing from plain connectivity (what smesh::PackedMesh<T>::create(mesh, {}, true)
  * does inside FunctionSpace::initialize_packed_mesh, frontend/sfem_FunctionSpace.cpp:236-239; smesh is absent from the reference

@@ -10,9 +10,11 @@
 //
 // Data layout in HBM (plan): connectivity SoA int32 [10][ne]; FFF SoA fp32 [6][ne] or adjugate SoA fp32 [9][ne] +
 // determinant [ne], streamed once per apply. A 10-node tet shares each corner with ~24 and each edge node with ~5
-// elements, so the default scatter is the patch kernel of patch.cuh (256 consecutive elements staged in shared memory,
-// one RED per unique node of the patch); B200FEM_SCATTER_ATOMIC is the thread-per-element form with one RED per
-// (element, node, component).
+// elements. Two scatters: B200FEM_SCATTER_PATCH, the patch kernel of patch.cuh (256 consecutive elements staged in shared
+// memory, one RED per unique node of the patch; the plan is built on first use), and B200FEM_SCATTER_ATOMIC, the
+// thread-per-element form with one RED per (element, node, component). The default per operator is the faster one as
+// measured on B200 (profiles/r02p2_extras.jsonl): ATOMIC for both Laplacians and macro_tet4 elasticity, PATCH for tet10
+// elasticity.
 #include <stdlib.h>
 #include <string.h>
 
@@ -174,16 +176,31 @@ __global__ void __launch_bounds__(128)
 
 static constexpr int kP2PatchE = 256;
 
+// The patch plan is built on first use (PATCH is not the default of every family, see make_p2tet_*): the plan keeps the host
+// connectivity for that.
+struct P2PatchHolder {
+    std::vector<int32_t> host_el;  // [10][ne]
+    PatchPlan patch;
+    int ensure(ptrdiff_t ne) {
+        if (patch.ready) return B200FEM_SUCCESS;
+        const int32_t *rows[10];
+        for (int v = 0; v < 10; ++v) rows[v] = host_el.data() + (size_t)v * ne;
+        return patch.build(10, kP2PatchE, ne, rows);
+    }
+};
+
 struct P2TetLaplacian final : OpBase {
     bool macro = false;
     DeviceArray<int32_t> elements;  // [10][ne]
     DeviceArray<float> fff;         // [6][ne]
-    PatchPlan patch;
+    P2PatchHolder ph;
+    PatchPlan &patch = ph.patch;
     int reference_diag = 1;  // tet10: reproduce the reference's diagonal (1/6 of the apply's, see p2_tet_local.cuh)
 
     template <typename T, bool MACRO>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         if (ne == 0) return B200FEM_SUCCESS;
+        if (scatter == B200FEM_SCATTER_PATCH && ph.ensure(ne)) return B200FEM_FAILURE;
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(1, sizeof(T)) + (size_t)20 * kP2PatchE + 2 * patch.max_u_pad() <= 200 * 1024)
             return launch_patch_apply_direct<T, 10, 1, kP2PatchE, 256, P2TetLaplacianLocal<T, MACRO>, true, true>(
                 patch, P2TetLaplacianLocal<T, MACRO>{fff.ptr, ne}, x, y, s);
@@ -231,12 +248,14 @@ struct P2TetLinearElasticity final : OpBase {
     DeviceArray<int32_t> elements;  // [10][ne]
     DeviceArray<float> adjugate;    // SoA [9][ne]
     DeviceArray<float> determinant;
-    PatchPlan patch;
+    P2PatchHolder ph;
+    PatchPlan &patch = ph.patch;
     double mu = 1, lambda = 1;
 
     template <typename T, bool MACRO>
     int apply_t(const T *x, T *y, cudaStream_t s) {
         if (ne == 0) return B200FEM_SUCCESS;
+        if (scatter == B200FEM_SCATTER_PATCH && ph.ensure(ne)) return B200FEM_FAILURE;
         if (scatter == B200FEM_SCATTER_PATCH && patch.ready && patch.smem_bytes_direct(3, sizeof(T)) + (size_t)20 * kP2PatchE + 2 * patch.max_u_pad() <= 200 * 1024)
             return launch_patch_apply_direct<T, 10, 3, kP2PatchE, 256, P2TetLELocal<T, MACRO>, true, false>(
                 patch, P2TetLELocal<T, MACRO>{adjugate.ptr, determinant.ptr, ne, (T)mu, (T)lambda}, x, y, s);
@@ -274,8 +293,8 @@ struct P2TetLinearElasticity final : OpBase {
     }
 };
 
-static bool upload_connectivity(ptrdiff_t ne, const int32_t *const *elements, DeviceArray<int32_t> &dst) {
-    std::vector<int32_t> el((size_t)10 * ne);
+static bool upload_connectivity(ptrdiff_t ne, const int32_t *const *elements, std::vector<int32_t> &el, DeviceArray<int32_t> &dst) {
+    el.resize((size_t)10 * ne);
     for (int v = 0; v < 10; ++v) std::copy(elements[v], elements[v] + ne, el.begin() + (size_t)v * ne);
     return dst.upload(el.data(), el.size()) != 0;
 }
@@ -293,11 +312,14 @@ OpBase *make_p2tet_laplacian(int element_type, ptrdiff_t ne, ptrdiff_t nn, const
     op->nn = nn;
     op->nxe = 10;
     op->geom_bytes_per_elem = 24;
-    op->scatter = B200FEM_SCATTER_PATCH;
+    // measured on B200 (profiles/r02p2_extras.jsonl, 2.96e6 elements, 4.0e6 nodes, SFC order, fp64): RED per corner 0.153 ms (tet10) /
+    // 0.157 ms (macro_tet4) against 0.170 / 0.215 ms for 256-element patches -- a 10-node patch has 650 unique nodes for 256
+    // elements (2.5 per element against 1.36 in the mesh), too little reuse to pay for the staging
+    op->scatter = B200FEM_SCATTER_ATOMIC;
     std::vector<float> f((size_t)6 * ne);
     for (ptrdiff_t e = 0; e < ne; ++e)
         for (int k = 0; k < 6; ++k) f[(size_t)k * ne + e] = fff[e * 6 + k];
-    if (op->patch.build(10, kP2PatchE, ne, elements) || upload_connectivity(ne, elements, op->elements) || op->fff.upload(f.data(), f.size())) {
+    if (upload_connectivity(ne, elements, op->ph.host_el, op->elements) || op->fff.upload(f.data(), f.size())) {
         delete op;
         return nullptr;
     }
@@ -321,11 +343,13 @@ OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t n
     op->geom_bytes_per_elem = 40;
     op->mu = mu;
     op->lambda = lambda;
-    op->scatter = B200FEM_SCATTER_PATCH;
+    // measured (same record): tet10 0.380 ms with patches against 0.510 ms with REDs (30 REDs per element); macro_tet4 0.550 ms with
+    // REDs against 0.673 ms with patches (its patch instance needs 244 registers)
+    op->scatter = op->macro ? B200FEM_SCATTER_ATOMIC : B200FEM_SCATTER_PATCH;
     std::vector<float> a((size_t)9 * ne);
     for (ptrdiff_t e = 0; e < ne; ++e)
         for (int k = 0; k < 9; ++k) a[(size_t)k * ne + e] = adjugate[e * 9 + k];
-    if (op->patch.build(10, kP2PatchE, ne, elements) || upload_connectivity(ne, elements, op->elements) ||
+    if (upload_connectivity(ne, elements, op->ph.host_el, op->elements) ||
         op->adjugate.upload(a.data(), a.size()) || op->determinant.upload(determinant, (size_t)ne)) {
         delete op;
         return nullptr;

@@ -13,12 +13,14 @@
 // produces exactly the arrays PackedLaplacian::apply reads (parity of the PACKER is unpinned; parity of the APPLY is
 // pinned by expanding the packed connectivity to global ids and running the reference's own *_laplacian_apply_opt).
 //
-// Kernels. One CTA per pack (persistent loop): the pack's node values are staged in shared memory -- ONE coalesced copy
-// of the owned range + a gather of the ghosts, instead of NXE gathers per element --, the element operator runs out of
-// shared memory and accumulates with shared-memory atomics, then the exclusively owned nodes are written with plain
-// read-modify-writes (no other pack touches them: the reference skips its `omp atomic` for the same nodes) and only
-// the shared / ghost nodes take a RED. Packs too large for shared memory (the format allows 65536 nodes) take the direct
-// kernel: one thread per element, local indices resolved to global ids on the fly, RED per corner.
+// Kernels. Staged form ("packed_kernel" = 0): one CTA per pack (persistent loop); the pack's node values are staged in
+// shared memory -- ONE coalesced copy of the owned range + a gather of the ghosts, instead of NXE gathers per element --,
+// the element operator runs out of shared memory and accumulates with shared-memory atomics, then the exclusively owned
+// nodes are written with plain read-modify-writes (no other pack touches them: the reference skips its `omp atomic` for
+// the same nodes) and only the shared / ghost nodes take a RED. Direct form (the default, and the only one for packs
+// beyond shared memory -- the format allows 65536 nodes): one thread per element, local indices resolved to global ids
+// on the fly, RED per corner.
+// Both read the 2-byte index stream; measured, the direct form is the faster one on B200 (see PackedLaplacian below).
 #include <stdlib.h>
 #include <string.h>
 
@@ -256,7 +258,10 @@ struct PackedLaplacian final : OpBase {
     DeviceArray<float> fff;
     DeviceArray<int64_t> owned_nodes_ptr, ghost_ptr;
     DeviceArray<int32_t> n_shared, ghost_idx;
-    int packed_kernel = 0;  // 0 = staged when a pack fits shared memory, 1 = always direct
+    // 1 = direct (default), 0 = staged when a pack fits shared memory. Measured on B200 (profiles/r02p2_extras.jsonl, 2.96e6
+    // elements, fp64): tet4 0.082 ms direct / 0.089 ms staged, tet10 0.153 / 0.202 ms -- the vectors of such meshes live in the
+    // 126 MB L2, so the staging buys no HBM traffic and its two barriers per pack cost
+    int packed_kernel = 1;
 
     PackedArrays arrays() const {
         return PackedArrays{ne, n_packs, epp, lidx.ptr, fff.ptr, owned_nodes_ptr.ptr, n_shared.ptr, ghost_ptr.ptr, ghost_idx.ptr};

@@ -312,8 +312,9 @@ def test_p2_tet_laplacian(oracles, real, family, scatter):
     assert _rel(fff, orc.tet4_fff_fill(el, pts)) < 1e-5
     fff = orc.tet4_fff_fill(el, pts)
     op = lib.laplacian(et, el10, fff, nn, _dt(real))
-    assert op.get_option("scatter") == lib.SCATTER_PATCH
+    assert op.get_option("scatter") == lib.SCATTER_ATOMIC  # the measured default of the 10-node Laplacians
     op.set_option("scatter", lib.SCATTER_PATCH if scatter == "patch" else lib.SCATTER_ATOMIC)
+    assert (op.get_option("patch_avg_unique_nodes") > 0) == False  # the patch plan is built on first use
     for seed in (0, 1):
         u = np.random.default_rng(seed).uniform(-1, 1, nn)
         ref = orc.p2tet_laplacian_apply_opt(family, el10, fff, u)
@@ -323,6 +324,7 @@ def test_p2_tet_laplacian(oracles, real, family, scatter):
         assert _rel(y.cpu().numpy(), ref) < TOL[real]
     op.apply(x, y)  # accumulate semantics
     assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    assert (op.get_option("patch_avg_unique_nodes") > 0) == (scatter == "patch")
     y.fill_(7.0)
     op.apply_overwrite(x, y)
     assert _rel(y.cpu().numpy(), ref) < TOL[real]
@@ -420,7 +422,9 @@ def test_packed_laplacian(oracles, real, family):
         fff = orc.tet4_fff_fill(g[:4], ppts)
         ref_apply = lambda u: orc.p2tet_laplacian_apply_opt(family, g, fff, u)
     op = lib.packed_laplacian(et, pm, fff, _dt(real))
-    assert op.get_option("packed_staged") == 1
+    assert op.get_option("packed_kernel") == 1 and op.get_option("packed_staged") == 0  # the direct kernel is the measured default
+    op.set_option("packed_kernel", 0)
+    assert op.get_option("packed_staged") == 1  # and these packs fit shared memory
     u = np.random.default_rng(21).uniform(-1, 1, nn)
     ref = ref_apply(u)
     x = torch.from_numpy(u).to(_dt(real)).cuda()
@@ -448,6 +452,7 @@ def test_packed_laplacian(oracles, real, family):
         bp = np.ascontiguousarray(ptb[:, big.new_to_old])
         fb = orc.hex8_fff_fill(gb, bp) if family == "hex8" else orc.tet4_fff_fill(gb, bp)
         opb = lib.packed_laplacian(et, big, fb, _dt(real))
+        opb.set_option("packed_kernel", 0)
         assert opb.get_option("packed_staged") == 0
         ub = np.random.default_rng(22).uniform(-1, 1, nb)
         refb = orc.hex8_laplacian_apply_opt(gb, fb, ub) if family == "hex8" else orc.tet4_laplacian_apply_opt(gb, fb, ub)

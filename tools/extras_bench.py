@@ -173,6 +173,42 @@ def run_extras(torch, which=("c1", "c2", "hex8lap", "c3f32", "c5le", "em", "tran
                               op.algorithmic_bytes, ms, {"fp_ops_TFLOPs": 2.0 * 576 * 512 * m["elements"].shape[1] / ms / 1e9}))
             del op, x, y
         del m
+    if "p2" in which:  # section 8 f3 / f4: 10-node tetrahedra and the packed (uint16) Laplacian, 80^3-corner cube in SFC order
+        el4, pts4 = mesh.sfc_reorder(*mesh.box_tet4(80, 80, 80))[:2]
+        el10, pts10 = mesh.tet4_to_tet10(el4, pts4)
+        nn4, nn10 = pts4.shape[1], pts10.shape[1]
+        fff = lib.fff_fill(lib.TET4, el4, pts4)
+        adj, det = lib.adjugate_and_det_fill(lib.TET4, el4, pts4)
+        for fam, et in (("tet10", lib.TET10), ("macro_tet4", lib.MACRO_TET4)):
+            for kind in ("laplacian", "linear elasticity"):
+                bs = 1 if kind == "laplacian" else 3
+                op = (lib.laplacian(et, el10, fff, nn10, torch.float64) if bs == 1 else
+                      lib.linear_elasticity(et, el10, adj, det, 1.0, 1.0, nn10, torch.float64))
+                x = torch.rand(nn10 * bs, dtype=torch.float64, device="cuda")
+                y = torch.zeros_like(x)
+                for scatter in ("patch", "atomic"):
+                    op.set_option("scatter", SC[scatter])
+                    ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                    out.append(_entry(f"{fam} {kind} f64 {el10.shape[1]} elements ({scatter}, SFC order, y = A x)", nn10 * bs,
+                                      op.algorithmic_bytes, ms, {"scatter": scatter, "patch_avg_unique_nodes": op.get_option("patch_avg_unique_nodes")}))
+                del op, x, y
+        for fam, et, el, nn, epp in (("tet4", lib.TET4, el4, nn4, 1024), ("tet10", lib.TET10, el10, nn10, 512)):
+            pm = lib.PackedMesh(el, nn, epp)
+            op = lib.packed_laplacian(et, pm, fff, torch.float64)  # FFF depends on the element only, not on the node numbering
+            ref = lib.laplacian(et, el, fff, nn, torch.float64)
+            x = torch.rand(nn, dtype=torch.float64, device="cuda")
+            y = torch.zeros_like(x)
+            # packed bytes: 2 B per corner + ghost ids, against 4 B per corner
+            alg = ref.algorithmic_bytes
+            for direct in (0, 1):
+                op.set_option("packed_kernel", direct)
+                ms = _time(lambda: op.apply_overwrite(x, y), torch)
+                out.append(_entry(f"packed {fam} laplacian f64 {el.shape[1]} elements ({'direct' if direct else 'staged'} kernel, {epp} per pack, y = A x)",
+                                  nn, alg, ms, {"streamed_bytes": op.streamed_bytes(True), "max_nodes_per_pack": pm.max_nodes_per_pack,
+                                                "ghost_entries": pm.n_ghost_entries, "alg_bytes_are": "the unpacked operator's (4 B indices)"}))
+            ms = _time(lambda: ref.apply_overwrite(x, y), torch)
+            out.append(_entry(f"unpacked {fam} laplacian f64 {el.shape[1]} elements (patch kernel, same mesh, y = A x)", nn, alg, ms))
+            del op, ref, x, y, pm
     if "blas" in which:
         from sfem_b200.lib import blas
 
