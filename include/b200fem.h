@@ -142,7 +142,9 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
  *                        as in the reference (its dispatcher has no tet4 case);
  *   diag               <- LumpedMass::hessian_diag -> assemble_lumped_mass (frontend/ops/sfem_LumpedMass.cpp, operators/mass.cpp:
  *                        65-114) -> hex8_assemble_lumped_mass (hex8_mass.cpp:62-103) / tet4_assemble_lumped_mass
- *                        (operators/tet4/tet4_mass.cpp:231-282): diag += row sums. Scalar fields (block_size 1). */
+ *                        (operators/tet4/tet4_mass.cpp:231-282) / tet10_assemble_lumped_mass (operators/tet10/tet10_mass.cpp:
+ *                        443-583; TET10, 10 rows of `elements`: -det/120 on corners, det/30 on edge nodes, as the reference):
+ *                        diag += row sums. Scalar fields (block_size 1). */
 /* Packed meshes: the Laplacian on smesh::PackedMesh<uint16_t> connectivity, the data PackedLaplacian::apply hands to
  * packed_laplacian_apply<uint16_t> (frontend/ops/sfem_PackedLaplacian.cpp:111-176, 551-612, 875-930; FunctionSpace::PackedIdxType,
  * frontend/sfem_FunctionSpace.hpp:19). Elements are cut into packs of n_elements_per_pack consecutive elements; pack p owns the

@@ -278,6 +278,17 @@ class Oracle:
            out.ctypes.data_as(C.POINTER(self.crt)))
         return out
 
+    def tet10_lumped_mass(self, elements, points, nnodes):
+        """tet10_assemble_lumped_mass (operators/tet10/tet10_mass.cpp:528-583; C++ linkage, void, prints its timing)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        fn = self._symbol("tet10_assemble_lumped_mass")
+        fn.restype = None
+        fn(C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float),
+           out.ctypes.data_as(C.POINTER(self.crt)))
+        return out
+
     def hex8_linear_elasticity_apply_isoparametric(self, elements, points, mu, lam, u, nnodes):
         el = np.ascontiguousarray(elements, dtype=np.int32)
         pts = np.ascontiguousarray(points, dtype=np.float32)

@@ -216,8 +216,8 @@ namespace sfem {
 
     b200fem_op_t B200Mass::create_plan(const OpDomain &domain) {
         DomainGeometry g = geometry_of(space, domain);
-        if (g.type != B200FEM_HEX8 && g.type != B200FEM_TET4 && g.type != B200FEM_SSHEX8) {
-            fprintf(stderr, "[b200fem] mass: hex8 (apply + lumped), tet4 and sshex8 (lumped) blocks only\n");
+        if (g.type != B200FEM_HEX8 && g.type != B200FEM_TET4 && g.type != B200FEM_TET10 && g.type != B200FEM_SSHEX8) {
+            fprintf(stderr, "[b200fem] mass: hex8 (apply + lumped), tet4, tet10 and sshex8 (lumped) blocks only\n");
             return nullptr;
         }
         b200fem_op_t plan = nullptr; /* apply_mass / assemble_lumped_mass read the mesh points, no cached geometry */

@@ -377,15 +377,18 @@ __global__ void __launch_bounds__(128)
 }
 
 // lumped mass of the P1 tet: det / 24 on each of its nodes (tet4_assemble_lumped_mass, operators/tet4/tet4_mass.cpp:66-92,
-// 231-282; the reference expands the determinant into its 24 monomials, here it is the triple product of the edge vectors)
-template <typename T>
+// 231-282; the reference expands the determinant into its 24 monomials, here it is the triple product of the edge vectors).
+// NXE = 10: the row sums of the P2 mass matrix on the affine tet of the 4 corners, -det / 120 on a corner and det / 30 on an
+// edge node (tet10_assemble_lumped_mass -> tet10_hrz_lumped_mass_kernel, operators/tet10/tet10_mass.cpp:443-583: the active
+// code of that routine is the plain row sum, negative on the corners; the HRZ-scaled variant above it is commented out)
+template <typename T, int NXE>
 __global__ void __launch_bounds__(256)
-    tet4_lumped_mass_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
-                            T *__restrict__ y) {
+    tet_lumped_mass_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                           T *__restrict__ y) {
     for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
-        int32_t ev[4];
+        int32_t ev[NXE];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        for (int v = 0; v < NXE; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
         T p[3][4];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -395,9 +398,15 @@ __global__ void __launch_bounds__(256)
         const T bx = p[0][2] - p[0][0], by = p[1][2] - p[1][0], bz = p[2][2] - p[2][0];
         const T cx = p[0][3] - p[0][0], cy = p[1][3] - p[1][0], cz = p[2][3] - p[2][0];
         const T det = ax * (by * cz - bz * cy) - ay * (bx * cz - bz * cx) + az * (bx * cy - by * cx);
-        const T m = det * T(1.0 / 24.0);
+        if (NXE == 4) {
+            const T m = det * T(1.0 / 24.0);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) red_add(&y[ev[v]], m);
+            for (int v = 0; v < 4; ++v) red_add(&y[ev[v]], m);
+        } else {
+            const T mc = -det * T(1.0 / 120.0), me = det * T(1.0 / 30.0);
+#pragma unroll
+            for (int v = 0; v < NXE; ++v) red_add(&y[ev[v]], v < 4 ? mc : me);
+        }
     }
 }
 
@@ -412,7 +421,7 @@ struct PointsOp final : OpBase {
     int apply_t(const T *x, T *y, cudaStream_t s) {
         if (ne == 0) return B200FEM_SUCCESS;
         if (mass) {
-            if (nxe != 8) B2_FAIL("mass apply: hex8 only (apply_mass, operators/mass.cpp:158-207, has no tet4 case)");
+            if (nxe != 8) B2_FAIL("mass apply: hex8 only (apply_mass, operators/mass.cpp:158-207, has no tet4 / tet10 case)");
             const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
             hex8_mass_kernel<T, false><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, x, y);
         } else if (elasticity && nxe == 4) {
@@ -444,10 +453,14 @@ struct PointsOp final : OpBase {
                     hex8_mass_kernel<float, true><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, nullptr, (float *)d);
             } else {
                 const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
-                if (f64)
-                    tet4_lumped_mass_kernel<double><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (double *)d);
+                if (nxe == 10 && f64)
+                    tet_lumped_mass_kernel<double, 10><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (double *)d);
+                else if (nxe == 10)
+                    tet_lumped_mass_kernel<float, 10><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float *)d);
+                else if (f64)
+                    tet_lumped_mass_kernel<double, 4><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (double *)d);
                 else
-                    tet4_lumped_mass_kernel<float><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float *)d);
+                    tet_lumped_mass_kernel<float, 4><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float *)d);
             }
             B2_CHECK_LAUNCH();
             return B200FEM_SUCCESS;
@@ -498,7 +511,7 @@ OpBase *make_tet4_laplacian_from_points(ptrdiff_t ne, ptrdiff_t nn, const int32_
 
 OpBase *make_mass_from_points(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *const *points,
                               int real_type) {
-    OpBase *op = make_points_op(element_type == B200FEM_HEX8 ? 8 : 4, ne, nn, elements, points, real_type, "mass");
+    OpBase *op = make_points_op(element_type == B200FEM_HEX8 ? 8 : element_type == B200FEM_TET10 ? 10 : 4, ne, nn, elements, points, real_type, "mass");
     if (op) {
         op->elem_type = element_type;
         static_cast<PointsOp *>(op)->mass = true;

@@ -316,7 +316,8 @@ int b200fem_mass_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdif
                         const float *const *points, int real_type) {
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
     if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
-    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4) B2_FAIL("mass: hex8 (apply + lumped) and tet4 (lumped) only");
+    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4 && element_type != B200FEM_TET10)
+        B2_FAIL("mass: hex8 (apply + lumped), tet4 and tet10 (lumped) only");
     OpBase *impl = make_mass_from_points(element_type, ne, nn, elements, points, real_type);
     if (!impl) return B200FEM_FAILURE;
     *op = new b200fem_op_s{impl};

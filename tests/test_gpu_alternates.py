@@ -526,3 +526,26 @@ def test_sshex8_lumped_mass(oracles, real, level):
     assert float(d.min()) > 0
     with pytest.raises(RuntimeError):
         op.apply(d, d)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_tet10_lumped_mass(oracles, real):
+    """b200fem_mass_create(TET10).diag against tet10_assemble_lumped_mass (operators/tet10/tet10_mass.cpp:443-583): the row sums
+    of the P2 mass matrix, negative on the corners. Bar 1e-10 in fp64 as for tet4 (the reference expands its determinant)."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    el, pts = mesh.box_tet4(6, 5, 7)
+    el10, pts10 = mesh.tet4_to_tet10(el, mesh.warp_points(pts))
+    nn = pts10.shape[1]
+    op = lib.mass(lib.TET10, el10, pts10, nn, _dt(real))
+    d = torch.zeros(nn, dtype=_dt(real), device="cuda")
+    op.diag(d)
+    ref = orc.tet10_lumped_mass(el10, pts10, nn)
+    assert _rel(d.cpu().numpy(), ref) < (1e-10 if real == "f64" else 1e-4)
+    assert float(d[: pts.shape[1]].max()) < 0 < float(d[pts.shape[1]:].min())
+    with pytest.raises(RuntimeError):
+        op.apply(d, d)
