@@ -444,6 +444,54 @@ def test_golden_vectors_on_gpu(real):
 
 
 @pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet10", "macro_tet4"])
+def test_golden_p2_tet_on_gpu(real, family):
+    """10-node tetrahedra against the committed reference outputs (tests/golden/p2_tet.npz, `make_golden.py p2_tet`): Laplacian and
+    linear elasticity, apply + diag, both scatters, the packed Laplacian, the tet10 lumped mass -- no oracle library needed."""
+    import os
+
+    torch = _torch()
+    from sfem_b200 import lib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "p2_tet.npz"))
+    dt = _dt(real)
+    el, nn = g["elements"], g["points"].shape[1]
+    et = lib.TET10 if family == "tet10" else lib.MACRO_TET4
+    le_tol = (1e-11 if family == "tet10" else 1e-12) if real == "f64" else 1e-5  # tet10: see test_p2_tet_linear_elasticity
+
+    def run(op, u):
+        x = torch.from_numpy(np.asarray(u)).to(dt).cuda()
+        y = torch.zeros_like(x)
+        op.apply(x, y)
+        return y.cpu().numpy()
+
+    lap = lib.laplacian(et, el, g["fff"], nn, dt)
+    le = lib.linear_elasticity(et, el, g["adjugate"], g["determinant"], float(g["mu"]), float(g["lam"]), nn, dt)
+    for sc in (lib.SCATTER_ATOMIC, lib.SCATTER_PATCH):
+        lap.set_option("scatter", sc)
+        le.set_option("scatter", sc)
+        assert _rel(run(lap, g["u"]), g[f"{family}_lap_{real}"]) < TOL[real], sc
+        assert _rel(run(le, g["u3"]), g[f"{family}_le_{real}"]) < le_tol, sc
+    if real == "f64":
+        d = torch.zeros(nn, dtype=dt, device="cuda")
+        lap.diag(d)
+        assert _rel(d.cpu().numpy(), g[f"{family}_lap_diag_f64"]) < 1e-12
+        d3 = torch.zeros(nn * 3, dtype=dt, device="cuda")
+        le.diag(d3)
+        assert _rel(d3.cpu().numpy(), g[f"{family}_le_diag_f64"]) < le_tol
+        if family == "tet10":
+            m = torch.zeros(nn, dtype=dt, device="cuda")
+            lib.mass(lib.TET10, el, g["points"], nn, dt).diag(m)
+            assert _rel(m.cpu().numpy(), g["lumped_tet10_f64"]) < 1e-10
+    # packed: the same operator in the packed numbering, y_packed[i] = y[new_to_old[i]]
+    pm = lib.PackedMesh(el, nn, 64)
+    pop = lib.packed_laplacian(et, pm, g["fff"], dt)
+    for kernel in (1, 0):
+        pop.set_option("packed_kernel", kernel)
+        assert _rel(run(pop, g["u"][pm.new_to_old]), g[f"{family}_lap_{real}"][pm.new_to_old]) < TOL[real], kernel
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
 def test_hex8_diagonals(oracles, real):
     """hex8 Laplacian diag, hex8 linear-elasticity diag and symmetric block diagonal against the reference's
     hex8_laplacian_diag / affine_hex8_linear_elasticity_diag / _block_diag_sym (operators/hex8/hex8_laplacian.hpp:36,

@@ -140,3 +140,77 @@ def test_elasticity_core_matches_reference(core_lib, oracles, real, family):
     fn(macro, 1, *args, None, d.ctypes.data_as(C.c_void_p))
     ref = orc.p2tet_linear_elasticity_diag_opt(family, el10, adj, det, mu, lam, nn)
     assert np.linalg.norm(d.astype(np.float64) - ref) / np.linalg.norm(ref) < tol
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", FAMILIES)
+def test_core_and_reference_reproduce_the_golden_vectors(core_lib, oracles, real, family):
+    """tests/golden/p2_tet.npz (written by `tests/golden/make_golden.py p2_tet` from oracle/_ref): the host run of the kernels'
+    header reproduces it, and so does the reference build where it is present."""
+    from oracle.ref import _soa_ptrs
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "p2_tet.npz"))
+    el = np.ascontiguousarray(g["elements"])
+    nn = g["points"].shape[1]
+    rt = np.float64 if real == "f64" else np.float32
+    macro = int(family == "macro_tet4")
+    tol = 1e-12 if real == "f64" else 1e-5
+    le_tol = (1e-11 if family == "tet10" else 1e-12) if real == "f64" else 1e-5
+    rel = lambda a, b: np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b)
+    fff, adj, det = (np.ascontiguousarray(g[k]) for k in ("fff", "adjugate", "determinant"))
+    pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    u = g["u"].astype(rt)
+    out = np.zeros(nn, dtype=rt)
+    getattr(core_lib, "p2_tet_laplacian_" + real)(macro, 0, 1, C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf(fff),
+                                                  u.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rel(out, g[f"{family}_lap_{real}"]) < tol
+    u3 = g["u3"].astype(rt)
+    out3 = np.zeros(nn * 3, dtype=rt)
+    getattr(core_lib, "p2_tet_elasticity_" + real)(macro, 0, C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), pf(adj), pf(det),
+                                                   C.c_double(float(g["mu"])), C.c_double(float(g["lam"])),
+                                                   u3.ctypes.data_as(C.c_void_p), out3.ctypes.data_as(C.c_void_p))
+    assert rel(out3, g[f"{family}_le_{real}"]) < le_tol
+    orc = oracles.get(("reference", real))
+    if orc is not None:
+        assert rel(orc.p2tet_laplacian_apply_opt(family, el, fff, g["u"]), g[f"{family}_lap_{real}"]) < tol
+        assert rel(orc.p2tet_linear_elasticity_apply_opt(family, el, adj, det, float(g["mu"]), float(g["lam"]), g["u3"]),
+                   g[f"{family}_le_{real}"]) < tol
+
+
+def test_tet10_is_exact_on_harmonic_quadratics(core_lib):
+    """Known answer that does not go through the reference: a quadratic field lies in the P2 space (straight-edged elements,
+    mid-edge nodes), so for a HARMONIC quadratic u the Galerkin rows of the interior nodes vanish, (K u)_i = -int phi_i lap(u) = 0,
+    whatever the mesh; the P1-iso-P2 operator (macro_tet4) has that property for linear fields only."""
+    from oracle.ref import _soa_ptrs
+    from sfem_b200 import mesh
+
+    el4, pts4 = mesh.box_tet4(5, 6, 4)
+    el, pts = mesh.tet4_to_tet10(el4, pts4)
+    nn = pts.shape[1]
+    p = pts.astype(np.float64)
+    # FFF of the corner tets in fp64, stored fp32 like the plan's cache
+    J = np.moveaxis(np.stack([p[:, el[c + 1]] - p[:, el[0]] for c in range(3)], axis=1), 2, 0)
+    det = np.linalg.det(J)
+    Ji = np.linalg.inv(J)
+    F = np.einsum("eij,ekj->eik", Ji, Ji) * (det / 6.0)[:, None, None]
+    fff = np.ascontiguousarray(np.stack([F[:, 0, 0], F[:, 0, 1], F[:, 0, 2], F[:, 1, 1], F[:, 1, 2], F[:, 2, 2]], axis=1).reshape(-1),
+                               dtype=np.float32)
+    interior = np.all((p > 1e-6) & (p < 1 - 1e-6), axis=0)
+    assert interior.sum() > 50
+    elc = np.ascontiguousarray(el)
+
+    def apply(macro, u):
+        out = np.zeros(nn)
+        core_lib.p2_tet_laplacian_f64(macro, 0, 1, C.c_ssize_t(elc.shape[1]), _soa_ptrs(elc, C.c_int32),
+                                      fff.ctypes.data_as(C.POINTER(C.c_float)), u.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    x, y, z = p
+    harmonic = x * x - 0.5 * y * y - 0.5 * z * z + 0.3 * x * y - 0.2 * y * z + x - 2 * z + 1
+    linear = 0.7 * x - 1.3 * y + 0.4 * z + 2
+    scale = np.abs(apply(0, x * x)).max()
+    # fp32 geometry: the rows vanish to the rounding of the stored FFF (1e-7 relative), far below the O(1) rows of x^2
+    assert np.abs(apply(0, harmonic)[interior]).max() < 5e-6 * scale
+    assert np.abs(apply(0, x * x)[interior]).max() > 0.01 * scale  # lap(x^2) = 2: not harmonic, rows do not vanish
+    assert np.abs(apply(1, linear)[interior]).max() < 5e-6 * scale
+    assert np.abs(apply(1, harmonic)[interior]).max() > 1e-3 * scale  # P1-iso-P2 is not exact on quadratics
