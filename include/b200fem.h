@@ -130,7 +130,12 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
  *   linear elasticity, TET4 <- tet4_linear_elasticity_apply / _diag (operators/tet4/tet4_linear_elasticity.cpp:86-230): the
  *                        reference's only tet4 elasticity path (its cached-adjugate twin is declared but not defined);
  *   linear elasticity, HEX8 <- hex8_linear_elasticity_apply (operators/hex8/hex8_linear_elasticity.cpp:86-324): the
- *                        isoparametric variant of SFEM_HEX8_ASSUME_AFFINE=0, Jacobian at each of the 2x2x2 Gauss points. */
+ *                        isoparametric variant of SFEM_HEX8_ASSUME_AFFINE=0, Jacobian at each of the 2x2x2 Gauss points;
+ *   laplacian / linear elasticity, TET10 and MACRO_TET4 <- tet10_laplacian_apply / _diag (operators/tet10/tet10_laplacian.cpp:
+ *                        65-230), macro_tet4_laplacian_apply / _diag (operators/macro_tet4/macro_tet4_laplacian.cpp:127-260),
+ *                        tet10_linear_elasticity_apply / _diag (operators/tet10/tet10_linear_elasticity.cpp:21-207),
+ *                        macro_tet4_linear_elasticity_apply / _diag (operators/macro_tet4/macro_tet4_linear_elasticity.cpp:
+ *                        137-204, 330-395): geometry of the 4 corners recomputed per element in the vector precision. */
 int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements, ptrdiff_t nnodes,
                                          const int32_t *const *elements, const float *const *points, int real_type);
 int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_type, int level, ptrdiff_t nelements,

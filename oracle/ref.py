@@ -409,6 +409,39 @@ class Oracle:
                    self.crt(mu), self.crt(lam), C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
+    def p2tet_laplacian_points(self, family, elements, points, u, nnodes, diag=False):
+        """tet10_laplacian_apply / _diag (operators/tet10/tet10_laplacian.cpp:65-230), macro_tet4_laplacian_apply / _diag
+        (operators/macro_tet4/macro_tet4_laplacian.cpp:127-260): FFF from the points in scalar_t"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes, dtype=self.rt)
+        po = out.ctypes.data_as(C.POINTER(self.crt))
+        if diag:
+            self._call(f"{family}_laplacian_diag", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                       _soa_ptrs(pts, C.c_float), po)
+        else:
+            u, pu = self._r(u)
+            self._call(f"{family}_laplacian_apply", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                       _soa_ptrs(pts, C.c_float), pu, po)
+        return out
+
+    def p2tet_linear_elasticity_points(self, family, elements, points, mu, lam, u, nnodes, diag=False):
+        """tet10_linear_elasticity_apply / _diag (operators/tet10/tet10_linear_elasticity.cpp:21-207), macro_tet4_linear_elasticity_apply
+        / _diag (operators/macro_tet4/macro_tet4_linear_elasticity.cpp:137-204, 330-395)"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 3, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+        head = (C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32), _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam))
+        if diag:
+            self._call(f"{family}_linear_elasticity_diag", *head, C.c_ssize_t(3), op[0], op[1], op[2])
+        else:
+            u, _ = self._r(u)
+            up = [C.cast(u.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(3)]
+            self._call(f"{family}_linear_elasticity_apply", *head, C.c_ssize_t(3), up[0], up[1], up[2], C.c_ssize_t(3), op[0], op[1], op[2])
+        return out
+
     def p2tet_linear_elasticity_diag_opt(self, family, elements, adjugate_aos, det, mu, lam, nnodes):
         """tet10_linear_elasticity_diag_opt (tet10_linear_elasticity.cpp:285-355) / macro_tet4_linear_elasticity_diag_opt
         (macro_tet4_linear_elasticity.cpp:397-437)"""

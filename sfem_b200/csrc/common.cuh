@@ -155,6 +155,8 @@ OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
 OpBase *make_p2tet_laplacian(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type);
 OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
                                      const float *determinant, double mu, double lambda, int real_type);
+OpBase *make_p2tet_from_points(int element_type, bool elasticity, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                               const float *const *points, double mu, double lambda, int real_type);
 OpBase *make_packed_laplacian(int element_type, ptrdiff_t n_packs, ptrdiff_t epp, ptrdiff_t ne, ptrdiff_t nn, ptrdiff_t max_nodes,
                               const uint16_t *const *elements, const float *fff, const ptrdiff_t *owned_nodes_ptr, const ptrdiff_t *n_shared,
                               const ptrdiff_t *ghost_ptr, const int32_t *ghost_idx, int real_type);

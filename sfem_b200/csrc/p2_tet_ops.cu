@@ -174,6 +174,95 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// From the points (the reference's non-cached paths: tet10_laplacian_apply / _diag, operators/tet10/tet10_laplacian.cpp:65-230;
+// macro_tet4_laplacian_apply / _diag, operators/macro_tet4/macro_tet4_laplacian.cpp:127-260; tet10_linear_elasticity_apply / _diag,
+// operators/tet10/tet10_linear_elasticity.cpp:21-207; macro_tet4_linear_elasticity_apply / _diag,
+// operators/macro_tet4/macro_tet4_linear_elasticity.cpp:137-204, 330-395): the adjugate / determinant / FFF of the corner tet
+// recomputed per element in the vector precision (tet4_adjugate_and_det_s / tet4_fff_s), then the same local operators.
+template <typename T, bool MACRO, bool LE, bool DIAG>
+__global__ void __launch_bounds__(128)
+    p2tet_points_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                        const T mu, const T lambda, const bool reference_diag, const T *__restrict__ u, T *__restrict__ y) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[10];
+#pragma unroll
+        for (int v = 0; v < 10; ++v) ev[v] = ldg_stream(&elements[v * ne + e]);
+        // J[r][c] = x_r(corner c + 1) - x_r(corner 0); A = adjugate = det J^-1; FFF = A A^T / (6 det)
+        T J[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const T p0 = (T)points[(size_t)r * nn + ev[0]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[r * 3 + c] = (T)points[(size_t)r * nn + ev[c + 1]] - p0;
+        }
+        T A[9];
+        A[0] = J[4] * J[8] - J[5] * J[7];
+        A[1] = J[2] * J[7] - J[1] * J[8];
+        A[2] = J[1] * J[5] - J[2] * J[4];
+        A[3] = J[5] * J[6] - J[3] * J[8];
+        A[4] = J[0] * J[8] - J[2] * J[6];
+        A[5] = J[2] * J[3] - J[0] * J[5];
+        A[6] = J[3] * J[7] - J[4] * J[6];
+        A[7] = J[1] * J[6] - J[0] * J[7];
+        A[8] = J[0] * J[4] - J[1] * J[3];
+        const T det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+        if (LE) {
+            T ul[10][3], ol[10][3];
+            if (DIAG) {
+                for (int v = 0; v < 10; ++v)
+                    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                        for (int j = 0; j < 10; ++j)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) ul[j][c] = (j == v && c == b) ? T(1) : T(0);
+                        p2tet_le_local<T, MACRO>(A, det, mu, lambda, ul, ol);
+                        T r = T(0);
+#pragma unroll
+                        for (int j = 0; j < 10; ++j)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                if (j == v && c == b) r = ol[j][c];
+                        red_add(&y[(ptrdiff_t)elements[v * ne + e] * 3 + b], r);
+                    }
+            } else {
+#pragma unroll
+                for (int v = 0; v < 10; ++v)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) ul[v][b] = u[(ptrdiff_t)ev[v] * 3 + b];
+                p2tet_le_local<T, MACRO>(A, det, mu, lambda, ul, ol);
+#pragma unroll
+                for (int v = 0; v < 10; ++v)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) red_add(&y[(ptrdiff_t)ev[v] * 3 + b], ol[v][b]);
+            }
+        } else {
+            const T sc = T(1) / (T(6) * det);
+            T f[6];
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = i; j < 3; ++j) f[k++] = (A[i * 3] * A[j * 3] + A[i * 3 + 1] * A[j * 3 + 1] + A[i * 3 + 2] * A[j * 3 + 2]) * sc;
+            T ul[10], ol[10];
+            if (DIAG) {
+                if (MACRO)
+                    macro_tet4_laplacian_local_diag(f, ol);
+                else
+                    tet10_laplacian_local_diag(f, reference_diag, ol);
+            } else {
+#pragma unroll
+                for (int v = 0; v < 10; ++v) ul[v] = u[ev[v]];
+                if (MACRO)
+                    macro_tet4_laplacian_local(f, ul, ol);
+                else
+                    tet10_laplacian_local(f, ul, ol);
+            }
+#pragma unroll
+            for (int v = 0; v < 10; ++v) red_add(&y[ev[v]], ol[v]);
+        }
+    }
+}
+
 static constexpr int kP2PatchE = 256;
 
 // The patch plan is built on first use (PATCH is not the default of every family, see make_p2tet_*): the plan keeps the host
@@ -293,6 +382,47 @@ struct P2TetLinearElasticity final : OpBase {
     }
 };
 
+struct P2TetPointsOp final : OpBase {
+    bool macro = false, elasticity = false;
+    DeviceArray<int32_t> elements;  // [10][ne]
+    DeviceArray<float> points;      // [3][nn]
+    double mu = 1, lambda = 1;
+    int reference_diag = 1;
+
+    template <typename T, bool DIAG>
+    int run(const T *x, T *y, cudaStream_t s) {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
+        const bool rd = reference_diag != 0;
+#define B2_P2_POINTS(MACRO, LE) \
+    p2tet_points_kernel<T, MACRO, LE, DIAG><<<grid, 128, 0, s>>>(ne, nn, elements.ptr, points.ptr, (T)mu, (T)lambda, rd, x, y)
+        if (elasticity) {
+            if (macro) B2_P2_POINTS(true, true); else B2_P2_POINTS(false, true);
+        } else {
+            if (macro) B2_P2_POINTS(true, false); else B2_P2_POINTS(false, false);
+        }
+#undef B2_P2_POINTS
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int apply(const void *x, void *y, bool overwrite, cudaStream_t s) override {
+        if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * block_size * real_type, s));
+        return real_type == B200FEM_F64 ? run<double, false>((const double *)x, (double *)y, s) : run<float, false>((const float *)x, (float *)y, s);
+    }
+    int diag(void *d, cudaStream_t s) override {
+        return real_type == B200FEM_F64 ? run<double, true>(nullptr, (double *)d, s) : run<float, true>(nullptr, (float *)d, s);
+    }
+    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "reference_diag")) { reference_diag = value; return B200FEM_SUCCESS; }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "reference_diag")) { *value = reference_diag; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
+    }
+};
+
 static bool upload_connectivity(ptrdiff_t ne, const int32_t *const *elements, std::vector<int32_t> &el, DeviceArray<int32_t> &dst) {
     el.resize((size_t)10 * ne);
     for (int v = 0; v < 10; ++v) std::copy(elements[v], elements[v] + ne, el.begin() + (size_t)v * ne);
@@ -351,6 +481,36 @@ OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t n
         for (int k = 0; k < 9; ++k) a[(size_t)k * ne + e] = adjugate[e * 9 + k];
     if (upload_connectivity(ne, elements, op->ph.host_el, op->elements) ||
         op->adjugate.upload(a.data(), a.size()) || op->determinant.upload(determinant, (size_t)ne)) {
+        delete op;
+        return nullptr;
+    }
+    return op;
+}
+
+OpBase *make_p2tet_from_points(int element_type, bool elasticity, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
+                               const float *const *points, double mu, double lambda, int real_type) {
+    if (!check_indices(10, ne, nn, elements)) {
+        set_error("tet10 / macro_tet4 (from points): node index out of range");
+        return nullptr;
+    }
+    auto *op = new P2TetPointsOp();
+    op->macro = element_type == B200FEM_MACRO_TET4;
+    op->elasticity = elasticity;
+    op->elem_type = element_type;
+    op->real_type = real_type;
+    op->block_size = elasticity ? 3 : 1;
+    op->ne = ne;
+    op->nn = nn;
+    op->nxe = 10;
+    op->geom_bytes_per_elem = 48;  // the 4 corner coordinates an element reads
+    op->mu = mu;
+    op->lambda = lambda;
+    op->scatter = B200FEM_SCATTER_ATOMIC;
+    std::vector<int32_t> el;
+    bool bad = upload_connectivity(ne, elements, el, op->elements) || op->points.alloc((size_t)3 * nn) != 0;
+    for (int d = 0; d < 3 && !bad; ++d)
+        bad = cudaMemcpy(op->points.ptr + (size_t)d * nn, points[d], (size_t)nn * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess;
+    if (bad) {
         delete op;
         return nullptr;
     }

@@ -250,7 +250,9 @@ int b200fem_laplacian_create_from_points(b200fem_op_t *op, int element_type, int
     switch (element_type) {
         case B200FEM_TET4: impl = make_tet4_laplacian_from_points(ne, nn, elements, points, real_type); break;
         case B200FEM_SSHEX8: impl = make_sshex8_nonaffine_laplacian(level, ne, nn, elements, points, real_type); break;
-        default: B2_FAIL("laplacian from points: tet4 (tet4_laplacian_apply) and sshex8 (sshex8_laplacian_apply) only");
+        case B200FEM_TET10:
+        case B200FEM_MACRO_TET4: impl = make_p2tet_from_points(element_type, false, ne, nn, elements, points, 0, 0, real_type); break;
+        default: B2_FAIL("laplacian from points: tet4, tet10, macro_tet4 (*_laplacian_apply) and sshex8 (sshex8_laplacian_apply) only");
     }
     if (!impl) return B200FEM_FAILURE;
     *op = new b200fem_op_s{impl};
@@ -330,10 +332,12 @@ int b200fem_linear_elasticity_create_from_points(b200fem_op_t *op, int element_t
     (void)level;
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;
     if (!points || !points[0] || !points[1] || !points[2]) B2_FAIL("points is NULL");
-    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4)
-        B2_FAIL("linear elasticity from points: tet4 (tet4_linear_elasticity_apply) and hex8 (hex8_linear_elasticity_apply, isoparametric) only");
-    OpBase *impl = element_type == B200FEM_TET4 ? make_tet4_le_from_points(ne, nn, elements, points, mu, lambda, real_type)
-                                                : make_hex8_le_isoparametric(ne, nn, elements, points, mu, lambda, real_type);
+    const bool p2 = element_type == B200FEM_TET10 || element_type == B200FEM_MACRO_TET4;
+    if (element_type != B200FEM_HEX8 && element_type != B200FEM_TET4 && !p2)
+        B2_FAIL("linear elasticity from points: tet4 / tet10 / macro_tet4 (*_linear_elasticity_apply) and hex8 (hex8_linear_elasticity_apply, isoparametric) only");
+    OpBase *impl = p2 ? make_p2tet_from_points(element_type, true, ne, nn, elements, points, mu, lambda, real_type)
+                   : element_type == B200FEM_TET4 ? make_tet4_le_from_points(ne, nn, elements, points, mu, lambda, real_type)
+                                                  : make_hex8_le_isoparametric(ne, nn, elements, points, mu, lambda, real_type);
     if (!impl) return B200FEM_FAILURE;
     *op = new b200fem_op_s{impl};
     return B200FEM_SUCCESS;

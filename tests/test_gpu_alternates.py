@@ -549,3 +549,45 @@ def test_tet10_lumped_mass(oracles, real):
     assert float(d[: pts.shape[1]].max()) < 0 < float(d[pts.shape[1]:].min())
     with pytest.raises(RuntimeError):
         op.apply(d, d)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet10", "macro_tet4"])
+def test_p2_tet_from_points(oracles, real, family):
+    """The 10-node tetrahedra from the points (b200fem_laplacian_create_from_points / b200fem_linear_elasticity_create_from_points
+    with TET10 / MACRO_TET4) against tet10_* / macro_tet4_* _apply and _diag of the reference (geometry recomputed per element in
+    the vector precision). tet10 elasticity fp64: 1e-11 (the reference's truncated quadrature points)."""
+    torch = _torch()
+    from sfem_b200 import lib, mesh
+
+    orc = oracles.get(("reference", real))
+    if orc is None:
+        pytest.skip("oracle/_ref not built")
+    el4, pts4 = mesh.box_tet4(6, 7, 5)
+    el, pts = mesh.tet4_to_tet10(el4, mesh.warp_points(pts4))
+    nn = pts.shape[1]
+    et = lib.TET10 if family == "tet10" else lib.MACRO_TET4
+    dt = _dt(real)
+    op = lib.laplacian_from_points(et, el, pts, nn, dt)
+    u = np.random.default_rng(31).uniform(-1, 1, nn)
+    x = torch.from_numpy(u).to(dt).cuda()
+    y = torch.zeros_like(x)
+    op.apply(x, y)
+    assert _rel(y.cpu().numpy(), orc.p2tet_laplacian_points(family, el, pts, u, nn)) < TOL[real]
+    d = torch.zeros_like(x)
+    op.diag(d)
+    assert _rel(d.cpu().numpy(), orc.p2tet_laplacian_points(family, el, pts, None, nn, diag=True)) < TOL[real]
+    mu, lam = 1.3, 0.7
+    tol = (1e-11 if family == "tet10" else 1e-12) if real == "f64" else 1e-5
+    le = lib.linear_elasticity_from_points(et, el, pts, mu, lam, nn, dt)
+    u3 = np.random.default_rng(32).uniform(-1, 1, nn * 3)
+    x3 = torch.from_numpy(u3).to(dt).cuda()
+    y3 = torch.zeros_like(x3)
+    le.apply(x3, y3)
+    assert _rel(y3.cpu().numpy(), orc.p2tet_linear_elasticity_points(family, el, pts, mu, lam, u3, nn)) < tol
+    y3.fill_(2.0)
+    le.apply_overwrite(x3, y3)
+    assert _rel(y3.cpu().numpy(), orc.p2tet_linear_elasticity_points(family, el, pts, mu, lam, u3, nn)) < tol
+    d3 = torch.zeros_like(x3)
+    le.diag(d3)
+    assert _rel(d3.cpu().numpy(), orc.p2tet_linear_elasticity_points(family, el, pts, mu, lam, None, nn, diag=True)) < tol
