@@ -173,6 +173,15 @@ int b200fem_packed_mesh_sizes(b200fem_packed_mesh_t pm, ptrdiff_t *n_packs, ptrd
 int b200fem_packed_mesh_arrays(b200fem_packed_mesh_t pm, const uint16_t *const **elements, const ptrdiff_t **owned_nodes_ptr,
                                const ptrdiff_t **n_shared, const ptrdiff_t **ghost_ptr, const int32_t **ghost_idx,
                                const int32_t **new_to_old);
+/* The reference's atomics-free two-pass apply (SFEM_PACKED_TWO_PASS -> PackedLaplacianApply::apply_two_pass,
+ * frontend/ops/sfem_PackedLaplacian.cpp:178-262): pass 1 writes the owned nodes of every pack plainly and parks the ghost results
+ * in a buffer, pass 2 adds, per shared node, its buffer entries in a fixed order -- no global atomics. Hand over
+ * packed->ghost_reduce_ptr / _idx / _dest (`b200fem_packed_mesh_ghost_reduce` for our packer) with _set_two_pass, then select it
+ * with option "packed_two_pass" = 1. Packs must fit shared memory (2 x max_nodes_per_pack scalars <= 200 KB). */
+int b200fem_packed_mesh_ghost_reduce(b200fem_packed_mesh_t pm, ptrdiff_t *n_rows, const ptrdiff_t **ghost_reduce_ptr,
+                                     const ptrdiff_t **ghost_reduce_idx, const int32_t **ghost_reduce_dest);
+int b200fem_packed_laplacian_set_two_pass(b200fem_op_t op, ptrdiff_t n_rows, const ptrdiff_t *ghost_reduce_ptr,
+                                          const ptrdiff_t *ghost_reduce_idx, const int32_t *ghost_reduce_dest);
 int b200fem_packed_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t n_packs, ptrdiff_t n_elements_per_pack,
                                     ptrdiff_t nelements, ptrdiff_t nnodes, ptrdiff_t max_nodes_per_pack,
                                     const uint16_t *const *elements, const float *fff, const ptrdiff_t *owned_nodes_ptr,

@@ -155,6 +155,7 @@ OpBase *make_tet4_linear_elasticity(ptrdiff_t ne, ptrdiff_t nn, const int32_t *c
 OpBase *make_p2tet_laplacian(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *fff, int real_type);
 OpBase *make_p2tet_linear_elasticity(int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, const float *adjugate,
                                      const float *determinant, double mu, double lambda, int real_type);
+int packed_laplacian_set_two_pass(OpBase *op, ptrdiff_t n_rows, const ptrdiff_t *ptr, const ptrdiff_t *idx, const int32_t *dest);
 OpBase *make_p2tet_from_points(int element_type, bool elasticity, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                                const float *const *points, double mu, double lambda, int real_type);
 OpBase *make_packed_laplacian(int element_type, ptrdiff_t n_packs, ptrdiff_t epp, ptrdiff_t ne, ptrdiff_t nn, ptrdiff_t max_nodes,

@@ -43,6 +43,10 @@ struct PackedMeshData {
     std::vector<ptrdiff_t> owned_nodes_ptr, n_shared, ghost_ptr;
     std::vector<int32_t> ghost_idx;   // new (packed) node ids
     std::vector<int32_t> new_to_old;  // node permutation: packed id -> id in the input mesh
+    // CSR of the two-pass apply (PackedLaplacianApply::apply_two_pass, frontend/ops/sfem_PackedLaplacian.cpp:178-262): row r
+    // collects the ghost-buffer entries ghost_reduce_idx[ghost_reduce_ptr[r] .. ghost_reduce_ptr[r + 1]) into node ghost_reduce_dest[r]
+    std::vector<ptrdiff_t> ghost_reduce_ptr, ghost_reduce_idx;
+    std::vector<int32_t> ghost_reduce_dest;
 };
 
 static int build_packed_mesh(PackedMeshData &pm, int nxe, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements, ptrdiff_t epp) {
@@ -128,6 +132,22 @@ static int build_packed_mesh(PackedMeshData &pm, int nxe, ptrdiff_t ne, ptrdiff_
     }
     pm.row_ptrs.clear();
     for (int v = 0; v < nxe; ++v) pm.row_ptrs.push_back(pm.rows[(size_t)v].data());
+    // ghost entries grouped by the node they stand for
+    const size_t ng = pm.ghost_idx.size();
+    pm.ghost_reduce_idx.resize(ng);
+    std::iota(pm.ghost_reduce_idx.begin(), pm.ghost_reduce_idx.end(), (ptrdiff_t)0);
+    std::stable_sort(pm.ghost_reduce_idx.begin(), pm.ghost_reduce_idx.end(),
+                     [&](ptrdiff_t a, ptrdiff_t b) { return pm.ghost_idx[(size_t)a] < pm.ghost_idx[(size_t)b]; });
+    pm.ghost_reduce_ptr.assign(1, 0);
+    pm.ghost_reduce_dest.clear();
+    for (size_t k = 0; k < ng; ++k) {
+        const int32_t n = pm.ghost_idx[(size_t)pm.ghost_reduce_idx[k]];
+        if (pm.ghost_reduce_dest.empty() || pm.ghost_reduce_dest.back() != n) {
+            if (!pm.ghost_reduce_dest.empty()) pm.ghost_reduce_ptr.push_back((ptrdiff_t)k);
+            pm.ghost_reduce_dest.push_back(n);
+        }
+    }
+    if (ng) pm.ghost_reduce_ptr.push_back((ptrdiff_t)ng);
     return B200FEM_SUCCESS;
 }
 
@@ -178,8 +198,11 @@ struct PackedArrays {
 };
 
 // one CTA per pack, node values and results staged in shared memory
-template <typename T, int FAM, int BT>
-__global__ void __launch_bounds__(BT) packed_laplacian_staged_kernel(const PackedArrays a, const T *__restrict__ u, T *__restrict__ y) {
+// TWO_PASS (the reference's atomics-free variant): every owned node takes a plain read-modify-write -- in this pass only the
+// owner pack writes it -- and the ghost results go to the pack's slots of `ghost_buf`; packed_ghost_reduce_kernel adds them up.
+template <typename T, int FAM, int BT, bool TWO_PASS = false>
+__global__ void __launch_bounds__(BT)
+    packed_laplacian_staged_kernel(const PackedArrays a, const T *__restrict__ u, T *__restrict__ y, T *__restrict__ ghost_buf) {
     using L = PackedLocal<T, FAM>;
     constexpr int NXE = L::NXE;
     extern __shared__ __align__(16) unsigned char packed_smem[];
@@ -217,10 +240,27 @@ __global__ void __launch_bounds__(BT) packed_laplacian_staged_kernel(const Packe
             for (int v = 0; v < NXE; ++v) atomicAdd(&ys[l[v]], ol[v]);
         }
         __syncthreads();
-        for (int k = tid; k < n_excl; k += BT) y[base + k] += ys[k];  // exclusively owned: no other pack writes these
-        for (int k = n_excl + tid; k < n_owned; k += BT) red_add(&y[base + k], ys[k]);
-        for (int k = tid; k < n_ghost; k += BT) red_add(&y[a.ghost_idx[g0 + k]], ys[n_owned + k]);
+        if (TWO_PASS) {
+            for (int k = tid; k < n_owned; k += BT) y[base + k] += ys[k];
+            for (int k = tid; k < n_ghost; k += BT) ghost_buf[g0 + k] = ys[n_owned + k];
+        } else {
+            for (int k = tid; k < n_excl; k += BT) y[base + k] += ys[k];  // exclusively owned: no other pack writes these
+            for (int k = n_excl + tid; k < n_owned; k += BT) red_add(&y[base + k], ys[k]);
+            for (int k = tid; k < n_ghost; k += BT) red_add(&y[a.ghost_idx[g0 + k]], ys[n_owned + k]);
+        }
         __syncthreads();
+    }
+}
+
+// second pass: one thread per shared node, fixed-order sum of its ghost-buffer entries (no atomics anywhere in global memory)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    packed_ghost_reduce_kernel(const ptrdiff_t n_rows, const int64_t *__restrict__ ptr, const int64_t *__restrict__ idx,
+                               const int32_t *__restrict__ dest, const T *__restrict__ ghost_buf, T *__restrict__ y) {
+    for (ptrdiff_t r = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (ptrdiff_t)gridDim.x * blockDim.x) {
+        T sum = T(0);
+        for (int64_t j = ptr[r]; j < ptr[r + 1]; ++j) sum += ghost_buf[idx[j]];
+        y[dest[r]] += sum;
     }
 }
 
@@ -262,6 +302,12 @@ struct PackedLaplacian final : OpBase {
     // elements, fp64): tet4 0.082 ms direct / 0.089 ms staged, tet10 0.153 / 0.202 ms -- the vectors of such meshes live in the
     // 126 MB L2, so the staging buys no HBM traffic and its two barriers per pack cost
     int packed_kernel = 1;
+    // two-pass form (b200fem_packed_laplacian_set_two_pass + option "packed_two_pass" = 1, the reference's SFEM_PACKED_TWO_PASS)
+    int two_pass = 0;
+    ptrdiff_t n_reduce_rows = 0;
+    DeviceArray<int64_t> reduce_ptr, reduce_idx;
+    DeviceArray<int32_t> reduce_dest;
+    DeviceArray<unsigned char> ghost_buf;
 
     PackedArrays arrays() const {
         return PackedArrays{ne, n_packs, epp, lidx.ptr, fff.ptr, owned_nodes_ptr.ptr, n_shared.ptr, ghost_ptr.ptr, ghost_idx.ptr};
@@ -269,6 +315,23 @@ struct PackedLaplacian final : OpBase {
     template <typename T, int FAM>
     int launch(const T *x, T *y, cudaStream_t s) {
         const size_t smem = (size_t)2 * max_nodes * sizeof(T);
+        if (two_pass) {
+            constexpr int BT = 256;
+            auto kern = packed_laplacian_staged_kernel<T, FAM, BT, true>;
+            static SmemOptIn opt;
+            if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            const int grid = (int)std::min<ptrdiff_t>(n_packs, (ptrdiff_t)sm_count() * per_sm);
+            kern<<<grid, BT, smem, s>>>(arrays(), x, y, reinterpret_cast<T *>(ghost_buf.ptr));
+            B2_CHECK_LAUNCH();
+            if (n_reduce_rows) {
+                const int g2 = (int)std::min<ptrdiff_t>((n_reduce_rows + 255) / 256, (ptrdiff_t)sm_count() * 16);
+                packed_ghost_reduce_kernel<T><<<g2, 256, 0, s>>>(n_reduce_rows, reduce_ptr.ptr, reduce_idx.ptr, reduce_dest.ptr,
+                                                                reinterpret_cast<const T *>(ghost_buf.ptr), y);
+                B2_CHECK_LAUNCH();
+            }
+            return B200FEM_SUCCESS;
+        }
         if (packed_kernel == 0 && smem <= 200 * 1024) {
             constexpr int BT = 256;
             auto kern = packed_laplacian_staged_kernel<T, FAM, BT>;
@@ -276,7 +339,7 @@ struct PackedLaplacian final : OpBase {
             if (opt.ensure(kern, smem)) return B200FEM_FAILURE;
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
             const int grid = (int)std::min<ptrdiff_t>(n_packs, (ptrdiff_t)sm_count() * per_sm);
-            kern<<<grid, BT, smem, s>>>(arrays(), x, y);
+            kern<<<grid, BT, smem, s>>>(arrays(), x, y, (T *)nullptr);
         } else {
             const int grid = (int)std::min<ptrdiff_t>((ne + 127) / 128, (ptrdiff_t)sm_count() * 16);
             packed_laplacian_direct_kernel<T, FAM><<<grid, 128, 0, s>>>(arrays(), x, y);
@@ -298,17 +361,23 @@ struct PackedLaplacian final : OpBase {
         if (overwrite) B2_CUDA(cudaMemsetAsync(y, 0, (size_t)nn * real_type, s));
         return real_type == B200FEM_F64 ? apply_t<double>((const double *)x, (double *)y, s) : apply_t<float>((const float *)x, (float *)y, s);
     }
-    int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
+    int launches(bool overwrite) const override { return 1 + (two_pass && n_reduce_rows ? 1 : 0) + (overwrite ? 1 : 0); }
     double streamed_bytes(bool overwrite) const override {
         return double(lidx.bytes() + fff.bytes() + ghost_idx.bytes() + owned_nodes_ptr.bytes() + ghost_ptr.bytes() + n_shared.bytes()) +
                double(nn) * real_type * (overwrite ? 2.0 : 3.0);
     }
     int set_option(const char *key, int value) override {
         if (!strcmp(key, "packed_kernel")) { packed_kernel = value; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "packed_two_pass")) {
+            if (value && !ghost_buf.ptr && ghost_idx.n) B2_FAIL("packed_two_pass: call b200fem_packed_laplacian_set_two_pass first");
+            two_pass = value;
+            return B200FEM_SUCCESS;
+        }
         return OpBase::set_option(key, value);
     }
     int get_option(const char *key, int *value) override {
         if (!strcmp(key, "packed_kernel")) { *value = packed_kernel; return B200FEM_SUCCESS; }
+        if (!strcmp(key, "packed_two_pass")) { *value = two_pass; return B200FEM_SUCCESS; }
         if (!strcmp(key, "packed_staged")) { *value = (packed_kernel == 0 && (size_t)2 * max_nodes * real_type <= 200 * 1024) ? 1 : 0; return B200FEM_SUCCESS; }
         return OpBase::get_option(key, value);
     }
@@ -381,6 +450,35 @@ OpBase *make_packed_laplacian(int element_type, ptrdiff_t n_packs, ptrdiff_t epp
     return op;
 }
 
+int packed_laplacian_set_two_pass(OpBase *base, ptrdiff_t n_rows, const ptrdiff_t *ptr, const ptrdiff_t *idx, const int32_t *dest) {
+    auto *op = dynamic_cast<PackedLaplacian *>(base);
+    if (!op) B2_FAIL("set_two_pass: not a packed laplacian");
+    const ptrdiff_t ng = (ptrdiff_t)op->ghost_idx.n;
+    if (n_rows < 0 || (n_rows > 0 && (!ptr || !idx || !dest))) B2_FAIL("set_two_pass: NULL arrays");
+    if ((size_t)2 * op->max_nodes * op->real_type > 200 * 1024)
+        B2_FAIL("set_two_pass: a pack does not fit shared memory (the two-pass form stages the pack), use fewer elements per pack");
+    // every ghost entry must be reduced exactly once, into the node it stands for
+    if ((n_rows ? ptr[n_rows] : 0) != ng) B2_FAIL("set_two_pass: the reduce lists do not cover the ghost entries");
+    std::vector<int32_t> host_ghost((size_t)ng);
+    if (ng) B2_CUDA(cudaMemcpy(host_ghost.data(), op->ghost_idx.ptr, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> seen((size_t)ng, 0);
+    for (ptrdiff_t r = 0; r < n_rows; ++r) {
+        if (dest[r] < 0 || dest[r] >= op->nn || ptr[r] > ptr[r + 1]) B2_FAIL("set_two_pass: bad row");
+        for (ptrdiff_t j = ptr[r]; j < ptr[r + 1]; ++j) {
+            if (idx[j] < 0 || idx[j] >= ng || seen[(size_t)idx[j]] || host_ghost[(size_t)idx[j]] != dest[r])
+                B2_FAIL("set_two_pass: reduce lists inconsistent with ghost_idx");
+            seen[(size_t)idx[j]] = 1;
+        }
+    }
+    std::vector<int64_t> p64(ptr, ptr + (n_rows ? n_rows + 1 : 0)), i64(idx, idx + ng);
+    if (p64.empty()) p64.push_back(0);
+    if (op->reduce_ptr.upload(p64.data(), p64.size()) || op->reduce_idx.upload(i64.data(), i64.size()) ||
+        op->reduce_dest.upload(dest, (size_t)n_rows) || op->ghost_buf.alloc((size_t)std::max<ptrdiff_t>(ng, 1) * op->real_type))
+        return B200FEM_FAILURE;
+    op->n_reduce_rows = n_rows;
+    return B200FEM_SUCCESS;
+}
+
 }  // namespace b200fem
 
 struct b200fem_packed_mesh_s {
@@ -430,6 +528,17 @@ int b200fem_packed_mesh_arrays(b200fem_packed_mesh_t pm, const uint16_t *const *
     if (ghost_ptr) *ghost_ptr = pm->d.ghost_ptr.data();
     if (ghost_idx) *ghost_idx = pm->d.ghost_idx.data();
     if (new_to_old) *new_to_old = pm->d.new_to_old.data();
+    return B200FEM_SUCCESS;
+}
+
+int b200fem_packed_mesh_ghost_reduce(b200fem_packed_mesh_t pm, ptrdiff_t *n_rows, const ptrdiff_t **ghost_reduce_ptr,
+                                     const ptrdiff_t **ghost_reduce_idx, const int32_t **ghost_reduce_dest) {
+    using namespace b200fem;
+    if (!pm) B2_FAIL("packed mesh: NULL handle");
+    if (n_rows) *n_rows = (ptrdiff_t)pm->d.ghost_reduce_dest.size();
+    if (ghost_reduce_ptr) *ghost_reduce_ptr = pm->d.ghost_reduce_ptr.data();
+    if (ghost_reduce_idx) *ghost_reduce_idx = pm->d.ghost_reduce_idx.data();
+    if (ghost_reduce_dest) *ghost_reduce_dest = pm->d.ghost_reduce_dest.data();
     return B200FEM_SUCCESS;
 }
 

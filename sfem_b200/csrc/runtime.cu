@@ -279,6 +279,12 @@ int b200fem_packed_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_
     return B200FEM_SUCCESS;
 }
 
+int b200fem_packed_laplacian_set_two_pass(b200fem_op_t op, ptrdiff_t n_rows, const ptrdiff_t *ghost_reduce_ptr,
+                                          const ptrdiff_t *ghost_reduce_idx, const int32_t *ghost_reduce_dest) {
+    if (!op || !op->impl) B2_FAIL("invalid operator handle");
+    return packed_laplacian_set_two_pass(op->impl, n_rows, ghost_reduce_ptr, ghost_reduce_idx, ghost_reduce_dest);
+}
+
 int b200fem_vector_laplacian_create(b200fem_op_t *op, int element_type, ptrdiff_t ne, ptrdiff_t nn, const int32_t *const *elements,
                                     const float *fff, int vector_size, int real_type) {
     if (check_common(op, ne, nn, elements, real_type)) return B200FEM_FAILURE;

@@ -64,6 +64,8 @@ _SIG = {
     "b200fem_packed_mesh_sizes": [vp, C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz)],
     "b200fem_packed_mesh_arrays": [vp, C.POINTER(C.POINTER(C.POINTER(C.c_uint16))), C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(ssz)),
                                    C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))],
+    "b200fem_packed_mesh_ghost_reduce": [vp, C.POINTER(ssz), C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(ssz)), C.POINTER(C.POINTER(C.c_int32))],
+    "b200fem_packed_laplacian_set_two_pass": [vp, ssz, C.POINTER(ssz), C.POINTER(ssz), C.POINTER(C.c_int32)],
     "b200fem_packed_laplacian_create": [C.POINTER(vp), i32, ssz, ssz, ssz, ssz, ssz, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_float),
                                         C.POINTER(ssz), C.POINTER(ssz), C.POINTER(ssz), C.POINTER(C.c_int32), i32],
     "b200fem_linear_elasticity_create_from_points": [C.POINTER(vp), i32, i32, ssz, ssz, c_idx_pp, c_f32_pp, f64, f64, i32],
@@ -369,6 +371,11 @@ class PackedMesh:
             self.ghost_ptr = cp(gp, self.n_packs + 1, np.int64)
             self.ghost_idx = cp(gi, self.n_ghost_entries, np.int32)
             self.new_to_old = cp(n2o, nnodes, np.int32)
+            nr, rp, ri, rd = ssz(), C.POINTER(ssz)(), C.POINTER(ssz)(), C.POINTER(C.c_int32)()
+            check(_lib.b200fem_packed_mesh_ghost_reduce(h, C.byref(nr), C.byref(rp), C.byref(ri), C.byref(rd)), "packed_mesh_ghost_reduce")
+            self.ghost_reduce_ptr = cp(rp, nr.value + 1, np.int64) if nr.value else np.zeros(1, dtype=np.int64)
+            self.ghost_reduce_idx = cp(ri, self.n_ghost_entries, np.int64)
+            self.ghost_reduce_dest = cp(rd, nr.value, np.int32)
         finally:
             _lib.b200fem_packed_mesh_destroy(h)
         self.n_nodes, self.n_elements = nnodes, ne
@@ -390,8 +397,9 @@ class PackedMesh:
         return out
 
 
-def packed_laplacian(element_type: int, pm: "PackedMesh", fff: np.ndarray, dtype) -> Op:
-    """PackedLaplacian on a PackedMesh (TET4 / HEX8 / TET10 / MACRO_TET4); vectors in the packed node numbering."""
+def packed_laplacian(element_type: int, pm: "PackedMesh", fff: np.ndarray, dtype, two_pass: bool = False) -> Op:
+    """PackedLaplacian on a PackedMesh (TET4 / HEX8 / TET10 / MACRO_TET4); vectors in the packed node numbering.
+    two_pass: hand over the ghost-reduce lists and select the atomics-free two-pass apply (SFEM_PACKED_TWO_PASS)."""
     el = np.ascontiguousarray(pm.elements, dtype=np.uint16)
     f = np.ascontiguousarray(fff, dtype=np.float32)
     onp = np.ascontiguousarray(pm.owned_nodes_ptr, dtype=np.int64)
@@ -403,7 +411,14 @@ def packed_laplacian(element_type: int, pm: "PackedMesh", fff: np.ndarray, dtype
     check(_lib.b200fem_packed_laplacian_create(C.byref(h), element_type, pm.n_packs, pm.n_elements_per_pack, pm.n_elements, pm.n_nodes,
                                                pm.max_nodes_per_pack, _soa_ptrs(el, C.c_uint16), P(f, C.c_float), P(onp, ssz), P(nsh, ssz),
                                                P(gp, ssz), P(gi, C.c_int32), _rt(dtype)), "packed_laplacian_create")
-    return Op(h, pm.n_nodes)
+    op = Op(h, pm.n_nodes)
+    if two_pass:
+        rp = np.ascontiguousarray(pm.ghost_reduce_ptr, dtype=np.int64)
+        ri = np.ascontiguousarray(pm.ghost_reduce_idx, dtype=np.int64)
+        rd = np.ascontiguousarray(pm.ghost_reduce_dest, dtype=np.int32)
+        check(_lib.b200fem_packed_laplacian_set_two_pass(h, rd.size, P(rp, ssz), P(ri, ssz), P(rd, C.c_int32)), "packed_laplacian_set_two_pass")
+        op.set_option("packed_two_pass", 1)
+    return op
 
 
 def vector_laplacian(element_type: int, elements: np.ndarray, fff: np.ndarray, nnodes: int, vector_size: int, dtype) -> Op:

@@ -438,6 +438,19 @@ def test_packed_laplacian(oracles, real, family):
         y.fill_(5.0)
         op.apply_overwrite(x, y)
         assert _rel(y.cpu().numpy(), ref) < TOL[real], direct
+    # the reference's atomics-free two-pass form (SFEM_PACKED_TWO_PASS, PackedLaplacianApply::apply_two_pass :178-262)
+    op2 = lib.packed_laplacian(et, pm, fff, _dt(real), two_pass=True)
+    assert op2.get_option("packed_two_pass") == 1 and op2.launches() == 2
+    y = torch.zeros_like(x)
+    op2.apply(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    op2.apply(x, y)
+    assert _rel(y.cpu().numpy(), 2 * ref) < TOL[real]
+    y.fill_(5.0)
+    op2.apply_overwrite(x, y)
+    assert _rel(y.cpu().numpy(), ref) < TOL[real]
+    with pytest.raises(RuntimeError):  # selecting it without the reduce lists is refused
+        op.set_option("packed_two_pass", 1)
     # the same operator as the unpacked one on the input numbering
     ones = torch.ones(nn, dtype=_dt(real), device="cuda")
     op.apply_overwrite(ones, y)

@@ -57,6 +57,12 @@ def test_packed_mesh_contract(kind, epp):
         sl = slice(p * E, min(ne, (p + 1) * E))
         assert pm.elements[:, sl].max() < n_local
     assert pm.max_nodes_per_pack == max_local <= 65536
+    # the two-pass lists: every ghost entry is reduced exactly once, into the node it stands for, one row per shared ghost node
+    assert pm.ghost_reduce_ptr[0] == 0 and pm.ghost_reduce_ptr[-1] == pm.n_ghost_entries
+    assert np.array_equal(np.sort(pm.ghost_reduce_idx), np.arange(pm.n_ghost_entries))
+    assert np.all(np.diff(pm.ghost_reduce_dest) > 0) and np.array_equal(pm.ghost_reduce_dest, np.unique(pm.ghost_idx))
+    rows = np.repeat(np.arange(pm.ghost_reduce_dest.size), np.diff(pm.ghost_reduce_ptr))
+    assert np.array_equal(pm.ghost_idx[pm.ghost_reduce_idx], pm.ghost_reduce_dest[rows])
 
 
 def test_packed_mesh_rejects_bad_input():
