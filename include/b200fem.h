@@ -48,7 +48,8 @@ extern "C" {
 #define B200FEM_SCATTER_ATOMIC 1  /* red.global.add on every element dof                        */
 #define B200FEM_SCATTER_COLORED 2 /* element colouring, plain read-modify-write, one launch/colour */
 #define B200FEM_SCATTER_PATCH 3   /* element patches staged in shared memory, fixed-order sums, one red per (patch, node):
-                                     the default of tet4 Laplacian and hex8 linear elasticity (hex8 Laplacian: ATOMIC) */
+                                     the default of tet4 Laplacian, hex8 and tet10 linear elasticity (hex8 / tet10 / macro_tet4
+                                     Laplacian and macro_tet4 linear elasticity: ATOMIC -- each default is the measured faster one) */
 
 typedef struct b200fem_op_s *b200fem_op_t; /* opaque operator plan (device connectivity + geometry) */
 
