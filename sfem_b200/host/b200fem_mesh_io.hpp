@@ -120,7 +120,7 @@ namespace b200fem {
         for (auto &e : m.elements)
             for (int32_t v : e)
                 if (v < 0 || v >= nn) return (*err = "connectivity refers to a node outside the coordinate arrays", 1);
-        if (m.element_type.empty()) m.element_type = m.nxe() == 4 ? "TET4" : (m.nxe() == 8 ? "HEX8" : "UNKNOWN");
+        if (m.element_type.empty()) m.element_type = m.nxe() == 4 ? "TET4" : (m.nxe() == 8 ? "HEX8" : (m.nxe() == 10 ? "TET10" : "UNKNOWN"));
         return 0;
     }
 

@@ -64,3 +64,27 @@ def test_round_trip_and_errors(tmp_path):
         host.read_mesh(folder)
     with pytest.raises(lib.B200FemError):
         host.read_mesh(str(tmp_path / "does_not_exist"))
+
+
+def test_tet10_folder_round_trip(tmp_path):
+    """10-node tetrahedra travel through the same folder format (i0.raw .. i9.raw); without meta.yaml 10 index files read as TET10
+    (MACRO_TET4 is the same connectivity under another element_type string)."""
+    host = _host()
+    from sfem_b200 import mesh
+
+    el4, pts4 = mesh.box_tet4(3, 4, 3)
+    el, pts = mesh.tet4_to_tet10(el4, mesh.warp_points(pts4))
+    assert el.shape[0] == 10 and np.array_equal(el[:4], el4)
+    # mid-edge nodes sit in the middle of their edge, every edge has one node
+    p = pts.astype(np.float64)
+    for k, (a, b) in enumerate(mesh.TET10_EDGES):
+        assert np.abs(p[:, el[4 + k]] - 0.5 * (p[:, el[a]] + p[:, el[b]])).max() < 1e-6
+    edges = {tuple(sorted((int(el[a, e]), int(el[b, e])))) for a, b in mesh.TET10_EDGES for e in range(el.shape[1])}
+    assert pts.shape[1] == pts4.shape[1] + len(edges)
+    for et in ("TET10", "MACRO_TET4"):
+        folder = str(tmp_path / et)
+        host.write_mesh(folder, et, el, pts)
+        m = host.read_mesh(folder)
+        assert m["element_type"] == et and np.array_equal(m["elements"], el) and np.array_equal(m["points"], pts)
+    os.remove(os.path.join(str(tmp_path / "TET10"), "meta.yaml"))
+    assert host.read_mesh(str(tmp_path / "TET10"))["element_type"] == "TET10"
