@@ -58,6 +58,24 @@ def _worker(rank, world, port, case):
                 lambda x: orc.tet4_laplacian_apply_opt(lm.elements, lfff, x))
             u_of_gid = lambda g: u[g]
             ref_of_gid = lambda g: ref[g]
+        elif case == "tet10":  # 10-node tetrahedra through the same element partition (the aura rule does not depend on the family)
+            if not available("reference"):
+                return  # the tet10 operator exists in the reference build of the oracle only
+            el4, pts4 = mesh.box_tet4(5, 4, 7)
+            el, pts = mesh.tet4_to_tet10(el4, mesh.warp_points(pts4))
+            nn = pts.shape[1]
+            u = mesh.quadratic_field(pts)
+            ref = orc.p2tet_laplacian_apply_opt("tet10", el, orc.tet4_fff_fill(el[:4], pts), u)
+            part = parallel.partition_elements_by_coordinate(el[:4], pts, world, axis=2)
+            lm = parallel.distribute(el, nn, part, rank, world)
+            if rank < world - 1:
+                assert lm.elements.shape[1] > lm.n_owned_elements, "no aura elements"
+            assert lm.n_local > lm.n_owned, "no ghost nodes"
+            lpts = pts[:, lm.global_ids]
+            lfff = orc.tet4_fff_fill(lm.elements[:4], lpts)
+            apply = lambda x: orc.p2tet_laplacian_apply_opt("tet10", lm.elements, lfff, x)
+            u_of_gid = lambda g: u[g]
+            ref_of_gid = lambda g: ref[g]
         elif case == "tet4_slab":  # per-rank generation of the strong-scaling tet4 box (config 4) against the one-piece box
             nx, ny, nz = 5, 9, 4
             el, pts = mesh.box_tet4(nx, ny, nz)
@@ -124,7 +142,7 @@ def _worker(rank, world, port, case):
         d = torch.tensor([float(x_local[: lm.n_owned].numpy() @ y_local[: lm.n_owned])], dtype=torch.float64)
         dist.all_reduce(d)
         tot = int(cnt.item())
-        gids = np.arange(tot) if case in ("hex8", "tet4", "tet4_slab") else None
+        gids = np.arange(tot) if case in ("hex8", "tet4", "tet4_slab", "tet10") else None
         if case == "sshex8":
             # FunctionSpace::derefine of the distributed mesh: the macro corners as their own [owned | ghosts] space,
             # its exchange plan, and a gather on it
@@ -146,7 +164,8 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2), ("sshex8", 3), ("tet4_slab", 2), ("tet4_slab", 3)])
+@pytest.mark.parametrize("case,world", [("hex8", 2), ("tet4", 3), ("sshex8", 2), ("sshex8", 3), ("tet4_slab", 2), ("tet4_slab", 3),
+                                        ("tet10", 2), ("tet10", 3)])
 def test_distributed_apply_matches_serial(case, world, oracles):
     import torch.multiprocessing as mp
 
