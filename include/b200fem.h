@@ -128,7 +128,9 @@ int b200fem_linear_elasticity_create(b200fem_op_t *op, int element_type, int lev
  *   laplacian, SSHEX8 <- sshex8_laplacian_apply (operators/sshex8/sshex8_laplacian.cpp:39-182): trilinear (non-affine) macro
  *                        elements, FFF at the 6 face-centre quadrature points of every micro element; `points` is indexed by
  *                        sshex8 node id, only the 8 macro corners of each element are read;
- *   linear elasticity, TET4 <- tet4_linear_elasticity_apply / _diag (operators/tet4/tet4_linear_elasticity.cpp:86-230): the
+ *   linear elasticity, TET4 <- tet4_linear_elasticity_apply / _diag / _block_diag_sym (operators/tet4/tet4_linear_elasticity.cpp:
+ *                        86-230, 360-440; the reference's block diagonal is 6 x the blocks of its apply: reproduced, option
+ *                        "reference_block_diag" = 0 gives the consistent ones; also on the cached-adjugate TET4 plan): the
  *                        reference's only tet4 elasticity path (its cached-adjugate twin is declared but not defined);
  *   linear elasticity, HEX8 <- hex8_linear_elasticity_apply (operators/hex8/hex8_linear_elasticity.cpp:86-324): the
  *                        isoparametric variant of SFEM_HEX8_ASSUME_AFFINE=0, Jacobian at each of the 2x2x2 Gauss points;

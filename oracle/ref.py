@@ -455,6 +455,18 @@ class Oracle:
                    self.crt(mu), self.crt(lam), C.c_ssize_t(3), op[0], op[1], op[2])
         return out
 
+    def tet4_linear_elasticity_block_diag_sym(self, elements, points, mu, lam, nnodes):
+        """tet4_linear_elasticity_block_diag_sym (operators/tet4/tet4_linear_elasticity.cpp:360-440; C++ linkage): [nn * 6] AoS,
+        entries (0,0) (0,1) (0,2) (1,1) (1,2) (2,2) of the 3 x 3 node block"""
+        el = np.ascontiguousarray(elements, dtype=np.int32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(nnodes * 6, dtype=self.rt)
+        sz = out.itemsize
+        op = [C.cast(out.ctypes.data + d * sz, C.POINTER(self.crt)) for d in range(6)]
+        self._call("tet4_linear_elasticity_block_diag_sym", C.c_ssize_t(el.shape[1]), C.c_ssize_t(nnodes), _soa_ptrs(el, C.c_int32),
+                   _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(6), *op)
+        return out
+
     def hex8_laplacian_diag(self, elements, points, nnodes):
         """hex8_laplacian_diag (operators/hex8/hex8_laplacian.hpp:36; geometry from the fp32 points, in scalar_t)."""
         el = np.ascontiguousarray(elements, dtype=np.int32)

@@ -7,6 +7,8 @@
 //     SFEM_HEX8_ASSUME_AFFINE=0 -- trilinear geometry, Jacobian at each of the 2x2x2 Gauss points (1-D tables :55-71).
 //
 // Both are one thread per element with RED.ADD scatter: they are fallbacks, the cached-geometry plans are the fast path.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -240,6 +242,74 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Symmetric 3 x 3 node blocks of the tet4 elasticity matrix, 6 entries (0,0) (0,1) (0,2) (1,1) (1,2) (2,2) per node, AoS [nn * 6]:
+// tet4_linear_elasticity_block_diag_sym (operators/tet4/tet4_linear_elasticity.cpp:360-440). Row b of the block of corner v is the
+// response at (v, :) to the unit vector (v, b). The reference calls its point kernel with weight 1 instead of the 1/6 of the
+// reference volume, so ITS blocks are 6 x the blocks of its own apply / diag; `scale` = 6 reproduces that (the default of the
+// plans, option "reference_block_diag"), 1 gives the consistent blocks. FROM_POINTS: geometry recomputed like the reference does.
+template <typename T, bool FROM_POINTS>
+__global__ void __launch_bounds__(256)
+    tet4_le_block_diag_kernel(const ptrdiff_t ne, const ptrdiff_t nn, const int32_t *__restrict__ elements, const float *__restrict__ points,
+                              const float *__restrict__ adjugate, const float *__restrict__ determinant, const T mu, const T lambda,
+                              const T scale, T *__restrict__ out6) {
+    for (ptrdiff_t e = (ptrdiff_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (ptrdiff_t)gridDim.x * blockDim.x) {
+        int32_t ev[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ev[v] = elements[v * ne + e];
+        T A[9], det;
+        if (FROM_POINTS) {
+            T J[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const T p0 = (T)points[(size_t)r * nn + ev[0]];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) J[r * 3 + c] = (T)points[(size_t)r * nn + ev[c + 1]] - p0;
+            }
+            A[0] = J[4] * J[8] - J[5] * J[7];
+            A[1] = J[2] * J[7] - J[1] * J[8];
+            A[2] = J[1] * J[5] - J[2] * J[4];
+            A[3] = J[5] * J[6] - J[3] * J[8];
+            A[4] = J[0] * J[8] - J[2] * J[6];
+            A[5] = J[2] * J[3] - J[0] * J[5];
+            A[6] = J[3] * J[7] - J[4] * J[6];
+            A[7] = J[1] * J[6] - J[0] * J[7];
+            A[8] = J[0] * J[4] - J[1] * J[3];
+            det = J[0] * A[0] + J[1] * A[3] + J[2] * A[6];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) A[k] = (T)adjugate[k * ne + e];
+            det = (T)determinant[e];
+        }
+        for (int v = 0; v < 4; ++v) {
+            T blk[3][3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                T ul[4][3], ol[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) ul[i][c] = (i == v && c == b) ? T(1) : T(0);
+                tet4_le_local(A, det, mu, lambda, ul, ol);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    T r = T(0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i == v) r = ol[i][c];
+                    blk[b][c] = r;
+                }
+            }
+            T *dst = &out6[(ptrdiff_t)ev[v] * 6];
+            red_add(&dst[0], scale * blk[0][0]);
+            red_add(&dst[1], scale * blk[0][1]);
+            red_add(&dst[2], scale * blk[0][2]);
+            red_add(&dst[3], scale * blk[1][1]);
+            red_add(&dst[4], scale * blk[1][2]);
+            red_add(&dst[5], scale * blk[2][2]);
+        }
+    }
+}
+
 // tet4_linear_elasticity_apply / _diag (operators/tet4/tet4_linear_elasticity.cpp:86-160, 162-230): adjugate and determinant
 // recomputed from the points in the vector precision (tet4_adjugate_and_det_s), then the same local operator
 template <typename T, bool DIAG>
@@ -321,6 +391,28 @@ struct Tet4LinearElasticity final : OpBase {
             tet4_le_diag_kernel<float><<<grid, 256, 0, s>>>(ne, elements.ptr, adjugate.ptr, determinant.ptr, (float)mu, (float)lambda, (float *)d);
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
+    }
+    int reference_block_diag = 1;  // reproduce the reference's 6 x blocks (see tet4_le_block_diag_kernel)
+    int block_diag_sym(void *d, cudaStream_t s) override {
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        const double sc = reference_block_diag ? 6.0 : 1.0;
+        if (real_type == B200FEM_F64)
+            tet4_le_block_diag_kernel<double, false><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, nullptr, adjugate.ptr, determinant.ptr, mu, lambda, sc,
+                                                                        (double *)d);
+        else
+            tet4_le_block_diag_kernel<float, false><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, nullptr, adjugate.ptr, determinant.ptr, (float)mu,
+                                                                       (float)lambda, (float)sc, (float *)d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "reference_block_diag")) { reference_block_diag = value; return B200FEM_SUCCESS; }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "reference_block_diag")) { *value = reference_block_diag; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
     }
     int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
 };
@@ -474,6 +566,28 @@ struct PointsOp final : OpBase {
             tet4_le_points_kernel<float, true><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, (float)mu, (float)lambda, nullptr, (float *)d);
         B2_CHECK_LAUNCH();
         return B200FEM_SUCCESS;
+    }
+    int reference_block_diag = 1;
+    int block_diag_sym(void *d, cudaStream_t s) override {
+        if (!(elasticity && nxe == 4)) return OpBase::block_diag_sym(d, s);
+        if (ne == 0) return B200FEM_SUCCESS;
+        const int grid = (int)std::min<ptrdiff_t>((ne + 255) / 256, (ptrdiff_t)sm_count() * 16);
+        const double sc = reference_block_diag ? 6.0 : 1.0;
+        if (real_type == B200FEM_F64)
+            tet4_le_block_diag_kernel<double, true><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, nullptr, nullptr, mu, lambda, sc, (double *)d);
+        else
+            tet4_le_block_diag_kernel<float, true><<<grid, 256, 0, s>>>(ne, nn, elements.ptr, points.ptr, nullptr, nullptr, (float)mu, (float)lambda,
+                                                                      (float)sc, (float *)d);
+        B2_CHECK_LAUNCH();
+        return B200FEM_SUCCESS;
+    }
+    int set_option(const char *key, int value) override {
+        if (!strcmp(key, "reference_block_diag")) { reference_block_diag = value; return B200FEM_SUCCESS; }
+        return OpBase::set_option(key, value);
+    }
+    int get_option(const char *key, int *value) override {
+        if (!strcmp(key, "reference_block_diag")) { *value = reference_block_diag; return B200FEM_SUCCESS; }
+        return OpBase::get_option(key, value);
     }
     int launches(bool overwrite) const override { return 1 + (overwrite ? 1 : 0); }
 };

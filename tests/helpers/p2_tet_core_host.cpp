@@ -79,6 +79,32 @@ int p2_tet_elasticity_f32(int macro, int diag, ptrdiff_t ne, const int32_t *cons
     elasticity<float>(macro, diag, ne, el, adj, det, mu, lambda, u, out);
     return 0;
 }
+// the assembly loop of tet4_le_block_diag_kernel (sfem_b200/csrc/from_points.cu) on the host: rows of the 3 x 3 block of corner v
+// from the responses to the unit vectors (v, b), 6 entries per node, scaled
+int tet4_le_block_diag_f64(ptrdiff_t ne, const int32_t *const *el, const float *adj, const float *det, double mu, double lambda, double scale,
+                           double *out6) {
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        double A[9];
+        for (int k = 0; k < 9; ++k) A[k] = (double)adj[e * 9 + k];
+        for (int v = 0; v < 4; ++v) {
+            double blk[3][3];
+            for (int b = 0; b < 3; ++b) {
+                double ul[10][3] = {}, ol[10][3] = {};
+                ul[v][b] = 1.0;
+                tet4_le_local_add(A, (double)det[e], mu, lambda, ul, ol, 0, 1, 2, 3);
+                for (int c = 0; c < 3; ++c) blk[b][c] = ol[v][c];
+            }
+            double *dst = out6 + (ptrdiff_t)el[v][e] * 6;
+            dst[0] += scale * blk[0][0];
+            dst[1] += scale * blk[0][1];
+            dst[2] += scale * blk[0][2];
+            dst[3] += scale * blk[1][1];
+            dst[4] += scale * blk[1][2];
+            dst[5] += scale * blk[2][2];
+        }
+    }
+    return 0;
+}
 // the sub-tet table, for the test that re-derives it from the node positions
 int p2_tet_macro_table(int s, int *nodes4, int *halfB9) {
     for (int v = 0; v < 4; ++v) nodes4[v] = MacroTet4::node(s, v);

@@ -234,7 +234,7 @@ def test_factory_creates_our_linear_elasticity(oracles, case):
     assert _rel(y.cpu().numpy(), ref) < (1e-11 if case == "tet10" else 1e-12)
     d3 = torch.zeros(nn * 3, dtype=torch.float64, device="cuda")
     assert h.adapter_op_hessian_diag(op, d3.data_ptr()) == 0 and float(d3.min()) > 0
-    if case in ("hex8", "sshex8"):  # the block diagonal exists for the hex families only (like the reference's dispatch)
+    if case in ("hex8", "sshex8"):  # tet4 has one too (6 x, tests/test_gpu_zz_tet4_block_diag.py); tet10 / macro_tet4 have none in the reference
         b6 = torch.zeros(nn * 6, dtype=torch.float64, device="cuda")
         assert h.adapter_op_hessian_block_diag_sym(op, b6.data_ptr()) == 0
         assert torch.allclose(b6.view(nn, 6)[:, [0, 3, 5]].reshape(-1), d3, rtol=1e-13, atol=0)

@@ -214,3 +214,37 @@ def test_tet10_is_exact_on_harmonic_quadratics(core_lib):
     assert np.abs(apply(0, x * x)[interior]).max() > 0.01 * scale  # lap(x^2) = 2: not harmonic, rows do not vanish
     assert np.abs(apply(1, linear)[interior]).max() < 5e-6 * scale
     assert np.abs(apply(1, harmonic)[interior]).max() > 1e-3 * scale  # P1-iso-P2 is not exact on quadratics
+
+
+def test_tet4_block_diag_assembly_and_the_reference_factor_six(core_lib, oracles):
+    """tet4_linear_elasticity_block_diag_sym (operators/tet4/tet4_linear_elasticity.cpp:360-440) calls its point kernel with weight 1
+    instead of 1/6: its blocks are 6 x the node blocks of tet4_linear_elasticity_apply / _diag. Pinned here, and the assembly loop of
+    tet4_le_block_diag_kernel (restated on the host over the same local operator) reproduces it with scale 6."""
+    from oracle.ref import _soa_ptrs
+    from sfem_b200 import mesh
+
+    orc = _ref(oracles, "f64")
+    el, pts = mesh.box_tet4(5, 4, 6)
+    pts = mesh.warp_points(pts)
+    nn = pts.shape[1]
+    mu, lam = 1.3, 0.7
+    ref = orc.tet4_linear_elasticity_block_diag_sym(el, pts, mu, lam, nn)
+    d = orc.tet4_linear_elasticity_diag_points(el, pts, mu, lam, nn)
+    assert np.allclose(ref.reshape(nn, 6)[:, [0, 3, 5]], 6 * d.reshape(nn, 3), rtol=1e-12)
+    adj, det = tet4_adjugate_and_det(el, pts)
+    elc = np.ascontiguousarray(el)
+    out = np.zeros(nn * 6)
+    core_lib.tet4_le_block_diag_f64(C.c_ssize_t(elc.shape[1]), _soa_ptrs(elc, C.c_int32), adj.ctypes.data_as(C.POINTER(C.c_float)),
+                                    det.ctypes.data_as(C.POINTER(C.c_float)), C.c_double(mu), C.c_double(lam), C.c_double(6.0),
+                                    out.ctypes.data_as(C.c_void_p))
+    # fp32 adjugate here against the reference's fp64 one from the points: 1e-6
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 1e-6
+    # off-diagonal entries against unit applies of the reference
+    i = 37
+    for b in range(3):
+        e = np.zeros(nn * 3)
+        e[i * 3 + b] = 1
+        row = orc.tet4_linear_elasticity_apply_points(el, pts, mu, lam, e, nn).reshape(nn, 3)[i]
+        blk = ref.reshape(nn, 6)[i]
+        full = np.array([[blk[0], blk[1], blk[2]], [blk[1], blk[3], blk[4]], [blk[2], blk[4], blk[5]]])
+        assert np.allclose(6 * row, full[b], rtol=1e-11)
