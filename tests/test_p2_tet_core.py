@@ -248,3 +248,40 @@ def test_tet4_block_diag_assembly_and_the_reference_factor_six(core_lib, oracles
         blk = ref.reshape(nn, 6)[i]
         full = np.array([[blk[0], blk[1], blk[2]], [blk[1], blk[3], blk[4]], [blk[2], blk[4], blk[5]]])
         assert np.allclose(6 * row, full[b], rtol=1e-11)
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_elasticity_rigid_modes_and_patch_test(core_lib, family):
+    """Known answers that do not go through the reference: rigid body motions (translation + infinitesimal rotation) lie in the null
+    space of the elasticity operator on every row, and a constant-strain field u = E x (in both the P2 and the P1-iso-P2 space)
+    produces a divergence-free stress, so the rows of the interior nodes vanish (patch test)."""
+    from oracle.ref import _soa_ptrs
+    from sfem_b200 import mesh
+
+    el4, pts4 = mesh.box_tet4(4, 5, 4)
+    el, pts = mesh.tet4_to_tet10(el4, pts4)
+    nn = pts.shape[1]
+    adj, det = tet4_adjugate_and_det(el4, pts4)
+    elc = np.ascontiguousarray(el)
+    macro = int(family == "macro_tet4")
+
+    def apply(u):
+        out = np.zeros(nn * 3)
+        core_lib.p2_tet_elasticity_f64(macro, 0, C.c_ssize_t(elc.shape[1]), _soa_ptrs(elc, C.c_int32), adj.ctypes.data_as(C.POINTER(C.c_float)),
+                                       det.ctypes.data_as(C.POINTER(C.c_float)), C.c_double(1.3), C.c_double(0.7),
+                                       np.ascontiguousarray(u).ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out.reshape(nn, 3)
+
+    p = pts.astype(np.float64).T  # [nn][3]
+    stretch = p * np.array([1.0, -0.5, 0.25])  # reference magnitude: a non-trivial strain
+    scale = np.abs(apply(stretch.reshape(-1))).max()
+    assert scale > 0.01
+    omega = np.array([0.3, -0.7, 0.5])
+    rigid = np.array([0.2, -1.0, 0.4]) + np.cross(np.broadcast_to(omega, p.shape), p)
+    assert np.abs(apply(rigid.reshape(-1))).max() < 1e-6 * scale  # fp32 adjugates: exact up to their rounding (dyadic box: exact)
+    E = np.array([[0.5, 0.2, -0.1], [0.3, -0.4, 0.6], [0.0, 0.7, 0.1]])
+    interior = np.all((p > 1e-6) & (p < 1 - 1e-6), axis=1)
+    assert interior.sum() > 20
+    r = apply((p @ E.T).reshape(-1))
+    assert np.abs(r[interior]).max() < 1e-6 * scale
+    assert np.abs(r[~interior]).max() > 1e-2 * scale  # boundary rows carry the traction
