@@ -17,6 +17,10 @@
  *   affine_hex8_linear_elasticity_apply_adjugate_soa   operators/hex8/hex8_linear_elasticity.cpp:625-787
  *   affine_sshex8_laplacian_stencil_apply_fff          operators/sshex8/sshex8_laplacian.cpp:698-769
  *   affine_sshex8_linear_elasticity_apply_macro_adjugate  operators/sshex8/sshex8_linear_elasticity.cpp:275-424
+ *   tet10_laplacian_apply_opt / _diag_opt, macro_tet4_laplacian_apply_opt / _diag_opt
+ *                                      operators/tet10/tet10_laplacian.cpp:232-302, operators/macro_tet4/macro_tet4_laplacian.cpp:401-490
+ *   packed_laplacian_apply_u16         the pack loop of PackedLaplacianApply::apply / ::apply_two_pass,
+ *                                      frontend/ops/sfem_PackedLaplacian.cpp:111-262 (needs smesh: not compilable into oracle/_ref)
  *
  * Types follow cmake/SFEMNumbers.cmake:5-14: idx_t int32, geom_t / jacobian_t fp32, real_t fp64
  * (-DORACLE_REAL_FLOAT32: fp32).
@@ -384,5 +388,202 @@ int affine_sshex8_linear_elasticity_apply_macro_adjugate(const int level, const 
         free(ev);
         free(K);
     }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- 10-node tetrahedra (P2 and P1-iso-P2 Laplacian)
+ * tet10_laplacian_apply_opt / _diag_opt     operators/tet10/tet10_laplacian.cpp:232-302
+ * macro_tet4_laplacian_apply_opt            operators/macro_tet4/macro_tet4_laplacian.cpp:401-440
+ * Textbook restatement: the 10 x 10 P2 stiffness matrix by the 4-point degree-2 Gauss rule of the tetrahedron (the integrand --
+ * a product of two linear gradients -- is quadratic, so the rule is exact; the reference uses an 8-point rule that is exact too),
+ * the macro element as 8 linear sub-tets on the mid-edge nodes with K_sub = G^T FFF G |T_sub| / |T| and G from the sub-tet's
+ * barycentric gradients in the parent's reference coordinates. Node order: 0-3 corners, 4 = (0,1), 5 = (1,2), 6 = (0,2),
+ * 7 = (0,3), 8 = (1,3), 9 = (2,3). The reference's tet10 diagonal is 1/6 of the matrix diagonal. */
+static const int P2_EDGE[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+static const double P2_GL[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}}; /* grad lambda_a */
+
+static void tet10_matrix(const scalar_t f[6], scalar_t K[10][10]) {
+    const double F[3][3] = {{f[0], f[1], f[2]}, {f[1], f[3], f[4]}, {f[2], f[4], f[5]}};
+    const double a = 0.58541019662496845446, b = 0.13819660112501051518;
+    memset(K, 0, sizeof(scalar_t) * 100);
+    double Kd[10][10] = {{0}};
+    for (int q = 0; q < 4; ++q) {
+        double lam[4] = {b, b, b, b};
+        lam[q] = a;
+        double g[10][3];
+        for (int v = 0; v < 4; ++v)
+            for (int d = 0; d < 3; ++d) g[v][d] = (4 * lam[v] - 1) * P2_GL[v][d];
+        for (int k = 0; k < 6; ++k)
+            for (int d = 0; d < 3; ++d)
+                g[4 + k][d] = 4 * (lam[P2_EDGE[k][0]] * P2_GL[P2_EDGE[k][1]][d] + lam[P2_EDGE[k][1]] * P2_GL[P2_EDGE[k][0]][d]);
+        for (int i = 0; i < 10; ++i)
+            for (int j = 0; j < 10; ++j) {
+                double s = 0;
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) s += g[i][r] * F[r][c] * g[j][c];
+                Kd[i][j] += 0.25 * s; /* weights sum to 1: FFF already carries det / 6 */
+            }
+    }
+    for (int i = 0; i < 10; ++i)
+        for (int j = 0; j < 10; ++j) K[i][j] = (scalar_t)Kd[i][j];
+}
+
+static void macro_tet4_matrix(const scalar_t f[6], scalar_t K[10][10]) {
+    static const int sub[8][4] = {{0, 4, 6, 7}, {4, 1, 5, 8}, {6, 5, 2, 9}, {7, 8, 9, 3}, {4, 5, 6, 8}, {7, 4, 6, 8}, {6, 5, 9, 8}, {7, 6, 9, 8}};
+    static const double P[10][3] = {{0, 0, 0},    {1, 0, 0},   {0, 1, 0},   {0, 0, 1},   {.5, 0, 0},
+                                    {.5, .5, 0},  {0, .5, 0},  {0, 0, .5},  {.5, 0, .5}, {0, .5, .5}};
+    const double F[3][3] = {{f[0], f[1], f[2]}, {f[1], f[3], f[4]}, {f[2], f[4], f[5]}};
+    double Kd[10][10] = {{0}};
+    for (int s = 0; s < 8; ++s) {
+        /* A = [p1 - p0 | p2 - p0 | p3 - p0]; gradients of the sub-tet's barycentric coordinates = rows of A^-1 */
+        double A[9], Ai[9], det;
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) A[r * 3 + c] = P[sub[s][c + 1]][r] - P[sub[s][0]][r];
+        adjugate3(A, Ai, &det);
+        double g[4][3];
+        for (int c = 0; c < 3; ++c) {
+            for (int d = 0; d < 3; ++d) g[c + 1][d] = Ai[c * 3 + d] / det;
+        }
+        for (int d = 0; d < 3; ++d) g[0][d] = -(g[1][d] + g[2][d] + g[3][d]);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double v = 0;
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) v += g[i][r] * F[r][c] * g[j][c];
+                Kd[sub[s][i]][sub[s][j]] += v * fabs(det); /* |T_sub| / |T_parent| = |det A| (both reference volumes are 1/6) */
+            }
+    }
+    for (int i = 0; i < 10; ++i)
+        for (int j = 0; j < 10; ++j) K[i][j] = (scalar_t)Kd[i][j];
+}
+
+static int p2_laplacian_apply(const int macro, const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff,
+                              const real_t *const u, real_t *const values) {
+#pragma omp parallel for
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        scalar_t f[6], K[10][10];
+        for (int k = 0; k < 6; ++k) f[k] = (scalar_t)fff[e * 6 + k];
+        if (macro)
+            macro_tet4_matrix(f, K);
+        else
+            tet10_matrix(f, K);
+        idx_t ev[10];
+        for (int v = 0; v < 10; ++v) ev[v] = elements[v][e];
+        for (int i = 0; i < 10; ++i) {
+            scalar_t s = 0;
+            for (int j = 0; j < 10; ++j) s += K[i][j] * u[ev[j]];
+#pragma omp atomic update
+            values[ev[i]] += s;
+        }
+    }
+    return 0;
+}
+int tet10_laplacian_apply_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff, const real_t *const u,
+                              real_t *const values) {
+    return p2_laplacian_apply(0, ne, elements, fff, u, values);
+}
+int macro_tet4_laplacian_apply_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff, const real_t *const u,
+                                   real_t *const values) {
+    return p2_laplacian_apply(1, ne, elements, fff, u, values);
+}
+static int p2_laplacian_diag(const int macro, const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff, real_t *const diag) {
+#pragma omp parallel for
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        scalar_t f[6], K[10][10];
+        for (int k = 0; k < 6; ++k) f[k] = (scalar_t)fff[e * 6 + k];
+        if (macro)
+            macro_tet4_matrix(f, K);
+        else
+            tet10_matrix(f, K);
+        for (int i = 0; i < 10; ++i) {
+            const scalar_t d = macro ? K[i][i] : K[i][i] / 6; /* the reference's tet10 diagonal: 1/6 of the matrix diagonal */
+#pragma omp atomic update
+            diag[elements[i][e]] += d;
+        }
+    }
+    return 0;
+}
+int tet10_laplacian_diag_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff, real_t *const diag) {
+    return p2_laplacian_diag(0, ne, elements, fff, diag);
+}
+int macro_tet4_laplacian_diag_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const fff, real_t *const diag) {
+    return p2_laplacian_diag(1, ne, elements, fff, diag);
+}
+
+/* ---------------------------------------------------------------- PackedLaplacian
+ * packed_laplacian_apply<uint16_t> -> PackedLaplacianApply<pack_idx_t, NXE, MicroKernel>::apply and ::apply_two_pass
+ * (frontend/ops/sfem_PackedLaplacian.cpp:111-176, 178-262, dispatch 551-700). The reference file needs smesh (absent) and cannot be
+ * compiled into oracle/_ref, so the pack loop is restated here as it is written there: per pack, copy the owned node range and
+ * gather the ghosts into a pack-local vector, run the element operator on the 16-bit local connectivity into a pack-local result,
+ * add the result back (owned range, then ghosts). Two-pass: owned range added in place, ghost results parked in a buffer and
+ * reduced per destination node through the CSR lists. element_type: 4 tet4, 8 hex8, 10 tet10, 100 macro_tet4 (smesh::ElemType). */
+static void packed_element(const int element_type, const scalar_t f[6], const scalar_t *in, const uint16_t *const *el, const ptrdiff_t e,
+                           scalar_t *out) {
+    if (element_type == 4) {
+        scalar_t K[4][4];
+        tet4_matrix(f, K);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) out[el[i][e]] += K[i][j] * in[el[j][e]];
+    } else if (element_type == 8) {
+        scalar_t K[8][8];
+        hex8_laplacian_matrix(f, K);
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 8; ++j) out[el[i][e]] += K[i][j] * in[el[j][e]];
+    } else {
+        scalar_t K[10][10];
+        if (element_type == 10)
+            tet10_matrix(f, K);
+        else
+            macro_tet4_matrix(f, K);
+        for (int i = 0; i < 10; ++i)
+            for (int j = 0; j < 10; ++j) out[el[i][e]] += K[i][j] * in[el[j][e]];
+    }
+}
+
+int packed_laplacian_apply_u16(const int element_type, const ptrdiff_t n_packs, const ptrdiff_t n_elements_per_pack, const ptrdiff_t n_elements,
+                               const ptrdiff_t max_nodes_per_pack, const uint16_t *const *elements, const jacobian_t *const fff,
+                               const ptrdiff_t *owned_nodes_ptr, const ptrdiff_t *n_shared_nodes, const ptrdiff_t *ghost_ptr,
+                               const idx_t *ghost_idx, const real_t *const u, real_t *const values,
+                               /* two-pass lists, all NULL for the one-pass form */
+                               const ptrdiff_t n_ghost_reduce_rows, const ptrdiff_t *ghost_reduce_ptr, const ptrdiff_t *ghost_reduce_idx,
+                               const idx_t *ghost_reduce_dest) {
+    (void)n_shared_nodes; /* sequential: the owned tail needs no atomics here */
+    if (element_type != 4 && element_type != 8 && element_type != 10 && element_type != 100) return 1;
+    const int two_pass = ghost_reduce_ptr != NULL;
+    scalar_t *in = (scalar_t *)malloc(sizeof(scalar_t) * (size_t)(max_nodes_per_pack > 0 ? max_nodes_per_pack : 1));
+    scalar_t *out = (scalar_t *)calloc((size_t)(max_nodes_per_pack > 0 ? max_nodes_per_pack : 1), sizeof(scalar_t));
+    real_t *ghost_buf = two_pass ? (real_t *)calloc((size_t)(ghost_ptr[n_packs] > 0 ? ghost_ptr[n_packs] : 1), sizeof(real_t)) : NULL;
+    for (ptrdiff_t p = 0; p < n_packs; ++p) {
+        const ptrdiff_t e0 = p * n_elements_per_pack, e1 = (p + 1) * n_elements_per_pack < n_elements ? (p + 1) * n_elements_per_pack : n_elements;
+        const ptrdiff_t n_contiguous = owned_nodes_ptr[p + 1] - owned_nodes_ptr[p], n_ghost = ghost_ptr[p + 1] - ghost_ptr[p];
+        const idx_t *ghosts = ghost_idx + ghost_ptr[p];
+        for (ptrdiff_t k = 0; k < n_contiguous; ++k) in[k] = u[owned_nodes_ptr[p] + k];
+        for (ptrdiff_t k = 0; k < n_ghost; ++k) in[n_contiguous + k] = u[ghosts[k]];
+        for (ptrdiff_t e = e0; e < e1; ++e) {
+            scalar_t f[6];
+            for (int k = 0; k < 6; ++k) f[k] = (scalar_t)fff[e * 6 + k];
+            packed_element(element_type, f, in, elements, e, out);
+        }
+        for (ptrdiff_t k = 0; k < n_contiguous; ++k) {
+            values[owned_nodes_ptr[p] + k] += out[k];
+            out[k] = 0;
+        }
+        for (ptrdiff_t k = 0; k < n_ghost; ++k) {
+            if (two_pass)
+                ghost_buf[ghost_ptr[p] + k] = out[n_contiguous + k];
+            else
+                values[ghosts[k]] += out[n_contiguous + k];
+            out[n_contiguous + k] = 0;
+        }
+    }
+    if (two_pass)
+        for (ptrdiff_t r = 0; r < n_ghost_reduce_rows; ++r) {
+            real_t sum = 0;
+            for (ptrdiff_t j = ghost_reduce_ptr[r]; j < ghost_reduce_ptr[r + 1]; ++j) sum += ghost_buf[ghost_reduce_idx[j]];
+            values[ghost_reduce_dest[r]] += sum;
+        }
+    free(in);
+    free(out);
+    free(ghost_buf);
     return 0;
 }

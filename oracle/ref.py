@@ -467,6 +467,29 @@ class Oracle:
                    _soa_ptrs(pts, C.c_float), self.crt(mu), self.crt(lam), C.c_ssize_t(6), *op)
         return out
 
+    def packed_laplacian_apply(self, element_type, pm, fff, u, two_pass=False):
+        """packed_laplacian_apply_u16 of oracle_port.c (port build only): the pack loop of PackedLaplacianApply::apply / ::apply_two_pass
+        (frontend/ops/sfem_PackedLaplacian.cpp:111-262) restated -- that file needs smesh and cannot be compiled into oracle/_ref.
+        `pm` carries the PackedMesh arrays (sfem_b200.lib.PackedMesh); element_type is the smesh::ElemType value (4, 8, 10, 100)."""
+        el = np.ascontiguousarray(pm.elements, dtype=np.uint16)
+        f, pf = self._f32(fff)
+        u, pu = self._r(u)
+        out = np.zeros_like(u)
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        onp, nsh, gp = i64(pm.owned_nodes_ptr), i64(pm.n_shared), i64(pm.ghost_ptr)
+        gi = np.ascontiguousarray(pm.ghost_idx, dtype=np.int32)
+        P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        if two_pass:
+            rp, ri = i64(pm.ghost_reduce_ptr), i64(pm.ghost_reduce_idx)
+            rd = np.ascontiguousarray(pm.ghost_reduce_dest, dtype=np.int32)
+            tail = (C.c_ssize_t(rd.size), P(rp, C.c_ssize_t), P(ri, C.c_ssize_t), P(rd, C.c_int32))
+        else:
+            tail = (C.c_ssize_t(0), None, None, None)
+        self._call("packed_laplacian_apply_u16", C.c_int(element_type), C.c_ssize_t(pm.n_packs), C.c_ssize_t(pm.n_elements_per_pack),
+                   C.c_ssize_t(pm.n_elements), C.c_ssize_t(pm.max_nodes_per_pack), _soa_ptrs(el, C.c_uint16), pf, P(onp, C.c_ssize_t),
+                   P(nsh, C.c_ssize_t), P(gp, C.c_ssize_t), P(gi, C.c_int32), pu, out.ctypes.data_as(C.POINTER(self.crt)), *tail)
+        return out
+
     def hex8_laplacian_diag(self, elements, points, nnodes):
         """hex8_laplacian_diag (operators/hex8/hex8_laplacian.hpp:36; geometry from the fp32 points, in scalar_t)."""
         el = np.ascontiguousarray(elements, dtype=np.int32)

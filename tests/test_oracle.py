@@ -170,3 +170,71 @@ def test_golden_vectors(oracles, real):
                 nn = g["u"].size
                 assert _rel(orc.sshex8_linear_elasticity_apply(L, g["elements"], g["adjugate"], g["determinant"], float(g["mu"]),
                                                                float(g["lam"]), g["u3"], nn), g["y_le_f64"]) < tol, (kind, L)
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_port_restates_the_ten_node_laplacians(oracles, real):
+    """oracle_port.c: tet10 / macro_tet4 Laplacian by textbook quadrature / sub-tet gradients against the reference's generated
+    routines (apply and diag; the tet10 diagonal with the reference's factor 1/6) and against tests/golden/p2_tet.npz."""
+    port = oracles.get(("port", real))
+    if port is None:
+        pytest.skip("port oracle not built")
+    g = np.load(os.path.join(GOLD, "p2_tet.npz"))
+    el, fff, nn = g["elements"], g["fff"], g["points"].shape[1]
+    tol = TOL[real]
+    for fam in ("tet10", "macro_tet4"):
+        assert _rel(port.p2tet_laplacian_apply_opt(fam, el, fff, g["u"]), g[f"{fam}_lap_{real}"]) < tol, fam
+        if real == "f64":
+            assert _rel(port.p2tet_laplacian_diag_opt(fam, el, fff, nn), g[f"{fam}_lap_diag_f64"]) < tol, fam
+    ref = oracles.get(("reference", real))
+    if ref is not None:
+        from sfem_b200 import mesh
+
+        el4, pts4 = mesh.box_tet4(5, 4, 6)
+        el10, pts10 = mesh.tet4_to_tet10(el4, mesh.warp_points(pts4))
+        f = ref.tet4_fff_fill(el10[:4], pts10)
+        u = np.random.default_rng(3).uniform(-1, 1, pts10.shape[1])
+        for fam in ("tet10", "macro_tet4"):
+            assert _rel(port.p2tet_laplacian_apply_opt(fam, el10, f, u), ref.p2tet_laplacian_apply_opt(fam, el10, f, u)) < tol, fam
+
+
+@pytest.mark.parametrize("real", ["f64", "f32"])
+@pytest.mark.parametrize("family", ["tet4", "hex8", "tet10", "macro_tet4"])
+def test_port_packed_laplacian_pack_loop(oracles, real, family):
+    """The restated pack loop of PackedLaplacianApply::apply and ::apply_two_pass (frontend/ops/sfem_PackedLaplacian.cpp:111-262, a
+    file that needs smesh and cannot be compiled here) gives the unpacked operator on the expanded connectivity -- the reference's
+    own *_laplacian_apply_opt where oracle/_ref exists -- for both forms."""
+    from sfem_b200 import lib, mesh
+
+    port = oracles.get(("port", real))
+    if port is None:
+        pytest.skip("port oracle not built")
+    ref = oracles.get(("reference", real)) or port
+    if family == "hex8":
+        el, pts = mesh.box_hex8(7, 6, 5)
+        pts = mesh.shear_points(pts)
+        et, epp = 8, 32
+    else:
+        el, pts = mesh.box_tet4(5, 6, 4)
+        pts = mesh.warp_points(pts)
+        et, epp = 4, 100
+        if family != "tet4":
+            el, pts = mesh.tet4_to_tet10(el, pts)
+            et = 10 if family == "tet10" else 100
+    nn = pts.shape[1]
+    pm = lib.PackedMesh(el, nn, epp)  # host code of libb200fem.so: needs no GPU
+    gl = pm.global_elements()
+    pp = np.ascontiguousarray(pts[:, pm.new_to_old])
+    if family == "hex8":
+        fff = ref.hex8_fff_fill(gl, pp)
+        expect = lambda u: ref.hex8_laplacian_apply_opt(gl, fff, u)
+    elif family == "tet4":
+        fff = ref.tet4_fff_fill(gl, pp)
+        expect = lambda u: ref.tet4_laplacian_apply_opt(gl, fff, u)
+    else:
+        fff = ref.tet4_fff_fill(gl[:4], pp)
+        expect = lambda u: ref.p2tet_laplacian_apply_opt(family, gl, fff, u)
+    u = np.random.default_rng(9).uniform(-1, 1, nn)
+    want = expect(u)
+    assert _rel(port.packed_laplacian_apply(et, pm, fff, u), want) < TOL[real]
+    assert _rel(port.packed_laplacian_apply(et, pm, fff, u, two_pass=True), want) < TOL[real]
