@@ -19,6 +19,8 @@
  *   affine_sshex8_linear_elasticity_apply_macro_adjugate  operators/sshex8/sshex8_linear_elasticity.cpp:275-424
  *   tet10_laplacian_apply_opt / _diag_opt, macro_tet4_laplacian_apply_opt / _diag_opt
  *                                      operators/tet10/tet10_laplacian.cpp:232-302, operators/macro_tet4/macro_tet4_laplacian.cpp:401-490
+ *   tet10_linear_elasticity_apply_opt, macro_tet4_linear_elasticity_apply_opt
+ *                                      operators/tet10/tet10_linear_elasticity.cpp:209-283, operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277
  *   packed_laplacian_apply_u16         the pack loop of PackedLaplacianApply::apply / ::apply_two_pass,
  *                                      frontend/ops/sfem_PackedLaplacian.cpp:111-262 (needs smesh: not compilable into oracle/_ref)
  *
@@ -586,4 +588,91 @@ int packed_laplacian_apply_u16(const int element_type, const ptrdiff_t n_packs, 
     free(out);
     free(ghost_buf);
     return 0;
+}
+
+/* ---------------------------------------------------------------- 10-node tetrahedra, linear elasticity
+ * tet10_linear_elasticity_apply_opt        operators/tet10/tet10_linear_elasticity.cpp:209-283
+ * macro_tet4_linear_elasticity_apply_opt   operators/macro_tet4/macro_tet4_linear_elasticity.cpp:206-277
+ * Textbook restatement: physical shape gradients grad phi_i = J^-T grad_ref phi_i = adjugate^T grad_ref phi_i / det, bilinear form
+ * a(u, v) = int lambda div(u) div(v) + 2 mu eps(u) : eps(v); tet10 by the exact 4-point degree-2 rule (the reference's 8-point rule
+ * carries face centroids written as 0.333333333333 and is 1.5e-12 off), macro_tet4 as 8 constant-strain sub-tets. u / out AoS-strided
+ * component pointers like the reference's signature. */
+static void p2_elasticity_element(const int macro, const scalar_t adj[9], const scalar_t det, const scalar_t mu, const scalar_t lambda,
+                                  const double u[10][3], double out[10][3]) {
+    static const int sub[8][4] = {{0, 4, 6, 7}, {4, 1, 5, 8}, {6, 5, 2, 9}, {7, 8, 9, 3}, {4, 5, 6, 8}, {7, 4, 6, 8}, {6, 5, 9, 8}, {7, 6, 9, 8}};
+    static const double P[10][3] = {{0, 0, 0},    {1, 0, 0},   {0, 1, 0},   {0, 0, 1},   {.5, 0, 0},
+                                    {.5, .5, 0},  {0, .5, 0},  {0, 0, .5},  {.5, 0, .5}, {0, .5, .5}};
+    const double a = 0.58541019662496845446, b = 0.13819660112501051518;
+    for (int i = 0; i < 10; ++i)
+        for (int c = 0; c < 3; ++c) out[i][c] = 0;
+    const int npieces = macro ? 8 : 4;
+    for (int q = 0; q < npieces; ++q) {
+        double gref[10][3] = {{0}}; /* reference gradients of the shape functions active on this piece */
+        double w;                   /* piece weight relative to the parent volume det / 6 */
+        if (!macro) {
+            double lam[4] = {b, b, b, b};
+            lam[q] = a;
+            for (int v = 0; v < 4; ++v)
+                for (int d = 0; d < 3; ++d) gref[v][d] = (4 * lam[v] - 1) * P2_GL[v][d];
+            for (int k = 0; k < 6; ++k)
+                for (int d = 0; d < 3; ++d)
+                    gref[4 + k][d] = 4 * (lam[P2_EDGE[k][0]] * P2_GL[P2_EDGE[k][1]][d] + lam[P2_EDGE[k][1]] * P2_GL[P2_EDGE[k][0]][d]);
+            w = 0.25;
+        } else {
+            double A[9], Ai[9], dA;
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r) A[r * 3 + c] = P[sub[q][c + 1]][r] - P[sub[q][0]][r];
+            adjugate3(A, Ai, &dA);
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) gref[sub[q][c + 1]][d] = Ai[c * 3 + d] / dA;
+            for (int d = 0; d < 3; ++d) gref[sub[q][0]][d] = -(gref[sub[q][1]][d] + gref[sub[q][2]][d] + gref[sub[q][3]][d]);
+            w = fabs(dA);
+        }
+        /* physical gradients: g_phys[d] = sum_j adj[j][d] gref[j] / det   (adjugate = det J^-1, row j = det grad xi_j) */
+        double g[10][3];
+        for (int i = 0; i < 10; ++i)
+            for (int d = 0; d < 3; ++d) g[i][d] = (adj[0 * 3 + d] * gref[i][0] + adj[1 * 3 + d] * gref[i][1] + adj[2 * 3 + d] * gref[i][2]) / det;
+        double H[3][3] = {{0}}; /* displacement gradient */
+        for (int i = 0; i < 10; ++i)
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) H[c][d] += u[i][c] * g[i][d];
+        const double tr = H[0][0] + H[1][1] + H[2][2];
+        double S[3][3];
+        for (int c = 0; c < 3; ++c)
+            for (int d = 0; d < 3; ++d) S[c][d] = mu * (H[c][d] + H[d][c]) + (c == d ? lambda * tr : 0);
+        const double vol = w * det / 6.0;
+        for (int i = 0; i < 10; ++i)
+            for (int c = 0; c < 3; ++c) out[i][c] += vol * (S[c][0] * g[i][0] + S[c][1] * g[i][1] + S[c][2] * g[i][2]);
+    }
+}
+
+static int p2_elasticity_apply(const int macro, const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const adjugate,
+                               const jacobian_t *const determinant, const real_t mu, const real_t lambda, const ptrdiff_t u_stride,
+                               const real_t *const ux, const real_t *const uy, const real_t *const uz, const ptrdiff_t out_stride,
+                               real_t *const outx, real_t *const outy, real_t *const outz) {
+    const real_t *const uc[3] = {ux, uy, uz};
+    real_t *const oc[3] = {outx, outy, outz};
+    for (ptrdiff_t e = 0; e < ne; ++e) {
+        scalar_t A[9];
+        for (int k = 0; k < 9; ++k) A[k] = (scalar_t)adjugate[e * 9 + k];
+        double ul[10][3], ol[10][3];
+        for (int v = 0; v < 10; ++v)
+            for (int c = 0; c < 3; ++c) ul[v][c] = uc[c][(ptrdiff_t)elements[v][e] * u_stride];
+        p2_elasticity_element(macro, A, (scalar_t)determinant[e], mu, lambda, ul, ol);
+        for (int v = 0; v < 10; ++v)
+            for (int c = 0; c < 3; ++c) oc[c][(ptrdiff_t)elements[v][e] * out_stride] += (real_t)ol[v][c];
+    }
+    return 0;
+}
+int tet10_linear_elasticity_apply_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const adjugate,
+                                      const jacobian_t *const determinant, const real_t mu, const real_t lambda, const ptrdiff_t u_stride,
+                                      const real_t *const ux, const real_t *const uy, const real_t *const uz, const ptrdiff_t out_stride,
+                                      real_t *const outx, real_t *const outy, real_t *const outz) {
+    return p2_elasticity_apply(0, ne, elements, adjugate, determinant, mu, lambda, u_stride, ux, uy, uz, out_stride, outx, outy, outz);
+}
+int macro_tet4_linear_elasticity_apply_opt(const ptrdiff_t ne, idx_t **const elements, const jacobian_t *const adjugate,
+                                           const jacobian_t *const determinant, const real_t mu, const real_t lambda,
+                                           const ptrdiff_t u_stride, const real_t *const ux, const real_t *const uy, const real_t *const uz,
+                                           const ptrdiff_t out_stride, real_t *const outx, real_t *const outy, real_t *const outz) {
+    return p2_elasticity_apply(1, ne, elements, adjugate, determinant, mu, lambda, u_stride, ux, uy, uz, out_stride, outx, outy, outz);
 }

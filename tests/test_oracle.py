@@ -238,3 +238,23 @@ def test_port_packed_laplacian_pack_loop(oracles, real, family):
     want = expect(u)
     assert _rel(port.packed_laplacian_apply(et, pm, fff, u), want) < TOL[real]
     assert _rel(port.packed_laplacian_apply(et, pm, fff, u, two_pass=True), want) < TOL[real]
+
+
+@pytest.mark.parametrize("family", ["tet10", "macro_tet4"])
+def test_port_ten_node_elasticity_and_the_reference_quadrature_points(oracles, family):
+    """oracle_port.c: tet10 / macro_tet4 linear elasticity from the textbook weak form (exact 4-point rule / constant-strain sub-tets)
+    against the reference's routines. A second, independent witness of the quirk DESIGN.md section 2 states: the reference's tet10
+    elasticity (face-centroid points written as 0.333333333333) is ~1.5e-12 from the exact integral, macro_tet4 is at rounding."""
+    port, ref = oracles.get(("port", "f64")), oracles.get(("reference", "f64"))
+    if port is None or ref is None:
+        pytest.skip("needs both oracle builds")
+    g = np.load(os.path.join(GOLD, "p2_tet.npz"))
+    el, adj, det = g["elements"], g["adjugate"], g["determinant"]
+    mine = port.p2tet_linear_elasticity_apply_opt(family, el, adj, det, float(g["mu"]), float(g["lam"]), g["u3"])
+    theirs = ref.p2tet_linear_elasticity_apply_opt(family, el, adj, det, float(g["mu"]), float(g["lam"]), g["u3"])
+    assert _rel(theirs, g[f"{family}_le_f64"]) < 1e-14
+    err = _rel(mine, theirs)
+    if family == "tet10":
+        assert 1e-13 < err < 1e-11, err  # the reference's truncated quadrature points, not rounding
+    else:
+        assert err < 1e-13, err

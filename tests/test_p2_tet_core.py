@@ -285,3 +285,25 @@ def test_elasticity_rigid_modes_and_patch_test(core_lib, family):
     r = apply((p @ E.T).reshape(-1))
     assert np.abs(r[interior]).max() < 1e-6 * scale
     assert np.abs(r[~interior]).max() > 1e-2 * scale  # boundary rows carry the traction
+
+
+def test_tet10_elasticity_core_equals_the_exact_restatement(core_lib, oracles):
+    """The corner-gradient form of the kernels' header against the textbook restatement of oracle_port.c (exact 4-point rule): both
+    integrate exactly and agree to rounding, where the reference (truncated quadrature points) sits 1.5e-12 away."""
+    from oracle.ref import _soa_ptrs
+
+    port = oracles.get(("port", "f64"))
+    if port is None:
+        pytest.skip("port oracle not built")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "p2_tet.npz"))
+    el = np.ascontiguousarray(g["elements"])
+    nn = g["points"].shape[1]
+    adj, det = np.ascontiguousarray(g["adjugate"]), np.ascontiguousarray(g["determinant"])
+    u3 = np.ascontiguousarray(g["u3"])
+    out = np.zeros(nn * 3)
+    core_lib.p2_tet_elasticity_f64(0, 0, C.c_ssize_t(el.shape[1]), _soa_ptrs(el, C.c_int32), adj.ctypes.data_as(C.POINTER(C.c_float)),
+                                   det.ctypes.data_as(C.POINTER(C.c_float)), C.c_double(float(g["mu"])), C.c_double(float(g["lam"])),
+                                   u3.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    exact = port.p2tet_linear_elasticity_apply_opt("tet10", el, adj, det, float(g["mu"]), float(g["lam"]), u3)
+    assert np.linalg.norm(out - exact) / np.linalg.norm(exact) < 1e-14
+    assert np.linalg.norm(out - g["tet10_le_f64"]) / np.linalg.norm(exact) > 1e-13
