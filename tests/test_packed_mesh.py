@@ -71,3 +71,19 @@ def test_packed_mesh_rejects_bad_input():
     el = np.array([[0], [1], [2], [7]], dtype=np.int32)
     with pytest.raises(RuntimeError):
         lib.PackedMesh(el, 4, 0)
+
+
+def test_packed_mesh_edge_cases():
+    """Empty mesh, a ragged last pack, nodes no element touches (they stay in the owned range of the last pack)."""
+    from sfem_b200 import lib
+
+    pm = lib.PackedMesh(np.zeros((4, 0), dtype=np.int32), 5, 0)
+    assert pm.n_packs == 0 and pm.n_ghost_entries == 0 and pm.elements.shape == (4, 0) and pm.ghost_reduce_ptr.tolist() == [0]
+    # 3 tets, 2 per pack, node 6 untouched
+    el = np.array([[0, 1, 2], [1, 2, 3], [2, 3, 4], [3, 4, 5]], dtype=np.int32)
+    pm = lib.PackedMesh(el, 7, 2)
+    assert pm.n_packs == 2 and pm.owned_nodes_ptr.tolist()[0] == 0 and pm.owned_nodes_ptr[-1] == 7
+    assert np.array_equal(pm.new_to_old[pm.global_elements()], el)
+    assert pm.new_to_old[-1] == 6  # the orphan node closes the last range
+    assert pm.n_shared.tolist() == [3, 0]  # nodes 2, 3, 4 of pack 0 are touched by pack 1 too; pack 1 shares nothing it owns
+    assert pm.ghost_ptr.tolist() == [0, 0, 3] and np.array_equal(np.sort(pm.new_to_old[pm.ghost_idx]), [2, 3, 4])
