@@ -25,7 +25,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -97,37 +99,57 @@ static int build_packed_mesh(PackedMeshData &pm, int nxe, ptrdiff_t ne, ptrdiff_
         if (shared[(size_t)o]) pm.n_shared[(size_t)p]++;
     }
     for (ptrdiff_t p = 0; p < np; ++p) pm.owned_nodes_ptr[(size_t)p + 1] += pm.owned_nodes_ptr[(size_t)p];
-    // ghosts + local connectivity
+    // ghosts + local connectivity: packs are independent once the numbering is fixed -- built on all host threads (like
+    // PatchPlan::build), every pack keeping its ghost list until the prefix sum
     pm.rows.assign((size_t)nxe, std::vector<uint16_t>((size_t)ne, 0));
+    std::vector<std::vector<int32_t>> pack_ghosts((size_t)np);
+    std::vector<ptrdiff_t> pack_local((size_t)np, 0);
+    std::atomic<bool> too_many{false};
+    auto work = [&](ptrdiff_t p_begin, ptrdiff_t p_end) {
+        for (ptrdiff_t p = p_begin; p < p_end; ++p) {
+            const ptrdiff_t e0 = p * epp, e1 = std::min(ne, e0 + epp);
+            const ptrdiff_t base = pm.owned_nodes_ptr[(size_t)p], n_owned = pm.owned_nodes_ptr[(size_t)p + 1] - base;
+            std::vector<int32_t> &ghosts = pack_ghosts[(size_t)p];
+            for (int v = 0; v < nxe; ++v)
+                for (ptrdiff_t e = e0; e < e1; ++e) {
+                    const int32_t n = old_to_new[(size_t)elements[v][e]];
+                    if (n < base || n >= base + n_owned) ghosts.push_back(n);
+                }
+            std::sort(ghosts.begin(), ghosts.end());
+            ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+            const ptrdiff_t n_local = n_owned + (ptrdiff_t)ghosts.size();
+            if (n_local > 65536) {
+                too_many = true;
+                return;
+            }
+            pack_local[(size_t)p] = n_local;
+            for (int v = 0; v < nxe; ++v)
+                for (ptrdiff_t e = e0; e < e1; ++e) {
+                    const int32_t n = old_to_new[(size_t)elements[v][e]];
+                    ptrdiff_t l;
+                    if (n >= base && n < base + n_owned)
+                        l = n - base;
+                    else
+                        l = n_owned + (std::lower_bound(ghosts.begin(), ghosts.end(), n) - ghosts.begin());
+                    pm.rows[(size_t)v][(size_t)e] = (uint16_t)l;
+                }
+        }
+    };
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const ptrdiff_t nthreads = std::max<ptrdiff_t>(1, std::min<ptrdiff_t>((ptrdiff_t)hw, np / 64));
+        std::vector<std::thread> pool;
+        for (ptrdiff_t t = 1; t < nthreads; ++t) pool.emplace_back(work, np * t / nthreads, np * (t + 1) / nthreads);
+        work(0, np / nthreads);
+        for (auto &th : pool) th.join();
+    }
+    if (too_many) B2_FAIL("packed mesh: a pack touches more than 65536 nodes, use fewer elements per pack");
     pm.ghost_ptr.assign((size_t)np + 1, 0);
     pm.ghost_idx.clear();
     pm.max_nodes_per_pack = 0;
-    std::vector<int32_t> ghosts;
     for (ptrdiff_t p = 0; p < np; ++p) {
-        const ptrdiff_t e0 = p * epp, e1 = std::min(ne, e0 + epp);
-        const ptrdiff_t base = pm.owned_nodes_ptr[(size_t)p], n_owned = pm.owned_nodes_ptr[(size_t)p + 1] - base;
-        ghosts.clear();
-        for (int v = 0; v < nxe; ++v)
-            for (ptrdiff_t e = e0; e < e1; ++e) {
-                const int32_t n = old_to_new[(size_t)elements[v][e]];
-                if (n < base || n >= base + n_owned) ghosts.push_back(n);
-            }
-        std::sort(ghosts.begin(), ghosts.end());
-        ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
-        const ptrdiff_t n_local = n_owned + (ptrdiff_t)ghosts.size();
-        if (n_local > 65536) B2_FAIL("packed mesh: a pack touches more than 65536 nodes, use fewer elements per pack");
-        pm.max_nodes_per_pack = std::max(pm.max_nodes_per_pack, n_local);
-        for (int v = 0; v < nxe; ++v)
-            for (ptrdiff_t e = e0; e < e1; ++e) {
-                const int32_t n = old_to_new[(size_t)elements[v][e]];
-                ptrdiff_t l;
-                if (n >= base && n < base + n_owned)
-                    l = n - base;
-                else
-                    l = n_owned + (std::lower_bound(ghosts.begin(), ghosts.end(), n) - ghosts.begin());
-                pm.rows[(size_t)v][(size_t)e] = (uint16_t)l;
-            }
-        pm.ghost_idx.insert(pm.ghost_idx.end(), ghosts.begin(), ghosts.end());
+        pm.max_nodes_per_pack = std::max(pm.max_nodes_per_pack, pack_local[(size_t)p]);
+        pm.ghost_idx.insert(pm.ghost_idx.end(), pack_ghosts[(size_t)p].begin(), pack_ghosts[(size_t)p].end());
         pm.ghost_ptr[(size_t)p + 1] = (ptrdiff_t)pm.ghost_idx.size();
     }
     pm.row_ptrs.clear();
